@@ -199,6 +199,7 @@ static void raster_triangle(Raster& R, const ShaderCtx& S, int objectAndLink) {
         float fd = frag_depth_and_bc(T, S.tri[2], x, y, bs, bc);
         int idx = x + y * ORC_W;
         if (bs[0] < 0 || bs[1] < 0 || bs[2] < 0 || R.z[idx] > fd) continue;
+        if (fd != fd) continue;      /* deviation: a NaN depth (degenerate perspective divide) is dropped, never stored */
         if (fd < -S.farPlane) continue;
         if (fd > -S.nearPlane) continue;
         uint8_t col[3]; fragment(S, bc, col);
@@ -216,6 +217,7 @@ static void raster_triangle_clipped(Raster& R, const ShaderCtx& S, const float c
         float fd = frag_depth_and_bc(T, clipped[2], x, y, bs, bc);
         int idx = x + y * ORC_W;
         if (bs[0] < 0 || bs[1] < 0 || bs[2] < 0 || R.z[idx] > fd) continue;
+        if (fd != fd) continue;
         float bs2[3], bc2[3];
         frag_depth_and_bc(O, S.tri[2], x, y, bs2, bc2);
         uint8_t col[3]; fragment(S, bc2, col);

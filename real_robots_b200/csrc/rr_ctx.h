@@ -1,0 +1,97 @@
+// Internal context of libreal_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/real_b200.h"
+
+#define RR_NSHAPES 22
+#define RR_NL RR_NUM_LINKS
+#define RR_NDOF RR_NUM_DOF
+#define RR_W RR_EYE_W
+#define RR_H RR_EYE_H
+#define RR_FRAME_STRIDE (RR_NSHAPES * 12)
+#define RR_MAX_TEX 16
+
+// ---- constant robot / scene description (uploaded to __constant__ memory once per process+device)
+struct RobotConst {
+    int parent[RR_NL], jtype[RR_NL], dof[RR_NL], link_of_dof[RR_NDOF];
+    double axis[RR_NL][3], dvec[RR_NL][3], evec[RR_NL][3], rot0[RR_NL][9];
+    double S[RR_NL][6];          // joint motion axis in the link COM frame: (axis, axis x evec)
+    double mass[RR_NL], inertia[RR_NL][3], damping[RR_NL], lower[RR_NL], upper[RR_NL];
+    double base_pos[3];
+    double table_R[9], table_pos[3], table_upper_pos[3];
+    double obj_mass[RR_MAX_OBJECTS], obj_inertia[RR_MAX_OBJECTS][3], obj_init[RR_MAX_OBJECTS][7];
+    int shape_body[RR_NSHAPES], shape_link[RR_NSHAPES];
+    int n_objects;
+    rr_config cfg;
+};
+
+struct TexConst { int w, h, uniform; long long offset; };
+struct ShapeRenderConst {
+    int tri_start, tri_count, tex, objectAndLink;
+    float rgba[4];
+    float aabb_min[3], aabb_max[3];
+};
+struct RenderConst {
+    ShapeRenderConst shape[RR_NSHAPES];
+    TexConst tex[RR_MAX_TEX];
+    float view[16], proj[16];        // row-major 4x4 (TinyRenderer's Matrix[i][j])
+    float light[3];
+    float nearPlane, farPlane;       // shader planes
+    float depthNear, depthFar;       // planes used by the depth output conversion
+    double camP[3];                  // camera position used by back-face culling
+    int n_shapes_active;
+};
+
+// ---- device state (structure of arrays; index [field][env] so a warp-wide access over envs is coalesced)
+struct DevState {
+    int N;
+    double* q;        // [11][N]
+    double* qd;       // [11][N]
+    double* target;   // [11][N]
+    double* obj;      // [3][13][N]   pos3 quat4 lin3 ang3
+    double* touch;    // [4][N]
+    double* link_frames;  // [16][12][N]  world_from_link R(9) + p(3), COM frames
+    float*  render_mats;  // [N][22][40] per-shape matrices for the rasteriser (see rr_render.cu)
+    int*    diag;     // [N][4]
+    long long* timestep;  // [N]
+};
+
+struct rr_ctx {
+    int device;
+    int N, n_objects;
+    rr_config cfg;
+    DevState st;
+    RobotConst robot;          // host copy
+    RenderConst render;        // host copy
+    // device geometry
+    float* d_tris;             // [T][3][8]
+    uint8_t* d_tex;
+    double* d_hull_verts;      // [V][3]
+    int hull_start[RR_NSHAPES], hull_count[RR_NSHAPES];
+    int n_tris;
+    // staging for the host-buffer path
+    double* d_cmd; uint8_t* d_mask; double* d_joint; double* d_touch; double* d_objpose;
+    uint8_t* d_rgb; float* d_depth; int32_t* d_seg;
+    size_t img_capacity;       // envs for which d_rgb/d_depth/d_seg are allocated
+    double* h_pinned; size_t h_pinned_bytes;
+    long long launches;
+    std::string err;
+};
+
+// kernels / launchers (defined in the .cu files)
+int rrk_upload_constants(rr_ctx* ctx);
+int rrk_reset(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s);
+int rrk_set_object_pose(rr_ctx* ctx, const uint8_t* mask, int obj, const double* pq, cudaStream_t s);
+int rrk_set_state(rr_ctx* ctx, const double* q, const double* qd, const double* obj, cudaStream_t s);
+int rrk_get_state(rr_ctx* ctx, double* q, double* qd, double* obj, cudaStream_t s);
+int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s);
+int rrk_read_state(rr_ctx* ctx, double* joint, double* touch, double* objpose, cudaStream_t s);
+int rrk_link_pose(rr_ctx* ctx, int link, double* out, cudaStream_t s);
+int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s);
+int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s);
+int rrk_render_upload_constants(rr_ctx* ctx);
+int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames_or_null, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);
+int rrk_ik(rr_ctx* ctx, const uint8_t* mask, const double* pos_quat, double* out, int max_iter, double residual, cudaStream_t s);

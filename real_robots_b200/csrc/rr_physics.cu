@@ -1,0 +1,765 @@
+// rr_physics.cu — batched articulated dynamics for the REALRobot2020 scene, sm_100a.
+//
+// Replaces pybullet's stepSimulation as called from the reference at real_robots/envs/env.py:340
+// (scene.global_step()), together with the Python prologue of step_joints (env.py:314-321 limitActionByJoint,
+// env.py:257-264 control_objects_limits, robot.py:188-201 apply_action) and the state read-out
+// (robot.py:203-211 calc_state, robot.py:152-163 get_touch_sensors).
+//
+// Design: ONE WARP PER ENV.  All link state of the env lives in shared memory (struct WarpMem); lanes split the
+// work inside each Featherstone step (the 36 entries of a 6x6 articulated inertia, the 6 components of a spatial
+// vector, the 16 links for per-link independent work, the 11 unit-impulse responses).  fp64 throughout, as in
+// pybullet's double-precision build.  Global state is structure-of-arrays [field][env] so the warps of a block
+// touch consecutive addresses.  No tensor cores: nothing here is a dense contraction.
+#include "rr_ctx.h"
+
+__constant__ RobotConst c_robot;
+
+#define WPB 4                 // envs (warps) per block
+#define FULL 0xffffffffu
+
+struct WarpMem {
+    double Rpc[RR_NL][9];     // parent -> link rotation
+    double rvec[RR_NL][3];    // parent COM -> link COM, link frame
+    double Rw[RR_NL][9];      // world_from_link
+    double pw[RR_NL][3];      // link COM, world
+    double v[RR_NL][6];       // spatial velocity (ang, lin) in link frame
+    double c[RR_NL][6];       // Coriolis acceleration
+    double p[RR_NL][6];       // zero-acceleration force
+    double IA[RR_NL][36];     // articulated inertia
+    double h[RR_NL][6];
+    double invD[RR_NL];
+    double Y[RR_NL];
+    double acc[RR_NL][6];
+    double X[36], T[36], Ia[36], pa[6], Ic[6];
+    double Minv[RR_NDOF][RR_NDOF];
+    double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF], tau[RR_NDOF], qdd[RR_NDOF];
+    // non-contact rows (limits then motors)
+    double r_rhs[32], r_inv[32], r_lo[32], r_hi[32], r_app[32], r_sign[32];
+    int r_dof[32];
+    int n_rows;
+};
+
+// ------------------------------------------------------------------------------------------- forward kinematics
+// lane i < 16 computes its link's joint transform; then a serial sweep down the tree builds world frames.
+__device__ __forceinline__ void fk_local(WarpMem& m, int lane) {
+    if (lane < RR_NL) {
+        const int i = lane;
+        double R0[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) R0[k] = c_robot.rot0[i][k];
+        double R[9];
+        if (c_robot.jtype[i] == 1) {
+            double th = -m.q[c_robot.dof[i]];
+            double s, c; sincos(th, &s, &c);
+            double ax = c_robot.axis[i][0], ay = c_robot.axis[i][1], az = c_robot.axis[i][2];
+            double t = 1.0 - c;
+            double A[9] = {c + ax * ax * t, ax * ay * t - az * s, ax * az * t + ay * s,
+                           ay * ax * t + az * s, c + ay * ay * t, ay * az * t - ax * s,
+                           az * ax * t - ay * s, az * ay * t + ax * s, c + az * az * t};
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) R[3 * a + b] = A[3 * a] * R0[b] + A[3 * a + 1] * R0[3 + b] + A[3 * a + 2] * R0[6 + b];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; k++) R[k] = R0[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) m.Rpc[i][k] = R[k];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+            m.rvec[i][a] = R[3 * a] * c_robot.dvec[i][0] + R[3 * a + 1] * c_robot.dvec[i][1] + R[3 * a + 2] * c_robot.dvec[i][2] + c_robot.evec[i][a];
+    }
+    __syncwarp();
+}
+
+// serial sweep: world frames (lanes 0..8 rotation entries, then lanes 0..2 position) and, if with_vel,
+// spatial velocities (lanes 16..21)
+__device__ __forceinline__ void fk_sweep(WarpMem& m, int lane, bool with_vel) {
+    for (int i = 0; i < RR_NL; i++) {
+        const int par = c_robot.parent[i];
+        if (lane < 9) {
+            int a = lane / 3, b = lane % 3;
+            double r;
+            if (par >= 0) r = m.Rw[par][3 * a] * m.Rpc[i][3 * b] + m.Rw[par][3 * a + 1] * m.Rpc[i][3 * b + 1] + m.Rw[par][3 * a + 2] * m.Rpc[i][3 * b + 2];
+            else r = m.Rpc[i][3 * b + a];       // identity base: Rw = Rpc^T
+            m.Rw[i][lane] = r;
+        } else if (with_vel && lane >= 16 && lane < 22) {
+            int k = lane - 16;
+            double wp[3] = {0, 0, 0}, vp[3] = {0, 0, 0};
+            if (par >= 0) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) { wp[a] = m.v[par][a]; vp[a] = m.v[par][3 + a]; }
+            }
+            double w[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) w[a] = m.Rpc[i][3 * a] * wp[0] + m.Rpc[i][3 * a + 1] * wp[1] + m.Rpc[i][3 * a + 2] * wp[2];
+            double qdj = (c_robot.jtype[i] == 1) ? m.qd[c_robot.dof[i]] : 0.0;
+            double out;
+            if (k < 3) out = w[k] + c_robot.S[i][k] * qdj;
+            else {
+                int a = k - 3;
+                double Rv = m.Rpc[i][3 * a] * vp[0] + m.Rpc[i][3 * a + 1] * vp[1] + m.Rpc[i][3 * a + 2] * vp[2];
+                const double* r = m.rvec[i];
+                double wxr = (a == 0) ? (w[1] * r[2] - w[2] * r[1]) : (a == 1) ? (w[2] * r[0] - w[0] * r[2]) : (w[0] * r[1] - w[1] * r[0]);
+                out = Rv + wxr + c_robot.S[i][k] * qdj;
+            }
+            m.v[i][k] = out;
+        }
+        __syncwarp();
+        if (lane < 3) {
+            double pp = (par >= 0) ? m.pw[par][lane] : c_robot.base_pos[lane];
+            m.pw[i][lane] = pp + m.Rw[i][3 * lane] * m.rvec[i][0] + m.Rw[i][3 * lane + 1] * m.rvec[i][1] + m.Rw[i][3 * lane + 2] * m.rvec[i][2];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------- ABA
+__device__ __forceinline__ double dot6(const double* a, const double* b) {
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+
+// per-link bias terms (lane = link): Coriolis acceleration c, zero-acceleration force p, rigid-body inertia
+__device__ __forceinline__ void aba_bias(WarpMem& m, int lane, const rr_config& cf) {
+    if (lane < RR_NL) {
+        const int i = lane;
+        double w[3] = {m.v[i][0], m.v[i][1], m.v[i][2]}, l[3] = {m.v[i][3], m.v[i][4], m.v[i][5]};
+        double qdj = (c_robot.jtype[i] == 1) ? m.qd[c_robot.dof[i]] : 0.0;
+        double ja[3] = {c_robot.S[i][0] * qdj, c_robot.S[i][1] * qdj, c_robot.S[i][2] * qdj};
+        double jl[3] = {c_robot.S[i][3] * qdj, c_robot.S[i][4] * qdj, c_robot.S[i][5] * qdj};
+        // c = v x_motion vJ : top = w x ja ; bottom = l x ja + w x jl
+        m.c[i][0] = w[1] * ja[2] - w[2] * ja[1];
+        m.c[i][1] = w[2] * ja[0] - w[0] * ja[2];
+        m.c[i][2] = w[0] * ja[1] - w[1] * ja[0];
+        m.c[i][3] = (l[1] * ja[2] - l[2] * ja[1]) + (w[1] * jl[2] - w[2] * jl[1]);
+        m.c[i][4] = (l[2] * ja[0] - l[0] * ja[2]) + (w[2] * jl[0] - w[0] * jl[2]);
+        m.c[i][5] = (l[0] * ja[1] - l[1] * ja[0]) + (w[0] * jl[1] - w[1] * jl[0]);
+        double I[3] = {c_robot.inertia[i][0], c_robot.inertia[i][1], c_robot.inertia[i][2]};
+        double mass = c_robot.mass[i];
+        double Iw[3] = {I[0] * w[0], I[1] * w[1], I[2] * w[2]};
+        double wn = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        double ln = sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+        double ka = cf.ang_damping + cf.ang_damping * wn, kl = cf.lin_damping + cf.lin_damping * ln;
+        double fz = mass * cf.gravity;    // world force (0,0,fz); in link frame: R^T * f = column... Rw^T row 2
+        double pa0 = Iw[0] * ka + (w[1] * Iw[2] - w[2] * Iw[1]);
+        double pa1 = Iw[1] * ka + (w[2] * Iw[0] - w[0] * Iw[2]);
+        double pa2 = Iw[2] * ka + (w[0] * Iw[1] - w[1] * Iw[0]);
+        double pl0 = -(m.Rw[i][6] * fz) + l[0] * mass * kl + (w[1] * l[2] - w[2] * l[1]) * mass;
+        double pl1 = -(m.Rw[i][7] * fz) + l[1] * mass * kl + (w[2] * l[0] - w[0] * l[2]) * mass;
+        double pl2 = -(m.Rw[i][8] * fz) + l[2] * mass * kl + (w[0] * l[1] - w[1] * l[0]) * mass;
+        m.p[i][0] = pa0; m.p[i][1] = pa1; m.p[i][2] = pa2; m.p[i][3] = pl0; m.p[i][4] = pl1; m.p[i][5] = pl2;
+    }
+    for (int e = lane; e < RR_NL * 36; e += 32) {
+        int i = e / 36, k = e % 36, r = k / 6, cc = k % 6;
+        double val = 0.0;
+        if (r == cc) val = (r < 3) ? c_robot.inertia[i][r] : c_robot.mass[i];
+        m.IA[i][k] = val;
+    }
+    __syncwarp();
+}
+
+// dense motion transform X (parent -> link): [[R,0],[-[r]x R, R]]
+__device__ __forceinline__ double X_entry(const double* R, const double* r, int a, int b) {
+    if (a < 3) return (b < 3) ? R[3 * a + b] : 0.0;
+    int i = a - 3;
+    if (b >= 3) return R[3 * i + (b - 3)];
+    // -(skew(r) R)[i][b] ; skew(r) row i = (i==0: 0,-rz,ry) (1: rz,0,-rx) (2: -ry,rx,0)
+    double k;
+    if (i == 0) k = -r[2] * R[3 + b] + r[1] * R[6 + b];
+    else if (i == 1) k = r[2] * R[b] - r[0] * R[6 + b];
+    else k = -r[1] * R[b] + r[0] * R[3 + b];
+    return -k;
+}
+
+__device__ __forceinline__ void aba_backward(WarpMem& m, int lane) {
+    for (int i = RR_NL - 1; i >= 0; i--) {
+        const bool rev = c_robot.jtype[i] == 1;
+        const int par = c_robot.parent[i];
+        // Ic = IA*c (lanes 0..5), h = IA*S (lanes 8..13), X entries (all lanes)
+        if (lane < 6) m.Ic[lane] = dot6(&m.IA[i][6 * lane], m.c[i]);
+        else if (lane >= 8 && lane < 14) { int k = lane - 8; m.h[i][k] = rev ? dot6(&m.IA[i][6 * k], c_robot.S[i]) : 0.0; }
+        if (par >= 0) for (int e = lane; e < 36; e += 32) m.X[e] = X_entry(m.Rpc[i], m.rvec[i], e / 6, e % 6);
+        __syncwarp();
+        double invD = 0.0, Y = 0.0;
+        if (rev) {
+            double D = dot6(c_robot.S[i], m.h[i]);
+            invD = 1.0 / D;
+            Y = m.tau[c_robot.dof[i]] - dot6(c_robot.S[i], m.p[i]) - dot6(m.c[i], m.h[i]);
+        }
+        if (lane == 0) { m.invD[i] = invD; m.Y[i] = Y; }
+        if (par >= 0) {
+            for (int e = lane; e < 36; e += 32) { int a = e / 6, b = e % 6; m.Ia[e] = m.IA[i][e] - m.h[i][a] * invD * m.h[i][b]; }
+            if (lane < 6) m.pa[lane] = m.p[i][lane] + m.Ic[lane] + m.h[i][lane] * (invD * Y);
+            __syncwarp();
+            // T = Ia * X
+            for (int e = lane; e < 36; e += 32) {
+                int a = e / 6, b = e % 6; double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; k++) s += m.Ia[6 * a + k] * m.X[6 * k + b];
+                m.T[e] = s;
+            }
+            __syncwarp();
+            // IA[par] += X^T T ; p[par] += X^T pa
+            for (int e = lane; e < 36; e += 32) {
+                int a = e / 6, b = e % 6; double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; k++) s += m.X[6 * k + a] * m.T[6 * k + b];
+                m.IA[par][e] += s;
+            }
+            if (lane < 6) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; k++) s += m.X[6 * k + lane] * m.pa[k];
+                m.p[par][lane] += s;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void aba_forward(WarpMem& m, int lane) {
+    for (int i = 0; i < RR_NL; i++) {
+        const int par = c_robot.parent[i];
+        const bool rev = c_robot.jtype[i] == 1;
+        double a6[6];
+        // every lane computes the transformed parent acceleration redundantly (6x6 on 6 values is cheap)
+        if (par >= 0) {
+            const double* R = m.Rpc[i]; const double* r = m.rvec[i]; const double* ap = m.acc[par];
+            double w[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) w[a] = R[3 * a] * ap[0] + R[3 * a + 1] * ap[1] + R[3 * a + 2] * ap[2];
+            a6[0] = w[0]; a6[1] = w[1]; a6[2] = w[2];
+            a6[3] = R[0] * ap[3] + R[1] * ap[4] + R[2] * ap[5] + (w[1] * r[2] - w[2] * r[1]);
+            a6[4] = R[3] * ap[3] + R[4] * ap[4] + R[5] * ap[5] + (w[2] * r[0] - w[0] * r[2]);
+            a6[5] = R[6] * ap[3] + R[7] * ap[4] + R[8] * ap[5] + (w[0] * r[1] - w[1] * r[0]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; k++) a6[k] = 0.0;
+        }
+        double qa = 0.0;
+        if (rev) qa = m.invD[i] * (m.Y[i] - dot6(m.h[i], a6));
+        __syncwarp();
+        if (lane < 6) m.acc[i][lane] = a6[lane] + m.c[i][lane] + (rev ? c_robot.S[i][lane] * qa : 0.0);
+        if (rev && lane == 6) m.qdd[c_robot.dof[i]] = qa;
+        __syncwarp();
+    }
+}
+
+// M^-1 columns: lane j < 11 runs the articulated-body delta pass (calcAccelerationDeltasMultiDof) for a unit
+// generalised force on dof j, using the cached h / invD / transforms.  Private accumulators stay in local memory.
+__device__ __forceinline__ void aba_minv(WarpMem& m, int lane) {
+    if (lane < RR_NDOF) {
+        double pz[RR_NL][6];
+        double Yd[RR_NL];
+#pragma unroll 1
+        for (int i = 0; i < RR_NL; i++) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) pz[i][k] = 0.0;
+        }
+#pragma unroll 1
+        for (int i = RR_NL - 1; i >= 0; i--) {
+            double pa[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) pa[k] = pz[i][k];
+            if (c_robot.jtype[i] == 1) {
+                double f = (c_robot.dof[i] == lane) ? 1.0 : 0.0;
+                double y = f - dot6(c_robot.S[i], pz[i]);
+                Yd[i] = y;
+                double s = m.invD[i] * y;
+#pragma unroll
+                for (int k = 0; k < 6; k++) pa[k] += m.h[i][k] * s;
+            } else Yd[i] = 0.0;
+            int par = c_robot.parent[i];
+            if (par >= 0) {
+                // X^T force transform: f_p = R^T f ; t_p = R^T (t + r x f)
+                const double* R = m.Rpc[i]; const double* r = m.rvec[i];
+                double t[3] = {pa[0] + (r[1] * pa[5] - r[2] * pa[4]), pa[1] + (r[2] * pa[3] - r[0] * pa[5]), pa[2] + (r[0] * pa[4] - r[1] * pa[3])};
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    pz[par][a] += R[a] * t[0] + R[3 + a] * t[1] + R[6 + a] * t[2];
+                    pz[par][3 + a] += R[a] * pa[3] + R[3 + a] * pa[4] + R[6 + a] * pa[5];
+                }
+            }
+        }
+        // forward: reuse pz as the acceleration store
+#pragma unroll 1
+        for (int i = 0; i < RR_NL; i++) {
+            int par = c_robot.parent[i];
+            double a6[6];
+            if (par >= 0) {
+                const double* R = m.Rpc[i]; const double* r = m.rvec[i]; const double* ap = pz[par];
+                double w[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++) w[a] = R[3 * a] * ap[0] + R[3 * a + 1] * ap[1] + R[3 * a + 2] * ap[2];
+                a6[0] = w[0]; a6[1] = w[1]; a6[2] = w[2];
+                a6[3] = R[0] * ap[3] + R[1] * ap[4] + R[2] * ap[5] + (w[1] * r[2] - w[2] * r[1]);
+                a6[4] = R[3] * ap[3] + R[4] * ap[4] + R[5] * ap[5] + (w[2] * r[0] - w[0] * r[2]);
+                a6[5] = R[6] * ap[3] + R[7] * ap[4] + R[8] * ap[5] + (w[0] * r[1] - w[1] * r[0]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) a6[k] = 0.0;
+            }
+            if (c_robot.jtype[i] == 1) {
+                double qa = m.invD[i] * (Yd[i] - dot6(m.h[i], a6));
+                m.Minv[c_robot.dof[i]][lane] = qa;
+#pragma unroll
+                for (int k = 0; k < 6; k++) a6[k] += c_robot.S[i][k] * qa;
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) pz[i][k] = a6[k];
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------- free rigid bodies
+struct ObjReg { double pos[3], quat[4], lin[3], ang[3]; };
+
+__device__ __forceinline__ void quat_to_mat(const double* q, double* R) {
+    double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    double s = 2.0 / d;
+    double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+    double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+    double yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    R[0] = 1.0 - (yy + zz); R[1] = xy - wz; R[2] = xz + wy;
+    R[3] = xy + wz; R[4] = 1.0 - (xx + zz); R[5] = yz - wx;
+    R[6] = xz - wy; R[7] = yz + wx; R[8] = 1.0 - (xx + yy);
+}
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// unconstrained velocity update of a free body (base-only btMultiBody ABA: gravity, k(1+|v|) damping, gyroscopic term)
+__device__ __forceinline__ void obj_free_update(ObjReg& b, int o, const rr_config& cf) {
+    double R[9]; quat_to_mat(b.quat, R);
+    double wl[3], vl[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        wl[a] = R[a] * b.ang[0] + R[3 + a] * b.ang[1] + R[6 + a] * b.ang[2];
+        vl[a] = R[a] * b.lin[0] + R[3 + a] * b.lin[1] + R[6 + a] * b.lin[2];
+    }
+    double I[3] = {c_robot.obj_inertia[o][0], c_robot.obj_inertia[o][1], c_robot.obj_inertia[o][2]};
+    double mass = c_robot.obj_mass[o];
+    double Iw[3] = {I[0] * wl[0], I[1] * wl[1], I[2] * wl[2]};
+    double wn = sqrt(wl[0] * wl[0] + wl[1] * wl[1] + wl[2] * wl[2]);
+    double ln = sqrt(vl[0] * vl[0] + vl[1] * vl[1] + vl[2] * vl[2]);
+    double ka = cf.ang_damping + cf.ang_damping * wn, kl = cf.lin_damping + cf.lin_damping * ln;
+    double fz = mass * cf.gravity;
+    double pt[3] = {Iw[0] * ka + (wl[1] * Iw[2] - wl[2] * Iw[1]), Iw[1] * ka + (wl[2] * Iw[0] - wl[0] * Iw[2]), Iw[2] * ka + (wl[0] * Iw[1] - wl[1] * Iw[0])};
+    double pf[3] = {-(R[6] * fz) + vl[0] * mass * kl, -(R[7] * fz) + vl[1] * mass * kl, -(R[8] * fz) + vl[2] * mass * kl};
+    double al[3] = {-pt[0] / I[0], -pt[1] / I[1], -pt[2] / I[2]};
+    double ll[3] = {pf[0] * (-1.0 / mass), pf[1] * (-1.0 / mass), pf[2] * (-1.0 / mass)};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        double wdot = R[3 * a] * al[0] + R[3 * a + 1] * al[1] + R[3 * a + 2] * al[2];
+        double vdot = R[3 * a] * ll[0] + R[3 * a + 1] * ll[1] + R[3 * a + 2] * ll[2];
+        b.ang[a] = clampd(b.ang[a] + wdot * cf.dt, -cf.max_coord_vel, cf.max_coord_vel);
+        b.lin[a] = clampd(b.lin[a] + vdot * cf.dt, -cf.max_coord_vel, cf.max_coord_vel);
+    }
+}
+
+__device__ __forceinline__ void obj_integrate(ObjReg& b, double dt) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) b.pos[a] += b.lin[a] * dt;
+    double w[3] = {b.ang[0], b.ang[1], b.ang[2]};
+    double ang = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    if (ang * dt > 0.7853981633974483) ang = 0.5 * 1.5707963267948966 / dt;
+    double k;
+    if (ang < 0.001) k = 0.5 * dt - (dt * dt * dt) * 0.020833333333 * ang * ang;
+    else k = sin(0.5 * ang * dt) / ang;
+    double dq[4] = {w[0] * k, w[1] * k, w[2] * k, cos(ang * dt * 0.5)};
+    const double* q = b.quat;
+    double r[4] = {dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1],
+                   dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2],
+                   dq[3] * q[2] + dq[2] * q[3] + dq[0] * q[1] - dq[1] * q[0],
+                   dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2]};
+    double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+#pragma unroll
+    for (int a = 0; a < 4; a++) b.quat[a] = r[a] / n;
+}
+
+// ------------------------------------------------------------------------------------------- step kernel
+__device__ __forceinline__ void store_frames(const WarpMem& m, const DevState& st, int e, int lane) {
+    for (int k = lane; k < RR_NL * 12; k += 32) {
+        int i = k / 12, j = k % 12;
+        st.link_frames[(size_t)k * st.N + e] = (j < 9) ? m.Rw[i][j] : m.pw[i][j - 9];
+    }
+}
+
+__global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __restrict__ cmd, rr_config cf, int n_objects) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpMem& m = reinterpret_cast<WarpMem*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (e >= st.N) return;
+    const int N = st.N;
+    const double dt = cf.dt;
+
+    if (lane < RR_NDOF) { m.q[lane] = st.q[(size_t)lane * N + e]; m.qd[lane] = st.qd[(size_t)lane * N + e]; }
+    __syncwarp();
+    // ---- action prologue (env.py:314-321, robot.py:188-201): lanes 0..8
+    {
+        double a = 0.0;
+        if (lane < RR_NUM_JOINTS) {
+            const double PI = 3.141592653589793;
+            double cur = (lane < 8) ? m.q[lane] : -m.q[8];
+            double md = (lane < 5) ? 0.2 : (lane < 7 ? 0.3 : 0.1);
+            double diff = fmin(md, cmd[(size_t)e * RR_NUM_JOINTS + lane] - cur);
+            diff = fmax(-md, diff);
+            a = cur + diff;
+            double lo = -PI * 0.944, hi = PI * 0.944;
+            if (lane == 0 || (lane & 1)) { lo = -PI * 0.666; hi = PI * 0.666; }
+            if (lane == 6) { lo = -PI * 0.972; hi = PI * 0.972; }
+            if (lane >= 7) { lo = 0.0; hi = PI / 2; }
+            a = fmax(lo, fmin(a, hi));
+        }
+        double a7 = __shfl_sync(FULL, a, 7);
+        if (lane == 8) a = fmax(0.0, fmin(2 * a7, a));
+        double a8 = __shfl_sync(FULL, a, 8);
+        if (lane < 7) m.target[lane] = a;
+        if (lane == 7) { m.target[7] = a7; m.target[9] = a7; }
+        if (lane == 8) { m.target[8] = -a8; m.target[10] = -a8; }
+    }
+    // ---- objects: lanes 0..n_objects-1 each own one free body (registers)
+    ObjReg ob;
+    const bool has_obj = lane < n_objects;
+    if (has_obj) {
+        const double* base = st.obj + (size_t)lane * 13 * N + e;
+#pragma unroll
+        for (int k = 0; k < 3; k++) ob.pos[k] = base[(size_t)k * N];
+#pragma unroll
+        for (int k = 0; k < 4; k++) ob.quat[k] = base[(size_t)(3 + k) * N];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ob.lin[k] = base[(size_t)(7 + k) * N]; ob.ang[k] = base[(size_t)(10 + k) * N]; }
+        // control_objects_limits (env.py:257-264)
+        if (ob.pos[2] < c_robot.table_pos[2] || (ob.pos[0] > 0.11 && ob.pos[2] < 0.29)) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { ob.pos[k] = c_robot.obj_init[lane][k]; ob.lin[k] = 0.0; ob.ang[k] = 0.0; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) ob.quat[k] = c_robot.obj_init[lane][3 + k];
+        }
+    }
+    __syncwarp();
+
+    // ---- forward dynamics
+    fk_local(m, lane);
+    fk_sweep(m, lane, true);
+    if (lane < RR_NDOF) m.tau[lane] = -c_robot.damping[c_robot.link_of_dof[lane]] * m.qd[lane];
+    aba_bias(m, lane, cf);
+    aba_backward(m, lane);
+    aba_forward(m, lane);
+    if (lane < RR_NDOF) m.qd[lane] = clampd(m.qd[lane] + m.qdd[lane] * dt, -cf.max_coord_vel, cf.max_coord_vel);
+    if (has_obj) obj_free_update(ob, lane, cf);
+    aba_minv(m, lane);
+
+    // ---- constraint rows: joint limits (link order) then motors (link order)
+    if (lane == 0) {
+        int n = 0;
+        for (int i = 0; i < RR_NL; i++) {
+            if (c_robot.jtype[i] != 1 || c_robot.lower[i] > c_robot.upper[i]) continue;
+            int d = c_robot.dof[i];
+            double pos[2] = {m.q[d] - c_robot.lower[i], c_robot.upper[i] - m.q[d]};
+            for (int row = 0; row < 2; row++) {
+                double pen = pos[row];
+                if (pen > 0) continue;
+                double sgn = row ? -1.0 : 1.0;
+                double dd = m.Minv[d][d];
+                double inv = dd > 0 ? 1.0 / dd : 0.0;
+                double rel = sgn * m.qd[d];
+                m.r_dof[n] = d; m.r_sign[n] = sgn; m.r_inv[n] = inv; m.r_lo[n] = 0.0; m.r_hi[n] = cf.limit_max_impulse;
+                m.r_rhs[n] = (-pen * cf.erp / dt - rel) * inv; m.r_app[n] = 0.0;
+                n++;
+            }
+        }
+        for (int d = 0; d < RR_NDOF; d++) {
+            double dd = m.Minv[d][d];
+            double inv = dd > 0 ? 1.0 / dd : 0.0;
+            double cur = m.qd[d];
+            double stab = 1.0 * (m.target[d] - m.q[d]) / dt;
+            double desired = cf.motor_kp * stab + cur + cf.motor_kd * (0.0 - cur);
+            double maxImp = cf.motor_max_force * dt;
+            m.r_dof[n] = d; m.r_sign[n] = 1.0; m.r_inv[n] = inv; m.r_lo[n] = -maxImp; m.r_hi[n] = maxImp;
+            m.r_rhs[n] = (desired - cur) * inv; m.r_app[n] = 0.0;
+            n++;
+        }
+        m.n_rows = n;
+    }
+    __syncwarp();
+    // ---- projected Gauss-Seidel (lane k < 11 owns dv[k])
+    double dv = 0.0;
+    int iters = 0; double res = 0.0;
+    {
+        const int n = m.n_rows;
+        for (int it = 0; it < cf.solver_iterations; it++) {
+            res = 0.0;
+            for (int j = 0; j < n; j++) {
+                int idx = (it & 1) ? j : n - 1 - j;
+                int d = m.r_dof[idx];
+                double sgn = m.r_sign[idx], inv = m.r_inv[idx];
+                double dvd = __shfl_sync(FULL, dv, d);
+                double app = m.r_app[idx];
+                double delta = m.r_rhs[idx] - (sgn * dvd) * inv;
+                double sum = app + delta;
+                double lo = m.r_lo[idx], hi = m.r_hi[idx];
+                if (sum < lo) { delta = lo - app; app = lo; }
+                else if (sum > hi) { delta = hi - app; app = hi; }
+                else app = sum;
+                __syncwarp();
+                if (lane == 0) m.r_app[idx] = app;
+                if (lane < RR_NDOF) dv += m.Minv[lane][d] * sgn * delta;
+                double r = inv != 0.0 ? delta / inv : 0.0;
+                res = fmax(res, r * r);
+                __syncwarp();
+            }
+            iters = it + 1;
+            if (res <= cf.residual_threshold) break;
+        }
+    }
+    if (lane < RR_NDOF) {
+        m.qd[lane] = clampd(m.qd[lane] + dv, -cf.max_coord_vel, cf.max_coord_vel);
+        m.q[lane] += m.qd[lane] * dt;
+    }
+    if (has_obj) obj_integrate(ob, dt);
+    __syncwarp();
+    // ---- epilogue: final kinematics, state write-back, observations
+    fk_local(m, lane);
+    fk_sweep(m, lane, false);
+    store_frames(m, st, e, lane);
+    if (lane < RR_NDOF) {
+        st.q[(size_t)lane * N + e] = m.q[lane]; st.qd[(size_t)lane * N + e] = m.qd[lane];
+        st.target[(size_t)lane * N + e] = m.target[lane];
+    }
+    if (has_obj) {
+        double* base = st.obj + (size_t)lane * 13 * N + e;
+#pragma unroll
+        for (int k = 0; k < 3; k++) base[(size_t)k * N] = ob.pos[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) base[(size_t)(3 + k) * N] = ob.quat[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { base[(size_t)(7 + k) * N] = ob.lin[k]; base[(size_t)(10 + k) * N] = ob.ang[k]; }
+    }
+    if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = 0.0;
+    if (lane == 0) {
+        st.diag[4 * e] = m.n_rows; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = 0; st.diag[4 * e + 3] = 0;
+        st.timestep[e] += 1;
+    }
+}
+
+// FK only (after reset / set_state): refresh link_frames
+__global__ void __launch_bounds__(WPB * 32) k_fk(DevState st) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpMem& m = reinterpret_cast<WarpMem*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (e >= st.N) return;
+    if (lane < RR_NDOF) m.q[lane] = st.q[(size_t)lane * st.N + e];
+    __syncwarp();
+    fk_local(m, lane);
+    fk_sweep(m, lane, false);
+    store_frames(m, st, e, lane);
+}
+
+__global__ void k_reset(DevState st, const uint8_t* __restrict__ mask, int n_objects) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    if (mask && !mask[e]) return;
+    const int N = st.N;
+    for (int d = 0; d < RR_NDOF; d++) { st.q[(size_t)d * N + e] = 0.0; st.qd[(size_t)d * N + e] = 0.0; st.target[(size_t)d * N + e] = 0.0; }
+    for (int o = 0; o < RR_MAX_OBJECTS; o++) {
+        double* base = st.obj + (size_t)o * 13 * N + e;
+        for (int k = 0; k < 7; k++) base[(size_t)k * N] = c_robot.obj_init[o][k];
+        for (int k = 7; k < 13; k++) base[(size_t)k * N] = 0.0;
+    }
+    for (int k = 0; k < RR_NUM_TOUCH; k++) st.touch[(size_t)k * N + e] = 0.0;
+    st.timestep[e] = 0;
+    for (int k = 0; k < 4; k++) st.diag[4 * e + k] = 0;
+}
+
+__global__ void k_set_object_pose(DevState st, const uint8_t* __restrict__ mask, int obj, const double* __restrict__ pq) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    if (mask && !mask[e]) return;
+    double* base = st.obj + (size_t)obj * 13 * st.N + e;
+    for (int k = 0; k < 7; k++) base[(size_t)k * st.N] = pq[(size_t)e * 7 + k];
+    for (int k = 7; k < 13; k++) base[(size_t)k * st.N] = 0.0;
+}
+
+// AoS [N,...] <-> SoA [...][N] transposes for the state hooks
+__global__ void k_set_state(DevState st, const double* __restrict__ q, const double* __restrict__ qd, const double* __restrict__ obj) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    const int N = st.N;
+    if (q) for (int d = 0; d < RR_NDOF; d++) st.q[(size_t)d * N + e] = q[(size_t)e * RR_NDOF + d];
+    if (qd) for (int d = 0; d < RR_NDOF; d++) st.qd[(size_t)d * N + e] = qd[(size_t)e * RR_NDOF + d];
+    if (obj) for (int k = 0; k < 39; k++) st.obj[(size_t)k * N + e] = obj[(size_t)e * 39 + k];
+}
+__global__ void k_get_state(DevState st, double* __restrict__ q, double* __restrict__ qd, double* __restrict__ obj) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    const int N = st.N;
+    if (q) for (int d = 0; d < RR_NDOF; d++) q[(size_t)e * RR_NDOF + d] = st.q[(size_t)d * N + e];
+    if (qd) for (int d = 0; d < RR_NDOF; d++) qd[(size_t)e * RR_NDOF + d] = st.qd[(size_t)d * N + e];
+    if (obj) for (int k = 0; k < 39; k++) obj[(size_t)e * 39 + k] = st.obj[(size_t)k * N + e];
+}
+
+// robot.py:203-211 calc_state, robot.py:152-163 touch, env.py:240-244 object positions
+__global__ void k_read_state(DevState st, double* __restrict__ joint, double* __restrict__ touch, double* __restrict__ objpose, int n_objects) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    const int N = st.N;
+    if (joint) {
+        for (int i = 0; i < 8; i++) joint[(size_t)e * 9 + i] = st.q[(size_t)i * N + e];
+        joint[(size_t)e * 9 + 8] = -st.q[(size_t)8 * N + e];
+    }
+    if (touch) for (int k = 0; k < RR_NUM_TOUCH; k++) touch[(size_t)e * 4 + k] = st.touch[(size_t)k * N + e];
+    if (objpose) for (int o = 0; o < n_objects; o++) for (int k = 0; k < 7; k++)
+        objpose[((size_t)e * n_objects + o) * 7 + k] = st.obj[((size_t)o * 13 + k) * N + e];
+}
+
+__device__ __forceinline__ void mat_to_quat(const double* R, double* q) {
+    double tr = R[0] + R[4] + R[8];
+    if (tr > 0) {
+        double s = sqrt(tr + 1.0);
+        q[3] = s * 0.5; s = 0.5 / s;
+        q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
+    } else {
+        int i = R[0] < R[4] ? (R[4] < R[8] ? 2 : 1) : (R[0] < R[8] ? 2 : 0);
+        int j = (i + 1) % 3, k = (i + 2) % 3;
+        double s = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        q[i] = s * 0.5; s = 0.5 / s;
+        q[3] = (R[3 * k + j] - R[3 * j + k]) * s; q[j] = (R[3 * j + i] + R[3 * i + j]) * s; q[k] = (R[3 * k + i] + R[3 * i + k]) * s;
+    }
+}
+
+__global__ void k_link_pose(DevState st, int link, double* __restrict__ out) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    double R[9], p[3];
+    if (link < 0) { for (int k = 0; k < 9; k++) R[k] = (k % 4 == 0) ? 1.0 : 0.0; for (int k = 0; k < 3; k++) p[k] = c_robot.base_pos[k]; }
+    else {
+        for (int k = 0; k < 9; k++) R[k] = st.link_frames[((size_t)link * 12 + k) * st.N + e];
+        for (int k = 0; k < 3; k++) p[k] = st.link_frames[((size_t)link * 12 + 9 + k) * st.N + e];
+    }
+    double q[4]; mat_to_quat(R, q);
+    for (int k = 0; k < 3; k++) out[(size_t)e * 7 + k] = p[k];
+    for (int k = 0; k < 4; k++) out[(size_t)e * 7 + 3 + k] = q[k];
+}
+
+// env.py:181-200 evaluateGoal
+__global__ void k_score(DevState st, const double* __restrict__ goal, double* __restrict__ score, int n_objects) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    const double pos_const = -log(0.25) / 0.10;
+    double s = 0.0;
+    for (int o = 0; o < n_objects; o++) {
+        double d2 = 0.0;
+        for (int k = 0; k < 3; k++) {
+            double d = goal[((size_t)e * n_objects + o) * 3 + k] - st.obj[((size_t)o * 13 + k) * st.N + e];
+            d2 += d * d;
+        }
+        s += exp(-pos_const * sqrt(d2));
+    }
+    score[e] = s;
+}
+
+// world frames of all 22 scene shapes, f64 [N][22][12] (render input / test hook)
+__global__ void k_shape_frames(DevState st, double* __restrict__ frames, int n_objects) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    const int N = st.N;
+    for (int s = 0; s < RR_NSHAPES; s++) {
+        double* f = frames + ((size_t)e * RR_NSHAPES + s) * 12;
+        int body = c_robot.shape_body[s], link = c_robot.shape_link[s];
+        if (body == 0) {
+            if (link < 0) { for (int k = 0; k < 9; k++) f[k] = (k % 4 == 0) ? 1.0 : 0.0; for (int k = 0; k < 3; k++) f[9 + k] = c_robot.base_pos[k]; }
+            else for (int k = 0; k < 12; k++) f[k] = st.link_frames[((size_t)link * 12 + k) * N + e];
+        } else if (body == 1) {
+            for (int k = 0; k < 9; k++) f[k] = c_robot.table_R[k];
+            for (int k = 0; k < 3; k++) f[9 + k] = (link < 0) ? c_robot.table_pos[k] : c_robot.table_upper_pos[k];
+        } else {
+            int o = body - 2;
+            double q[4], R[9];
+            for (int k = 0; k < 4; k++) q[k] = st.obj[((size_t)o * 13 + 3 + k) * N + e];
+            quat_to_mat(q, R);
+            for (int k = 0; k < 9; k++) f[k] = R[k];
+            for (int k = 0; k < 3; k++) f[9 + k] = st.obj[((size_t)o * 13 + k) * N + e];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host launchers
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return -1; } } while (0)
+
+int rrk_upload_constants(rr_ctx* ctx) {
+    CK(cudaMemcpyToSymbol(c_robot, &ctx->robot, sizeof(RobotConst)));
+    CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
+    CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
+    return 0;
+}
+static inline int nblk(int n, int b) { return (n + b - 1) / b; }
+
+static int launch_fk(rr_ctx* ctx, cudaStream_t s) {
+    k_fk<<<nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s>>>(ctx->st);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int rrk_reset(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
+    k_reset<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, mask, ctx->n_objects);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return launch_fk(ctx, s);
+}
+int rrk_set_object_pose(rr_ctx* ctx, const uint8_t* mask, int obj, const double* pq, cudaStream_t s) {
+    k_set_object_pose<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, mask, obj, pq);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int rrk_set_state(rr_ctx* ctx, const double* q, const double* qd, const double* obj, cudaStream_t s) {
+    k_set_state<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, q, qd, obj);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return launch_fk(ctx, s);
+}
+int rrk_get_state(rr_ctx* ctx, double* q, double* qd, double* obj, cudaStream_t s) {
+    k_get_state<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, q, qd, obj);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
+    k_step<<<nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s>>>(ctx->st, cmd, ctx->cfg, ctx->n_objects);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int rrk_read_state(rr_ctx* ctx, double* joint, double* touch, double* objpose, cudaStream_t s) {
+    k_read_state<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, joint, touch, objpose, ctx->n_objects);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int rrk_link_pose(rr_ctx* ctx, int link, double* out, cudaStream_t s) {
+    k_link_pose<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, link, out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s) {
+    k_score<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, goal, score, ctx->n_objects);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s) {
+    k_shape_frames<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, frames, ctx->n_objects);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int rrk_ik(rr_ctx* ctx, const uint8_t*, const double*, double*, int, double, cudaStream_t) {
+    ctx->err = "rr_ik: not implemented yet";
+    return -2;
+}

@@ -1,0 +1,495 @@
+// rr_render.cu — batched strip rasteriser with TinyRenderer's conventions, sm_100a.  Compile with -fmad=false.
+//
+// Replaces getCameraImage(320,240, TinyRenderer) as called by the reference at real_robots/envs/env.py:553-558
+// (EyeCamera.renderTarget; view matrix env.py:543-546, projection env.py:548-551) and the output slicing at
+// env.py:560-567: RGB u8[240,320,3], depth f32[240,320], segmentation mask i32[240,320].
+//
+// Pipeline per env (all fp32, same operation order as TinyRenderer's vec/mat templates, no FMA contraction):
+//   k_render_setup : one thread per (env, shape): model / projection*view*model / inverse-transpose matrices and a
+//                    conservative screen-row range of the shape.
+//   k_raster       : one CTA per (env, strip of STRIP_ROWS raster rows).  A 64-bit key per pixel lives in shared
+//                    memory: (order-preserving depth bits << 32) | (triangle index + 1).  Threads walk the triangles
+//                    of the shapes that can touch the strip, set them up (vertex shader, back-face cull, near-plane
+//                    clip, viewport, bounding box) and atomicMax the key of every covered pixel — the z-test
+//                    "later triangle wins ties" of the sequential renderer is exactly max over (depth, index).
+//                    Large triangles are deferred to a queue and rasterised by the whole CTA.  After a barrier the
+//                    CTA resolves: one fragment-shader evaluation per pixel for the winning triangle, then
+//                    coalesced 12/16/16-byte stores of RGB, depth and mask rows (vertical flip folded in).
+// Images are written once; meshes (1.7 MB) and textures (10 MB) are shared by all envs and stay L2 resident.
+#include "rr_ctx.h"
+#include <cfloat>
+
+__constant__ RenderConst c_render;
+
+#define STRIP_ROWS 40
+#define NSTRIPS (RR_H / STRIP_ROWS)
+#define RTHREADS 256
+#define MAT_STRIDE 40          // floats per (env, shape): pmv[16] model[12] invT[9] ylo yhi flag
+#define BIG_AREA 48            // pixels in-strip above which a triangle goes to the cooperative queue
+#define BIGQ 512
+
+// --------------------------------------------------------------------------------------------- float helpers
+__device__ __forceinline__ float dot4r(const float* a, const float* b) { float r = 0.f; r += a[3] * b[3]; r += a[2] * b[2]; r += a[1] * b[1]; r += a[0] * b[0]; return r; }
+__device__ __forceinline__ float dot4r(const float* a, float b0, float b1, float b2, float b3) { float r = 0.f; r += a[3] * b3; r += a[2] * b2; r += a[1] * b1; r += a[0] * b0; return r; }
+__device__ __forceinline__ float dot3r(float a0, float a1, float a2, const float* b) { float r = 0.f; r += a2 * b[2]; r += a1 * b[1]; r += a0 * b[0]; return r; }
+
+__device__ float det2r(const float* m) {   // 2x2 row-major, expansion along row 0 from the last column
+    float ret = 0.f;
+    ret += m[1] * (m[2] * -1.f);
+    ret += m[0] * (m[3] * 1.f);
+    return ret;
+}
+__device__ float det3r(const float* m) {   // 3x3 row-major
+    float ret = 0.f;
+#pragma unroll
+    for (int i = 2; i >= 0; i--) {
+        float mn[4]; int k = 0;
+#pragma unroll
+        for (int r = 1; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) if (c != i) mn[k++] = m[3 * r + c];
+        float cof = det2r(mn) * ((i % 2) ? -1.f : 1.f);
+        ret += m[i] * cof;
+    }
+    return ret;
+}
+__device__ float cofactor4(const float M[4][4], int row, int col) {
+    float mn[9]; int k = 0;
+    for (int r = 0; r < 4; r++) if (r != row) for (int c = 0; c < 4; c++) if (c != col) mn[k++] = M[r][c];
+    return det3r(mn) * (((row + col) % 2) ? -1.f : 1.f);
+}
+
+// --------------------------------------------------------------------------------------------- setup kernel
+// frames: f64 [N][22][12] or NULL (then read the simulated state)
+__global__ void k_render_setup(DevState st, const double* __restrict__ frames, float* __restrict__ mats, int n_objects,
+                               const double* __restrict__ static_frames /* [22][12] for non-robot, non-object shapes */) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= st.N * RR_NSHAPES) return;
+    int e = gid / RR_NSHAPES, s = gid % RR_NSHAPES;
+    float* out = mats + (size_t)gid * MAT_STRIDE;
+    const ShapeRenderConst& sh = c_render.shape[s];
+    int body = sh.objectAndLink & 0xffffff, link = (sh.objectAndLink >> 24) - 1;
+    bool active = !(body >= 2 && body - 2 >= n_objects) && sh.rgba[3] != 0.f;
+    double F[12];
+    if (frames) {
+        for (int k = 0; k < 12; k++) F[k] = frames[((size_t)e * RR_NSHAPES + s) * 12 + k];
+    } else if (body == 0 && link >= 0) {
+        for (int k = 0; k < 12; k++) F[k] = st.link_frames[((size_t)link * 12 + k) * st.N + e];
+    } else if (body >= 2) {
+        int o = body - 2;
+        double q[4];
+        for (int k = 0; k < 4; k++) q[k] = st.obj[((size_t)o * 13 + 3 + k) * st.N + e];
+        double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+        double sc = 2.0 / d;
+        double xs = q[0] * sc, ys = q[1] * sc, zs = q[2] * sc;
+        double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+        double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+        double yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+        F[0] = 1.0 - (yy + zz); F[1] = xy - wz; F[2] = xz + wy;
+        F[3] = xy + wz; F[4] = 1.0 - (xx + zz); F[5] = yz - wx;
+        F[6] = xz - wy; F[7] = yz + wx; F[8] = 1.0 - (xx + yy);
+        for (int k = 0; k < 3; k++) F[9 + k] = st.obj[((size_t)o * 13 + k) * st.N + e];
+    } else {
+        for (int k = 0; k < 12; k++) F[k] = static_frames[s * 12 + k];
+    }
+    float model[4][4];
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) model[i][j] = (float)F[3 * i + j]; model[i][3] = (float)F[9 + i]; }
+    model[3][0] = model[3][1] = model[3][2] = 0.f; model[3][3] = 1.f;
+    float mv[4][4], pmv[4][4];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++)
+        mv[i][j] = dot4r(&c_render.view[4 * i], model[0][j], model[1][j], model[2][j], model[3][j]);
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++)
+        pmv[i][j] = dot4r(&c_render.proj[4 * i], mv[0][j], mv[1][j], mv[2][j], mv[3][j]);
+    // invert_transpose: adjugate / (adj[0] . model[0])
+    float adj0[4];
+    for (int j = 0; j < 4; j++) adj0[j] = cofactor4(model, 0, j);
+    float tmp = dot4r(adj0, model[0]);
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out[4 * i + j] = pmv[i][j];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) out[16 + 4 * i + j] = model[i][j];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[28 + 3 * i + j] = ((i == 0) ? adj0[j] : cofactor4(model, i, j)) / tmp;
+    // conservative raster-row range from the 8 corners of the local AABB
+    float ylo = 0.f, yhi = (float)(RR_H - 1);
+    bool all_front = true; float mn = FLT_MAX, mx = -FLT_MAX;
+    for (int c = 0; c < 8; c++) {
+        float p[4] = {(c & 1) ? sh.aabb_max[0] : sh.aabb_min[0], (c & 2) ? sh.aabb_max[1] : sh.aabb_min[1], (c & 4) ? sh.aabb_max[2] : sh.aabb_min[2], 1.f};
+        float cy = dot4r(pmv[1], p), cw = dot4r(pmv[3], p);
+        if (!(cw > 1e-3f)) { all_front = false; break; }
+        float y = (RR_H / 2.f) * cw + (RR_H / 2.f) * cy;
+        y = y / cw;
+        mn = fminf(mn, y); mx = fmaxf(mx, y);
+    }
+    if (all_front) { ylo = mn - 2.f; yhi = mx + 2.f; }
+    out[37] = ylo; out[38] = yhi; out[39] = active ? 1.f : 0.f;
+}
+
+// --------------------------------------------------------------------------------------------- triangle setup
+struct Tri {
+    float c[4][3];         // clip coordinates: row (x,y,z,w) x vertex
+};
+struct Screen {
+    float p2[3][2];        // screen x/w, y/w
+    float w[3];
+    int x0, x1, y0, y1;
+    bool any;
+};
+
+__device__ __forceinline__ void load_corner(const float* __restrict__ tv, int j, float* v) {
+    const float4* p = reinterpret_cast<const float4*>(tv + 8 * j);
+    float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// vertex shader for the three corners + back-face test.  returns false if culled.
+__device__ __forceinline__ bool tri_vertex(const float* __restrict__ M, const float* __restrict__ tv, Tri& T) {
+    float wv[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tv + 8 * j));
+        float px = a.x * 1.f, py = a.y * 1.f, pz = a.z * 1.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) T.c[k][j] = dot4r(M + 4 * k, px, py, pz, 1.f);
+#pragma unroll
+        for (int k = 0; k < 3; k++) wv[k][j] = dot4r(M + 16 + 4 * k, px, py, pz, 1.f);
+    }
+    double v0[3], e1[3], e2[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { v0[k] = (double)wv[k][0]; e1[k] = (double)wv[k][1] - v0[k]; e2[k] = (double)wv[k][2] - v0[k]; }
+    double Nx = e1[1] * e2[2] - e1[2] * e2[1], Ny = e1[2] * e2[0] - e1[0] * e2[2], Nz = e1[0] * e2[1] - e1[1] * e2[0];
+    double dd = (v0[0] - c_render.camP[0]) * Nx + (v0[1] - c_render.camP[1]) * Ny + (v0[2] - c_render.camP[2]) * Nz;
+    return !(dd >= 0);
+}
+
+__device__ __forceinline__ void screen_setup(const float c[4][3], Screen& S) {
+    const float W = RR_W, H = RR_H;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float cx = c[0][i], cy = c[1][i], cz = c[2][i], cw = c[3][i];
+        float x = 0.f; x += (W / 2.f) * cw; x += 0.f * cz; x += 0.f * cy; x += (W / 2.f) * cx;
+        float y = 0.f; y += (H / 2.f) * cw; y += 0.f * cz; y += (H / 2.f) * cy; y += 0.f * cx;
+        float w = 0.f; w += 1.f * cw; w += 0.f * cz; w += 0.f * cy; w += 0.f * cx;
+        S.w[i] = w;
+        S.p2[i][0] = x / w; S.p2[i][1] = y / w;
+    }
+    float mn[2] = {FLT_MAX, FLT_MAX}, mx[2] = {-FLT_MAX, -FLT_MAX};
+    const float cl[2] = {W - 1, H - 1};
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            float a = mn[j] < S.p2[i][j] ? mn[j] : S.p2[i][j];
+            mn[j] = 0.f > a ? 0.f : a;
+            float b = mx[j] > S.p2[i][j] ? mx[j] : S.p2[i][j];
+            mx[j] = cl[j] < b ? cl[j] : b;
+        }
+    S.x0 = (int)mn[0]; S.y0 = (int)mn[1];
+    S.any = ((float)S.x0 <= mx[0]) && ((float)S.y0 <= mx[1]);
+    S.x1 = S.any ? (int)floorf(mx[0]) : -1;
+    S.y1 = S.any ? (int)floorf(mx[1]) : -1;
+}
+
+__device__ __forceinline__ void barycentric(const Screen& S, float px, float py, float* out) {
+    const float* A = S.p2[0]; const float* B = S.p2[1]; const float* C = S.p2[2];
+    float s00 = C[0] - A[0], s01 = B[0] - A[0], s02 = A[0] - px;
+    float s10 = C[1] - A[1], s11 = B[1] - A[1], s12 = A[1] - py;
+    float ux = s01 * s12 - s02 * s11;
+    float uy = s02 * s10 - s00 * s12;
+    float uz = s00 * s11 - s01 * s10;
+    if ((double)fabsf(uz) > 1e-2) { out[0] = 1.f - (ux + uy) / uz; out[1] = uy / uz; out[2] = ux / uz; }
+    else { out[0] = -1.f; out[1] = 1.f; out[2] = 1.f; }
+}
+
+__device__ __forceinline__ float frag_depth(const Screen& S, const float* clipz, int px, int py, float* bs, float* bc) {
+    barycentric(S, (float)px, (float)py, bs);
+    float b0 = bs[0] / S.w[0], b1 = bs[1] / S.w[1], b2 = bs[2] / S.w[2];
+    float s = b0 + b1 + b2;
+    bc[0] = b0 / s; bc[1] = b1 / s; bc[2] = b2 / s;
+    return -1.f * dot3r(clipz[0], clipz[1], clipz[2], bc);
+}
+
+__device__ __forceinline__ unsigned int order_bits(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unorder_bits(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// near-plane clipping (TinyRenderer.cpp clipEdge / clipTriangleAgainstNearplane). returns #triangles, -1 = unclipped
+__device__ __noinline__ int clip_near(const float tri[4][3], float out[3][4][3]) {
+    if (tri[3][0] < 0 && tri[3][1] < 0 && tri[3][2] < 0) return 0;
+    if (tri[3][0] >= 0 && tri[3][1] >= 0 && tri[3][2] >= 0) return -1;
+    float verts[8][4]; int nv = 0;
+    for (int e = 0; e < 3; e++) {
+        int ia = e, ib = (e + 1) % 3;
+        float v0[4], v1[4];
+        for (int k = 0; k < 4; k++) { v0[k] = tri[k][ia]; v1[k] = tri[k][ib]; }
+        bool in0 = v0[3] > 0.f && v0[2] > -v0[3];
+        bool in1 = v1[3] > 0.f && v1[2] > -v1[3];
+        if (in0 && in1) {
+        } else if (in0 || in1) {
+            float d0 = v0[2] + v0[3], d1 = v1[2] + v1[3];
+            float factor = (float)(1.0 / (double)(d1 - d0));
+            float nv4[4];
+            for (int k = 0; k < 4; k++) nv4[k] = (v0[k] * d1 - v1[k] * d0) * factor;
+            if (in0) { for (int k = 0; k < 4; k++) v1[k] = nv4[k]; } else { for (int k = 0; k < 4; k++) v0[k] = nv4[k]; }
+        } else continue;
+        if (nv == 0 || !(verts[nv - 1][0] == v0[0] && verts[nv - 1][1] == v0[1] && verts[nv - 1][2] == v0[2] && verts[nv - 1][3] == v0[3])) {
+            for (int k = 0; k < 4; k++) verts[nv][k] = v0[k];
+            nv++;
+        }
+        for (int k = 0; k < 4; k++) verts[nv][k] = v1[k];
+        nv++;
+    }
+    if (nv < 3) return 0;
+    if (verts[0][0] == verts[nv - 1][0] && verts[0][1] == verts[nv - 1][1] && verts[0][2] == verts[nv - 1][2] && verts[0][3] == verts[nv - 1][3]) nv--;
+    int nt = 0;
+    for (int i = 1; i < nv - 1 && nt < 3; i++) {
+        for (int k = 0; k < 4; k++) { out[nt][k][0] = verts[0][k]; out[nt][k][1] = verts[i][k]; out[nt][k][2] = verts[i + 1][k]; }
+        nt++;
+    }
+    return nt;
+}
+
+// rasterise the pixels [xa..xb] x [ya..yb] of one screen triangle into the strip key buffer
+__device__ __forceinline__ void raster_pixels(unsigned long long* keys, const Screen& S, const float* clipz, unsigned int tri_id1,
+                                              bool planes, int row0, int start, int stride) {
+    int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
+    if (!S.any || ya > yb) return;
+    int wdt = S.x1 - S.x0 + 1, hgt = yb - ya + 1;
+    int n = wdt * hgt;
+    for (int i = start; i < n; i += stride) {
+        int x = S.x0 + i % wdt, y = ya + i / wdt;
+        float bs[3], bc[3];
+        float fd = frag_depth(S, clipz, x, y, bs, bc);
+        if (bs[0] < 0 || bs[1] < 0 || bs[2] < 0) continue;
+        if (!(fd >= -1e30f)) continue;                                  // z-buffer cleared to -1e30 (also drops NaN)
+        if (planes && (fd < -c_render.farPlane || fd > -c_render.nearPlane)) continue;
+        unsigned long long key = ((unsigned long long)order_bits(fd) << 32) | tri_id1;
+        atomicMax(&keys[(y - row0) * RR_W + x], key);
+    }
+}
+
+__device__ __noinline__ void raster_clipped(unsigned long long* keys, const Tri& T, unsigned int tri_id1, int row0, int start, int stride) {
+    float out[3][4][3];
+    int nc = clip_near(T.c, out);
+    for (int c = 0; c < nc; c++) {
+        Screen S; screen_setup(out[c], S);
+        raster_pixels(keys, S, out[c][2], tri_id1, false, row0, start, stride);
+    }
+}
+
+// --------------------------------------------------------------------------------------------- fragment shader
+__device__ __forceinline__ void texel_fetch(int tex, const uint8_t* __restrict__ texdata, float u, float v, int* c) {
+    if (tex < 0) { c[0] = c[1] = c[2] = 255; return; }
+    const TexConst& t = c_render.tex[tex];
+    float uf = u, vf = v;
+    if (!(u >= 0.f && u < 1.f)) { double ip; uf = (float)modf((double)u, &ip); }
+    if (!(v >= 0.f && v < 1.f)) { double ip; vf = (float)modf((double)v, &ip); }
+    int x = (int)(uf * (float)t.w), y = (int)(vf * (float)t.h);
+    if (x < 0 || y < 0 || x >= t.w || y >= t.h) { c[0] = c[1] = c[2] = 0; return; }
+    const uint8_t* p = texdata + t.offset + (t.uniform ? 0 : ((size_t)x + (size_t)y * t.w) * 3);
+    c[0] = __ldg(p); c[1] = __ldg(p + 1); c[2] = __ldg(p + 2);
+}
+
+// full shading of pixel (x, y) by triangle (shape s, triangle data tv): returns packed rgb
+__device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M, const ShapeRenderConst& sh, const float* __restrict__ tv,
+                                                    const uint8_t* __restrict__ texdata, int x, int y) {
+    Tri T; float nrm[3][3], uv[2][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        float v[8]; load_corner(tv, j, v);
+        float px = v[0] * 1.f, py = v[1] * 1.f, pz = v[2] * 1.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) T.c[k][j] = dot4r(M + 4 * k, px, py, pz, 1.f);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { float r = 0.f; r += 0.f; r += M[28 + 3 * k + 2] * v[5]; r += M[28 + 3 * k + 1] * v[4]; r += M[28 + 3 * k] * v[3]; nrm[k][j] = r; }
+        uv[0][j] = v[6]; uv[1][j] = v[7];
+    }
+    Screen S; screen_setup(T.c, S);
+    float bs[3], bar[3];
+    frag_depth(S, T.c[2], x, y, bs, bar);
+    float bn[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) bn[i] = dot3r(nrm[i][0], nrm[i][1], nrm[i][2], bar);
+    float nl = sqrtf(bn[0] * bn[0] + bn[1] * bn[1] + bn[2] * bn[2]);
+    float k = 1.f / nl;
+#pragma unroll
+    for (int i = 0; i < 3; i++) bn[i] = bn[i] * k;
+    float u = dot3r(uv[0][0], uv[0][1], uv[0][2], bar), v = dot3r(uv[1][0], uv[1][1], uv[1][2], bar);
+    float ndl = dot3r(bn[0], bn[1], bn[2], c_render.light);
+    float t2 = ndl * 2.f;
+    float rd0 = bn[0] * t2 - c_render.light[0], rd1 = bn[1] * t2 - c_render.light[1], rd2 = bn[2] * t2 - c_render.light[2];
+    float rl = sqrtf(rd0 * rd0 + rd1 * rd1 + rd2 * rd2);
+    float rz = rd2 * (1.f / rl);
+    float sp = rz > 0.f ? rz : 0.f;
+    float specular = sp * sp;
+    float diffuse = ndl > 0.f ? ndl : 0.f;
+    int c[3]; texel_fetch(sh.tex, texdata, u, v, c);
+    const float ambient = 0.6f, dc = 0.35f, sc = 0.05f, shadow = 1.0f;
+    unsigned int packed = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        int ci = (int)((float)c[i] * sh.rgba[i]) & 0xff;
+        float fc = ambient * (float)ci + shadow * (dc * diffuse + sc * specular) * (float)ci * 1.0f;
+        int oc = 0;
+        if (fc == fc) oc = (int)fc;
+        oc = oc < 255 ? oc : 255;
+        packed |= ((unsigned int)oc & 0xffu) << (8 * i);
+    }
+    return packed;
+}
+
+__device__ __forceinline__ int shape_of_tri(int tri) {
+    int s = 0;
+#pragma unroll 1
+    for (int k = 1; k < RR_NSHAPES; k++) if (tri >= c_render.shape[k].tri_start) s = k;
+    return s;
+}
+
+// --------------------------------------------------------------------------------------------- raster kernel
+__global__ void __launch_bounds__(RTHREADS, 2)
+k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ texdata,
+         const uint8_t* __restrict__ env_mask, uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int N) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    float* M = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);
+    int* bigq = reinterpret_cast<int*>(M + RR_NSHAPES * MAT_STRIDE);
+    __shared__ int bign;
+    const int strip = blockIdx.x, e = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int row0 = strip * STRIP_ROWS;                 // first raster row (origin bottom-left)
+    const size_t img = (size_t)e * RR_W * RR_H;
+    const bool on = env_mask ? (env_mask[e] != 0) : true;
+
+    if (!on) {   // reference returns cached zero arrays when render is off (env.py:114-122, 273-275)
+        for (int i = tid; i < STRIP_ROWS * RR_W / 4; i += RTHREADS) {
+            int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
+            size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
+            if (rgb) { unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3); p[0] = 0; p[1] = 0; p[2] = 0; }
+            if (depth) *reinterpret_cast<float4*>(depth + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (seg) *reinterpret_cast<int4*>(seg + o) = make_int4(0, 0, 0, 0);
+        }
+        return;
+    }
+    for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = 0ull;
+    for (int i = tid; i < RR_NSHAPES * MAT_STRIDE; i += RTHREADS) M[i] = mats[(size_t)e * RR_NSHAPES * MAT_STRIDE + i];
+    if (tid == 0) bign = 0;
+    __syncthreads();
+
+    // ---- pass 1: small triangles, one per thread
+    for (int s = 0; s < RR_NSHAPES; s++) {
+        const float* Ms = M + s * MAT_STRIDE;
+        if (Ms[39] == 0.f) continue;
+        if (Ms[38] < (float)row0 || Ms[37] > (float)(row0 + STRIP_ROWS - 1)) continue;
+        const ShapeRenderConst& sh = c_render.shape[s];
+        for (int t = tid; t < sh.tri_count; t += RTHREADS) {
+            const int gt = sh.tri_start + t;
+            const float* tv = tris + (size_t)gt * 24;
+            Tri T;
+            if (!tri_vertex(Ms, tv, T)) continue;
+            const bool front = (T.c[3][0] >= 0 && T.c[3][1] >= 0 && T.c[3][2] >= 0);
+            if (!front) {
+                if (T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0) continue;
+                int slot = atomicAdd(&bign, 1);
+                if (slot < BIGQ) bigq[slot] = gt | 0x40000000;          // clipped triangles normally take the cooperative path
+                else raster_clipped(keys, T, (unsigned int)gt + 1u, row0, 0, 1);
+                continue;
+            }
+            Screen S; screen_setup(T.c, S);
+            int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
+            if (!S.any || ya > yb) continue;
+            int area = (S.x1 - S.x0 + 1) * (yb - ya + 1);
+            if (area > BIG_AREA) {
+                int slot = atomicAdd(&bign, 1);
+                if (slot < BIGQ) { bigq[slot] = gt; continue; }
+            }
+            raster_pixels(keys, S, T.c[2], (unsigned int)gt + 1u, true, row0, 0, 1);
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: large / clipped triangles, whole CTA per triangle
+    {
+        int nb = min(bign, BIGQ);
+        for (int b = 0; b < nb; b++) {
+            int ent = bigq[b];
+            int gt = ent & 0x3fffffff;
+            int s = shape_of_tri(gt);
+            const float* Ms = M + s * MAT_STRIDE;
+            const float* tv = tris + (size_t)gt * 24;
+            Tri T; tri_vertex(Ms, tv, T);
+            if (ent & 0x40000000) raster_clipped(keys, T, (unsigned int)gt + 1u, row0, tid, RTHREADS);
+            else { Screen S; screen_setup(T.c, S); raster_pixels(keys, S, T.c[2], (unsigned int)gt + 1u, true, row0, tid, RTHREADS); }
+        }
+    }
+    __syncthreads();
+    // ---- resolve: 4 consecutive pixels per thread-iteration, vector stores
+    const float nearP = c_render.depthNear, farP = c_render.depthFar;
+    for (int i = tid; i < STRIP_ROWS * RR_W / 4; i += RTHREADS) {
+        int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
+        unsigned int col[4]; float dep[4]; int sg[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int x = 4 * x4 + k;
+            unsigned long long key = keys[r * RR_W + x];
+            float z;
+            if (key == 0ull) { col[k] = 0xffffffu; sg[k] = -1; z = -1e30f; }
+            else {
+                int gt = (int)(key & 0xffffffffu) - 1;
+                z = unorder_bits((unsigned int)(key >> 32));
+                int s = shape_of_tri(gt);
+                const ShapeRenderConst& sh = c_render.shape[s];
+                col[k] = shade_pixel(M + s * MAT_STRIDE, sh, tris + (size_t)gt * 24, texdata, x, row0 + r);
+                sg[k] = sh.objectAndLink & 0xffffff;
+            }
+            float z_c = -z;
+            dep[k] = (float)((double)(farP * (nearP + z_c)) / (2. * (double)farP * (double)nearP + (double)(farP * z_c) - (double)(nearP * z_c)));
+        }
+        size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
+        if (rgb) {
+            unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3);
+            // 4 pixels x 3 bytes -> 3 little-endian words
+            p[0] = (col[0] & 0xffffffu) | (col[1] << 24);
+            p[1] = ((col[1] >> 8) & 0xffffu) | (col[2] << 16);
+            p[2] = ((col[2] >> 16) & 0xffu) | (col[3] << 8);
+        }
+        if (depth) *reinterpret_cast<float4*>(depth + o) = make_float4(dep[0], dep[1], dep[2], dep[3]);
+        if (seg) *reinterpret_cast<int4*>(seg + o) = make_int4(sg[0], sg[1], sg[2], sg[3]);
+    }
+}
+
+// --------------------------------------------------------------------------------------------- host side
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return -1; } } while (0)
+
+static const size_t RASTER_SMEM = (size_t)STRIP_ROWS * RR_W * 8 + RR_NSHAPES * MAT_STRIDE * 4 + BIGQ * 4;
+static double* g_static_frames[16] = {0};
+
+int rrk_render_upload_constants(rr_ctx* ctx) {
+    CK(cudaMemcpyToSymbol(c_render, &ctx->render, sizeof(RenderConst)));
+    CK(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RASTER_SMEM));
+    // static frames (robot base, table) as doubles
+    double sf[RR_NSHAPES * 12];
+    for (int s = 0; s < RR_NSHAPES; s++) {
+        double* f = sf + 12 * s;
+        int body = ctx->robot.shape_body[s], link = ctx->robot.shape_link[s];
+        for (int k = 0; k < 12; k++) f[k] = 0;
+        if (body == 0) { f[0] = f[4] = f[8] = 1.0; for (int k = 0; k < 3; k++) f[9 + k] = ctx->robot.base_pos[k]; }
+        else if (body == 1) { for (int k = 0; k < 9; k++) f[k] = ctx->robot.table_R[k]; for (int k = 0; k < 3; k++) f[9 + k] = link < 0 ? ctx->robot.table_pos[k] : ctx->robot.table_upper_pos[k]; }
+    }
+    if (ctx->device < 16) {
+        if (!g_static_frames[ctx->device]) CK(cudaMalloc(&g_static_frames[ctx->device], sizeof sf));
+        CK(cudaMemcpy(g_static_frames[ctx->device], sf, sizeof sf, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s) {
+    int total = ctx->N * RR_NSHAPES;
+    k_render_setup<<<(total + 127) / 128, 128, 0, s>>>(ctx->st, frames, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device]);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    dim3 grid(NSTRIPS, ctx->N);
+    k_raster<<<grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tex, mask, rgb, depth, seg, ctx->N);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
