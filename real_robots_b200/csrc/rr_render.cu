@@ -25,7 +25,7 @@ __constant__ RenderConst c_render;
 #define NSTRIPS (RR_H / STRIP_ROWS)
 #define RTHREADS 256
 #define MAT_STRIDE 40          // floats per (env, shape): pmv[16] model[12] invT[9] ylo yhi flag
-#define BIG_AREA 48            // pixels in-strip above which a triangle goes to the cooperative queue
+#define SMALL_AREA 6            // in-strip bounding-box pixels up to which a triangle is rasterised by its own lane
 #define BIGQ 512
 
 // --------------------------------------------------------------------------------------------- float helpers
@@ -109,17 +109,21 @@ __global__ void k_render_setup(DevState st, const double* __restrict__ frames, f
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[28 + 3 * i + j] = ((i == 0) ? adj0[j] : cofactor4(model, i, j)) / tmp;
     // conservative raster-row range from the 8 corners of the local AABB
     float ylo = 0.f, yhi = (float)(RR_H - 1);
-    bool all_front = true; float mn = FLT_MAX, mx = -FLT_MAX;
+    bool all_front = true, all_behind = true; float mn = FLT_MAX, mx = -FLT_MAX;
     for (int c = 0; c < 8; c++) {
+        {   // a shape whose 8 AABB corners all have w < -eps lies behind the camera: every triangle is discarded
+            float q[4] = {(c & 1) ? sh.aabb_max[0] : sh.aabb_min[0], (c & 2) ? sh.aabb_max[1] : sh.aabb_min[1], (c & 4) ? sh.aabb_max[2] : sh.aabb_min[2], 1.f};
+            if (!(dot4r(pmv[3], q) < -1e-3f)) all_behind = false;
+        }
         float p[4] = {(c & 1) ? sh.aabb_max[0] : sh.aabb_min[0], (c & 2) ? sh.aabb_max[1] : sh.aabb_min[1], (c & 4) ? sh.aabb_max[2] : sh.aabb_min[2], 1.f};
         float cy = dot4r(pmv[1], p), cw = dot4r(pmv[3], p);
-        if (!(cw > 1e-3f)) { all_front = false; break; }
+        if (!(cw > 1e-3f)) { all_front = false; continue; }
         float y = (RR_H / 2.f) * cw + (RR_H / 2.f) * cy;
         y = y / cw;
         mn = fminf(mn, y); mx = fmaxf(mx, y);
     }
     if (all_front) { ylo = mn - 2.f; yhi = mx + 2.f; }
-    out[37] = ylo; out[38] = yhi; out[39] = active ? 1.f : 0.f;
+    out[37] = ylo; out[38] = yhi; out[39] = (active && !all_behind) ? 1.f : 0.f;
 }
 
 // --------------------------------------------------------------------------------------------- triangle setup
@@ -187,19 +191,46 @@ __device__ __forceinline__ void screen_setup(const float c[4][3], Screen& S) {
     S.y1 = S.any ? (int)floorf(mx[1]) : -1;
 }
 
-__device__ __forceinline__ void barycentric(const Screen& S, float px, float py, float* out) {
+// per-triangle part of TinyRenderer's barycentric(): s[i][0] = C-A, s[i][1] = B-A, and u.z (pixel independent)
+struct Edge { float s00, s01, s10, s11, uz; bool degenerate; };
+__device__ __forceinline__ void edge_setup(const Screen& S, Edge& E) {
     const float* A = S.p2[0]; const float* B = S.p2[1]; const float* C = S.p2[2];
-    float s00 = C[0] - A[0], s01 = B[0] - A[0], s02 = A[0] - px;
-    float s10 = C[1] - A[1], s11 = B[1] - A[1], s12 = A[1] - py;
-    float ux = s01 * s12 - s02 * s11;
-    float uy = s02 * s10 - s00 * s12;
-    float uz = s00 * s11 - s01 * s10;
-    if ((double)fabsf(uz) > 1e-2) { out[0] = 1.f - (ux + uy) / uz; out[1] = uy / uz; out[2] = ux / uz; }
+    E.s00 = C[0] - A[0]; E.s01 = B[0] - A[0];
+    E.s10 = C[1] - A[1]; E.s11 = B[1] - A[1];
+    E.uz = E.s00 * E.s11 - E.s01 * E.s10;
+    E.degenerate = !((double)fabsf(E.uz) > 1e-2);
+}
+__device__ __forceinline__ void bary_u(const Screen& S, const Edge& E, float px, float py, float& ux, float& uy) {
+    float s02 = S.p2[0][0] - px, s12 = S.p2[0][1] - py;
+    ux = E.s01 * s12 - s02 * E.s11;
+    uy = s02 * E.s10 - E.s00 * s12;
+}
+// exact sign classification of bc_screen = (1-(ux+uy)/uz, uy/uz, ux/uz) without dividing.
+// returns 0 = some component is negative (pixel rejected), 1 = all non-negative, 2 = too close to call (do the divisions)
+__device__ __forceinline__ int coverage_class(float ux, float uy, float uz) {
+    const bool zn = uz < 0.f;
+    // uy/uz < 0  <=>  signs differ and the rounded quotient is not a zero (no underflow when |uy| >= 1e-30, |uz| < 1e7)
+    float auy = fabsf(uy), aux = fabsf(ux);
+    if (!(fabsf(uz) < 1e7f)) return 2;
+    if (auy < 1e-30f) { if (uy != 0.f) return 2; }
+    else if ((uy < 0.f) != zn) return 0;
+    if (aux < 1e-30f) { if (ux != 0.f) return 2; }
+    else if ((ux < 0.f) != zn) return 0;
+    // 1 - RN(t/uz) < 0  <=>  RN(t/uz) > 1
+    float t = ux + uy;
+    float at = zn ? -t : t, az = zn ? -uz : uz;          // az > 0
+    if (at <= az) return 1;                               // exact quotient <= 1, rounding is monotonic
+    if (at > az * 1.000001f) return 0;                    // exact quotient > 1 + 2^-23: rounds above 1
+    return 2;
+}
+__device__ __forceinline__ void barycentric(const Screen& S, const Edge& E, float px, float py, float* out) {
+    float ux, uy; bary_u(S, E, px, py, ux, uy);
+    if (!E.degenerate) { out[0] = 1.f - (ux + uy) / E.uz; out[1] = uy / E.uz; out[2] = ux / E.uz; }
     else { out[0] = -1.f; out[1] = 1.f; out[2] = 1.f; }
 }
 
-__device__ __forceinline__ float frag_depth(const Screen& S, const float* clipz, int px, int py, float* bs, float* bc) {
-    barycentric(S, (float)px, (float)py, bs);
+__device__ __forceinline__ float frag_depth(const Screen& S, const Edge& E, const float* clipz, int px, int py, float* bs, float* bc) {
+    barycentric(S, E, (float)px, (float)py, bs);
     float b0 = bs[0] / S.w[0], b1 = bs[1] / S.w[1], b2 = bs[2] / S.w[2];
     float s = b0 + b1 + b2;
     bc[0] = b0 / s; bc[1] = b1 / s; bc[2] = b2 / s;
@@ -250,31 +281,41 @@ __device__ __noinline__ int clip_near(const float tri[4][3], float out[3][4][3])
     return nt;
 }
 
-// rasterise the pixels [xa..xb] x [ya..yb] of one screen triangle into the strip key buffer
-__device__ __forceinline__ void raster_pixels(unsigned long long* keys, const Screen& S, const float* clipz, unsigned int tri_id1,
+// rasterise the in-strip bounding box of one screen triangle into the strip key buffer.
+// keylo = ((triangle index + 1) << 5) | shape: ties in depth resolve to the later-submitted triangle.
+__device__ __forceinline__ void raster_pixels(unsigned long long* keys, const Screen& S, const float* clipz, unsigned int keylo,
                                               bool planes, int row0, int start, int stride) {
     int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
     if (!S.any || ya > yb) return;
+    Edge E; edge_setup(S, E);
+    if (E.degenerate) return;                 // bc_screen = (-1,1,1): every pixel rejected
     int wdt = S.x1 - S.x0 + 1, hgt = yb - ya + 1;
     int n = wdt * hgt;
+    int x = S.x0 + start % wdt, y = ya + start / wdt;
+    const int dx = stride % wdt, dy = stride / wdt;
     for (int i = start; i < n; i += stride) {
-        int x = S.x0 + i % wdt, y = ya + i / wdt;
+        const int px = x, py = y;
+        x += dx; y += dy; if (x > S.x1) { x -= wdt; y++; }
+        float ux, uy; bary_u(S, E, (float)px, (float)py, ux, uy);
+        int cls = coverage_class(ux, uy, E.uz);
+        if (cls == 0) continue;
         float bs[3], bc[3];
-        float fd = frag_depth(S, clipz, x, y, bs, bc);
-        if (bs[0] < 0 || bs[1] < 0 || bs[2] < 0) continue;
+        float fd = frag_depth(S, E, clipz, px, py, bs, bc);
+        if (cls == 2 && (bs[0] < 0 || bs[1] < 0 || bs[2] < 0)) continue;
         if (!(fd >= -1e30f)) continue;                                  // z-buffer cleared to -1e30 (also drops NaN)
         if (planes && (fd < -c_render.farPlane || fd > -c_render.nearPlane)) continue;
-        unsigned long long key = ((unsigned long long)order_bits(fd) << 32) | tri_id1;
-        atomicMax(&keys[(y - row0) * RR_W + x], key);
+        unsigned long long key = ((unsigned long long)order_bits(fd) << 32) | keylo;
+        unsigned long long* slot = &keys[(py - row0) * RR_W + px];
+        if (*reinterpret_cast<volatile unsigned long long*>(slot) < key) atomicMax(slot, key);
     }
 }
 
-__device__ __noinline__ void raster_clipped(unsigned long long* keys, const Tri& T, unsigned int tri_id1, int row0, int start, int stride) {
+__device__ __noinline__ void raster_clipped(unsigned long long* keys, const Tri& T, unsigned int keylo, int row0, int start, int stride) {
     float out[3][4][3];
     int nc = clip_near(T.c, out);
     for (int c = 0; c < nc; c++) {
         Screen S; screen_setup(out[c], S);
-        raster_pixels(keys, S, out[c][2], tri_id1, false, row0, start, stride);
+        raster_pixels(keys, S, out[c][2], keylo, false, row0, start, stride);
     }
 }
 
@@ -306,8 +347,9 @@ __device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M,
         uv[0][j] = v[6]; uv[1][j] = v[7];
     }
     Screen S; screen_setup(T.c, S);
+    Edge E; edge_setup(S, E);
     float bs[3], bar[3];
-    frag_depth(S, T.c[2], x, y, bs, bar);
+    frag_depth(S, E, T.c[2], x, y, bs, bar);
     float bn[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) bn[i] = dot3r(nrm[i][0], nrm[i][1], nrm[i][2], bar);
@@ -337,13 +379,6 @@ __device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M,
         packed |= ((unsigned int)oc & 0xffu) << (8 * i);
     }
     return packed;
-}
-
-__device__ __forceinline__ int shape_of_tri(int tri) {
-    int s = 0;
-#pragma unroll 1
-    for (int k = 1; k < RR_NSHAPES; k++) if (tri >= c_render.shape[k].tri_start) s = k;
-    return s;
 }
 
 // --------------------------------------------------------------------------------------------- raster kernel
@@ -376,49 +411,87 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
     if (tid == 0) bign = 0;
     __syncthreads();
 
-    // ---- pass 1: small triangles, one per thread
-    for (int s = 0; s < RR_NSHAPES; s++) {
-        const float* Ms = M + s * MAT_STRIDE;
-        if (Ms[39] == 0.f) continue;
-        if (Ms[38] < (float)row0 || Ms[37] > (float)(row0 + STRIP_ROWS - 1)) continue;
-        const ShapeRenderConst& sh = c_render.shape[s];
-        for (int t = tid; t < sh.tri_count; t += RTHREADS) {
-            const int gt = sh.tri_start + t;
-            const float* tv = tris + (size_t)gt * 24;
-            Tri T;
-            if (!tri_vertex(Ms, tv, T)) continue;
-            const bool front = (T.c[3][0] >= 0 && T.c[3][1] >= 0 && T.c[3][2] >= 0);
-            if (!front) {
-                if (T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0) continue;
-                int slot = atomicAdd(&bign, 1);
-                if (slot < BIGQ) bigq[slot] = gt | 0x40000000;          // clipped triangles normally take the cooperative path
-                else raster_clipped(keys, T, (unsigned int)gt + 1u, row0, 0, 1);
-                continue;
+    // ---- pass 1: one triangle per lane.  Triangles with a small in-strip bounding box are rasterised by their own
+    //      lane; medium ones are broadcast (shuffles) and rasterised by the whole warp, 32 pixels at a time; huge and
+    //      near-plane-clipped ones are deferred to the CTA-wide queue.
+    {
+        const int lane = tid & 31;
+        for (int s = 0; s < RR_NSHAPES; s++) {
+            const float* Ms = M + s * MAT_STRIDE;
+            if (Ms[39] == 0.f) continue;
+            if (Ms[38] < (float)row0 || Ms[37] > (float)(row0 + STRIP_ROWS - 1)) continue;
+            const ShapeRenderConst& sh = c_render.shape[s];
+            for (int tb = tid - lane; tb < sh.tri_count; tb += RTHREADS) {
+                const int t = tb + lane;
+                int state = 0;                       // 0 nothing, 1 own lane, 2 warp-cooperative
+                Screen S; float cz[3] = {0.f, 0.f, 0.f};
+                unsigned int keylo = 0;
+                if (t < sh.tri_count) {
+                    const int gt = sh.tri_start + t;
+                    const float* tv = tris + (size_t)gt * 24;
+                    keylo = (((unsigned int)gt + 1u) << 5) | (unsigned int)s;
+                    Tri T;
+                    if (tri_vertex(Ms, tv, T)) {
+                        const bool front = (T.c[3][0] >= 0 && T.c[3][1] >= 0 && T.c[3][2] >= 0);
+                        if (!front) {
+                            if (!(T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0)) {
+                                int slot = atomicAdd(&bign, 1);
+                                if (slot < BIGQ) bigq[slot] = gt | (s << 20) | 0x40000000;
+                                else raster_clipped(keys, T, keylo, row0, 0, 1);
+                            }
+                        } else {
+                            screen_setup(T.c, S);
+                            cz[0] = T.c[2][0]; cz[1] = T.c[2][1]; cz[2] = T.c[2][2];
+                            int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
+                            if (S.any && ya <= yb) {
+                                int area = (S.x1 - S.x0 + 1) * (yb - ya + 1);
+                                state = area <= SMALL_AREA ? 1 : 2;
+                                if (area > 2048) {
+                                    int slot = atomicAdd(&bign, 1);
+                                    if (slot < BIGQ) { bigq[slot] = gt | (s << 20) | 0x20000000; state = 0; }
+                                }
+                            }
+                        }
+                    }
+                }
+                unsigned med = __ballot_sync(0xffffffffu, state == 2);
+                while (med) {
+                    const int src = __ffs(med) - 1; med &= med - 1;
+                    Screen B; float bz[3];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        B.p2[i][0] = __shfl_sync(0xffffffffu, S.p2[i][0], src); B.p2[i][1] = __shfl_sync(0xffffffffu, S.p2[i][1], src);
+                        B.w[i] = __shfl_sync(0xffffffffu, S.w[i], src); bz[i] = __shfl_sync(0xffffffffu, cz[i], src);
+                    }
+                    B.x0 = __shfl_sync(0xffffffffu, S.x0, src); B.x1 = __shfl_sync(0xffffffffu, S.x1, src);
+                    B.y0 = __shfl_sync(0xffffffffu, S.y0, src); B.y1 = __shfl_sync(0xffffffffu, S.y1, src);
+                    B.any = true;
+                    unsigned int bk = __shfl_sync(0xffffffffu, keylo, src);
+                    raster_pixels(keys, B, bz, bk, true, row0, lane, 32);
+                }
+                if (state == 1) raster_pixels(keys, S, cz, keylo, true, row0, 0, 1);
             }
-            Screen S; screen_setup(T.c, S);
-            int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
-            if (!S.any || ya > yb) continue;
-            int area = (S.x1 - S.x0 + 1) * (yb - ya + 1);
-            if (area > BIG_AREA) {
-                int slot = atomicAdd(&bign, 1);
-                if (slot < BIGQ) { bigq[slot] = gt; continue; }
-            }
-            raster_pixels(keys, S, T.c[2], (unsigned int)gt + 1u, true, row0, 0, 1);
         }
     }
     __syncthreads();
-    // ---- pass 2: large / clipped triangles, whole CTA per triangle
+    // ---- pass 2: deferred triangles.  Medium ones are rasterised by one warp each (lanes stride the bounding
+    //      box), huge ones (flag bit 29) and near-plane-clipped ones (bit 30) by the whole CTA.
     {
-        int nb = min(bign, BIGQ);
+        const int nb = min(bign, BIGQ);
+        const int warp = tid >> 5, lane = tid & 31;
         for (int b = 0; b < nb; b++) {
-            int ent = bigq[b];
-            int gt = ent & 0x3fffffff;
-            int s = shape_of_tri(gt);
+            const int ent = bigq[b];
+            const bool cta_wide = (ent & 0x60000000) != 0;
+            if (!cta_wide && (b & (RTHREADS / 32 - 1)) != warp) continue;
+            const int gt = ent & 0xfffff;
+            const int s = (ent >> 20) & 31;
+            const unsigned int keylo = (((unsigned int)gt + 1u) << 5) | (unsigned int)s;
             const float* Ms = M + s * MAT_STRIDE;
             const float* tv = tris + (size_t)gt * 24;
             Tri T; tri_vertex(Ms, tv, T);
-            if (ent & 0x40000000) raster_clipped(keys, T, (unsigned int)gt + 1u, row0, tid, RTHREADS);
-            else { Screen S; screen_setup(T.c, S); raster_pixels(keys, S, T.c[2], (unsigned int)gt + 1u, true, row0, tid, RTHREADS); }
+            const int start = cta_wide ? tid : lane, stride = cta_wide ? RTHREADS : 32;
+            if (ent & 0x40000000) raster_clipped(keys, T, keylo, row0, start, stride);
+            else { Screen S; screen_setup(T.c, S); raster_pixels(keys, S, T.c[2], keylo, true, row0, start, stride); }
         }
     }
     __syncthreads();
@@ -434,9 +507,9 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
             float z;
             if (key == 0ull) { col[k] = 0xffffffu; sg[k] = -1; z = -1e30f; }
             else {
-                int gt = (int)(key & 0xffffffffu) - 1;
+                int gt = (int)((key & 0xffffffffu) >> 5) - 1;
                 z = unorder_bits((unsigned int)(key >> 32));
-                int s = shape_of_tri(gt);
+                int s = (int)(key & 31u);
                 const ShapeRenderConst& sh = c_render.shape[s];
                 col[k] = shade_pixel(M + s * MAT_STRIDE, sh, tris + (size_t)gt * 24, texdata, x, row0 + r);
                 sg[k] = sh.objectAndLink & 0xffffff;
