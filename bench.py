@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec incl. retina render at 4096 envs/GPU (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the oracle port on all host cores
+
+Our arm: one step = rr_step (action prologue + physics) + rr_read_state + rr_render (RGB + depth + mask) for 4096
+envs with 3 objects per GPU, actions from the vectorised cli.RandomPolicy (p = 0.05 resample, seed 1234 + rank)
+pre-generated on the device.  `value` is timed with CUDA events between barriers, max over ranks; `e2e` times
+the same step through rr_step_host (pinned host buffers, H2D of the commands and D2H of every observation inside
+the timed region).  The roofline entry is for the rasteriser kernel (k_raster): algorithmic bytes = the
+844 800 B/env of image output it must write over its CUDA-event duration.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ENVS = 4096
+N_OBJECTS = 3
+IMG_BYTES = 240 * 320 * (3 + 4 + 4)          # rgb u8x3 + depth f32 + mask i32 = 844 800
+STATE_BYTES = 3824                            # BASELINE.md §4 physics bytes per env-step
+METRIC = "env_steps_per_sec_with_retina_4096_envs_per_gpu"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for i, n in enumerate(names):
+                if len(s) > 3 + i and s[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def random_policy_actions(torch, steps, n, device, seed):
+    """Vectorised real_robots/cli.py:12-20 RandomPolicy: sample from the action Box, resample with p = 0.05."""
+    import math
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lo = torch.full((9,), -math.pi * 0.944, dtype=torch.float64, device=device)
+    hi = -lo.clone()
+    for i in (0, 1, 3, 5):
+        lo[i], hi[i] = -math.pi * 0.666, math.pi * 0.666
+    lo[6], hi[6] = -math.pi * 0.972, math.pi * 0.972
+    lo[7:] = 0.0
+    hi[7:] = math.pi / 2
+    acts = torch.empty(steps, n, 9, dtype=torch.float64, device=device)
+    cur = lo + (hi - lo) * torch.rand(n, 9, dtype=torch.float64, device=device, generator=g)
+    for t in range(steps):
+        resample = torch.rand(n, device=device, generator=g) < 0.05
+        new = lo + (hi - lo) * torch.rand(n, 9, dtype=torch.float64, device=device, generator=g)
+        cur = torch.where(resample[:, None], new, cur)
+        acts[t] = cur
+    return acts
+
+
+def oracle_worker(args):
+    """One CPU process: one oracle env, `steps` env-steps with render; returns wall seconds for the timed part."""
+    seed, steps, warm = args
+    import numpy as np
+    from oracle.orc import Oracle
+    rng = np.random.default_rng(seed)
+    o = Oracle(N_OBJECTS)
+    lo = np.array([-2.09, -2.09, -2.96, -2.09, -2.96, -2.09, -3.05, 0, 0])
+    hi = -lo
+    hi[7:] = np.pi / 2
+    a = rng.uniform(lo, hi)
+    for _ in range(warm):
+        o.step(a); o.read(); o.render()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        if rng.random() < 0.05:
+            a = rng.uniform(lo, hi)
+        o.step(a); o.read(); o.render()
+    return time.perf_counter() - t0
+
+
+def cpu_run(steps_per_worker, workers):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        times = pool.map(oracle_worker, [(1234 + w, steps_per_worker, 3) for w in range(workers)])
+    wall = max(times)
+    return workers * steps_per_worker / wall, wall
+
+
+def run_reference(args):
+    """CPU arm: pybullet is not installable here (absent from /root/reference and the wheelhouse), so this times
+    the oracle port — the CPU restatement of the reference's step path — one process per host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import orc
+    orc.build()
+    cores = os.cpu_count() or 1
+    per_step = 25                       # env-steps per worker per bench "step" (bounded sample)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_run(5, cores)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, wall = cpu_run(per_step, cores)
+        vals.append(v); t_all += wall
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 physics / f32 raster", "data": "synthetic",
+        "config": {"workload": "REALRobot2020-R1J3 joints action, random policy, physics + RGB/depth/mask retina 240x320; CPU arm runs "
+                               "one env per host core, %d env-steps per core per bench step" % per_step,
+                   "n_envs_per_gpu": N_ENVS, "n_objects": N_OBJECTS},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d processes x %d env-steps with render per bench step (oracle port; pybullet not installable)" % (cores, per_step)},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from real_robots_b200.sim import BatchedSim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, max(args.warmup, 3)
+    sim = BatchedSim(args.envs, N_OBJECTS, device=local)
+    acts = random_policy_actions(torch, K + W, args.envs, dev, 1234 + rank)
+
+    def step(t):
+        sim.step(acts[t])
+        sim.read_state()
+        sim.render()
+
+    for t in range(W):
+        step(t)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sim.profile(True)
+    l0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for t in range(W, W + K):
+        step(t)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sim.launch_count() - l0
+    prof = sim.profile_read()
+    sim.profile(False)
+    sampler.stop_flag = True
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = world * args.envs * K / (ms_max * 1e-3)
+
+    # ---- end-to-end leg through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
+    Ke = max(3, min(K, args.e2e_steps))
+    host_acts = acts[:Ke + 2].cpu().pin_memory().numpy()
+    mask = torch.ones(args.envs, dtype=torch.uint8).pin_memory().numpy()
+    out = sim.alloc_host(images=True, want_mask=True, pinned=True)
+    for t in range(2):
+        sim.step_host(host_acts[t], mask, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(2, 2 + Ke):
+        sim.step_host(host_acts[t], mask, out=out)
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    tt = torch.tensor([te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.envs * Ke / float(tt.item())
+    h2d = args.envs * 9 * 8 + args.envs
+    d2h = args.envs * (9 * 8 + 4 * 8 + N_OBJECTS * 7 * 8 + IMG_BYTES)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        r_ms, r_n = prof["raster"]
+        s_ms, s_n = prof["step"]
+        raster_ms = r_ms / max(r_n, 1)
+        achieved = args.envs * IMG_BYTES / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 physics / f32 raster", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: REALRobot2020 R1J3 joints action, %d envs/GPU, 3 objects, random policy "
+                                   "(p=0.05 resample), physics + touch + RGB/depth/mask retina 240x320" % args.envs,
+                       "n_envs_per_gpu": args.envs, "n_objects": N_OBJECTS, "parallelism": "envs sharded, %d rank(s), no collective" % world,
+                       "l2": "outputs larger than L2 (%.2f GB written per step per GPU)" % (args.envs * IMG_BYTES / 1e9)},
+            "roofline": {"kernel": "k_raster", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": args.traffic, "peak_source": peak_src,
+                         "ms_per_launch": raster_ms, "launches": r_n,
+                         "physics_kernel": {"kernel": "k_step", "ms_per_launch": s_ms / max(s_n, 1),
+                                            "achieved_gbs": args.envs * STATE_BYTES / (s_ms / max(s_n, 1) * 1e-3) / 1e9 if s_ms > 0 else None}},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+        }
+        if args.cpu_baseline:
+            from oracle import orc
+            orc.build()
+            n_cpu = 1200
+            wall = oracle_worker((1234, n_cpu, 3))
+            line["cpu_baseline"] = {"value": n_cpu / wall, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                                    "sample": "1 oracle env x %d env-steps with render (%.1f s)" % (n_cpu, wall)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per k_raster launch from an ncu --set full capture")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if int(os.environ.get("RANK", "0")) != 0:
+            args.cpu_baseline = False
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

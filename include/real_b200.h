@@ -113,6 +113,14 @@ int  rr_step_host(rr_ctx* ctx, const double* joint_cmd_host, const uint8_t* rend
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 long long rr_launch_count(rr_ctx* ctx);
 
+/* Optional per-kernel device timing (CUDA events on the launch stream) for bench.py's roofline line.
+ * rr_profile(ctx, 1) starts recording, rr_profile(ctx, 0) stops; rr_profile_read synchronises the device and
+ * returns, per kernel kind (0 = physics step, 1 = render set-up, 2 = rasteriser, 3 = collision), the summed
+ * duration in ms and the number of launches since profiling was enabled, then clears the counters. */
+#define RR_PROFILE_KINDS 4
+int  rr_profile(rr_ctx* ctx, int enable);
+int  rr_profile_read(rr_ctx* ctx, double* ms_total /*[4]*/, long long* launches /*[4]*/);
+
 /* Per-env diagnostics of the last step: i32[N,4] = rows, iterations, contacts, flags. */
 int  rr_diag(rr_ctx* ctx, int32_t* out, void* stream);
 

@@ -117,3 +117,12 @@ int orc_ik(void* p, const double* pos3, const double* quat4, int max_iter, doubl
 }
 
 }  /* extern "C" */
+
+bool orc_closest_points_shapes(const OrcScene* sc, int sa, const OrcFrame& fa, int sb, const OrcFrame& fb, double* out10);
+extern "C" int orc_test_closest(void* p, int sa, const double* fa12, int sb, const double* fb12, double* out10) {
+    OrcHandle* h = (OrcHandle*)p;
+    OrcFrame A, B;
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { A.R.m[a][b] = fa12[3 * a + b]; B.R.m[a][b] = fb12[3 * a + b]; }
+    A.p = V3(fa12[9], fa12[10], fa12[11]); B.p = V3(fb12[9], fb12[10], fb12[11]);
+    return orc_closest_points_shapes(&h->scene, sa, A, sb, B, out10) ? 1 : 0;
+}

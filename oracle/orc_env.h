@@ -4,7 +4,7 @@
 #define ORC_ENV_H
 #include "orc_scene.h"
 
-#define ORC_MAX_MANIFOLDS 64
+#define ORC_MAX_MANIFOLDS 24
 #define ORC_MAX_ROWS 1024
 
 struct OrcContactPoint {

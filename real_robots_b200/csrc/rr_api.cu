@@ -146,7 +146,17 @@ static int fill_constants(rr_ctx* ctx, const Blob& b) {
         for (int k = 0; k < 3; k++) R.obj_inertia[o][k] = ((const double*)e_oi->data)[3 * o + k];
         for (int k = 0; k < 7; k++) R.obj_init[o][k] = ((const double*)e_op->data)[7 * o + k];
     }
-    for (int s = 0; s < RR_NSHAPES; s++) { R.shape_body[s] = ((const int32_t*)e_sb->data)[s]; R.shape_link[s] = ((const int32_t*)e_sl->data)[s]; }
+    const Entry* e_fr = b.get("shape.friction", 3, err); if (!e_fr) return -1;
+    const Entry* e_re = b.get("shape.restitution", 3, err); if (!e_re) return -1;
+    for (int s = 0; s < RR_NSHAPES; s++) {
+        R.shape_body[s] = ((const int32_t*)e_sb->data)[s]; R.shape_link[s] = ((const int32_t*)e_sl->data)[s];
+        R.shape_friction[s] = ((const double*)e_fr->data)[s]; R.shape_restitution[s] = ((const double*)e_re->data)[s];
+    }
+    for (int i = 0; i < RR_NL; i++) {
+        int mask = 0;
+        for (int k = i; k >= 0; k = R.parent[k]) if (R.jtype[k] == 1) mask |= 1 << R.dof[k];
+        R.anc[i] = mask;
+    }
     R.n_objects = ctx->n_objects; R.cfg = ctx->cfg;
 
     RenderConst& C = ctx->render;
@@ -162,6 +172,10 @@ static int fill_constants(rr_ctx* ctx, const Blob& b) {
             sh.aabb_max[k] = (float)((const double*)e_amax->data)[3 * s + k] + 1e-4f;
         }
         ctx->hull_start[s] = ((const int32_t*)e_hs->data)[s]; ctx->hull_count[s] = ((const int32_t*)e_hc->data)[s];
+        for (int k = 0; k < 3; k++) {
+            double lo = ((const double*)e_amin->data)[3 * s + k], hi = ((const double*)e_amax->data)[3 * s + k];
+            ctx->aabb_c[s][k] = (lo + hi) * 0.5; ctx->aabb_h[s][k] = (hi - lo) * 0.5;
+        }
     }
     int K = (int)e_tm->shape[0];
     if (K > RR_MAX_TEX) { err = "too many textures"; return -1; }
@@ -222,7 +236,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_err = "rr_create: no CUDA device (this library has no CPU fallback)"; return -1; }
     if (device < 0 || device >= ndev) { g_create_err = "rr_create: bad device index"; return -1; }
     rr_ctx* ctx = new rr_ctx();
-    ctx->device = device; ctx->N = n_envs; ctx->n_objects = n_objects; ctx->launches = 0;
+    ctx->device = device; ctx->N = n_envs; ctx->n_objects = n_objects; ctx->launches = 0; ctx->prof_on = false;
     ctx->d_cmd = nullptr; ctx->d_mask = nullptr; ctx->d_joint = ctx->d_touch = ctx->d_objpose = nullptr;
     ctx->d_rgb = nullptr; ctx->d_depth = nullptr; ctx->d_seg = nullptr; ctx->img_capacity = 0; ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0;
     if (cfg) ctx->cfg = *cfg; else rr_config_default(&ctx->cfg);
@@ -231,6 +245,8 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     Blob b;
     if (!b.load(blob_path, ctx->err)) return fail(-1);
     if (fill_constants(ctx, b) != 0) return fail(-1);
+    if (rrk_collide_upload_constants(ctx) != 0) return fail(-1);      // also builds the candidate pair table
+    for (int i = 0; i < ctx->n_pairs; i++) { ctx->robot.pair_a[i] = ctx->pair_a[i]; ctx->robot.pair_b[i] = ctx->pair_b[i]; }
     if (rrk_upload_constants(ctx) != 0) return fail(-1);
     if (rrk_render_upload_constants(ctx) != 0) return fail(-1);
     DevState& st = ctx->st;
@@ -243,7 +259,13 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     alloc((void**)&st.render_mats, N * RR_NSHAPES * 40 * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.timestep, N * 8);
     alloc((void**)&ctx->d_cmd, N * 9 * 8); alloc((void**)&ctx->d_mask, N); alloc((void**)&ctx->d_joint, N * 9 * 8);
     alloc((void**)&ctx->d_touch, N * 4 * 8); alloc((void**)&ctx->d_objpose, N * 3 * 7 * 8);
+    for (int k = 0; k < 2; k++) {
+        alloc((void**)&st.man_hdr[k], N * RR_MAX_MANIFOLDS * 2 * 4);
+        alloc((void**)&st.man_pts[k], N * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE * 8);
+    }
+    alloc((void**)&st.rows, N * 3 * RR_MAX_CONTACTS * RR_ROW_STRIDE * 8);
     if (e != cudaSuccess) { ctx->err = std::string("rr_create: device allocation failed: ") + cudaGetErrorString(e); return fail(-1); }
+    ctx->man_parity = 0;
     if (rrk_reset(ctx, nullptr, 0) != 0) return fail(-1);
     if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "rr_create: initial reset failed"; return fail(-1); }
     *out = ctx;
@@ -255,6 +277,7 @@ int rr_destroy(rr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     DevState& st = ctx->st;
     void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.timestep,
+                    st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.rows,
                     ctx->d_cmd, ctx->d_mask, ctx->d_joint, ctx->d_touch, ctx->d_objpose, ctx->d_rgb, ctx->d_depth, ctx->d_seg,
                     ctx->d_tris, ctx->d_tex, ctx->d_hull_verts};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -299,6 +322,27 @@ int rr_link_pose(rr_ctx* ctx, int link_index, double* pos_quat, void* stream) {
 int rr_score(rr_ctx* ctx, const double* goal_xyz, double* score, void* stream) {
     ARG(goal_xyz && score, "rr_score: NULL argument");
     return rrk_score(ctx, goal_xyz, score, (cudaStream_t)stream);
+}
+int rr_profile(rr_ctx* ctx, int enable) {
+    for (int k = 0; k < RR_PROFILE_KINDS; k++) { for (cudaEvent_t e : ctx->prof_ev[k]) cudaEventDestroy(e); ctx->prof_ev[k].clear(); }
+    ctx->prof_on = enable != 0;
+    return 0;
+}
+int rr_profile_read(rr_ctx* ctx, double* ms_total, long long* launches) {
+    cudaSetDevice(ctx->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "rr_profile_read: device synchronize failed"; return -1; }
+    for (int k = 0; k < RR_PROFILE_KINDS; k++) {
+        double tot = 0; long long n = 0;
+        std::vector<cudaEvent_t>& ev = ctx->prof_ev[k];
+        for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) { tot += ms; n++; }
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        ev.clear();
+        ms_total[k] = tot; launches[k] = n;
+    }
+    return 0;
 }
 int rr_diag(rr_ctx* ctx, int32_t* out, void* stream) {
     cudaError_t e = cudaMemcpyAsync(out, ctx->st.diag, (size_t)ctx->N * 16, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);

@@ -13,6 +13,11 @@
 #define RR_H RR_EYE_H
 #define RR_FRAME_STRIDE (RR_NSHAPES * 12)
 #define RR_MAX_TEX 16
+#define RR_MAX_PAIRS 96          // candidate collision pairs (92 for 3 objects)
+#define RR_MAX_MANIFOLDS 24      // cached manifolds per env (<= 32: one lane per slot)
+#define RR_PT_STRIDE 17          // doubles per contact point: localA3 localB3 normalB3 dist impulse worldA3 worldB3
+#define RR_MAX_CONTACTS 32       // contact points per env that get solver rows
+#define RR_ROW_STRIDE 72         // doubles per solver row in the global row scratch
 
 // ---- constant robot / scene description (uploaded to __constant__ memory once per process+device)
 struct RobotConst {
@@ -26,6 +31,9 @@ struct RobotConst {
     int shape_body[RR_NSHAPES], shape_link[RR_NSHAPES];
     int n_objects;
     rr_config cfg;
+    int anc[RR_NL];              // bit d set: dof d lies on the path from link to the base (incl. the link's own joint)
+    int pair_a[RR_MAX_PAIRS], pair_b[RR_MAX_PAIRS];
+    double shape_friction[RR_NSHAPES], shape_restitution[RR_NSHAPES];
 };
 
 struct TexConst { int w, h, uniform; long long offset; };
@@ -57,6 +65,9 @@ struct DevState {
     float*  render_mats;  // [N][22][40] per-shape matrices for the rasteriser (see rr_render.cu)
     int*    diag;     // [N][4]
     long long* timestep;  // [N]
+    int*    man_hdr[2];   // [N][RR_MAX_MANIFOLDS][2]  (pair index or -1, point count), double buffered
+    double* man_pts[2];   // [N][RR_MAX_MANIFOLDS][4][RR_PT_STRIDE]
+    double* rows;         // [N][3*RR_MAX_CONTACTS][RR_ROW_STRIDE] solver row scratch
 };
 
 struct rr_ctx {
@@ -71,6 +82,9 @@ struct rr_ctx {
     uint8_t* d_tex;
     double* d_hull_verts;      // [V][3]
     int hull_start[RR_NSHAPES], hull_count[RR_NSHAPES];
+    double aabb_c[RR_NSHAPES][3], aabb_h[RR_NSHAPES][3];
+    int pair_a[RR_MAX_PAIRS], pair_b[RR_MAX_PAIRS], n_pairs;
+    int man_parity;            // which manifold buffer holds the current contacts
     int n_tris;
     // staging for the host-buffer path
     double* d_cmd; uint8_t* d_mask; double* d_joint; double* d_touch; double* d_objpose;
@@ -79,6 +93,24 @@ struct rr_ctx {
     double* h_pinned; size_t h_pinned_bytes;
     long long launches;
     std::string err;
+    // optional event profiling
+    bool prof_on;
+    std::vector<cudaEvent_t> prof_ev[RR_PROFILE_KINDS];   // start/stop pairs
+};
+
+// RAII-free helper: records an event pair around a launch when profiling is on
+struct ProfScope {
+    rr_ctx* ctx; int kind; cudaStream_t s; cudaEvent_t stop;
+    ProfScope(rr_ctx* c, int k, cudaStream_t st) : ctx(c), kind(k), s(st), stop(nullptr) {
+        if (!ctx->prof_on || ctx->prof_ev[k].size() >= 16384) return;
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess) return;
+        if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); return; }
+        cudaEventRecord(a, s);
+        ctx->prof_ev[k].push_back(a); ctx->prof_ev[k].push_back(b);
+        stop = b;
+    }
+    ~ProfScope() { if (stop) cudaEventRecord(stop, s); }
 };
 
 // kernels / launchers (defined in the .cu files)
@@ -94,4 +126,7 @@ int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s);
 int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s);
 int rrk_render_upload_constants(rr_ctx* ctx);
 int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames_or_null, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);
+int rrk_collide_upload_constants(rr_ctx* ctx);
+int rrk_collide(rr_ctx* ctx, cudaStream_t s);
+int rrk_clear_manifolds(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s);
 int rrk_ik(rr_ctx* ctx, const uint8_t* mask, const double* pos_quat, double* out, int max_iter, double residual, cudaStream_t s);

@@ -37,7 +37,18 @@ struct WarpMem {
     double r_rhs[32], r_inv[32], r_lo[32], r_hi[32], r_app[32], r_sign[32];
     int r_dof[32];
     int n_rows;
+    // contacts
+    double dof_axis[RR_NDOF][3], dof_piv[RR_NDOF][3];   // world joint axis / pivot per dof
+    double opos[RR_MAX_OBJECTS][3], ovel[RR_MAX_OBJECTS][6], oIinv[RR_MAX_OBJECTS][9], oinvm[RR_MAX_OBJECTS];
+    double Jtmp[32];
+    double app[3 * RR_MAX_CONTACTS];                    // applied impulses: normals [0,MAXC), friction pairs after
 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------- forward kinematics
 // lane i < 16 computes its link's joint transform; then a serial sweep down the tree builds world frames.
@@ -387,7 +398,7 @@ __device__ __forceinline__ void store_frames(const WarpMem& m, const DevState& s
     }
 }
 
-__global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __restrict__ cmd, rr_config cf, int n_objects) {
+__global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __restrict__ cmd, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpMem& m = reinterpret_cast<WarpMem*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -486,11 +497,132 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
         m.n_rows = n;
     }
     __syncwarp();
-    // ---- projected Gauss-Seidel (lane k < 11 owns dv[k])
+    // ---- contact rows (btMultiBodyConstraintSolver::convertMultiBodyContact): normal + two friction directions per
+    //      manifold point.  A row is a 29-vector in "owner" layout: lanes 0..10 = arm dofs, lane 11+6o+k = component k
+    //      (ang xyz, lin xyz) of object o.  J and M^-1 J^T go to the global row scratch; impulses stay in smem.
+    const double vel = (lane < RR_NDOF) ? m.qd[lane] : 0.0;
+    double ovel = 0.0;      // object velocity component owned by this lane (lanes 11..28)
+    int nc = 0, overflow = 0;
+    int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
+    double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
+    double* rows = st.rows + (size_t)e * 3 * RR_MAX_CONTACTS * RR_ROW_STRIDE;
+    if (cf.enable_contacts) {
+        if (lane < RR_NDOF) {
+            const int i = c_robot.link_of_dof[lane];
+            const double* R = m.Rw[i];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                m.dof_axis[lane][a] = R[3 * a] * c_robot.axis[i][0] + R[3 * a + 1] * c_robot.axis[i][1] + R[3 * a + 2] * c_robot.axis[i][2];
+                m.dof_piv[lane][a] = m.pw[i][a] - (R[3 * a] * c_robot.evec[i][0] + R[3 * a + 1] * c_robot.evec[i][1] + R[3 * a + 2] * c_robot.evec[i][2]);
+            }
+        }
+        if (has_obj) {
+            double R[9]; quat_to_mat(ob.quat, R);
+            const double ii[3] = {1.0 / c_robot.obj_inertia[lane][0], 1.0 / c_robot.obj_inertia[lane][1], 1.0 / c_robot.obj_inertia[lane][2]};
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) m.oIinv[lane][3 * a + b] = R[3 * a] * ii[0] * R[3 * b] + R[3 * a + 1] * ii[1] * R[3 * b + 1] + R[3 * a + 2] * ii[2] * R[3 * b + 2];
+            m.oinvm[lane] = 1.0 / c_robot.obj_mass[lane];
+#pragma unroll
+            for (int a = 0; a < 3; a++) { m.opos[lane][a] = ob.pos[a]; m.ovel[lane][a] = ob.ang[a]; m.ovel[lane][3 + a] = ob.lin[a]; }
+        }
+        __syncwarp();
+        const int myo = (lane >= 11 && lane < 29) ? (lane - 11) / 6 : -1, myk = (lane >= 11 && lane < 29) ? (lane - 11) % 6 : 0;
+        if (myo >= 0 && myo < n_objects) ovel = m.ovel[myo][myk];
+        for (int slot = 0; slot < RR_MAX_MANIFOLDS; slot++) {
+            const int pi = hdr[2 * slot];
+            if (pi < 0) break;
+            const int npt = hdr[2 * slot + 1];
+            const int sa = c_robot.pair_a[pi], sb = c_robot.pair_b[pi];
+            const int bodyA = c_robot.shape_body[sa], linkA = c_robot.shape_link[sa], bodyB = c_robot.shape_body[sb];
+            const bool armA = bodyA == 0 && linkA >= 0;
+            const int oA = bodyA >= 2 ? bodyA - 2 : -1, oB = bodyB >= 2 ? bodyB - 2 : -1;
+            const double mu = c_robot.shape_friction[sa] * c_robot.shape_friction[sb];
+            const double rest = c_robot.shape_restitution[sa] * c_robot.shape_restitution[sb];
+            for (int k = 0; k < npt; k++) {
+                const double* P = pts + ((size_t)slot * 4 + k) * RR_PT_STRIDE;
+                const double dist = P[9];
+                if (dist > cf.contact_breaking) continue;
+                if (nc >= RR_MAX_CONTACTS) { overflow = 1; continue; }
+                const double nB[3] = {P[6], P[7], P[8]}, wA[3] = {P[11], P[12], P[13]}, wB[3] = {P[14], P[15], P[16]};
+                double t1[3], t2[3];
+                if (fabs(nB[2]) > 0.7071067811865475244008443621048490) {        // btPlaneSpace1
+                    double a = nB[1] * nB[1] + nB[2] * nB[2], kk = 1.0 / sqrt(a);
+                    t1[0] = 0; t1[1] = -nB[2] * kk; t1[2] = nB[1] * kk;
+                    t2[0] = a * kk; t2[1] = -nB[0] * t1[2]; t2[2] = nB[0] * t1[1];
+                } else {
+                    double a = nB[0] * nB[0] + nB[1] * nB[1], kk = 1.0 / sqrt(a);
+                    t1[0] = -nB[1] * kk; t1[1] = nB[0] * kk; t1[2] = 0;
+                    t2[0] = -nB[2] * t1[1]; t2[1] = nB[2] * t1[0]; t2[2] = a * kk;
+                }
+                {
+                    double l1 = 1.0 / sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]), l2 = 1.0 / sqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+                    for (int a = 0; a < 3; a++) { t1[a] *= l1; t2[a] *= l2; }
+                }
+                for (int di = 0; di < 3; di++) {
+                    const double* d = di == 0 ? nB : (di == 1 ? t1 : t2);
+                    double J = 0.0;
+                    if (lane < RR_NDOF) {
+                        if (armA && ((c_robot.anc[linkA] >> lane) & 1)) {
+                            const double* aw = m.dof_axis[lane]; const double* pv = m.dof_piv[lane];
+                            double r0 = wA[0] - pv[0], r1 = wA[1] - pv[1], r2 = wA[2] - pv[2];
+                            J = d[0] * (aw[1] * r2 - aw[2] * r1) + d[1] * (aw[2] * r0 - aw[0] * r2) + d[2] * (aw[0] * r1 - aw[1] * r0);
+                        }
+                    } else if (myo >= 0 && (myo == oA || myo == oB)) {
+                        const double sg = myo == oA ? 1.0 : -1.0;
+                        const double* w = myo == oA ? wA : wB;
+                        double r0 = w[0] - m.opos[myo][0], r1 = w[1] - m.opos[myo][1], r2 = w[2] - m.opos[myo][2];
+                        double dd0 = d[0] * sg, dd1 = d[1] * sg, dd2 = d[2] * sg;
+                        if (myk == 0) J = r1 * dd2 - r2 * dd1; else if (myk == 1) J = r2 * dd0 - r0 * dd2; else if (myk == 2) J = r0 * dd1 - r1 * dd0;
+                        else J = myk == 3 ? dd0 : (myk == 4 ? dd1 : dd2);
+                    }
+                    m.Jtmp[lane] = J;
+                    __syncwarp();
+                    double rr = 0.0;
+                    if (lane < RR_NDOF) {
+                        if (armA) {
+#pragma unroll
+                            for (int j = 0; j < RR_NDOF; j++) rr += m.Minv[lane][j] * m.Jtmp[j];
+                        }
+                    } else if (myo >= 0 && (myo == oA || myo == oB)) {
+                        if (myk < 3) rr = m.oIinv[myo][3 * myk] * m.Jtmp[11 + 6 * myo] + m.oIinv[myo][3 * myk + 1] * m.Jtmp[12 + 6 * myo] + m.oIinv[myo][3 * myk + 2] * m.Jtmp[13 + 6 * myo];
+                        else rr = J * m.oinvm[myo];
+                    }
+                    const double den = warp_sum(J * rr);
+                    const double relv = warp_sum(J * (lane < RR_NDOF ? vel : ovel));
+                    const double inv = den > 0 ? 1.0 / den : 0.0;
+                    double rhs, app0 = 0.0;
+                    if (di == 0) {
+                        double restitution = (fabs(relv) < cf.restitution_threshold) ? 0.0 : rest * -relv;
+                        if (restitution <= 0) restitution = 0;
+                        const double pen = dist + cf.linear_slop;
+                        double positional = 0, velocity = restitution - relv;
+                        const double erp = (pen > -0.04) ? cf.erp : cf.erp2;
+                        if (pen > 0) velocity -= pen / dt; else positional = -pen * erp / dt;
+                        rhs = (positional + velocity) * inv;
+                        app0 = P[10] * cf.warmstart;
+                    } else rhs = (0.0 - relv) * inv;
+                    const int ri = di == 0 ? nc : RR_MAX_CONTACTS + 2 * nc + (di - 1);
+                    double* rowp = rows + (size_t)ri * RR_ROW_STRIDE;
+                    rowp[lane] = J; rowp[32 + lane] = rr;
+                    if (lane == 0) { rowp[64] = rhs; rowp[65] = inv; rowp[66] = mu; m.app[ri] = app0; }
+                    __syncwarp();
+                }
+                nc++;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- projected Gauss-Seidel.  dv in owner layout: lane k < 11 owns the arm dof k, lane 11+6o+c the object component.
     double dv = 0.0;
     int iters = 0; double res = 0.0;
     {
         const int n = m.n_rows;
+        for (int c = 0; c < nc; c++) {                       // warm start (normal rows only)
+            const double a = m.app[c];
+            if (a != 0.0) dv += rows[(size_t)c * RR_ROW_STRIDE + 32 + lane] * a;
+        }
         for (int it = 0; it < cf.solver_iterations; it++) {
             res = 0.0;
             for (int j = 0; j < n; j++) {
@@ -512,6 +644,42 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
                 res = fmax(res, r * r);
                 __syncwarp();
             }
+            for (int c = 0; c < nc; c++) {                   // normal rows
+                const double* rowp = rows + (size_t)c * RR_ROW_STRIDE;
+                const double J = rowp[lane], rr = rowp[32 + lane], rhs = rowp[64], inv = rowp[65];
+                const double s = warp_sum(J * dv);
+                double app = m.app[c];
+                double delta = rhs - s * inv;
+                const double sum = app + delta;
+                if (sum < 0.0) { delta = 0.0 - app; app = 0.0; }
+                else if (sum > 1e10) { delta = 1e10 - app; app = 1e10; }
+                else app = sum;
+                __syncwarp();
+                if (lane == 0) m.app[c] = app;
+                dv += rr * delta;
+                const double r = inv != 0.0 ? delta / inv : 0.0;
+                res = fmax(res, r * r);
+                __syncwarp();
+            }
+            for (int c = 0; c < nc; c++) {                   // friction pairs with the implicit cone
+                const int r0 = RR_MAX_CONTACTS + 2 * c;
+                const double* ra = rows + (size_t)r0 * RR_ROW_STRIDE; const double* rb = ra + RR_ROW_STRIDE;
+                const double Ja = ra[lane], rra = ra[32 + lane], Jb = rb[lane], rrb = rb[32 + lane];
+                const double inva = ra[65], invb = rb[65];
+                const double lim = ra[66] * m.app[c];
+                const double sa_ = warp_sum(Ja * dv), sb_ = warp_sum(Jb * dv);
+                const double appa = m.app[r0], appb = m.app[r0 + 1];
+                double wa = appa + (ra[64] - sa_ * inva), wb = appb + (rb[64] - sb_ * invb);
+                const double len2 = wa * wa + wb * wb;
+                if (len2 > lim * lim) { const double sc = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= sc; wb *= sc; }
+                const double da = wa - appa, db = wb - appb;
+                __syncwarp();
+                if (lane == 0) { m.app[r0] = wa; m.app[r0 + 1] = wb; }
+                dv += rra * da; dv += rrb * db;
+                const double qa = inva != 0.0 ? da / inva : 0.0, qb = invb != 0.0 ? db / invb : 0.0;
+                res = fmax(res, fmax(qa * qa, qb * qb));
+                __syncwarp();
+            }
             iters = it + 1;
             if (res <= cf.residual_threshold) break;
         }
@@ -519,6 +687,38 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
     if (lane < RR_NDOF) {
         m.qd[lane] = clampd(m.qd[lane] + dv, -cf.max_coord_vel, cf.max_coord_vel);
         m.q[lane] += m.qd[lane] * dt;
+    }
+    {   // hand the object delta-velocities back to the lanes that own the bodies
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double da = __shfl_sync(FULL, dv, 11 + 6 * (lane % 3) + k), dl = __shfl_sync(FULL, dv, 14 + 6 * (lane % 3) + k);
+            if (has_obj) {
+                ob.ang[k] = clampd(ob.ang[k] + da, -cf.max_coord_vel, cf.max_coord_vel);
+                ob.lin[k] = clampd(ob.lin[k] + dl, -cf.max_coord_vel, cf.max_coord_vel);
+            }
+        }
+    }
+    // ---- impulse write-back (warm start of the next step) and gripper touch sensors (robot.py:131-163)
+    double touch[4] = {0.0, 0.0, 0.0, 0.0};
+    if (cf.enable_contacts) {
+        int c = 0;
+        for (int slot = 0; slot < RR_MAX_MANIFOLDS; slot++) {
+            const int pi = hdr[2 * slot];
+            if (pi < 0) break;
+            const int npt = hdr[2 * slot + 1];
+            const int sa = c_robot.pair_a[pi], sb = c_robot.pair_b[pi];
+            const int linkA = c_robot.shape_link[sa];
+            const bool sens = c_robot.shape_body[sa] == 0 && c_robot.shape_body[sb] != 0 && c_robot.shape_link[sb] == -1;
+            const int sensor = linkA == 11 ? 0 : (linkA == 10 ? 1 : (linkA == 15 ? 2 : (linkA == 14 ? 3 : -1)));
+            bool any = false; double best = 0.0;
+            for (int k = 0; k < npt; k++) {
+                double* P = pts + ((size_t)slot * 4 + k) * RR_PT_STRIDE;
+                double imp = P[10];
+                if (!(P[9] > cf.contact_breaking) && c < RR_MAX_CONTACTS) { imp = m.app[c]; if (lane == 0) P[10] = imp; c++; }
+                if (sens && sensor >= 0 && fabs(P[9]) < 0.1) { const double f = imp / dt; if (!any || f > best) { best = f; any = true; } }
+            }
+            if (any && sens && sensor >= 0 && best > touch[sensor]) touch[sensor] = best;
+        }
     }
     if (has_obj) obj_integrate(ob, dt);
     __syncwarp();
@@ -539,9 +739,9 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
 #pragma unroll
         for (int k = 0; k < 3; k++) { base[(size_t)(7 + k) * N] = ob.lin[k]; base[(size_t)(10 + k) * N] = ob.ang[k]; }
     }
-    if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = 0.0;
+    if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
     if (lane == 0) {
-        st.diag[4 * e] = m.n_rows; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = 0; st.diag[4 * e + 3] = 0;
+        st.diag[4 * e] = m.n_rows + 3 * nc; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow;
         st.timestep[e] += 1;
     }
 }
@@ -560,10 +760,11 @@ __global__ void __launch_bounds__(WPB * 32) k_fk(DevState st) {
     store_frames(m, st, e, lane);
 }
 
-__global__ void k_reset(DevState st, const uint8_t* __restrict__ mask, int n_objects) {
+__global__ void k_reset(DevState st, const uint8_t* __restrict__ mask, int n_objects, int* __restrict__ man_hdr) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= st.N) return;
     if (mask && !mask[e]) return;
+    for (int k = 0; k < RR_MAX_MANIFOLDS; k++) { man_hdr[((size_t)e * RR_MAX_MANIFOLDS + k) * 2] = -1; man_hdr[((size_t)e * RR_MAX_MANIFOLDS + k) * 2 + 1] = 0; }
     const int N = st.N;
     for (int d = 0; d < RR_NDOF; d++) { st.q[(size_t)d * N + e] = 0.0; st.qd[(size_t)d * N + e] = 0.0; st.target[(size_t)d * N + e] = 0.0; }
     for (int o = 0; o < RR_MAX_OBJECTS; o++) {
@@ -706,7 +907,7 @@ static int launch_fk(rr_ctx* ctx, cudaStream_t s) {
     return 0;
 }
 int rrk_reset(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
-    k_reset<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, mask, ctx->n_objects);
+    k_reset<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, mask, ctx->n_objects, ctx->st.man_hdr[ctx->man_parity]);
     ctx->launches++;
     CK(cudaGetLastError());
     return launch_fk(ctx, s);
@@ -717,7 +918,20 @@ int rrk_set_object_pose(rr_ctx* ctx, const uint8_t* mask, int obj, const double*
     CK(cudaGetLastError());
     return 0;
 }
+__global__ void k_clear_manifolds(int N, const uint8_t* __restrict__ mask, int* __restrict__ man_hdr) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    if (mask && !mask[e]) return;
+    for (int k = 0; k < RR_MAX_MANIFOLDS; k++) { man_hdr[((size_t)e * RR_MAX_MANIFOLDS + k) * 2] = -1; man_hdr[((size_t)e * RR_MAX_MANIFOLDS + k) * 2 + 1] = 0; }
+}
+int rrk_clear_manifolds(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
+    k_clear_manifolds<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->N, mask, ctx->st.man_hdr[ctx->man_parity]);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
 int rrk_set_state(rr_ctx* ctx, const double* q, const double* qd, const double* obj, cudaStream_t s) {
+    if (rrk_clear_manifolds(ctx, nullptr, s) != 0) return -1;
     k_set_state<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, q, qd, obj);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -730,7 +944,9 @@ int rrk_get_state(rr_ctx* ctx, double* q, double* qd, double* obj, cudaStream_t 
     return 0;
 }
 int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
-    k_step<<<nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s>>>(ctx->st, cmd, ctx->cfg, ctx->n_objects);
+    if (ctx->cfg.enable_contacts && rrk_collide(ctx, s) != 0) return -1;
+    ProfScope ps(ctx, 0, s);
+    k_step<<<nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s>>>(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

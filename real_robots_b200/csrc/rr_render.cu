@@ -557,11 +557,17 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
 
 int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s) {
     int total = ctx->N * RR_NSHAPES;
-    k_render_setup<<<(total + 127) / 128, 128, 0, s>>>(ctx->st, frames, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device]);
+    {
+        ProfScope ps(ctx, 1, s);
+        k_render_setup<<<(total + 127) / 128, 128, 0, s>>>(ctx->st, frames, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device]);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     dim3 grid(NSTRIPS, ctx->N);
-    k_raster<<<grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tex, mask, rgb, depth, seg, ctx->N);
+    {
+        ProfScope ps(ctx, 2, s);
+        k_raster<<<grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tex, mask, rgb, depth, seg, ctx->N);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -158,6 +158,17 @@ class BatchedSim:
         self._ck(self.lib.rr_diag(self.ctx, _ptr(out), self._stream()), "rr_diag")
         return out
 
+    def profile(self, enable=True):
+        self._ck(self.lib.rr_profile(self.ctx, 1 if enable else 0), "rr_profile")
+
+    def profile_read(self):
+        """-> dict kind -> (total ms, launches) for kinds step / render_setup / raster / collide."""
+        ms = (C.c_double * 4)()
+        n = (C.c_longlong * 4)()
+        self._ck(self.lib.rr_profile_read(self.ctx, ms, n), "rr_profile_read")
+        names = ["step", "render_setup", "raster", "collide"]
+        return {names[i]: (ms[i], n[i]) for i in range(4)}
+
     def launch_count(self):
         return int(self.lib.rr_launch_count(self.ctx))
 
