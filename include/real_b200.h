@@ -121,6 +121,14 @@ long long rr_launch_count(rr_ctx* ctx);
 int  rr_profile(rr_ctx* ctx, int enable);
 int  rr_profile_read(rr_ctx* ctx, double* ms_total /*[4]*/, long long* launches /*[4]*/);
 
+/* replaces: getContactPoints as used by Kuka.get_contacts (robot.py:131-150): the cached contact manifolds of the
+ * last step.  hdr i32[N,24,2] = (candidate pair index or -1, point count); pts f64[N,24,4,17] = per point
+ * localA3 localB3 normalOnB3 distance normalImpulse worldA3 worldB3; pairs i32[96,2] = (shapeA, shapeB) per pair index
+ * (HOST pointer, may be NULL); returns the number of candidate pairs through n_pairs_host (may be NULL). */
+#define RR_MAX_MANIFOLDS_PER_ENV 24
+#define RR_CONTACT_POINT_DOUBLES 17
+int  rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, int* n_pairs_host, void* stream);
+
 /* Per-env diagnostics of the last step: i32[N,4] = rows, iterations, contacts, flags. */
 int  rr_diag(rr_ctx* ctx, int32_t* out, void* stream);
 

@@ -1,0 +1,2 @@
+from real_robots_b200.envs.env import REALRobotEnv, Goal  # noqa: F401
+from . import env  # noqa: F401

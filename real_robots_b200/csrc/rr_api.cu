@@ -323,6 +323,18 @@ int rr_score(rr_ctx* ctx, const double* goal_xyz, double* score, void* stream) {
     ARG(goal_xyz && score, "rr_score: NULL argument");
     return rrk_score(ctx, goal_xyz, score, (cudaStream_t)stream);
 }
+int rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, int* n_pairs_host, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int p = ctx->man_parity;
+    const size_t N = (size_t)ctx->N;
+    cudaError_t e = cudaSuccess;
+    if (hdr) e = cudaMemcpyAsync(hdr, ctx->st.man_hdr[p], N * RR_MAX_MANIFOLDS * 2 * 4, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && pts) e = cudaMemcpyAsync(pts, ctx->st.man_pts[p], N * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE * 8, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) { ctx->err = std::string("rr_contacts: ") + cudaGetErrorString(e); return -1; }
+    if (pairs_host) for (int i = 0; i < ctx->n_pairs; i++) { pairs_host[2 * i] = ctx->pair_a[i]; pairs_host[2 * i + 1] = ctx->pair_b[i]; }
+    if (n_pairs_host) *n_pairs_host = ctx->n_pairs;
+    return 0;
+}
 int rr_profile(rr_ctx* ctx, int enable) {
     for (int k = 0; k < RR_PROFILE_KINDS; k++) { for (cudaEvent_t e : ctx->prof_ev[k]) cudaEventDestroy(e); ctx->prof_ev[k].clear(); }
     ctx->prof_on = enable != 0;

@@ -975,7 +975,104 @@ int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s) {
     CK(cudaGetLastError());
     return 0;
 }
-int rrk_ik(rr_ctx* ctx, const uint8_t*, const double*, double*, int, double, cudaStream_t) {
-    ctx->err = "rr_ik: not implemented yet";
-    return -2;
+// ------------------------------------------------------------------------------------------- inverse kinematics
+// Replaces pybullet.calculateInverseKinematics(0, 7, pos, orn, maxNumIterations, residualThreshold) (env.py:372-375,
+// 423-426): damped least squares on position + orientation of the gripper base link, seeded from the env's current
+// joints, damping 0.5, 45 degree step clamp, stops on the position residual.  One thread per request: the problem is a
+// 7-dof serial chain and is off the per-step path (it only runs when the cartesian request changes or a macro plan is built).
+__global__ void k_ik(DevState st, const uint8_t* __restrict__ mask, const double* __restrict__ pos_quat, double* __restrict__ out,
+                     int max_iter, double residual) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    const int N = st.N;
+    double q[RR_NDOF];
+    for (int d = 0; d < RR_NDOF; d++) q[d] = st.q[(size_t)d * N + e];
+    if (mask && !mask[e]) { for (int d = 0; d < RR_NDOF; d++) out[(size_t)e * RR_NDOF + d] = q[d]; return; }
+    const double* pq = pos_quat + (size_t)e * 7;
+    const double tgt[3] = {pq[0], pq[1], pq[2]};
+    double tq[4] = {pq[3], pq[4], pq[5], pq[6]};
+    {
+        double n = sqrt(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
+        if (n > 0) { for (int k = 0; k < 4; k++) tq[k] /= n; } else { tq[0] = tq[1] = tq[2] = 0; tq[3] = 1; }
+    }
+    const double damp = 0.5, max_angle = 45.0 * 3.14159265358979323846 / 180.0, PI = 3.14159265358979323846;
+    for (int it = 0; it < max_iter; it++) {
+        double Rw[8][9], pw[8][3];
+        for (int i = 0; i <= 7; i++) {
+            double R[9];
+            for (int k = 0; k < 9; k++) R[k] = c_robot.rot0[i][k];
+            if (c_robot.jtype[i] == 1) {
+                double s, c; sincos(-q[c_robot.dof[i]], &s, &c);
+                double ax = c_robot.axis[i][0], ay = c_robot.axis[i][1], az = c_robot.axis[i][2], t = 1.0 - c;
+                double A[9] = {c + ax * ax * t, ax * ay * t - az * s, ax * az * t + ay * s,
+                               ay * ax * t + az * s, c + ay * ay * t, ay * az * t - ax * s,
+                               az * ax * t - ay * s, az * ay * t + ax * s, c + az * az * t};
+                double T[9];
+                for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) T[3 * a + b] = A[3 * a] * R[b] + A[3 * a + 1] * R[3 + b] + A[3 * a + 2] * R[6 + b];
+                for (int k = 0; k < 9; k++) R[k] = T[k];
+            }
+            double r[3];
+            for (int a = 0; a < 3; a++) r[a] = R[3 * a] * c_robot.dvec[i][0] + R[3 * a + 1] * c_robot.dvec[i][1] + R[3 * a + 2] * c_robot.dvec[i][2] + c_robot.evec[i][a];
+            const int par = c_robot.parent[i];
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+                if (par >= 0) Rw[i][3 * a + b] = Rw[par][3 * a] * R[3 * b] + Rw[par][3 * a + 1] * R[3 * b + 1] + Rw[par][3 * a + 2] * R[3 * b + 2];
+                else Rw[i][3 * a + b] = R[3 * b + a];
+            }
+            for (int a = 0; a < 3; a++) pw[i][a] = (par >= 0 ? pw[par][a] : c_robot.base_pos[a]) + Rw[i][3 * a] * r[0] + Rw[i][3 * a + 1] * r[1] + Rw[i][3 * a + 2] * r[2];
+        }
+        const double* ee = pw[7];
+        double dp[3] = {tgt[0] - ee[0], tgt[1] - ee[1], tgt[2] - ee[2]};
+        if (sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) <= residual) break;
+        double cq[4]; mat_to_quat(Rw[7], cq);
+        const double ix = -cq[0], iy = -cq[1], iz = -cq[2], iw = cq[3];
+        double dq[4] = {tq[3] * ix + tq[0] * iw + tq[1] * iz - tq[2] * iy,
+                        tq[3] * iy + tq[1] * iw + tq[2] * ix - tq[0] * iz,
+                        tq[3] * iz + tq[2] * iw + tq[0] * iy - tq[1] * ix,
+                        tq[3] * iw - tq[0] * ix - tq[1] * iy - tq[2] * iz};
+        double w = dq[3] > 1 ? 1 : (dq[3] < -1 ? -1 : dq[3]);
+        double angle = 2.0 * acos(w);
+        double s2 = 1.0 - dq[3] * dq[3];
+        double axis[3] = {1, 0, 0};
+        if (s2 >= 10 * 2.220446049250313e-16) { double s = 1.0 / sqrt(s2); axis[0] = dq[0] * s; axis[1] = dq[1] * s; axis[2] = dq[2] * s; }
+        if (angle > PI) angle -= 2.0 * PI; else if (angle < -PI) angle += 2.0 * PI;
+        double an = sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+        double k_ = an > 0 ? 1.0 / an : 1.0;
+        double dS[6] = {dp[0], dp[1], dp[2], axis[0] * k_ * angle, axis[1] * k_ * angle, axis[2] * k_ * angle};
+        double J[6][7];
+        for (int k = 0; k < 7; k++) {
+            double aw[3], piv[3];
+            for (int a = 0; a < 3; a++) {
+                aw[a] = Rw[k][3 * a] * c_robot.axis[k][0] + Rw[k][3 * a + 1] * c_robot.axis[k][1] + Rw[k][3 * a + 2] * c_robot.axis[k][2];
+                piv[a] = pw[k][a] - (Rw[k][3 * a] * c_robot.evec[k][0] + Rw[k][3 * a + 1] * c_robot.evec[k][1] + Rw[k][3 * a + 2] * c_robot.evec[k][2]);
+            }
+            double r0 = ee[0] - piv[0], r1 = ee[1] - piv[1], r2 = ee[2] - piv[2];
+            J[0][k] = aw[1] * r2 - aw[2] * r1; J[1][k] = aw[2] * r0 - aw[0] * r2; J[2][k] = aw[0] * r1 - aw[1] * r0;
+            J[3][k] = aw[0]; J[4][k] = aw[1]; J[5][k] = aw[2];
+        }
+        double L[7][7], b[7];
+        for (int i = 0; i < 7; i++) {
+            for (int j = 0; j <= i; j++) { double s = 0; for (int r = 0; r < 6; r++) s += J[r][i] * J[r][j]; L[i][j] = s; }
+            L[i][i] += damp;
+            double s = 0; for (int r = 0; r < 6; r++) s += J[r][i] * dS[r]; b[i] = s;
+        }
+        for (int i = 0; i < 7; i++) for (int j = 0; j <= i; j++) {       // in-place Cholesky of the lower triangle
+            double s = L[i][j];
+            for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+            L[i][j] = (i == j) ? sqrt(s) : s / L[j][j];
+        }
+        double y[7], dth[7];
+        for (int i = 0; i < 7; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
+        for (int i = 6; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < 7; k++) s -= L[k][i] * dth[k]; dth[i] = s / L[i][i]; }
+        double mx = 0; for (int i = 0; i < 7; i++) mx = fmax(mx, fabs(dth[i]));
+        if (mx > max_angle) for (int i = 0; i < 7; i++) dth[i] *= max_angle / mx;
+        for (int i = 0; i < 7; i++) q[i] += dth[i];
+    }
+    for (int d = 0; d < RR_NDOF; d++) out[(size_t)e * RR_NDOF + d] = q[d];
+}
+
+int rrk_ik(rr_ctx* ctx, const uint8_t* mask, const double* pos_quat, double* out, int max_iter, double residual, cudaStream_t s) {
+    k_ik<<<nblk(ctx->N, 64), 64, 0, s>>>(ctx->st, mask, pos_quat, out, max_iter, residual);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
 }

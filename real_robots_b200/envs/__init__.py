@@ -1,0 +1,1 @@
+from .env import REALRobotEnv, Goal  # noqa: F401

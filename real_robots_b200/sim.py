@@ -153,6 +153,16 @@ class BatchedSim:
         self._ck(self.lib.rr_ik(self.ctx, _ptr(m), _ptr(pos_quat), _ptr(out), int(max_iter), float(residual), self._stream()), "rr_ik")
         return out
 
+    def contacts(self):
+        """-> (hdr i32[N,24,2], pts f64[N,24,4,17], pairs i32[n_pairs,2]) — cached manifolds of the last step."""
+        N, dev = self.n_envs, self.device
+        hdr = torch.empty(N, 24, 2, dtype=torch.int32, device=dev)
+        pts = torch.empty(N, 24, 4, 17, dtype=torch.float64, device=dev)
+        pairs = np.zeros((96, 2), np.int32)
+        n = C.c_int(0)
+        self._ck(self.lib.rr_contacts(self.ctx, _ptr(hdr), _ptr(pts), pairs.ctypes.data_as(C.c_void_p), C.byref(n), self._stream()), "rr_contacts")
+        return hdr, pts, pairs[:n.value]
+
     def diag(self):
         out = torch.empty(self.n_envs, 4, dtype=torch.int32, device=self.device)
         self._ck(self.lib.rr_diag(self.ctx, _ptr(out), self._stream()), "rr_diag")

@@ -1,4 +1,4 @@
-"""Dev check: contact-rich parity CUDA vs oracle."""
+"""Dev check: contact-rich parity CUDA vs oracle under the random policy (cli.py:12-20 semantics)."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
@@ -10,24 +10,34 @@ rng = np.random.default_rng(3)
 sim = BatchedSim(N, 3)
 orcs = [Oracle(3) for _ in range(N)]
 lo = np.array([-2.09, -2.09, -2.96, -2.09, -2.96, -2.09, -3.05, 0, 0]); hi = -lo; hi[7:] = np.pi / 2
-act = np.zeros((N, 9))
+act = rng.uniform(lo, hi, size=(N, 9))
 first_div = [None] * N
+arm_steps = np.zeros(N, int); touch_steps = np.zeros(N, int)
 for t in range(steps):
-    if t % 40 == 0 and t > 0:
-        act = rng.uniform(lo, hi, size=(N, 9)); act[0] = 0
+    res = rng.random(N) < 0.05
+    new = rng.uniform(lo, hi, size=(N, 9))
+    act = np.where(res[:, None], new, act)
     sim.step(torch.from_numpy(act).cuda())
     q, qd, obj = [x.cpu().numpy() for x in sim.get_state()]
     d = sim.diag().cpu().numpy()
+    tch = sim.read_state()[1].cpu().numpy()
     for e in range(N): orcs[e].step(act[e])
     oq = np.array([o.get_state()[0] for o in orcs]); oobj = np.array([o.get_state()[2] for o in orcs])
-    od = [o.diag() for o in orcs]
+    otch = np.array([o.read()[1] for o in orcs])
     eq = abs(q - oq).max(axis=1); eo = abs(obj - oobj).max(axis=(1, 2))
     for e in range(N):
+        A, B, D = orcs[e].contacts()
+        if (A < 17).any(): arm_steps[e] += 1
+        if otch[e].max() > 0: touch_steps[e] += 1
         if first_div[e] is None and (eq[e] > 1e-6 or eo[e] > 1e-6): first_div[e] = t
-    if t % 20 == 0 or t == steps - 1:
-        print("t %3d |dq| %.2e |dobj| %.2e  contacts gpu %s orc %s  iters gpu %s orc %s ovf %d" % (
-            t, eq.max(), eo.max(), d[:4, 2], [x['contacts'] for x in od[:4]], d[:4, 1], [x['iterations'] for x in od[:4]], d[:, 3].sum()))
+    if t % 50 == 0 or t == steps - 1:
+        ok = np.array([f is None for f in first_div])
+        print("t %3d  envs still within 1e-6: %d/%d  max|dq| among them %.2e  |dobj| %.2e  touch err %.2e  contacts(max) gpu %d  ovf %d  finite %s" % (
+            t, ok.sum(), N, eq[ok].max() if ok.any() else -1, eo[ok].max() if ok.any() else -1, abs(tch - otch)[ok].max() if ok.any() else -1,
+            d[:, 2].max(), d[:, 3].sum(), np.isfinite(q).all() and np.isfinite(obj).all()))
 print("first divergence step per env (>1e-6):", first_div)
-j, tch, op = sim.read_state()
-print("touch gpu", tch[:4].cpu().numpy().round(3)); print("touch orc", np.array([o.read()[1] for o in orcs[:4]]).round(3))
-print("obj z gpu", obj[:4, :, 2].round(4)); print("obj z orc", oobj[:4, :, 2].round(4))
+print("oracle steps with arm contact per env:", arm_steps.tolist())
+print("oracle steps with touch>0 per env:", touch_steps.tolist())
+# statistical comparison at the end (all envs): object heights and joint positions
+print("final obj z gpu mean %s  orc mean %s" % (obj[:, :, 2].mean(0).round(4), oobj[:, :, 2].mean(0).round(4)))
+print("final |q| gpu mean %.4f orc mean %.4f" % (abs(q).mean(), abs(oq).mean()))

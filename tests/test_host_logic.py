@@ -1,0 +1,110 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU): ids, spaces, goals, plans, scoring."""
+import pickle
+
+import numpy as np
+import pytest
+
+import real_robots
+import real_robots_b200
+from real_robots_b200.envs.env import Goal, REALRobotEnv, macro_plan
+from real_robots_b200.envs.robot import Kuka
+from real_robots_b200.evaluate import build_score_object, shard_range, EvaluationService
+from real_robots_b200.policy import BasePolicy
+
+
+def test_registered_ids_match_reference():
+    # real_robots/__init__.py:16-28
+    ids = sorted(real_robots_b200.REGISTRY)
+    assert len(ids) == 18
+    assert 'REALRobot2020-R2J3-v0' in ids and 'REALRobot2020-R1M1-v0' in ids
+    kw = real_robots_b200.REGISTRY['REALRobot2020-R2J3-v0']
+    assert kw == dict(additional_obs=False, objects=3, action_type='joints')
+    with pytest.raises(KeyError):
+        real_robots_b200.make('REALRobot-v0')         # stale id used by the reference's examples
+
+
+def test_action_and_observation_spaces():
+    k = Kuka(additional_obs=True, objects=3)
+    # SURVEY App. A.4 (robot.py:58-67)
+    lo, hi = k.action_space.low, k.action_space.high
+    assert np.allclose(hi[[0, 1, 3, 5]], np.pi * 0.666) and np.allclose(hi[[2, 4]], np.pi * 0.944)
+    assert np.isclose(hi[6], np.pi * 0.972) and np.allclose(lo[7:], 0) and np.allclose(hi[7:], np.pi / 2)
+    assert np.allclose(lo[:7], -hi[:7])
+    sp = k.observation_space.spaces
+    assert sp['retina'].shape == (240, 320, 3) and sp['retina'].dtype == np.uint8
+    assert sp['mask'].dtype == np.int32 and sp['depth'].shape == (240, 320)
+    assert set(sp['object_positions'].spaces) == {'cube', 'tomato', 'mustard'}
+    assert set(Kuka(False, 1).observation_space.spaces) == {'joint_positions', 'touch_sensors', 'retina', 'depth', 'goal'}
+    assert Kuka(True, 2).used_objects == ['table', 'cube', 'tomato']
+
+
+def test_env_construction_and_errors():
+    env = real_robots.make('REALRobot2020-R1C2-v0')
+    assert isinstance(env, REALRobotEnv)
+    assert set(env.action_space.spaces) == {'cartesian_command', 'gripper_command', 'render'}
+    assert np.allclose(env.cartesian_space.low, [-0.25, -0.5, 0.40, -1, -1, -1, -1])
+    assert np.allclose(env.macro_space.high, [[0.05, 0.5], [0.05, 0.5]])
+    assert env.intrinsic_timesteps == int(15e6) and env.extrinsic_timesteps == int(10e3) and env.extrinsic_trials == 50
+    assert (env.goal.retina == 0).all() and env.goal_idx == -1 and env.goals is None
+    with pytest.raises(ValueError):
+        REALRobotEnv(action_type='bogus')
+    with pytest.raises(AssertionError):
+        env.set_goals_dataset_path('/nonexistent/goals.npz')
+    assert env.render('human').size == 0 and env.isRender
+
+
+def test_goal_pickle_roundtrip_under_reference_class_path(tmp_path):
+    g = Goal(initial_state={'cube': np.arange(7.0)}, final_state={'cube': np.arange(7.0) + 1}, challenge='2D',
+             retina=np.zeros((240, 320, 3), np.uint8), mask=np.zeros((240, 320), np.int32))
+    assert pickle.loads(pickle.dumps(g)).__class__ is Goal
+    assert b"real_robots.envs.env" in pickle.dumps(g)
+    # the reference's file format: np.savez_compressed(path, list_of_goals) (generate_goals.py:435, env.py:143-145)
+    path = str(tmp_path / "goals.npy")
+    np.savez_compressed(path, np.array([g, g], dtype=object))
+    env = real_robots.make('REALRobot2020-R1J1-v0')
+    env.set_goals_dataset_path(path + ".npz")
+    env.load_goals()
+    assert len(env.goals) == 2 and env.goals[0].challenge == '2D'
+
+
+def test_macro_plan_layout():
+    # env.py:447-458: 100 home2, 100 p1 high, 50 p1 low, 500 sweep, 50 p2 high, 100 home2, 100 home = 1000 rows
+    calls = []
+
+    def fake_ik(coords):
+        calls.append(np.array(coords))
+        return np.full(9, float(len(calls)))
+    plan = macro_plan(fake_ik, np.array([-0.2, -0.4]), np.array([0.0, 0.4]))
+    assert plan.shape == (1000, 9)
+    assert np.allclose(plan[0], [0, 0, 0, 0, 0, np.pi / 2, np.pi / 2, 0, 0]) and np.allclose(plan[-1], 0)
+    dist = np.linalg.norm([0.2, 0.8])
+    pieces = int(dist / 0.05) + 1
+    assert len(calls) == 4 + pieces                       # 4 + pieces IK solves
+    assert np.allclose(plan[100], 1) and np.allclose(plan[200], 2)
+    chunk = 500 // pieces
+    assert np.allclose(plan[250], 5) and np.allclose(plan[250 + chunk], 6)     # first two sweep pieces (IK calls 5 and 6)
+    assert np.allclose(plan[750], 3) and np.allclose(plan[749], 4 + pieces)    # p2 high after the last sweep piece
+    assert np.allclose(calls[0], [-0.2, -0.4, 0.6]) and np.allclose(calls[1], [-0.2, -0.4, 0.46])
+    assert np.allclose(calls[4], [-0.2 + 0.2 / pieces, -0.4 + 0.8 / pieces, 0.46])
+
+
+def test_score_object_and_sharding():
+    so = build_score_object({'2D': [0.2, 0.4], '3D': [1.0]})
+    assert np.isclose(so['score_2D'], 0.3) and so['score_2.5D'] == 0 and np.isclose(so['score_3D'], 1.0)
+    assert np.isclose(so['score_total'], np.mean([0.2, 0.4, 1.0]))
+    assert [shard_range(50, r, 8) for r in range(8)] == [(0, 7), (7, 14), (14, 21), (21, 28), (28, 35), (35, 42), (42, 49), (49, 50)]
+    assert shard_range(3, 5, 8) == (3, 3)
+
+
+def test_evaluation_service_checks():
+    class P(BasePolicy):
+        pass
+    with pytest.raises(Exception, match="macro_action in Round 2"):
+        EvaluationService(P, environment='R2', action_type='macro_action', visualize=False)
+    with pytest.raises(Exception, match="R1 or R2"):
+        EvaluationService(P, environment='R3', visualize=False)
+    with pytest.raises(Exception, match="1, 2 or 3"):
+        EvaluationService(P, environment='R1', action_type='joints', n_objects=4, visualize=False)
+    with pytest.raises(Exception, match="Sub-Class"):
+        EvaluationService(object, environment='R1', action_type='joints', n_objects=1, visualize=False,
+                          goals_dataset_path=__file__)
