@@ -21,9 +21,10 @@
 
 __constant__ RenderConst c_render;
 
-#define STRIP_ROWS 40
+#define STRIP_ROWS 80
 #define NSTRIPS (RR_H / STRIP_ROWS)
-#define RTHREADS 256
+#define RTHREADS 512
+#define RBLOCKS 1             // resident CTAs per SM (shared memory bound)
 #define MAT_STRIDE 40          // floats per (env, shape): pmv[16] model[12] invT[9] ylo yhi flag
 #define SMALL_AREA 6            // in-strip bounding-box pixels up to which a triangle is rasterised by its own lane
 #define BIGQ 512
@@ -223,17 +224,44 @@ __device__ __forceinline__ int coverage_class(float ux, float uy, float uz) {
     if (at > az * 1.000001f) return 0;                    // exact quotient > 1 + 2^-23: rounds above 1
     return 2;
 }
-__device__ __forceinline__ void barycentric(const Screen& S, const Edge& E, float px, float py, float* out) {
-    float ux, uy; bary_u(S, E, px, py, ux, uy);
-    if (!E.degenerate) { out[0] = 1.f - (ux + uy) / E.uz; out[1] = uy / E.uz; out[2] = ux / E.uz; }
-    else { out[0] = -1.f; out[1] = 1.f; out[2] = 1.f; }
+// Correctly rounded a / b from a correctly rounded reciprocal y = RN(1/b) and two FMA residual corrections
+// (Markstein): bit-identical to IEEE division inside the guarded range, several times cheaper when y is shared.
+// Checked against true division on 2e9 random operand pairs (incl. significands near 1.0 and near all-ones).
+__device__ __forceinline__ float div_fast(float a, float b, float y, bool ok) {
+    const float aa = fabsf(a);
+    if (ok && (aa == 0.f || (aa > 1e-25f && aa < 1e25f))) {
+        float q = a * y;
+        if (aa == 0.f) return q;
+        float r = __fmaf_rn(-b, q, a); q = __fmaf_rn(r, y, q);
+        r = __fmaf_rn(-b, q, a); q = __fmaf_rn(r, y, q);
+        return q;
+    }
+    return a / b;
 }
-
+__device__ __forceinline__ bool recip_ok(float b) { const float ab = fabsf(b); return ab > 1e-12f && ab < 1e12f; }
+struct Recip { float yuz, yw[3]; bool ok; };
+__device__ __forceinline__ void recip_setup(const Screen& S, const Edge& E, Recip& R) {
+    R.ok = recip_ok(E.uz) && recip_ok(S.w[0]) && recip_ok(S.w[1]) && recip_ok(S.w[2]);
+    R.yuz = __frcp_rn(E.uz); R.yw[0] = __frcp_rn(S.w[0]); R.yw[1] = __frcp_rn(S.w[1]); R.yw[2] = __frcp_rn(S.w[2]);
+}
+// bc_screen (bs) and the perspective-correct bc_clip (bc) of pixel (px, py): same quotients as TinyRenderer's triangle()
+__device__ __forceinline__ void frag_bar_r(const Screen& S, const Edge& E, const Recip& R, int px, int py, float* bs, float* bc) {
+    float ux, uy; bary_u(S, E, (float)px, (float)py, ux, uy);
+    if (!E.degenerate) {
+        bs[0] = 1.f - div_fast(ux + uy, E.uz, R.yuz, R.ok); bs[1] = div_fast(uy, E.uz, R.yuz, R.ok); bs[2] = div_fast(ux, E.uz, R.yuz, R.ok);
+    } else { bs[0] = -1.f; bs[1] = 1.f; bs[2] = 1.f; }
+    const float b0 = div_fast(bs[0], S.w[0], R.yw[0], R.ok), b1 = div_fast(bs[1], S.w[1], R.yw[1], R.ok), b2 = div_fast(bs[2], S.w[2], R.yw[2], R.ok);
+    const float s = b0 + b1 + b2;
+    const bool oks = recip_ok(s);
+    const float ys = __frcp_rn(s);
+    bc[0] = div_fast(b0, s, ys, oks); bc[1] = div_fast(b1, s, ys, oks); bc[2] = div_fast(b2, s, ys, oks);
+}
+__device__ __forceinline__ void frag_bar(const Screen& S, const Edge& E, int px, int py, float* bs, float* bc) {
+    Recip R; recip_setup(S, E, R);
+    frag_bar_r(S, E, R, px, py, bs, bc);
+}
 __device__ __forceinline__ float frag_depth(const Screen& S, const Edge& E, const float* clipz, int px, int py, float* bs, float* bc) {
-    barycentric(S, E, (float)px, (float)py, bs);
-    float b0 = bs[0] / S.w[0], b1 = bs[1] / S.w[1], b2 = bs[2] / S.w[2];
-    float s = b0 + b1 + b2;
-    bc[0] = b0 / s; bc[1] = b1 / s; bc[2] = b2 / s;
+    frag_bar(S, E, px, py, bs, bc);
     return -1.f * dot3r(clipz[0], clipz[1], clipz[2], bc);
 }
 
@@ -282,40 +310,40 @@ __device__ __noinline__ int clip_near(const float tri[4][3], float out[3][4][3])
 }
 
 // rasterise the in-strip bounding box of one screen triangle into the strip key buffer.
-// keylo = ((triangle index + 1) << 5) | shape: ties in depth resolve to the later-submitted triangle.
+// keylo: ties in depth resolve to the later-submitted triangle (larger key).
+__device__ __forceinline__ void raster_one(unsigned long long* keys, const Screen& S, const Edge& E, const Recip& R, const float* clipz,
+                                           unsigned int keylo, bool planes, int row0, int px, int py) {
+    float ux, uy; bary_u(S, E, (float)px, (float)py, ux, uy);
+    const int cls = coverage_class(ux, uy, E.uz);
+    if (cls == 0) return;
+    float bs[3], bc[3];
+    frag_bar_r(S, E, R, px, py, bs, bc);
+    const float fd = -1.f * dot3r(clipz[0], clipz[1], clipz[2], bc);
+    if (cls == 2 && (bs[0] < 0 || bs[1] < 0 || bs[2] < 0)) return;
+    if (!(fd >= -1e30f)) return;                                  // z-buffer cleared to -1e30 (also drops NaN)
+    if (planes && (fd < -c_render.farPlane || fd > -c_render.nearPlane)) return;
+    const unsigned long long key = ((unsigned long long)order_bits(fd) << 32) | keylo;
+    unsigned long long* slot = &keys[(py - row0) * RR_W + px];
+    if (*reinterpret_cast<volatile unsigned long long*>(slot) < key) atomicMax(slot, key);
+}
 __device__ __forceinline__ void raster_pixels(unsigned long long* keys, const Screen& S, const float* clipz, unsigned int keylo,
                                               bool planes, int row0, int start, int stride) {
-    int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
+    const int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
     if (!S.any || ya > yb) return;
     Edge E; edge_setup(S, E);
     if (E.degenerate) return;                 // bc_screen = (-1,1,1): every pixel rejected
-    int wdt = S.x1 - S.x0 + 1, hgt = yb - ya + 1;
-    int n = wdt * hgt;
+    Recip R; recip_setup(S, E, R);
+    if (stride == 1) {
+        for (int py = ya; py <= yb; py++)
+            for (int px = S.x0; px <= S.x1; px++) raster_one(keys, S, E, R, clipz, keylo, planes, row0, px, py);
+        return;
+    }
+    const int wdt = S.x1 - S.x0 + 1, n = wdt * (yb - ya + 1);
     int x = S.x0 + start % wdt, y = ya + start / wdt;
     const int dx = stride % wdt, dy = stride / wdt;
     for (int i = start; i < n; i += stride) {
-        const int px = x, py = y;
+        raster_one(keys, S, E, R, clipz, keylo, planes, row0, x, y);
         x += dx; y += dy; if (x > S.x1) { x -= wdt; y++; }
-        float ux, uy; bary_u(S, E, (float)px, (float)py, ux, uy);
-        int cls = coverage_class(ux, uy, E.uz);
-        if (cls == 0) continue;
-        float bs[3], bc[3];
-        float fd = frag_depth(S, E, clipz, px, py, bs, bc);
-        if (cls == 2 && (bs[0] < 0 || bs[1] < 0 || bs[2] < 0)) continue;
-        if (!(fd >= -1e30f)) continue;                                  // z-buffer cleared to -1e30 (also drops NaN)
-        if (planes && (fd < -c_render.farPlane || fd > -c_render.nearPlane)) continue;
-        unsigned long long key = ((unsigned long long)order_bits(fd) << 32) | keylo;
-        unsigned long long* slot = &keys[(py - row0) * RR_W + px];
-        if (*reinterpret_cast<volatile unsigned long long*>(slot) < key) atomicMax(slot, key);
-    }
-}
-
-__device__ __noinline__ void raster_clipped(unsigned long long* keys, const Tri& T, unsigned int keylo, int row0, int start, int stride) {
-    float out[3][4][3];
-    int nc = clip_near(T.c, out);
-    for (int c = 0; c < nc; c++) {
-        Screen S; screen_setup(out[c], S);
-        raster_pixels(keys, S, out[c][2], keylo, false, row0, start, stride);
     }
 }
 
@@ -332,24 +360,64 @@ __device__ __forceinline__ void texel_fetch(int tex, const uint8_t* __restrict__
     c[0] = __ldg(p); c[1] = __ldg(p + 1); c[2] = __ldg(p + 2);
 }
 
-// full shading of pixel (x, y) by triangle (shape s, triangle data tv): returns packed rgb
-__device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M, const ShapeRenderConst& sh, const float* __restrict__ tv,
-                                                    const uint8_t* __restrict__ texdata, int x, int y) {
-    Tri T; float nrm[3][3], uv[2][3];
+// --------------------------------------------------------------------------------------------- raster kernel
+// Visible-triangle record written by the geometry phase (16 words = 64 B, one coalesced row per lane):
+//   w0 = x0 | x1 << 16, w1 = y0 | y1 << 16 (clamped bounding box), w2 = key low word, w3 = flags (1 = piece of a
+//   near-plane-clipped triangle: no near/far discard, shading from the original triangle), then p2[3][2], w[3], z[3].
+struct __align__(16) Rec { unsigned int bx, by, keylo, flags; float p2[3][2]; float w[3]; float z[3]; };
+static_assert(sizeof(Rec) == 64, "record must be 64 bytes");
+#define REC_MAX 24576          // records per env (17 578 triangles + clipped pieces), < 2^15
+#define REC_CLIPPED 1u
+
+__device__ __forceinline__ int agg_inc(int* ctr) {      // warp-aggregated atomic increment of a shared counter
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(ctr, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void emit_record(Rec* __restrict__ recs, int* nrec, const Screen& S, const float* z, unsigned int gt, unsigned int flags) {
+    if (!S.any) return;
+    const int slot = agg_inc(nrec);
+    if (slot >= REC_MAX) return;
+    Rec r;
+    r.bx = (unsigned)S.x0 | ((unsigned)S.x1 << 16); r.by = (unsigned)S.y0 | ((unsigned)S.y1 << 16);
+    r.keylo = ((gt + 1u) << 15) | (unsigned)slot; r.flags = flags;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { r.p2[i][0] = S.p2[i][0]; r.p2[i][1] = S.p2[i][1]; r.w[i] = S.w[i]; r.z[i] = z[i]; }
+    const uint4* src = reinterpret_cast<const uint4*>(&r);
+    uint4* dst = reinterpret_cast<uint4*>(recs + slot);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+
+__device__ __noinline__ void emit_clipped(Rec* __restrict__ recs, int* nrec, const Tri& T, unsigned int gt) {
+    float out[3][4][3];
+    const int nc = clip_near(T.c, out);
+    for (int c = 0; c < nc; c++) {
+        Screen S; screen_setup(out[c], S);
+        emit_record(recs, nrec, S, out[c][2], gt, REC_CLIPPED);
+    }
+}
+
+__device__ __forceinline__ void rec_to_screen(const Rec& r, Screen& S, float* z) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { S.p2[i][0] = r.p2[i][0]; S.p2[i][1] = r.p2[i][1]; S.w[i] = r.w[i]; z[i] = r.z[i]; }
+    S.x0 = r.bx & 0xffff; S.x1 = r.bx >> 16; S.y0 = r.by & 0xffff; S.y1 = r.by >> 16; S.any = true;
+}
+
+// shading of pixel (x, y) from barycentrics of the ORIGINAL triangle (fast path: from the record; slow path: recomputed)
+__device__ __forceinline__ unsigned int shade_bar(const float* __restrict__ M, const ShapeRenderConst& sh, const float* __restrict__ tv,
+                                                  const uint8_t* __restrict__ texdata, const float* bar) {
+    float nrm[3][3], uv[2][3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         float v[8]; load_corner(tv, j, v);
-        float px = v[0] * 1.f, py = v[1] * 1.f, pz = v[2] * 1.f;
-#pragma unroll
-        for (int k = 0; k < 4; k++) T.c[k][j] = dot4r(M + 4 * k, px, py, pz, 1.f);
 #pragma unroll
         for (int k = 0; k < 3; k++) { float r = 0.f; r += 0.f; r += M[28 + 3 * k + 2] * v[5]; r += M[28 + 3 * k + 1] * v[4]; r += M[28 + 3 * k] * v[3]; nrm[k][j] = r; }
         uv[0][j] = v[6]; uv[1][j] = v[7];
     }
-    Screen S; screen_setup(T.c, S);
-    Edge E; edge_setup(S, E);
-    float bs[3], bar[3];
-    frag_depth(S, E, T.c[2], x, y, bs, bar);
     float bn[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) bn[i] = dot3r(nrm[i][0], nrm[i][1], nrm[i][2], bar);
@@ -381,76 +449,106 @@ __device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M,
     return packed;
 }
 
-// --------------------------------------------------------------------------------------------- raster kernel
-__global__ void __launch_bounds__(RTHREADS, 2)
-k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ texdata,
-         const uint8_t* __restrict__ env_mask, uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int N) {
+// slow path (winner is a piece of a near-clipped triangle): barycentrics of the original triangle from scratch
+__device__ __noinline__ unsigned int shade_clipped(const float* __restrict__ M, const ShapeRenderConst& sh, const float* __restrict__ tv,
+                                                   const uint8_t* __restrict__ texdata, int x, int y) {
+    Tri T;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tv + 8 * j));
+        float px = a.x * 1.f, py = a.y * 1.f, pz = a.z * 1.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) T.c[k][j] = dot4r(M + 4 * k, px, py, pz, 1.f);
+    }
+    Screen S; screen_setup(T.c, S);
+    Edge E; edge_setup(S, E);
+    float bs[3], bar[3];
+    frag_depth(S, E, T.c[2], x, y, bs, bar);
+    return shade_bar(M, sh, tv, texdata, bar);
+}
+
+// Persistent kernel: each CTA takes envs from a global work counter.  Per env:
+//   geometry : one triangle per thread — vertex shader, back-face cull, near-plane clip, viewport, bounding box; the
+//              survivors become 64-byte records in the CTA's private scratch (rewritten every env, so it stays in L2);
+//   per strip of STRIP_ROWS raster rows: clear the 64-bit key buffer in shared memory; scan the records (coalesced),
+//              rasterise the ones that touch the strip (small: own lane, medium: whole warp via shuffles, huge: whole CTA)
+//              with atomicMax on (depth bits, triangle index); resolve: one fragment shader per pixel, vector stores.
+__global__ void __launch_bounds__(RTHREADS, RBLOCKS)
+k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const uint8_t* __restrict__ texdata,
+         const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, int* __restrict__ work_counter,
+         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int N) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* M = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);
     int* bigq = reinterpret_cast<int*>(M + RR_NSHAPES * MAT_STRIDE);
-    __shared__ int bign;
-    const int strip = blockIdx.x, e = blockIdx.y;
-    const int tid = threadIdx.x;
-    const int row0 = strip * STRIP_ROWS;                 // first raster row (origin bottom-left)
-    const size_t img = (size_t)e * RR_W * RR_H;
-    const bool on = env_mask ? (env_mask[e] != 0) : true;
+    __shared__ int s_env, s_nrec, s_bign;
+    const int tid = threadIdx.x, lane = tid & 31;
+    Rec* recs = rec_scratch + (size_t)blockIdx.x * REC_MAX;
+    const float nearP = c_render.depthNear, farP = c_render.depthFar;
+    const float bg_depth = (float)((double)(farP * (nearP + 1e30f)) / (2. * (double)farP * (double)nearP + (double)(farP * 1e30f) - (double)(nearP * 1e30f)));
 
-    if (!on) {   // reference returns cached zero arrays when render is off (env.py:114-122, 273-275)
-        for (int i = tid; i < STRIP_ROWS * RR_W / 4; i += RTHREADS) {
-            int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
-            size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
-            if (rgb) { unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3); p[0] = 0; p[1] = 0; p[2] = 0; }
-            if (depth) *reinterpret_cast<float4*>(depth + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (seg) *reinterpret_cast<int4*>(seg + o) = make_int4(0, 0, 0, 0);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_env = atomicAdd(work_counter, 1); s_nrec = 0; }
+        __syncthreads();
+        const int e = s_env;
+        if (e >= N) break;
+        const size_t img = (size_t)e * RR_W * RR_H;
+        const bool on = env_mask ? (env_mask[e] != 0) : true;
+        if (!on) {   // reference returns cached zero arrays when render is off (env.py:114-122, 273-275)
+            for (int i = tid; i < RR_H * RR_W / 4; i += RTHREADS) {
+                size_t o = img + 4 * (size_t)i;
+                if (rgb) { unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3); p[0] = 0; p[1] = 0; p[2] = 0; }
+                if (depth) *reinterpret_cast<float4*>(depth + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (seg) *reinterpret_cast<int4*>(seg + o) = make_int4(0, 0, 0, 0);
+            }
+            continue;
         }
-        return;
-    }
-    for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = 0ull;
-    for (int i = tid; i < RR_NSHAPES * MAT_STRIDE; i += RTHREADS) M[i] = mats[(size_t)e * RR_NSHAPES * MAT_STRIDE + i];
-    if (tid == 0) bign = 0;
-    __syncthreads();
-
-    // ---- pass 1: one triangle per lane.  Triangles with a small in-strip bounding box are rasterised by their own
-    //      lane; medium ones are broadcast (shuffles) and rasterised by the whole warp, 32 pixels at a time; huge and
-    //      near-plane-clipped ones are deferred to the CTA-wide queue.
-    {
-        const int lane = tid & 31;
+        for (int i = tid; i < RR_NSHAPES * MAT_STRIDE; i += RTHREADS) M[i] = mats[(size_t)e * RR_NSHAPES * MAT_STRIDE + i];
+        __syncthreads();
+        // ---- geometry phase
         for (int s = 0; s < RR_NSHAPES; s++) {
             const float* Ms = M + s * MAT_STRIDE;
             if (Ms[39] == 0.f) continue;
-            if (Ms[38] < (float)row0 || Ms[37] > (float)(row0 + STRIP_ROWS - 1)) continue;
             const ShapeRenderConst& sh = c_render.shape[s];
-            for (int tb = tid - lane; tb < sh.tri_count; tb += RTHREADS) {
-                const int t = tb + lane;
-                int state = 0;                       // 0 nothing, 1 own lane, 2 warp-cooperative
-                Screen S; float cz[3] = {0.f, 0.f, 0.f};
-                unsigned int keylo = 0;
-                if (t < sh.tri_count) {
-                    const int gt = sh.tri_start + t;
-                    const float* tv = tris + (size_t)gt * 24;
-                    keylo = (((unsigned int)gt + 1u) << 5) | (unsigned int)s;
-                    Tri T;
-                    if (tri_vertex(Ms, tv, T)) {
-                        const bool front = (T.c[3][0] >= 0 && T.c[3][1] >= 0 && T.c[3][2] >= 0);
-                        if (!front) {
-                            if (!(T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0)) {
-                                int slot = atomicAdd(&bign, 1);
-                                if (slot < BIGQ) bigq[slot] = gt | (s << 20) | 0x40000000;
-                                else raster_clipped(keys, T, keylo, row0, 0, 1);
-                            }
-                        } else {
-                            screen_setup(T.c, S);
-                            cz[0] = T.c[2][0]; cz[1] = T.c[2][1]; cz[2] = T.c[2][2];
-                            int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
-                            if (S.any && ya <= yb) {
-                                int area = (S.x1 - S.x0 + 1) * (yb - ya + 1);
-                                state = area <= SMALL_AREA ? 1 : 2;
-                                if (area > 2048) {
-                                    int slot = atomicAdd(&bign, 1);
-                                    if (slot < BIGQ) { bigq[slot] = gt | (s << 20) | 0x20000000; state = 0; }
-                                }
-                            }
+            for (int t = tid; t < sh.tri_count; t += RTHREADS) {
+                const unsigned int gt = sh.tri_start + t;
+                const float* tv = tris + (size_t)gt * 24;
+                Tri T;
+                if (!tri_vertex(Ms, tv, T)) continue;
+                const bool front = (T.c[3][0] >= 0 && T.c[3][1] >= 0 && T.c[3][2] >= 0);
+                if (front) { Screen S; screen_setup(T.c, S); emit_record(recs, &s_nrec, S, T.c[2], gt, 0u); }
+                else if (!(T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0)) emit_clipped(recs, &s_nrec, T, gt);
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        const int nrec = min(s_nrec, REC_MAX);
+        // ---- strips
+        for (int strip = 0; strip < NSTRIPS; strip++) {
+            const int row0 = strip * STRIP_ROWS;
+            for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = 0ull;
+            if (tid == 0) s_bign = 0;
+            __syncthreads();
+            for (int rb = tid - lane; rb < nrec; rb += RTHREADS) {
+                const int r = rb + lane;
+                int state = 0;                           // 0 nothing, 1 own lane, 2 warp-cooperative
+                Screen S; float cz[3] = {0.f, 0.f, 0.f}; unsigned int keylo = 0; bool planes = true;
+                if (r < nrec) {
+                    const uint4 h = *reinterpret_cast<const uint4*>(recs + r);
+                    const int y0 = h.y & 0xffff, y1 = h.y >> 16;
+                    const int ya = max(y0, row0), yb = min(y1, row0 + STRIP_ROWS - 1);
+                    if (ya <= yb) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(recs + r);
+                        Rec rec; uint4* d = reinterpret_cast<uint4*>(&rec);
+                        d[0] = h; d[1] = rp[1]; d[2] = rp[2]; d[3] = rp[3];
+                        rec_to_screen(rec, S, cz);
+                        keylo = rec.keylo; planes = !(rec.flags & REC_CLIPPED);
+                        const int area = (S.x1 - S.x0 + 1) * (yb - ya + 1);
+                        state = area <= SMALL_AREA ? 1 : 2;
+                        if (area > 2048) {
+                            int slot = atomicAdd(&s_bign, 1);
+                            if (slot < BIGQ) { bigq[slot] = r; state = 0; }
                         }
                     }
                 }
@@ -466,67 +564,64 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                     B.x0 = __shfl_sync(0xffffffffu, S.x0, src); B.x1 = __shfl_sync(0xffffffffu, S.x1, src);
                     B.y0 = __shfl_sync(0xffffffffu, S.y0, src); B.y1 = __shfl_sync(0xffffffffu, S.y1, src);
                     B.any = true;
-                    unsigned int bk = __shfl_sync(0xffffffffu, keylo, src);
-                    raster_pixels(keys, B, bz, bk, true, row0, lane, 32);
+                    const unsigned int bk = __shfl_sync(0xffffffffu, keylo, src);
+                    const bool bp = __shfl_sync(0xffffffffu, (int)planes, src) != 0;
+                    raster_pixels(keys, B, bz, bk, bp, row0, lane, 32);
                 }
-                if (state == 1) raster_pixels(keys, S, cz, keylo, true, row0, 0, 1);
+                if (state == 1) raster_pixels(keys, S, cz, keylo, planes, row0, 0, 1);
             }
-        }
-    }
-    __syncthreads();
-    // ---- pass 2: deferred triangles.  Medium ones are rasterised by one warp each (lanes stride the bounding
-    //      box), huge ones (flag bit 29) and near-plane-clipped ones (bit 30) by the whole CTA.
-    {
-        const int nb = min(bign, BIGQ);
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int b = 0; b < nb; b++) {
-            const int ent = bigq[b];
-            const bool cta_wide = (ent & 0x60000000) != 0;
-            if (!cta_wide && (b & (RTHREADS / 32 - 1)) != warp) continue;
-            const int gt = ent & 0xfffff;
-            const int s = (ent >> 20) & 31;
-            const unsigned int keylo = (((unsigned int)gt + 1u) << 5) | (unsigned int)s;
-            const float* Ms = M + s * MAT_STRIDE;
-            const float* tv = tris + (size_t)gt * 24;
-            Tri T; tri_vertex(Ms, tv, T);
-            const int start = cta_wide ? tid : lane, stride = cta_wide ? RTHREADS : 32;
-            if (ent & 0x40000000) raster_clipped(keys, T, keylo, row0, start, stride);
-            else { Screen S; screen_setup(T.c, S); raster_pixels(keys, S, T.c[2], keylo, true, row0, start, stride); }
-        }
-    }
-    __syncthreads();
-    // ---- resolve: 4 consecutive pixels per thread-iteration, vector stores
-    const float nearP = c_render.depthNear, farP = c_render.depthFar;
-    for (int i = tid; i < STRIP_ROWS * RR_W / 4; i += RTHREADS) {
-        int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
-        unsigned int col[4]; float dep[4]; int sg[4];
+            __syncthreads();
+            {   // huge triangles: whole CTA per record
+                const int nb = min(s_bign, BIGQ);
+                for (int b = 0; b < nb; b++) {
+                    const Rec rec = recs[bigq[b]];
+                    Screen S; float cz[3]; rec_to_screen(rec, S, cz);
+                    raster_pixels(keys, S, cz, rec.keylo, !(rec.flags & REC_CLIPPED), row0, tid, RTHREADS);
+                }
+            }
+            __syncthreads();
+            // ---- resolve: 4 consecutive pixels per thread-iteration, vector stores
+            for (int i = tid; i < STRIP_ROWS * RR_W / 4; i += RTHREADS) {
+                const int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
+                unsigned int col[4]; float dep[4]; int sg[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int x = 4 * x4 + k;
-            unsigned long long key = keys[r * RR_W + x];
-            float z;
-            if (key == 0ull) { col[k] = 0xffffffu; sg[k] = -1; z = -1e30f; }
-            else {
-                int gt = (int)((key & 0xffffffffu) >> 5) - 1;
-                z = unorder_bits((unsigned int)(key >> 32));
-                int s = (int)(key & 31u);
-                const ShapeRenderConst& sh = c_render.shape[s];
-                col[k] = shade_pixel(M + s * MAT_STRIDE, sh, tris + (size_t)gt * 24, texdata, x, row0 + r);
-                sg[k] = sh.objectAndLink & 0xffffff;
+                for (int k = 0; k < 4; k++) {
+                    const int x = 4 * x4 + k;
+                    const unsigned long long key = keys[r * RR_W + x];
+                    if (key == 0ull) { col[k] = 0xffffffu; sg[k] = -1; dep[k] = bg_depth; continue; }
+                    const unsigned int lo = (unsigned int)(key & 0xffffffffu);
+                    const int gt = (int)(lo >> 15) - 1, ri = (int)(lo & 0x7fffu);
+                    const float z = unorder_bits((unsigned int)(key >> 32));
+                    const int s = tri_shape[gt];
+                    const ShapeRenderConst& sh = c_render.shape[s];
+                    const float* tv = tris + (size_t)gt * 24;
+                    const Rec* rp = recs + ri;
+                    if (rp->flags & REC_CLIPPED) col[k] = shade_clipped(M + s * MAT_STRIDE, sh, tv, texdata, x, row0 + r);
+                    else {
+                        Screen S;
+#pragma unroll
+                        for (int j = 0; j < 3; j++) { S.p2[j][0] = rp->p2[j][0]; S.p2[j][1] = rp->p2[j][1]; S.w[j] = rp->w[j]; }
+                        Edge E; edge_setup(S, E);
+                        float bs[3], bar[3];
+                        frag_bar(S, E, x, row0 + r, bs, bar);
+                        col[k] = shade_bar(M + s * MAT_STRIDE, sh, tv, texdata, bar);
+                    }
+                    sg[k] = sh.objectAndLink & 0xffffff;
+                    const float z_c = -z;
+                    dep[k] = (float)((double)(farP * (nearP + z_c)) / (2. * (double)farP * (double)nearP + (double)(farP * z_c) - (double)(nearP * z_c)));
+                }
+                const size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
+                if (rgb) {
+                    unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3);
+                    p[0] = (col[0] & 0xffffffu) | (col[1] << 24);
+                    p[1] = ((col[1] >> 8) & 0xffffu) | (col[2] << 16);
+                    p[2] = ((col[2] >> 16) & 0xffu) | (col[3] << 8);
+                }
+                if (depth) *reinterpret_cast<float4*>(depth + o) = make_float4(dep[0], dep[1], dep[2], dep[3]);
+                if (seg) *reinterpret_cast<int4*>(seg + o) = make_int4(sg[0], sg[1], sg[2], sg[3]);
             }
-            float z_c = -z;
-            dep[k] = (float)((double)(farP * (nearP + z_c)) / (2. * (double)farP * (double)nearP + (double)(farP * z_c) - (double)(nearP * z_c)));
+            __syncthreads();
         }
-        size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
-        if (rgb) {
-            unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3);
-            // 4 pixels x 3 bytes -> 3 little-endian words
-            p[0] = (col[0] & 0xffffffu) | (col[1] << 24);
-            p[1] = ((col[1] >> 8) & 0xffffu) | (col[2] << 16);
-            p[2] = ((col[2] >> 16) & 0xffu) | (col[3] << 8);
-        }
-        if (depth) *reinterpret_cast<float4*>(depth + o) = make_float4(dep[0], dep[1], dep[2], dep[3]);
-        if (seg) *reinterpret_cast<int4*>(seg + o) = make_int4(sg[0], sg[1], sg[2], sg[3]);
     }
 }
 
@@ -539,6 +634,21 @@ static double* g_static_frames[16] = {0};
 int rrk_render_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_render, &ctx->render, sizeof(RenderConst)));
     CK(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RASTER_SMEM));
+    {
+        cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raster, RTHREADS, RASTER_SMEM));
+        if (per_sm < 1) { ctx->err = "k_raster does not fit on this device"; return -1; }
+        ctx->raster_grid = prop.multiProcessorCount * per_sm;           // persistent: one wave of CTAs, envs pulled from a counter
+        if (ctx->raster_grid > ctx->N) ctx->raster_grid = ctx->N;
+        CK(cudaMalloc(&ctx->d_rec_scratch, (size_t)ctx->raster_grid * REC_MAX * sizeof(Rec)));
+        CK(cudaMalloc(&ctx->d_work_counter, sizeof(int)));
+        std::vector<uint8_t> ts(ctx->n_tris);
+        for (int sidx = 0; sidx < RR_NSHAPES; sidx++)
+            for (int t = 0; t < ctx->render.shape[sidx].tri_count; t++) ts[ctx->render.shape[sidx].tri_start + t] = (uint8_t)sidx;
+        CK(cudaMalloc(&ctx->d_tri_shape, ts.size()));
+        CK(cudaMemcpy(ctx->d_tri_shape, ts.data(), ts.size(), cudaMemcpyHostToDevice));
+    }
     // static frames (robot base, table) as doubles
     double sf[RR_NSHAPES * 12];
     for (int s = 0; s < RR_NSHAPES; s++) {
@@ -563,10 +673,11 @@ int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* 
     }
     ctx->launches++;
     CK(cudaGetLastError());
-    dim3 grid(NSTRIPS, ctx->N);
+    CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), s));
     {
         ProfScope ps(ctx, 2, s);
-        k_raster<<<grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tex, mask, rgb, depth, seg, ctx->N);
+        k_raster<<<ctx->raster_grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, ctx->d_tex, mask,
+                                                                 (Rec*)ctx->d_rec_scratch, ctx->d_work_counter, rgb, depth, seg, ctx->N);
     }
     ctx->launches++;
     CK(cudaGetLastError());
