@@ -213,9 +213,9 @@ __device__ __forceinline__ int coverage_class(float ux, float uy, float uz) {
     // uy/uz < 0  <=>  signs differ and the rounded quotient is not a zero (no underflow when |uy| >= 1e-30, |uz| < 1e7)
     float auy = fabsf(uy), aux = fabsf(ux);
     if (!(fabsf(uz) < 1e7f)) return 2;
-    if (auy < 1e-30f) { if (uy != 0.f) return 2; }
+    if (auy < 1e-10f || auy > 1e13f) { if (uy != 0.f) return 2; }
     else if ((uy < 0.f) != zn) return 0;
-    if (aux < 1e-30f) { if (ux != 0.f) return 2; }
+    if (aux < 1e-10f || aux > 1e13f) { if (ux != 0.f) return 2; }
     else if ((ux < 0.f) != zn) return 0;
     // 1 - RN(t/uz) < 0  <=>  RN(t/uz) > 1
     float t = ux + uy;
@@ -238,10 +238,20 @@ __device__ __forceinline__ float div_fast(float a, float b, float y, bool ok) {
     }
     return a / b;
 }
+// same, without the range guards: only valid when the caller has established the operand ranges (see raster_one)
+__device__ __forceinline__ float div_fast_ng(float a, float b, float y) {
+    float q = a * y;
+    if (a == 0.f) return q;
+    float r = __fmaf_rn(-b, q, a); q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-b, q, a); q = __fmaf_rn(r, y, q);
+    return q;
+}
 __device__ __forceinline__ bool recip_ok(float b) { const float ab = fabsf(b); return ab > 1e-12f && ab < 1e12f; }
-struct Recip { float yuz, yw[3]; bool ok; };
+struct Recip { float yuz, yw[3]; bool ok, tight; };
+__device__ __forceinline__ bool w_tight(float w) { return w > 1e-6f && w < 1e6f; }
 __device__ __forceinline__ void recip_setup(const Screen& S, const Edge& E, Recip& R) {
     R.ok = recip_ok(E.uz) && recip_ok(S.w[0]) && recip_ok(S.w[1]) && recip_ok(S.w[2]);
+    R.tight = R.ok && fabsf(E.uz) < 1e7f && w_tight(S.w[0]) && w_tight(S.w[1]) && w_tight(S.w[2]);
     R.yuz = __frcp_rn(E.uz); R.yw[0] = __frcp_rn(S.w[0]); R.yw[1] = __frcp_rn(S.w[1]); R.yw[2] = __frcp_rn(S.w[2]);
 }
 // bc_screen (bs) and the perspective-correct bc_clip (bc) of pixel (px, py): same quotients as TinyRenderer's triangle()
@@ -255,6 +265,17 @@ __device__ __forceinline__ void frag_bar_r(const Screen& S, const Edge& E, const
     const bool oks = recip_ok(s);
     const float ys = __frcp_rn(s);
     bc[0] = div_fast(b0, s, ys, oks); bc[1] = div_fast(b1, s, ys, oks); bc[2] = div_fast(b2, s, ys, oks);
+}
+// Fast variant for pixels whose coverage class is 1 (all three bc_screen components clearly >= 0) on a triangle with
+// R.ok: then every numerator is either exactly 0 or lies in [1e-23, 1e20], every quotient and FMA residual is a
+// normal float, and the guarded and unguarded divisions coincide.  (ux, uy in {0} U [1e-10, 1e13] by coverage_class,
+// uz in [1e-2, 1e7], w in [1e-6, 1e6], bs0 = 1 - q is 0 or >= 2^-24, s >= the largest b_i > 0.)
+__device__ __forceinline__ void frag_bar_in(const Screen& S, const Edge& E, const Recip& R, float ux, float uy, float* bc) {
+    const float bs0 = 1.f - div_fast_ng(ux + uy, E.uz, R.yuz), bs1 = div_fast_ng(uy, E.uz, R.yuz), bs2 = div_fast_ng(ux, E.uz, R.yuz);
+    const float b0 = div_fast_ng(bs0, S.w[0], R.yw[0]), b1 = div_fast_ng(bs1, S.w[1], R.yw[1]), b2 = div_fast_ng(bs2, S.w[2], R.yw[2]);
+    const float s = b0 + b1 + b2;
+    const float ys = __frcp_rn(s);
+    bc[0] = div_fast_ng(b0, s, ys); bc[1] = div_fast_ng(b1, s, ys); bc[2] = div_fast_ng(b2, s, ys);
 }
 __device__ __forceinline__ void frag_bar(const Screen& S, const Edge& E, int px, int py, float* bs, float* bc) {
     Recip R; recip_setup(S, E, R);
@@ -317,9 +338,12 @@ __device__ __forceinline__ void raster_one(unsigned long long* keys, const Scree
     const int cls = coverage_class(ux, uy, E.uz);
     if (cls == 0) return;
     float bs[3], bc[3];
-    frag_bar_r(S, E, R, px, py, bs, bc);
+    if (cls == 1 && R.tight) frag_bar_in(S, E, R, ux, uy, bc);
+    else {
+        frag_bar_r(S, E, R, px, py, bs, bc);
+        if (cls == 2 && (bs[0] < 0 || bs[1] < 0 || bs[2] < 0)) return;
+    }
     const float fd = -1.f * dot3r(clipz[0], clipz[1], clipz[2], bc);
-    if (cls == 2 && (bs[0] < 0 || bs[1] < 0 || bs[2] < 0)) return;
     if (!(fd >= -1e30f)) return;                                  // z-buffer cleared to -1e30 (also drops NaN)
     if (planes && (fd < -c_render.farPlane || fd > -c_render.nearPlane)) return;
     const unsigned long long key = ((unsigned long long)order_bits(fd) << 32) | keylo;
@@ -481,7 +505,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* M = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);
     int* bigq = reinterpret_cast<int*>(M + RR_NSHAPES * MAT_STRIDE);
-    __shared__ int s_env, s_nrec, s_bign;
+    __shared__ int s_env, s_nrec, s_bign, s_chunk;
     const int tid = threadIdx.x, lane = tid & 31;
     Rec* recs = rec_scratch + (size_t)blockIdx.x * REC_MAX;
     const float nearP = c_render.depthNear, farP = c_render.depthFar;
@@ -528,9 +552,13 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         for (int strip = 0; strip < NSTRIPS; strip++) {
             const int row0 = strip * STRIP_ROWS;
             for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = 0ull;
-            if (tid == 0) s_bign = 0;
+            if (tid == 0) { s_bign = 0; s_chunk = 0; }
             __syncthreads();
-            for (int rb = tid - lane; rb < nrec; rb += RTHREADS) {
+            for (;;) {
+                int rb = 0;
+                if (lane == 0) rb = atomicAdd(&s_chunk, 32);
+                rb = __shfl_sync(0xffffffffu, rb, 0);
+                if (rb >= nrec) break;
                 const int r = rb + lane;
                 int state = 0;                           // 0 nothing, 1 own lane, 2 warp-cooperative
                 Screen S; float cz[3] = {0.f, 0.f, 0.f}; unsigned int keylo = 0; bool planes = true;
