@@ -86,7 +86,7 @@ struct rr_ctx {
     int pair_a[RR_MAX_PAIRS], pair_b[RR_MAX_PAIRS], n_pairs;
     int man_parity;            // which manifold buffer holds the current contacts
     int n_tris;
-    void* d_rec_scratch; int* d_work_counter; uint8_t* d_tri_shape; int raster_grid;   // persistent rasteriser
+    void* d_rec_scratch; void* d_list_scratch; int* d_work_counter; uint8_t* d_tri_shape; int raster_grid;   // persistent rasteriser
     // staging for the host-buffer path
     double* d_cmd; uint8_t* d_mask; double* d_joint; double* d_touch; double* d_objpose;
     uint8_t* d_rgb; float* d_depth; int32_t* d_seg;

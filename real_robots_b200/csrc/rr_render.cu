@@ -350,21 +350,19 @@ __device__ __forceinline__ void raster_one(unsigned long long* keys, const Scree
     unsigned long long* slot = &keys[(py - row0) * RR_W + px];
     if (*reinterpret_cast<volatile unsigned long long*>(slot) < key) atomicMax(slot, key);
 }
-__device__ __forceinline__ void raster_pixels(unsigned long long* keys, const Screen& S, const float* clipz, unsigned int keylo,
-                                              bool planes, int row0, int start, int stride) {
+__device__ __forceinline__ void raster_pixels(unsigned long long* keys, const Screen& S, const Edge& E, const Recip& R, const float* clipz,
+                                              unsigned int keylo, bool planes, int row0, int start, int stride) {
     const int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
-    if (!S.any || ya > yb) return;
-    Edge E; edge_setup(S, E);
-    if (E.degenerate) return;                 // bc_screen = (-1,1,1): every pixel rejected
-    Recip R; recip_setup(S, E, R);
+    if (ya > yb) return;
     if (stride == 1) {
         for (int py = ya; py <= yb; py++)
             for (int px = S.x0; px <= S.x1; px++) raster_one(keys, S, E, R, clipz, keylo, planes, row0, px, py);
         return;
     }
     const int wdt = S.x1 - S.x0 + 1, n = wdt * (yb - ya + 1);
-    int x = S.x0 + start % wdt, y = ya + start / wdt;
-    const int dx = stride % wdt, dy = stride / wdt;
+    const int sy = start / wdt, dy = stride / wdt;
+    int x = S.x0 + (start - sy * wdt), y = ya + sy;
+    const int dx = stride - dy * wdt;
     for (int i = start; i < n; i += stride) {
         raster_one(keys, S, E, R, clipz, keylo, planes, row0, x, y);
         x += dx; y += dy; if (x > S.x1) { x -= wdt; y++; }
@@ -385,13 +383,16 @@ __device__ __forceinline__ void texel_fetch(int tex, const uint8_t* __restrict__
 }
 
 // --------------------------------------------------------------------------------------------- raster kernel
-// Visible-triangle record written by the geometry phase (16 words = 64 B, one coalesced row per lane):
-//   w0 = x0 | x1 << 16, w1 = y0 | y1 << 16 (clamped bounding box), w2 = key low word, w3 = flags (1 = piece of a
-//   near-plane-clipped triangle: no near/far discard, shading from the original triangle), then p2[3][2], w[3], z[3].
-struct __align__(16) Rec { unsigned int bx, by, keylo, flags; float p2[3][2]; float w[3]; float z[3]; };
-static_assert(sizeof(Rec) == 64, "record must be 64 bytes");
+// Visible-triangle record written by the geometry phase (20 words = 80 B):
+//   bx = x0 | x1 << 16, by = y0 | y1 << 16 (clamped bounding box), keylo = (triangle + 1) << 15 | record index,
+//   flags (REC_*), screen coordinates p2[3][2], w[3], clip z[3], and the correctly rounded reciprocals of u.z and w[3].
+struct __align__(16) Rec { unsigned int bx, by, keylo, flags; float p2[3][2]; float w[3]; float z[3]; float yuz; float yw[3]; };
+static_assert(sizeof(Rec) == 80, "record must be 80 bytes");
 #define REC_MAX 24576          // records per env (17 578 triangles + clipped pieces), < 2^15
-#define REC_CLIPPED 1u
+#define REC_CLIPPED 1u         // piece of a near-plane-clipped triangle: no near/far discard, shading from the original triangle
+#define REC_OK 2u              // reciprocal operands inside the guarded range
+#define REC_TIGHT 4u           // ... and inside the tighter range of the unguarded fast path
+#define REC_DEGENERATE 8u      // |u.z| <= 1e-2: TinyRenderer rejects every pixel
 
 __device__ __forceinline__ int agg_inc(int* ctr) {      // warp-aggregated atomic increment of a shared counter
     const unsigned m = __activemask();
@@ -402,36 +403,65 @@ __device__ __forceinline__ int agg_inc(int* ctr) {      // warp-aggregated atomi
     return base + __popc(m & ((1u << lane) - 1u));
 }
 
-__device__ __forceinline__ void emit_record(Rec* __restrict__ recs, int* nrec, const Screen& S, const float* z, unsigned int gt, unsigned int flags) {
+__device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist,
+                                            const Screen& S, const float* z, unsigned int gt, unsigned int flags) {
     if (!S.any) return;
+    Edge E; edge_setup(S, E);
+    if (E.degenerate) return;                               // bc_screen = (-1,1,1) everywhere: nothing is ever drawn
     const int slot = agg_inc(nrec);
     if (slot >= REC_MAX) return;
+    Recip R; recip_setup(S, E, R);
     Rec r;
     r.bx = (unsigned)S.x0 | ((unsigned)S.x1 << 16); r.by = (unsigned)S.y0 | ((unsigned)S.y1 << 16);
-    r.keylo = ((gt + 1u) << 15) | (unsigned)slot; r.flags = flags;
+    r.keylo = ((gt + 1u) << 15) | (unsigned)slot;
+    r.flags = flags | (R.ok ? REC_OK : 0u) | (R.tight ? REC_TIGHT : 0u);
 #pragma unroll
-    for (int i = 0; i < 3; i++) { r.p2[i][0] = S.p2[i][0]; r.p2[i][1] = S.p2[i][1]; r.w[i] = S.w[i]; r.z[i] = z[i]; }
+    for (int i = 0; i < 3; i++) { r.p2[i][0] = S.p2[i][0]; r.p2[i][1] = S.p2[i][1]; r.w[i] = S.w[i]; r.z[i] = z[i]; r.yw[i] = R.yw[i]; }
+    r.yuz = R.yuz;
     const uint4* src = reinterpret_cast<const uint4*>(&r);
     uint4* dst = reinterpret_cast<uint4*>(recs + slot);
-    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+#pragma unroll
+    for (int k = 0; k < 5; k++) dst[k] = src[k];
+    const int s0 = S.y0 / STRIP_ROWS, s1 = S.y1 / STRIP_ROWS;
+    for (int st = s0; st <= s1; st++) {
+        // lanes of the warp may be appending to different strips: aggregate per counter
+        const unsigned grp = __match_any_sync(__activemask(), st);
+        const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&nlist[st], __popc(grp));
+        base = __shfl_sync(grp, base, leader);
+        const int pos = base + __popc(grp & ((1u << lane) - 1u));
+        lists[(size_t)st * REC_MAX + pos] = (unsigned short)slot;
+    }
 }
 
-__device__ __noinline__ void emit_clipped(Rec* __restrict__ recs, int* nrec, const Tri& T, unsigned int gt) {
+__device__ __noinline__ void emit_clipped(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist, const Tri& T, unsigned int gt) {
     float out[3][4][3];
     const int nc = clip_near(T.c, out);
     for (int c = 0; c < nc; c++) {
         Screen S; screen_setup(out[c], S);
-        emit_record(recs, nrec, S, out[c][2], gt, REC_CLIPPED);
+        emit_record(recs, lists, nrec, nlist, S, out[c][2], gt, REC_CLIPPED);
     }
 }
 
-__device__ __forceinline__ void rec_to_screen(const Rec& r, Screen& S, float* z) {
+__device__ __forceinline__ void rec_unpack(const Rec& r, Screen& S, Edge& E, Recip& R, float* z) {
 #pragma unroll
-    for (int i = 0; i < 3; i++) { S.p2[i][0] = r.p2[i][0]; S.p2[i][1] = r.p2[i][1]; S.w[i] = r.w[i]; z[i] = r.z[i]; }
+    for (int i = 0; i < 3; i++) { S.p2[i][0] = r.p2[i][0]; S.p2[i][1] = r.p2[i][1]; S.w[i] = r.w[i]; z[i] = r.z[i]; R.yw[i] = r.yw[i]; }
     S.x0 = r.bx & 0xffff; S.x1 = r.bx >> 16; S.y0 = r.by & 0xffff; S.y1 = r.by >> 16; S.any = true;
+    R.yuz = r.yuz; R.ok = (r.flags & REC_OK) != 0; R.tight = (r.flags & REC_TIGHT) != 0;
+    E.s00 = S.p2[2][0] - S.p2[0][0]; E.s01 = S.p2[1][0] - S.p2[0][0];
+    E.s10 = S.p2[2][1] - S.p2[0][1]; E.s11 = S.p2[1][1] - S.p2[0][1];
+    E.uz = E.s00 * E.s11 - E.s01 * E.s10;
+    E.degenerate = false;
+}
+__device__ __forceinline__ Rec load_rec(const Rec* __restrict__ p) {
+    Rec r; uint4* d = reinterpret_cast<uint4*>(&r); const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int k = 0; k < 5; k++) d[k] = s[k];
+    return r;
 }
 
-// shading of pixel (x, y) from barycentrics of the ORIGINAL triangle (fast path: from the record; slow path: recomputed)
+// shading of a pixel from barycentrics of the ORIGINAL triangle (Shader::fragment)
 __device__ __forceinline__ unsigned int shade_bar(const float* __restrict__ M, const ShapeRenderConst& sh, const float* __restrict__ tv,
                                                   const uint8_t* __restrict__ texdata, const float* bar) {
     float nrm[3][3], uv[2][3];
@@ -492,28 +522,32 @@ __device__ __noinline__ unsigned int shade_clipped(const float* __restrict__ M, 
 }
 
 // Persistent kernel: each CTA takes envs from a global work counter.  Per env:
-//   geometry : one triangle per thread — vertex shader, back-face cull, near-plane clip, viewport, bounding box; the
-//              survivors become 64-byte records in the CTA's private scratch (rewritten every env, so it stays in L2);
-//   per strip of STRIP_ROWS raster rows: clear the 64-bit key buffer in shared memory; scan the records (coalesced),
-//              rasterise the ones that touch the strip (small: own lane, medium: whole warp via shuffles, huge: whole CTA)
-//              with atomicMax on (depth bits, triangle index); resolve: one fragment shader per pixel, vector stores.
+//   geometry : one triangle per thread — vertex shader, back-face cull, near-plane clip, viewport, bounding box, edge and
+//              reciprocal set-up; survivors become 80-byte records in the CTA's private scratch (rewritten every env, so
+//              it stays in L2) and their indices are appended to the list of every strip their bounding box touches;
+//   per strip of STRIP_ROWS raster rows: clear the 64-bit key buffer in shared memory; warps pull 32-record chunks of the
+//              strip's list and rasterise them (small boxes: own lane; medium: whole warp; huge: whole CTA) with atomicMax
+//              on (depth bits, triangle index); resolve A: one fragment shader per covered pixel (lane per pixel),
+//              resolve B: pack and write RGB / depth / mask rows with 12/16/16-byte stores.
 __global__ void __launch_bounds__(RTHREADS, RBLOCKS)
 k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const uint8_t* __restrict__ texdata,
-         const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, int* __restrict__ work_counter,
+         const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch, int* __restrict__ work_counter,
          uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int N) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* M = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);
     int* bigq = reinterpret_cast<int*>(M + RR_NSHAPES * MAT_STRIDE);
-    __shared__ int s_env, s_nrec, s_bign, s_chunk;
+    __shared__ int s_env, s_nrec, s_bign, s_chunk, s_nlist[NSTRIPS];
     const int tid = threadIdx.x, lane = tid & 31;
     Rec* recs = rec_scratch + (size_t)blockIdx.x * REC_MAX;
+    unsigned short* lists = list_scratch + (size_t)blockIdx.x * NSTRIPS * REC_MAX;
     const float nearP = c_render.depthNear, farP = c_render.depthFar;
     const float bg_depth = (float)((double)(farP * (nearP + 1e30f)) / (2. * (double)farP * (double)nearP + (double)(farP * 1e30f) - (double)(nearP * 1e30f)));
 
     for (;;) {
         __syncthreads();
         if (tid == 0) { s_env = atomicAdd(work_counter, 1); s_nrec = 0; }
+        if (tid < NSTRIPS) s_nlist[tid] = 0;
         __syncthreads();
         const int e = s_env;
         if (e >= N) break;
@@ -541,16 +575,17 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 Tri T;
                 if (!tri_vertex(Ms, tv, T)) continue;
                 const bool front = (T.c[3][0] >= 0 && T.c[3][1] >= 0 && T.c[3][2] >= 0);
-                if (front) { Screen S; screen_setup(T.c, S); emit_record(recs, &s_nrec, S, T.c[2], gt, 0u); }
-                else if (!(T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0)) emit_clipped(recs, &s_nrec, T, gt);
+                if (front) { Screen S; screen_setup(T.c, S); emit_record(recs, lists, &s_nrec, s_nlist, S, T.c[2], gt, 0u); }
+                else if (!(T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0)) emit_clipped(recs, lists, &s_nrec, s_nlist, T, gt);
             }
         }
         __threadfence_block();
         __syncthreads();
-        const int nrec = min(s_nrec, REC_MAX);
         // ---- strips
         for (int strip = 0; strip < NSTRIPS; strip++) {
             const int row0 = strip * STRIP_ROWS;
+            const int nlist = min(s_nlist[strip], REC_MAX);
+            const unsigned short* list = lists + (size_t)strip * REC_MAX;
             for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = 0ull;
             if (tid == 0) { s_bign = 0; s_chunk = 0; }
             __syncthreads();
@@ -558,84 +593,78 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 int rb = 0;
                 if (lane == 0) rb = atomicAdd(&s_chunk, 32);
                 rb = __shfl_sync(0xffffffffu, rb, 0);
-                if (rb >= nrec) break;
-                const int r = rb + lane;
-                int state = 0;                           // 0 nothing, 1 own lane, 2 warp-cooperative
-                Screen S; float cz[3] = {0.f, 0.f, 0.f}; unsigned int keylo = 0; bool planes = true;
-                if (r < nrec) {
-                    const uint4 h = *reinterpret_cast<const uint4*>(recs + r);
-                    const int y0 = h.y & 0xffff, y1 = h.y >> 16;
+                if (rb >= nlist) break;
+                int state = 0, ridx = 0;                 // 0 nothing, 1 own lane, 2 warp-cooperative
+                Rec rec;
+                if (rb + lane < nlist) {
+                    ridx = list[rb + lane];
+                    rec = load_rec(recs + ridx);
+                    const int y0 = rec.by & 0xffff, y1 = rec.by >> 16, x0 = rec.bx & 0xffff, x1 = rec.bx >> 16;
                     const int ya = max(y0, row0), yb = min(y1, row0 + STRIP_ROWS - 1);
-                    if (ya <= yb) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(recs + r);
-                        Rec rec; uint4* d = reinterpret_cast<uint4*>(&rec);
-                        d[0] = h; d[1] = rp[1]; d[2] = rp[2]; d[3] = rp[3];
-                        rec_to_screen(rec, S, cz);
-                        keylo = rec.keylo; planes = !(rec.flags & REC_CLIPPED);
-                        const int area = (S.x1 - S.x0 + 1) * (yb - ya + 1);
-                        state = area <= SMALL_AREA ? 1 : 2;
-                        if (area > 2048) {
-                            int slot = atomicAdd(&s_bign, 1);
-                            if (slot < BIGQ) { bigq[slot] = r; state = 0; }
-                        }
+                    const int area = (x1 - x0 + 1) * (yb - ya + 1);
+                    state = area <= SMALL_AREA ? 1 : 2;
+                    if (area > 2048) {
+                        int slot = atomicAdd(&s_bign, 1);
+                        if (slot < BIGQ) { bigq[slot] = ridx; state = 0; }
                     }
                 }
                 unsigned med = __ballot_sync(0xffffffffu, state == 2);
                 while (med) {
                     const int src = __ffs(med) - 1; med &= med - 1;
-                    Screen B; float bz[3];
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        B.p2[i][0] = __shfl_sync(0xffffffffu, S.p2[i][0], src); B.p2[i][1] = __shfl_sync(0xffffffffu, S.p2[i][1], src);
-                        B.w[i] = __shfl_sync(0xffffffffu, S.w[i], src); bz[i] = __shfl_sync(0xffffffffu, cz[i], src);
-                    }
-                    B.x0 = __shfl_sync(0xffffffffu, S.x0, src); B.x1 = __shfl_sync(0xffffffffu, S.x1, src);
-                    B.y0 = __shfl_sync(0xffffffffu, S.y0, src); B.y1 = __shfl_sync(0xffffffffu, S.y1, src);
-                    B.any = true;
-                    const unsigned int bk = __shfl_sync(0xffffffffu, keylo, src);
-                    const bool bp = __shfl_sync(0xffffffffu, (int)planes, src) != 0;
-                    raster_pixels(keys, B, bz, bk, bp, row0, lane, 32);
+                    const int bi = __shfl_sync(0xffffffffu, ridx, src);
+                    const Rec br = load_rec(recs + bi);
+                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
+                    raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, lane, 32);
                 }
-                if (state == 1) raster_pixels(keys, S, cz, keylo, planes, row0, 0, 1);
+                if (state == 1) {
+                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(rec, S, E, R, cz);
+                    raster_pixels(keys, S, E, R, cz, rec.keylo, !(rec.flags & REC_CLIPPED), row0, 0, 1);
+                }
             }
             __syncthreads();
             {   // huge triangles: whole CTA per record
                 const int nb = min(s_bign, BIGQ);
                 for (int b = 0; b < nb; b++) {
-                    const Rec rec = recs[bigq[b]];
-                    Screen S; float cz[3]; rec_to_screen(rec, S, cz);
-                    raster_pixels(keys, S, cz, rec.keylo, !(rec.flags & REC_CLIPPED), row0, tid, RTHREADS);
+                    const Rec br = load_rec(recs + bigq[b]);
+                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
+                    raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, tid, RTHREADS);
                 }
             }
             __syncthreads();
-            // ---- resolve: 4 consecutive pixels per thread-iteration, vector stores
+            // ---- resolve A: lane per pixel; the winner's colour replaces the low key word: 1 << 31 | shape << 24 | rgb
+            for (int p = tid; p < STRIP_ROWS * RR_W; p += RTHREADS) {
+                const unsigned long long key = keys[p];
+                if (key == 0ull) continue;
+                const int r = p / RR_W, x = p - r * RR_W;
+                const unsigned int lo = (unsigned int)(key & 0xffffffffu);
+                const int gt = (int)(lo >> 15) - 1, ri = (int)(lo & 0x7fffu);
+                const int s = tri_shape[gt];
+                const ShapeRenderConst& sh = c_render.shape[s];
+                const float* tv = tris + (size_t)gt * 24;
+                const Rec rec = load_rec(recs + ri);
+                unsigned int col;
+                if (rec.flags & REC_CLIPPED) col = shade_clipped(M + s * MAT_STRIDE, sh, tv, texdata, x, row0 + r);
+                else {
+                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(rec, S, E, R, cz);
+                    float bs[3], bar[3];
+                    frag_bar_r(S, E, R, x, row0 + r, bs, bar);
+                    col = shade_bar(M + s * MAT_STRIDE, sh, tv, texdata, bar);
+                }
+                keys[p] = (key & 0xffffffff00000000ull) | 0x80000000ull | ((unsigned long long)s << 24) | (unsigned long long)(col & 0xffffffu);
+            }
+            __syncthreads();
+            // ---- resolve B: 4 consecutive pixels per thread-iteration, vector stores, vertical flip folded in
             for (int i = tid; i < STRIP_ROWS * RR_W / 4; i += RTHREADS) {
                 const int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
                 unsigned int col[4]; float dep[4]; int sg[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const int x = 4 * x4 + k;
-                    const unsigned long long key = keys[r * RR_W + x];
+                    const unsigned long long key = keys[r * RR_W + 4 * x4 + k];
                     if (key == 0ull) { col[k] = 0xffffffu; sg[k] = -1; dep[k] = bg_depth; continue; }
                     const unsigned int lo = (unsigned int)(key & 0xffffffffu);
-                    const int gt = (int)(lo >> 15) - 1, ri = (int)(lo & 0x7fffu);
-                    const float z = unorder_bits((unsigned int)(key >> 32));
-                    const int s = tri_shape[gt];
-                    const ShapeRenderConst& sh = c_render.shape[s];
-                    const float* tv = tris + (size_t)gt * 24;
-                    const Rec* rp = recs + ri;
-                    if (rp->flags & REC_CLIPPED) col[k] = shade_clipped(M + s * MAT_STRIDE, sh, tv, texdata, x, row0 + r);
-                    else {
-                        Screen S;
-#pragma unroll
-                        for (int j = 0; j < 3; j++) { S.p2[j][0] = rp->p2[j][0]; S.p2[j][1] = rp->p2[j][1]; S.w[j] = rp->w[j]; }
-                        Edge E; edge_setup(S, E);
-                        float bs[3], bar[3];
-                        frag_bar(S, E, x, row0 + r, bs, bar);
-                        col[k] = shade_bar(M + s * MAT_STRIDE, sh, tv, texdata, bar);
-                    }
-                    sg[k] = sh.objectAndLink & 0xffffff;
-                    const float z_c = -z;
+                    col[k] = lo & 0xffffffu;
+                    sg[k] = c_render.shape[(lo >> 24) & 31].objectAndLink & 0xffffff;
+                    const float z_c = -unorder_bits((unsigned int)(key >> 32));
                     dep[k] = (float)((double)(farP * (nearP + z_c)) / (2. * (double)farP * (double)nearP + (double)(farP * z_c) - (double)(nearP * z_c)));
                 }
                 const size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
@@ -671,6 +700,7 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
         if (ctx->raster_grid > ctx->N) ctx->raster_grid = ctx->N;
         CK(cudaMalloc(&ctx->d_rec_scratch, (size_t)ctx->raster_grid * REC_MAX * sizeof(Rec)));
         CK(cudaMalloc(&ctx->d_work_counter, sizeof(int)));
+        CK(cudaMalloc(&ctx->d_list_scratch, (size_t)ctx->raster_grid * NSTRIPS * REC_MAX * sizeof(unsigned short)));
         std::vector<uint8_t> ts(ctx->n_tris);
         for (int sidx = 0; sidx < RR_NSHAPES; sidx++)
             for (int t = 0; t < ctx->render.shape[sidx].tri_count; t++) ts[ctx->render.shape[sidx].tri_start + t] = (uint8_t)sidx;
@@ -705,7 +735,7 @@ int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* 
     {
         ProfScope ps(ctx, 2, s);
         k_raster<<<ctx->raster_grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, ctx->d_tex, mask,
-                                                                 (Rec*)ctx->d_rec_scratch, ctx->d_work_counter, rgb, depth, seg, ctx->N);
+                                                                 (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, ctx->d_work_counter, rgb, depth, seg, ctx->N);
     }
     ctx->launches++;
     CK(cudaGetLastError());
