@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libreal_b200.so")
+LIB_PATH = os.environ.get("RR_LIB", os.path.join(_HERE, "libreal_b200.so"))   # RR_LIB: A/B builds during tuning
 DEFAULT_BLOB = os.path.join(_HERE, "assets", "scene.rrb")
 
 NUM_JOINTS, NUM_DOF, NUM_TOUCH, EYE_W, EYE_H, MAX_OBJECTS, NUM_LINKS, NUM_SHAPES = 9, 11, 4, 320, 240, 3, 16, 22

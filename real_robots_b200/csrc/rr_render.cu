@@ -21,13 +21,27 @@
 
 __constant__ RenderConst c_render;
 
-#define STRIP_ROWS 80
+#ifndef STRIP_ROWS
+#define STRIP_ROWS 40
+#endif
 #define NSTRIPS (RR_H / STRIP_ROWS)
+#ifndef RTHREADS
 #define RTHREADS 512
-#define RBLOCKS 1             // resident CTAs per SM (shared memory bound)
+#endif
+#ifndef RBLOCKS
+#define RBLOCKS 2
+#endif
+//            // resident CTAs per SM (shared memory bound)
 #define MAT_STRIDE 40          // floats per (env, shape): pmv[16] model[12] invT[9] ylo yhi flag
-#define SMALL_AREA 6            // in-strip bounding-box pixels up to which a triangle is rasterised by its own lane
+#ifndef SMALL_AREA
+#define SMALL_AREA 16
+#endif
+//           // in-strip bounding-box pixels up to which a triangle is rasterised by its own lane
 #define BIGQ 512
+#ifndef HUGE_AREA
+#define HUGE_AREA 256
+#endif
+//         // in-strip bounding-box pixels above which the whole CTA rasterises the triangle
 
 // --------------------------------------------------------------------------------------------- float helpers
 __device__ __forceinline__ float dot4r(const float* a, const float* b) { float r = 0.f; r += a[3] * b[3]; r += a[2] * b[2]; r += a[1] * b[1]; r += a[0] * b[0]; return r; }
@@ -330,8 +344,6 @@ __device__ __noinline__ int clip_near(const float tri[4][3], float out[3][4][3])
     return nt;
 }
 
-// rasterise the in-strip bounding box of one screen triangle into the strip key buffer.
-// keylo: ties in depth resolve to the later-submitted triangle (larger key).
 __device__ __forceinline__ void raster_one(unsigned long long* keys, const Screen& S, const Edge& E, const Recip& R, const float* clipz,
                                            unsigned int keylo, bool planes, int row0, int px, int py) {
     float ux, uy; bary_u(S, E, (float)px, (float)py, ux, uy);
@@ -368,6 +380,7 @@ __device__ __forceinline__ void raster_pixels(unsigned long long* keys, const Sc
         x += dx; y += dy; if (x > S.x1) { x -= wdt; y++; }
     }
 }
+
 
 // --------------------------------------------------------------------------------------------- fragment shader
 __device__ __forceinline__ void texel_fetch(int tex, const uint8_t* __restrict__ texdata, float u, float v, int* c) {
@@ -603,7 +616,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                     const int ya = max(y0, row0), yb = min(y1, row0 + STRIP_ROWS - 1);
                     const int area = (x1 - x0 + 1) * (yb - ya + 1);
                     state = area <= SMALL_AREA ? 1 : 2;
-                    if (area > 2048) {
+                    if (area > HUGE_AREA) {
                         int slot = atomicAdd(&s_bign, 1);
                         if (slot < BIGQ) { bigq[slot] = ridx; state = 0; }
                     }
