@@ -269,7 +269,7 @@ static double resolve_row(Solver& S, Row& c) {
     else if (sum > c.hi) { delta = c.hi - c.applied; c.applied = c.hi; }
     else c.applied = sum;
     apply_impulse(S, c, delta);
-    return c.jacDiagABInv != 0 ? delta / c.jacDiagABInv : 0.0;
+    return c.jacDiagABInv != 0 ? delta * (1.0 / c.jacDiagABInv) : 0.0;     /* deltaImpulse * (1. / m_jacDiagABInv) */
 }
 /* btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows (implicit friction cone over the two directions) */
 static double resolve_cone(Solver& S, Row& a, Row& b, double limit) {
@@ -287,7 +287,7 @@ static double resolve_cone(Solver& S, Row& a, Row& b, double limit) {
         double delta = want[k] - c.applied;
         c.applied = want[k];
         apply_impulse(S, c, delta);
-        double r = c.jacDiagABInv != 0 ? delta / c.jacDiagABInv : 0.0;
+        double r = c.jacDiagABInv != 0 ? delta * (1.0 / c.jacDiagABInv) : 0.0;
         res = std::max(res, r * r);
     }
     return res;

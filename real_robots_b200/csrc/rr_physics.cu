@@ -34,7 +34,7 @@ struct WarpMem {
     double Minv[RR_NDOF][RR_NDOF];
     double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF], tau[RR_NDOF], qdd[RR_NDOF];
     // non-contact rows (limits then motors)
-    double r_rhs[32], r_inv[32], r_lo[32], r_hi[32], r_app[32], r_sign[32];
+    double r_rhs[32], r_inv[32], r_rinv[32], r_lo[32], r_hi[32], r_app[32], r_sign[32];
     int r_dof[32];
     int n_rows;
     // contacts
@@ -44,6 +44,15 @@ struct WarpMem {
     double app[3 * RR_MAX_CONTACTS];                    // applied impulses: normals [0,MAXC), friction pairs after
 };
 
+// two warp reductions for the price of one: after the first exchange the lower half-warp carries a, the upper b
+__device__ __forceinline__ void warp_sum2(double a, double b, double& sa, double& sb) {
+    const bool hi = (threadIdx.x & 16) != 0;
+    double keep = hi ? b : a, send = hi ? a : b;
+    keep += __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, off);
+    sa = __shfl_sync(0xffffffffu, keep, 0); sb = __shfl_sync(0xffffffffu, keep, 16);
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -478,7 +487,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
                 double dd = m.Minv[d][d];
                 double inv = dd > 0 ? 1.0 / dd : 0.0;
                 double rel = sgn * m.qd[d];
-                m.r_dof[n] = d; m.r_sign[n] = sgn; m.r_inv[n] = inv; m.r_lo[n] = 0.0; m.r_hi[n] = cf.limit_max_impulse;
+                m.r_dof[n] = d; m.r_sign[n] = sgn; m.r_inv[n] = inv; m.r_rinv[n] = inv != 0.0 ? 1.0 / inv : 0.0; m.r_lo[n] = 0.0; m.r_hi[n] = cf.limit_max_impulse;
                 m.r_rhs[n] = (-pen * cf.erp / dt - rel) * inv; m.r_app[n] = 0.0;
                 n++;
             }
@@ -490,7 +499,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
             double stab = 1.0 * (m.target[d] - m.q[d]) / dt;
             double desired = cf.motor_kp * stab + cur + cf.motor_kd * (0.0 - cur);
             double maxImp = cf.motor_max_force * dt;
-            m.r_dof[n] = d; m.r_sign[n] = 1.0; m.r_inv[n] = inv; m.r_lo[n] = -maxImp; m.r_hi[n] = maxImp;
+            m.r_dof[n] = d; m.r_sign[n] = 1.0; m.r_inv[n] = inv; m.r_rinv[n] = inv != 0.0 ? 1.0 / inv : 0.0; m.r_lo[n] = -maxImp; m.r_hi[n] = maxImp;
             m.r_rhs[n] = (desired - cur) * inv; m.r_app[n] = 0.0;
             n++;
         }
@@ -606,7 +615,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
                     const int ri = di == 0 ? nc : RR_MAX_CONTACTS + 2 * nc + (di - 1);
                     double* rowp = rows + (size_t)ri * RR_ROW_STRIDE;
                     rowp[lane] = J; rowp[32 + lane] = rr;
-                    if (lane == 0) { rowp[64] = rhs; rowp[65] = inv; rowp[66] = mu; m.app[ri] = app0; }
+                    if (lane == 0) { rowp[64] = rhs; rowp[65] = inv; rowp[66] = mu; rowp[67] = inv != 0.0 ? 1.0 / inv : 0.0; m.app[ri] = app0; }
                     __syncwarp();
                 }
                 nc++;
@@ -640,7 +649,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
                 __syncwarp();
                 if (lane == 0) m.r_app[idx] = app;
                 if (lane < RR_NDOF) dv += m.Minv[lane][d] * sgn * delta;
-                double r = inv != 0.0 ? delta / inv : 0.0;
+                double r = delta * m.r_rinv[idx];
                 res = fmax(res, r * r);
                 __syncwarp();
             }
@@ -657,7 +666,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
                 __syncwarp();
                 if (lane == 0) m.app[c] = app;
                 dv += rr * delta;
-                const double r = inv != 0.0 ? delta / inv : 0.0;
+                const double r = delta * rowp[67];
                 res = fmax(res, r * r);
                 __syncwarp();
             }
@@ -667,7 +676,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
                 const double Ja = ra[lane], rra = ra[32 + lane], Jb = rb[lane], rrb = rb[32 + lane];
                 const double inva = ra[65], invb = rb[65];
                 const double lim = ra[66] * m.app[c];
-                const double sa_ = warp_sum(Ja * dv), sb_ = warp_sum(Jb * dv);
+                double sa_, sb_; warp_sum2(Ja * dv, Jb * dv, sa_, sb_);
                 const double appa = m.app[r0], appb = m.app[r0 + 1];
                 double wa = appa + (ra[64] - sa_ * inva), wb = appb + (rb[64] - sb_ * invb);
                 const double len2 = wa * wa + wb * wb;
@@ -676,7 +685,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
                 __syncwarp();
                 if (lane == 0) { m.app[r0] = wa; m.app[r0 + 1] = wb; }
                 dv += rra * da; dv += rrb * db;
-                const double qa = inva != 0.0 ? da / inva : 0.0, qb = invb != 0.0 ? db / invb : 0.0;
+                const double qa = da * ra[67], qb = db * rb[67];
                 res = fmax(res, fmax(qa * qa, qb * qb));
                 __syncwarp();
             }
