@@ -86,6 +86,12 @@ int  rr_read_state(rr_ctx* ctx, double* joint_pos, double* touch, double* obj_po
  * arrays (env.py:114-122,273-275).  rgb u8[N,240,320,3]; depth f32[N,240,320]; mask i32[N,240,320] or NULL. */
 int  rr_render(rr_ctx* ctx, const uint8_t* env_mask, uint8_t* rgb, float* depth, int32_t* mask, void* stream);
 
+/* replaces: REALRobotEnv.render('rgb_array') -> EnvCamera.render (env.py:221-228, 470-513): same rasteriser with a
+ * caller-supplied camera.  view16_host / proj16_host: column-major float[16] HOST arrays as pybullet's
+ * computeViewMatrix* / computeProjectionMatrixFOV return them.  Synchronises the stream. */
+int  rr_render_camera(rr_ctx* ctx, const float* view16_host, const float* proj16_host, const uint8_t* env_mask,
+                      uint8_t* rgb, float* depth, int32_t* mask, void* stream);
+
 /* test hook: render from explicit body frames instead of the simulated state.
  * frames f64[N,22,12] = world_from_local rotation (row-major 9) + position (3) per scene shape. */
 int  rr_render_frames(rr_ctx* ctx, const double* frames, uint8_t* rgb, float* depth, int32_t* mask, void* stream);

@@ -43,6 +43,7 @@ SYMBOLS = {
     "rr_step": (_I, [_VP, _VP, _VP]),
     "rr_read_state": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "rr_render": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "rr_render_camera": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rr_render_frames": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "rr_shape_frames": (_I, [_VP, _VP, _VP]),
     "rr_ik": (_I, [_VP, _VP, _VP, _VP, _I, _D, _VP]),

@@ -92,6 +92,21 @@ void eye_camera(float* view, float* proj) {
 }
 }  // namespace
 
+// camera-dependent render constants from column-major view / projection matrices (as pybullet returns them)
+void rr_set_camera_consts(RenderConst& C, const float* view, const float* proj) {
+    float V[4][4];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { C.view[4 * i + j] = view[i + 4 * j]; C.proj[4 * i + j] = proj[i + 4 * j]; V[i][j] = view[i + 4 * j]; }
+    C.depthNear = proj[14] / (proj[10] - 1);
+    C.depthFar = proj[14] / (proj[10] + 1);
+    C.nearPlane = C.proj[4 * 2 + 3] / (C.proj[4 * 2 + 2] - 1);
+    C.farPlane = C.proj[4 * 2 + 3] / (C.proj[4 * 2 + 2] + 1);
+    // camera position = translation column of viewMatrix.invert() (adjugate / determinant, float)
+    float adj[4][4];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) adj[i][j] = hcof4(V, i, j);
+    float tmp = hdot4r(adj[0], V[0]);
+    for (int k = 0; k < 3; k++) C.camP[k] = (double)(adj[3][k] / tmp);
+}
+
 #define CKC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); g_create_err = ctx->err; return -1; } } while (0)
 
 static int fill_constants(rr_ctx* ctx, const Blob& b) {
@@ -184,18 +199,7 @@ static int fill_constants(rr_ctx* ctx, const Blob& b) {
         C.tex[k].w = (int)m[0]; C.tex[k].h = (int)m[1]; C.tex[k].offset = m[2]; C.tex[k].uniform = (int)m[3];
     }
     float view[16], proj[16]; eye_camera(view, proj);
-    float V[4][4];
-    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { C.view[4 * i + j] = view[i + 4 * j]; C.proj[4 * i + j] = proj[i + 4 * j]; V[i][j] = view[i + 4 * j]; }
-    C.depthNear = proj[14] / (proj[10] - 1);
-    C.depthFar = proj[14] / (proj[10] + 1);
-    C.nearPlane = C.proj[4 * 2 + 3] / (C.proj[4 * 2 + 2] - 1);
-    C.farPlane = C.proj[4 * 2 + 3] / (C.proj[4 * 2 + 2] + 1);
-    {   // camera position = translation column of viewMatrix.invert() (adjugate / determinant, float)
-        float adj[4][4];
-        for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) adj[i][j] = hcof4(V, i, j);
-        float tmp = hdot4r(adj[0], V[0]);
-        for (int k = 0; k < 3; k++) C.camP[k] = (double)(adj[3][k] / tmp);
-    }
+    rr_set_camera_consts(C, view, proj);
     {   // light direction normalize(-50, 30, 100) in double, stored as float (z-up default)
         double ld[3] = {-50.0, 30.0, 100.0};
         double ll = sqrt(ld[0] * ld[0] + ld[1] * ld[1] + ld[2] * ld[2]);
@@ -309,6 +313,13 @@ int rr_render(rr_ctx* ctx, const uint8_t* env_mask, uint8_t* rgb, float* depth, 
 int rr_render_frames(rr_ctx* ctx, const double* frames, uint8_t* rgb, float* depth, int32_t* mask, void* stream) {
     ARG(frames != nullptr, "rr_render_frames: frames is NULL");
     return rrk_render(ctx, nullptr, frames, rgb, depth, mask, (cudaStream_t)stream);
+}
+int rr_render_camera(rr_ctx* ctx, const float* view16_host, const float* proj16_host, const uint8_t* env_mask,
+                     uint8_t* rgb, float* depth, int32_t* mask, void* stream) {
+    ARG(view16_host && proj16_host, "rr_render_camera: NULL matrix");
+    RenderConst C = ctx->render;
+    rr_set_camera_consts(C, view16_host, proj16_host);
+    return rrk_render_camera(ctx, &C, env_mask, rgb, depth, mask, (cudaStream_t)stream);
 }
 int rr_shape_frames(rr_ctx* ctx, double* frames, void* stream) { return rrk_shape_frames(ctx, frames, (cudaStream_t)stream); }
 int rr_ik(rr_ctx* ctx, const uint8_t* env_mask, const double* pos_quat, double* joints_out, int max_iter, double residual, void* stream) {

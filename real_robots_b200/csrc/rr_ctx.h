@@ -127,6 +127,8 @@ int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s);
 int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s);
 int rrk_render_upload_constants(rr_ctx* ctx);
 int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames_or_null, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);
+int rrk_render_camera(rr_ctx* ctx, const RenderConst* cam, const uint8_t* mask, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);
+void rr_set_camera_consts(RenderConst& C, const float* view16, const float* proj16);
 int rrk_collide_upload_constants(rr_ctx* ctx);
 int rrk_collide(rr_ctx* ctx, cudaStream_t s);
 int rrk_clear_manifolds(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s);

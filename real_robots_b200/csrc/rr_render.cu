@@ -754,3 +754,13 @@ int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* 
     CK(cudaGetLastError());
     return 0;
 }
+
+// Render with another camera (EnvCamera / render('rgb_array'), reference env.py:221-228, 470-513): the camera part of
+// the constants is swapped in stream order around the two kernels and the eye camera restored afterwards.
+int rrk_render_camera(rr_ctx* ctx, const RenderConst* cam, const uint8_t* mask, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s) {
+    CK(cudaMemcpyToSymbolAsync(c_render, cam, sizeof(RenderConst), 0, cudaMemcpyHostToDevice, s));
+    int rc = rrk_render(ctx, mask, nullptr, rgb, depth, seg, s);
+    CK(cudaMemcpyToSymbolAsync(c_render, &ctx->render, sizeof(RenderConst), 0, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));          // `cam` lives on the caller's stack
+    return rc;
+}

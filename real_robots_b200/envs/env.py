@@ -172,8 +172,14 @@ class REALRobotEnv:
             self.isRender = True
         if mode != "rgb_array":
             return np.array([])
-        # the reference uses the OpenGL debug camera here (env.py:470-513); served by the same rasteriser from the eye
-        return self.get_retina()[0]
+        # EnvCamera.render (env.py:470-513): yaw-pitch-roll debug camera.  The reference asks pybullet for the OpenGL
+        # renderer here; this build serves the same camera from the TinyRenderer-convention rasteriser (no OpenGL).
+        from .. import cameras
+        self._ensure_sim()
+        view = cameras.view_from_yaw_pitch_roll(self._cam_pos, self._cam_dist, self._cam_yaw, self._cam_pitch, self._cam_roll, 2)
+        proj = cameras.projection_fov(80, float(self._render_width) / self._render_height, 0.1, 100.0)
+        rgb, _, _ = self._sim.render_camera(view, proj)
+        return rgb[0].cpu().numpy()
 
     def close(self):
         if self._sim is not None:

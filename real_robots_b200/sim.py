@@ -124,6 +124,16 @@ class BatchedSim:
                  "rr_render")
         return rgb, depth, seg
 
+    def render_camera(self, view16, proj16, mask=None):
+        """Render with a caller-supplied camera (column-major float32[16] view / projection, pybullet convention)."""
+        v = np.ascontiguousarray(view16, np.float32)
+        p = np.ascontiguousarray(proj16, np.float32)
+        rgb, depth, seg = self.images()
+        m = self._mask(mask)
+        self._ck(self.lib.rr_render_camera(self.ctx, v.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), _ptr(m),
+                                           _ptr(rgb), _ptr(depth), _ptr(seg), self._stream()), "rr_render_camera")
+        return rgb, depth, seg
+
     def render_frames(self, frames):
         self._chk(frames, (self.n_envs, L.NUM_SHAPES, 12), torch.float64, "frames")
         rgb, depth, seg = self.images()

@@ -1,0 +1,21 @@
+"""Small run for compute-sanitizer: physics with contacts, IK, render, host path."""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch
+from real_robots_b200.sim import BatchedSim
+N = 6
+sim = BatchedSim(N, 3)
+rng = np.random.default_rng(0)
+lo = np.array([-2.09, -2.09, -2.96, -2.09, -2.96, -2.09, -3.05, 0, 0]); hi = -lo; hi[7:] = np.pi / 2
+a = torch.from_numpy(rng.uniform(lo, hi, (N, 9))).cuda()
+for t in range(45):
+    if t == 30: a = torch.from_numpy(rng.uniform(lo, hi, (N, 9))).cuda()
+    sim.step(a)
+sim.read_state(); sim.render()
+sim.render(mask=torch.tensor([1, 0, 1, 0, 1, 1], dtype=torch.uint8, device="cuda"))
+pq = torch.tensor([[-0.1, 0.0, 0.5, 0.7, 0.7, 0, 0]] * N, dtype=torch.float64, device="cuda")
+sim.ik(pq, 200, 1e-3)
+sim.step_host(a.cpu().numpy(), np.ones(N, np.uint8))
+sim.contacts(); sim.shape_frames(); sim.link_pose(7); sim.reset()
+torch.cuda.synchronize()
+print("sanitize run ok")

@@ -1,0 +1,189 @@
+"""GPU tests of the reference-facing Python surface: REALRobotEnv (N = 1 gym facade), VecREALRobotEnv, the debug
+camera, macro / cartesian actions and evaluate(), checked against the oracle where arithmetic is involved."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import real_robots  # noqa: E402
+from oracle.orc import Oracle, eye_matrices  # noqa: E402
+from real_robots_b200 import cameras  # noqa: E402
+from real_robots_b200.envs.env import Goal  # noqa: E402
+from real_robots_b200.envs.vec_env import VecREALRobotEnv  # noqa: E402
+from real_robots_b200.policy import BasePolicy, RandomBatchedPolicy  # noqa: E402
+
+
+def test_gym_facade_joints_matches_oracle():
+    env = real_robots.make('REALRobot2020-R1J3-v0')
+    obs = env.reset()
+    assert set(obs) == {'joint_positions', 'touch_sensors', 'retina', 'depth', 'mask', 'object_positions', 'goal',
+                        'goal_mask', 'goal_positions'}
+    assert isinstance(obs['joint_positions'], list) and len(obs['joint_positions']) == 9      # robot.py:204-211 returns a list
+    assert obs['retina'].shape == (240, 320, 3) and obs['retina'].dtype == np.uint8
+    assert obs['mask'].dtype == np.int32 and set(np.unique(obs['mask'])) == {-1, 0, 1, 2, 3, 4}
+    assert (obs['goal'] == 0).all() and obs['goal_mask'] is None
+    o = Oracle(3)
+    r0, d0, m0 = o.render()
+    assert (obs['mask'] == m0).all() and (obs['retina'] == r0).all() and (obs['depth'] == d0).all()
+    rng = np.random.default_rng(0)
+    a = rng.uniform(env.action_space['joint_command'].low, env.action_space['joint_command'].high)
+    for t in range(40):
+        obs, reward, done, info = env.step({'joint_command': a, 'render': t == 39})
+        o.step(a)
+    assert reward == 0 and done is False and info == {}
+    assert np.allclose(obs['joint_positions'], o.read()[0], atol=1e-9)
+    assert np.allclose(obs['object_positions']['cube'], o.get_state()[2][0, :3], atol=1e-7)
+    assert set(obs['object_positions']) == {'cube', 'tomato', 'mustard'}
+    assert (obs['mask'] == o.render()[2]).mean() > 0.9999
+    # render off -> cached zero arrays (env.py:273-275)
+    obs, _, _, _ = env.step({'joint_command': a, 'render': False})
+    assert (obs['retina'] == 0).all() and (obs['depth'] == 0).all() and (obs['mask'] == 0).all()
+    # None command = zeros(9) (env.py:333-334); part / object accessors (env.py:230-247)
+    env.step({'joint_command': None, 'render': False})
+    assert np.allclose(env.get_part_pos('base'), env.robot.parts['base'].get_position())
+    assert env.get_obj_pose('cube').shape == (7,) and isinstance(env.get_contacts(), dict)
+    # done flag (env.py:345-352)
+    env.intrinsic_timesteps = env.timestep + 1
+    assert env.step({'joint_command': a, 'render': False})[2] is True
+    env.close()
+
+
+def test_render_rgb_array_debug_camera_matches_oracle():
+    env = real_robots.make('REALRobot2020-R2J2-v0')
+    env.reset()
+    img = env.render('rgb_array')
+    assert img.shape == (240, 320, 3) and img.dtype == np.uint8
+    view = cameras.view_from_yaw_pitch_roll([0, 0, .4], 1.2, 30, -30, 0, 2)
+    proj = cameras.projection_fov(80, 320.0 / 240, 0.1, 100.0)
+    o = Oracle(2)
+    ref = o.render_frames(o.shape_frames(), view, proj)[0]
+    assert (img == ref).all()
+    assert (img != 255).any(axis=2).mean() > 0.05          # something is visible
+    # the Python float32 camera helpers reproduce the oracle's eye camera bit for bit
+    v, p = eye_matrices()
+    assert (cameras.view_from_positions([0.01, 0, 1.2], [0, 0, 0.08], [0, 0, 1]) == v).all()
+    assert (cameras.projection_fov(80, 320.0 / 240, 0.1, 100.0) == p).all()
+    # and the eye render is unchanged afterwards (the constants were restored)
+    assert (env.get_retina()[0] == o.render()[0]).all()
+    env.close()
+
+
+def test_cartesian_and_macro_actions():
+    env = real_robots.make('REALRobot2020-R1C1-v0')
+    env.reset()
+    quat = real_robots_b200_quat()
+    cmd = np.concatenate([[-0.1, 0.1, 0.5], quat])
+    for t in range(300):
+        obs, _, _, _ = env.step({'cartesian_command': cmd, 'gripper_command': np.array([0.3, 0.2]), 'render': False})
+    assert np.linalg.norm(env.get_part_pos('base') - cmd[:3]) < 0.01       # tests/test_actions.py:69 tolerance
+    assert abs(obs['joint_positions'][7] - 0.3) < 0.02 and abs(obs['joint_positions'][8] - 0.2) < 0.02
+    assert env.last_ik is not None and np.all(env.requested_coords == cmd[:3])
+    env.close()
+    # macro action: the plan passes the reference test script's checkpoints (tests/test_actions.py:143-152)
+    env = real_robots.make('REALRobot2020-R1M1-v0')
+    env.reset()
+    env.robot.object_bodies['cube'].reset_pose([-0.1, 0.45, 0.6], [0, 0, 0, 1])     # out of the way, as :94-97 does
+    macro = np.array([[-0.10, -0.30], [-0.05, 0.20]])
+    checkpoints = {199: None, 249: None, 749: None, 849: None, 999: None}
+    for t in range(1000):
+        env.step({'macro_action': macro, 'render': False})
+        if t in checkpoints:
+            checkpoints[t] = env.get_part_pos('base').copy()
+    assert env.planned_actions.shape == (1000, 9) and env.plan_step == 999
+    assert np.linalg.norm(checkpoints[199] - [-0.10, -0.30, 0.6]) < 0.01
+    assert np.linalg.norm(checkpoints[249] - [-0.10, -0.30, 0.46]) < 0.01
+    assert np.linalg.norm(checkpoints[749] - [-0.05, 0.20, 0.46]) < 0.015
+    # joint motion is rate limited to 10% of min(error, 0.2..0.3 rad) per step (env.py:314-321 + the motor gain), so 100
+    # steps after leaving p2 the arm is still approaching home2
+    assert np.linalg.norm(checkpoints[849] - [-0.419, 0, 1.14]) < 0.12      # home2
+    assert np.linalg.norm(checkpoints[999] - [-0.55, 0, 1.271]) < 0.05      # home
+    env.close()
+
+
+def real_robots_b200_quat():
+    from real_robots_b200.util import euler_to_quat
+    return euler_to_quat([0, 3.14, -1.57])
+
+
+def test_vec_env_matches_single_env_semantics():
+    N = 8
+    env = VecREALRobotEnv(N, objects=3, action_type='joints', additional_obs=True)
+    obs = env.reset()
+    assert obs['retina'].shape == (N, 240, 320, 3) and obs['mask'].shape == (N, 240, 320) and obs['object_positions'].shape == (N, 3, 3)
+    pol = RandomBatchedPolicy(env, seed=3)
+    orcs = [Oracle(3) for _ in range(N)]
+    for t in range(50):
+        act = pol.step(obs, None, None)
+        act['render'] = t == 49
+        obs, reward, done, _ = env.step(act)
+        a = act['joint_command'].cpu().numpy()
+        for e in range(N):
+            orcs[e].step(a[e])
+    assert reward.shape == (N,) and not bool(done.any())
+    assert np.allclose(obs['joint_positions'].cpu().numpy(), np.array([o.read()[0] for o in orcs]), atol=1e-8)
+    # macro actions, batched plans == the N = 1 reference logic run per env
+    menv = VecREALRobotEnv(4, objects=1, action_type='macro_action')
+    menv.reset(render=False)
+    macro = torch.tensor([[[-0.2, -0.3], [0.0, 0.3]], [[-0.1, 0.2], [-0.2, -0.2]], [[0.0, 0.0], [0.05, 0.4]], [[-0.25, -0.45], [-0.25, 0.45]]],
+                         dtype=torch.float64, device='cuda')
+    menv.step({'macro_action': macro, 'render': False})
+    plan = menv.plan.cpu().numpy()
+    from real_robots_b200.envs.env import macro_plan
+    quat = real_robots_b200_quat()
+    for e in range(4):
+        o = Oracle(1)
+        ref = macro_plan(lambda c: o.ik(c, quat)[0][:9], macro[e, 0].cpu().numpy(), macro[e, 1].cpu().numpy())
+        assert np.abs(plan[e] - ref).max() < 1e-7
+    assert int(menv.plan_step[0]) == 0
+    menv.step({'macro_action': macro, 'render': False})
+    assert int(menv.plan_step[0]) == 1
+    env.close(); menv.close()
+
+
+def test_evaluate_with_goal_file(tmp_path):
+    """real_robots.evaluate() end to end on a synthetic goals file in the reference's pickle format."""
+    goals = []
+    for k in range(2):
+        pos = np.array([-0.1 + 0.02 * k, 0.05 * k, 0.45, 0, 0, 0, 1.0])
+        goals.append(Goal(initial_state={'cube': pos}, final_state={'cube': pos + [0.1, 0, 0.3214 - 0.45, 0, 0, 0, 0]}, challenge='2D',
+                          retina=np.zeros((240, 320, 3), np.uint8), mask=np.zeros((240, 320), np.int32)))
+    path = str(tmp_path / "goals.npy")
+    np.savez_compressed(path, np.array(goals, dtype=object))
+
+    class Still(BasePolicy):
+        calls = 0
+
+        def step(self, observation, reward, done):
+            Still.calls += 1
+            return {'joint_command': np.zeros(9), 'render': False}
+
+    score, scores = real_robots.evaluate(Still, environment='R1', action_type='joints', n_objects=1, intrinsic_timesteps=5,
+                                         extrinsic_timesteps=120, extrinsic_trials=2, visualize=False, goals_dataset_path=path + ".npz")
+    assert Still.calls == 5 + 2 * 120
+    assert set(score) == {'score_2D', 'score_2.5D', 'score_3D', 'score_total'} and len(scores['2D']) == 2
+    # the cube is dropped at its start pose and rests there: final xy ~ initial, goal is 10 cm away -> score ~ 0.25 (env.py:192-194)
+    assert all(0.15 < s < 0.30 for s in scores['2D'])
+
+
+def test_evaluate_vectorised_single_rank():
+    from real_robots_b200.evaluate import evaluate_vectorised
+    G = 6
+    rng = np.random.default_rng(2020)
+    init = np.zeros((G, 1, 7)); init[:, 0, :3] = np.c_[rng.uniform(-0.25, 0.05, G), rng.uniform(-0.45, 0.45, G), np.full(G, 0.40)]; init[:, 0, 6] = 1
+    final = init[:, :, :3].copy(); final[:, 0, 0] += 0.1
+    score, scores, vec = evaluate_vectorised(lambda env: _Still(env), dict(initial=init, final=final), n_objects=1, action_type='joints',
+                                             extrinsic_timesteps=100)
+    assert vec.shape == (G,) and np.isfinite(vec).all() and (vec > 0.1).all() and (vec < 0.35).all()
+    assert np.isclose(score['score_total'], vec.mean())
+
+
+class _Still:
+    def __init__(self, env):
+        self.z = torch.zeros(env.n_envs, 9, dtype=torch.float64, device=env.device)
+
+    def step(self, obs, reward, done):
+        return {'joint_command': self.z, 'render': False}
