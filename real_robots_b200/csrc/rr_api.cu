@@ -240,7 +240,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_err = "rr_create: no CUDA device (this library has no CPU fallback)"; return -1; }
     if (device < 0 || device >= ndev) { g_create_err = "rr_create: bad device index"; return -1; }
     rr_ctx* ctx = new rr_ctx();
-    ctx->device = device; ctx->N = n_envs; ctx->n_objects = n_objects; ctx->launches = 0; ctx->prof_on = false; ctx->d_rec_scratch = nullptr; ctx->d_list_scratch = nullptr; ctx->d_work_counter = nullptr; ctx->d_tri_shape = nullptr; ctx->raster_grid = 0;
+    ctx->device = device; ctx->N = n_envs; ctx->n_objects = n_objects; ctx->launches = 0; ctx->prof_on = false; ctx->host_compute = nullptr; ctx->host_copy = nullptr; ctx->d_rec_scratch = nullptr; ctx->d_list_scratch = nullptr; ctx->d_work_counter = nullptr; ctx->d_tri_shape = nullptr; ctx->raster_grid = 0;
     ctx->d_cmd = nullptr; ctx->d_mask = nullptr; ctx->d_joint = ctx->d_touch = ctx->d_objpose = nullptr;
     ctx->d_rgb = nullptr; ctx->d_depth = nullptr; ctx->d_seg = nullptr; ctx->img_capacity = 0; ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0;
     if (cfg) ctx->cfg = *cfg; else rr_config_default(&ctx->cfg);
@@ -380,26 +380,43 @@ int rr_step_host(rr_ctx* ctx, const double* cmd_h, const uint8_t* render_mask_h,
     ARG(cmd_h != nullptr, "rr_step_host: joint_cmd_host is NULL");
     CKH(cudaSetDevice(ctx->device));
     const size_t N = (size_t)ctx->N, PX = (size_t)RR_W * RR_H;
-    cudaStream_t s = 0;
     const bool want_img = render_mask_h && (rgb_h || depth_h || mask_h);
+    if (!ctx->host_compute) {
+        CKH(cudaStreamCreateWithFlags(&ctx->host_compute, cudaStreamNonBlocking));
+        CKH(cudaStreamCreateWithFlags(&ctx->host_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 16; i++) CKH(cudaEventCreateWithFlags(&ctx->host_ev[i], cudaEventDisableTiming));
+    }
     if (want_img && ctx->img_capacity < N) {
         CKH(cudaMalloc(&ctx->d_rgb, N * PX * 3)); CKH(cudaMalloc(&ctx->d_depth, N * PX * 4)); CKH(cudaMalloc(&ctx->d_seg, N * PX * 4));
         ctx->img_capacity = N;
     }
+    CKH(cudaDeviceSynchronize());             // order after whatever the caller enqueued on other streams
+    cudaStream_t s = ctx->host_compute, cs = ctx->host_copy;
     CKH(cudaMemcpyAsync(ctx->d_cmd, cmd_h, N * 9 * 8, cudaMemcpyHostToDevice, s));
     if (want_img) CKH(cudaMemcpyAsync(ctx->d_mask, render_mask_h, N, cudaMemcpyHostToDevice, s));
     if (rrk_step(ctx, ctx->d_cmd, s) != 0) return -1;
     if (rrk_read_state(ctx, ctx->d_joint, ctx->d_touch, ctx->d_objpose, s) != 0) return -1;
-    if (want_img && rrk_render(ctx, ctx->d_mask, nullptr, ctx->d_rgb, ctx->d_depth, mask_h ? ctx->d_seg : nullptr, s) != 0) return -1;
     if (joint_h) CKH(cudaMemcpyAsync(joint_h, ctx->d_joint, N * 9 * 8, cudaMemcpyDeviceToHost, s));
     if (touch_h) CKH(cudaMemcpyAsync(touch_h, ctx->d_touch, N * 4 * 8, cudaMemcpyDeviceToHost, s));
     if (objpose_h) CKH(cudaMemcpyAsync(objpose_h, ctx->d_objpose, N * ctx->n_objects * 7 * 8, cudaMemcpyDeviceToHost, s));
     if (want_img) {
-        if (rgb_h) CKH(cudaMemcpyAsync(rgb_h, ctx->d_rgb, N * PX * 3, cudaMemcpyDeviceToHost, s));
-        if (depth_h) CKH(cudaMemcpyAsync(depth_h, ctx->d_depth, N * PX * 4, cudaMemcpyDeviceToHost, s));
-        if (mask_h) CKH(cudaMemcpyAsync(mask_h, ctx->d_seg, N * PX * 4, cudaMemcpyDeviceToHost, s));
+        // render in chunks of envs; the device->host copy of chunk c runs on the copy stream while chunk c+1 renders
+        const int chunks = N >= 1024 ? 16 : (N >= 64 ? 4 : 1);
+        const int per = (int)((N + chunks - 1) / chunks);
+        for (int c = 0; c < chunks; c++) {
+            const int lo = c * per, cnt = (int)N - lo < per ? (int)N - lo : per;
+            if (cnt <= 0) break;
+            if (rrk_render_range(ctx, ctx->d_mask, nullptr, ctx->d_rgb, ctx->d_depth, mask_h ? ctx->d_seg : nullptr, lo, cnt, s) != 0) return -1;
+            CKH(cudaEventRecord(ctx->host_ev[c], s));
+            CKH(cudaStreamWaitEvent(cs, ctx->host_ev[c], 0));
+            const size_t o = (size_t)lo * PX, n = (size_t)cnt * PX;
+            if (rgb_h) CKH(cudaMemcpyAsync(rgb_h + o * 3, ctx->d_rgb + o * 3, n * 3, cudaMemcpyDeviceToHost, cs));
+            if (depth_h) CKH(cudaMemcpyAsync(depth_h + o, ctx->d_depth + o, n * 4, cudaMemcpyDeviceToHost, cs));
+            if (mask_h) CKH(cudaMemcpyAsync(mask_h + o, ctx->d_seg + o, n * 4, cudaMemcpyDeviceToHost, cs));
+        }
     }
     CKH(cudaStreamSynchronize(s));
+    CKH(cudaStreamSynchronize(cs));
     return 0;
 }
 

@@ -91,6 +91,7 @@ struct rr_ctx {
     double* d_cmd; uint8_t* d_mask; double* d_joint; double* d_touch; double* d_objpose;
     uint8_t* d_rgb; float* d_depth; int32_t* d_seg;
     size_t img_capacity;       // envs for which d_rgb/d_depth/d_seg are allocated
+    cudaStream_t host_compute, host_copy; cudaEvent_t host_ev[16];   // rr_step_host: render chunk c overlaps the D2H copy of chunk c-1
     double* h_pinned; size_t h_pinned_bytes;
     long long launches;
     std::string err;
@@ -127,6 +128,7 @@ int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s);
 int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s);
 int rrk_render_upload_constants(rr_ctx* ctx);
 int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames_or_null, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);
+int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg, int env_begin, int env_count, cudaStream_t s);
 int rrk_render_camera(rr_ctx* ctx, const RenderConst* cam, const uint8_t* mask, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);
 void rr_set_camera_consts(RenderConst& C, const float* view16, const float* proj16);
 int rrk_collide_upload_constants(rr_ctx* ctx);

@@ -38,6 +38,9 @@ __constant__ RenderConst c_render;
 #endif
 //           // in-strip bounding-box pixels up to which a triangle is rasterised by its own lane
 #define BIGQ 512
+#ifndef HUGE_GROUP
+#define HUGE_GROUP 256         // threads that share one huge triangle
+#endif
 #ifndef HUGE_AREA
 #define HUGE_AREA 256
 #endif
@@ -77,11 +80,12 @@ __device__ float cofactor4(const float M[4][4], int row, int col) {
 // --------------------------------------------------------------------------------------------- setup kernel
 // frames: f64 [N][22][12] or NULL (then read the simulated state)
 __global__ void k_render_setup(DevState st, const double* __restrict__ frames, float* __restrict__ mats, int n_objects,
-                               const double* __restrict__ static_frames /* [22][12] for non-robot, non-object shapes */) {
+                               const double* __restrict__ static_frames /* [22][12] for non-robot, non-object shapes */,
+                               int env_begin, int env_count) {
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= st.N * RR_NSHAPES) return;
-    int e = gid / RR_NSHAPES, s = gid % RR_NSHAPES;
-    float* out = mats + (size_t)gid * MAT_STRIDE;
+    if (gid >= env_count * RR_NSHAPES) return;
+    int e = env_begin + gid / RR_NSHAPES, s = gid % RR_NSHAPES;
+    float* out = mats + ((size_t)e * RR_NSHAPES + s) * MAT_STRIDE;
     const ShapeRenderConst& sh = c_render.shape[s];
     int body = sh.objectAndLink & 0xffffff, link = (sh.objectAndLink >> 24) - 1;
     bool active = !(body >= 2 && body - 2 >= n_objects) && sh.rgba[3] != 0.f;
@@ -545,7 +549,7 @@ __device__ __noinline__ unsigned int shade_clipped(const float* __restrict__ M, 
 __global__ void __launch_bounds__(RTHREADS, RBLOCKS)
 k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const uint8_t* __restrict__ texdata,
          const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch, int* __restrict__ work_counter,
-         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int N) {
+         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* M = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);
@@ -562,8 +566,8 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         if (tid == 0) { s_env = atomicAdd(work_counter, 1); s_nrec = 0; }
         if (tid < NSTRIPS) s_nlist[tid] = 0;
         __syncthreads();
-        const int e = s_env;
-        if (e >= N) break;
+        if (s_env >= N) break;
+        const int e = env_begin + s_env;
         const size_t img = (size_t)e * RR_W * RR_H;
         const bool on = env_mask ? (env_mask[e] != 0) : true;
         if (!on) {   // reference returns cached zero arrays when render is off (env.py:114-122, 273-275)
@@ -635,12 +639,13 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 }
             }
             __syncthreads();
-            {   // huge triangles: whole CTA per record
+            {   // huge triangles: groups of HUGE_GROUP threads take the queued records round-robin
                 const int nb = min(s_bign, BIGQ);
-                for (int b = 0; b < nb; b++) {
+                const int grp = tid / HUGE_GROUP, gt_ = tid % HUGE_GROUP;
+                for (int b = grp; b < nb; b += RTHREADS / HUGE_GROUP) {
                     const Rec br = load_rec(recs + bigq[b]);
                     Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
-                    raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, tid, RTHREADS);
+                    raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, gt_, HUGE_GROUP);
                 }
             }
             __syncthreads();
@@ -736,23 +741,30 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
     return 0;
 }
 
-int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s) {
-    int total = ctx->N * RR_NSHAPES;
+int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg,
+                     int env_begin, int env_count, cudaStream_t s) {
+    if (env_count <= 0) return 0;
+    int total = env_count * RR_NSHAPES;
     {
         ProfScope ps(ctx, 1, s);
-        k_render_setup<<<(total + 127) / 128, 128, 0, s>>>(ctx->st, frames, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device]);
+        k_render_setup<<<(total + 127) / 128, 128, 0, s>>>(ctx->st, frames, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device], env_begin, env_count);
     }
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), s));
     {
         ProfScope ps(ctx, 2, s);
-        k_raster<<<ctx->raster_grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, ctx->d_tex, mask,
-                                                                 (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, ctx->d_work_counter, rgb, depth, seg, ctx->N);
+        int grid = ctx->raster_grid < env_count ? ctx->raster_grid : env_count;
+        k_raster<<<grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, ctx->d_tex, mask,
+                                                     (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, ctx->d_work_counter, rgb, depth, seg,
+                                                     env_begin, env_count);
     }
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s) {
+    return rrk_render_range(ctx, mask, frames, rgb, depth, seg, 0, ctx->N, s);
 }
 
 // Render with another camera (EnvCamera / render('rgb_array'), reference env.py:221-228, 470-513): the camera part of
