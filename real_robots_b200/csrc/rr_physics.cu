@@ -42,7 +42,16 @@ struct WarpMem {
     double opos[RR_MAX_OBJECTS][3], ovel[RR_MAX_OBJECTS][6], oIinv[RR_MAX_OBJECTS][9], oinvm[RR_MAX_OBJECTS];
     double Jtmp[32];
     double app[3 * RR_MAX_CONTACTS];                    // applied impulses: normals [0,MAXC), friction pairs after
+    unsigned char olist[RR_MAX_OBJECTS][RR_MAX_CONTACTS];   // per object: its contact indices, in solver order
+    int ocnt[RR_MAX_OBJECTS];
+    int simple;                                         // every contact is object-vs-static: objects solve independently
 };
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
 
 // two warp reductions for the price of one: after the first exchange the lower half-warp carries a, the upper b
 __device__ __forceinline__ void warp_sum2(double a, double b, double& sa, double& sb) {
@@ -512,6 +521,9 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
     const double vel = (lane < RR_NDOF) ? m.qd[lane] : 0.0;
     double ovel = 0.0;      // object velocity component owned by this lane (lanes 11..28)
     int nc = 0, overflow = 0;
+    if (lane < RR_MAX_OBJECTS) m.ocnt[lane] = 0;
+    if (lane == 0) m.simple = 1;
+    __syncwarp();
     int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
     double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
     double* rows = st.rows + (size_t)e * 3 * RR_MAX_CONTACTS * RR_ROW_STRIDE;
@@ -618,6 +630,10 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
                     if (lane == 0) { rowp[64] = rhs; rowp[65] = inv; rowp[66] = mu; rowp[67] = inv != 0.0 ? 1.0 / inv : 0.0; m.app[ri] = app0; }
                     __syncwarp();
                 }
+                if (lane == 0) {
+                    if (!armA && oA >= 0 && oB < 0) m.olist[oA][m.ocnt[oA]++] = (unsigned char)nc;
+                    else m.simple = 0;
+                }
                 nc++;
             }
         }
@@ -653,41 +669,101 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
                 res = fmax(res, r * r);
                 __syncwarp();
             }
+            if (m.simple) {
+                // Object-parallel sweep: every contact row touches exactly one free object, so the rows of different
+                // objects commute and the Gauss-Seidel order is preserved while lanes 11+6o..16+6o solve object o.
+                const int og = (lane >= 11 && lane < 29) ? (lane - 11) / 6 : -1;
+                const int ob0 = og >= 0 ? 11 + 6 * og : lane;
+                const int maxcnt = max(m.ocnt[0], max(m.ocnt[1], m.ocnt[2]));
+                for (int k = 0; k < maxcnt; k++) {               // normal rows
+                    const bool act = og >= 0 && k < m.ocnt[og];
+                    const int c = act ? m.olist[og][k] : 0;
+                    const double* rowp = rows + (size_t)c * RR_ROW_STRIDE;
+                    const double J = act ? rowp[lane] : 0.0, rr = act ? rowp[32 + lane] : 0.0;
+                    const double pr = J * dv;
+                    double sdot = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 6; j++) sdot += __shfl_sync(FULL, pr, ob0 + (og >= 0 ? j : 0));
+                    double app = 0.0, delta = 0.0;
+                    if (act) {
+                        app = m.app[c];
+                        delta = rowp[64] - sdot * rowp[65];
+                        const double sum = app + delta;
+                        if (sum < 0.0) { delta = 0.0 - app; app = 0.0; }
+                        else if (sum > 1e10) { delta = 1e10 - app; app = 1e10; }
+                        else app = sum;
+                        dv += rr * delta;
+                        const double r = delta * rowp[67];
+                        res = fmax(res, r * r);
+                    }
+                    __syncwarp();
+                    if (act && lane == ob0) m.app[c] = app;
+                    __syncwarp();
+                }
+                for (int k = 0; k < maxcnt; k++) {               // friction pairs with the implicit cone
+                    const bool act = og >= 0 && k < m.ocnt[og];
+                    const int c = act ? m.olist[og][k] : 0;
+                    const int r0 = RR_MAX_CONTACTS + 2 * c;
+                    const double* ra = rows + (size_t)r0 * RR_ROW_STRIDE; const double* rb = ra + RR_ROW_STRIDE;
+                    const double Ja = act ? ra[lane] : 0.0, rra = act ? ra[32 + lane] : 0.0, Jb = act ? rb[lane] : 0.0, rrb = act ? rb[32 + lane] : 0.0;
+                    const double pa = Ja * dv, pb = Jb * dv;
+                    double sa_ = 0.0, sb_ = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 6; j++) { const int src = ob0 + (og >= 0 ? j : 0); sa_ += __shfl_sync(FULL, pa, src); sb_ += __shfl_sync(FULL, pb, src); }
+                    double wa = 0.0, wb = 0.0;
+                    if (act) {
+                        const double lim = ra[66] * m.app[c];
+                        const double appa = m.app[r0], appb = m.app[r0 + 1];
+                        wa = appa + (ra[64] - sa_ * ra[65]); wb = appb + (rb[64] - sb_ * rb[65]);
+                        const double len2 = wa * wa + wb * wb;
+                        if (len2 > lim * lim) { const double sc = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= sc; wb *= sc; }
+                        const double da = wa - appa, db = wb - appb;
+                        dv += rra * da; dv += rrb * db;
+                        const double qa = da * ra[67], qb = db * rb[67];
+                        res = fmax(res, fmax(qa * qa, qb * qb));
+                    }
+                    __syncwarp();
+                    if (act && lane == ob0) { m.app[r0] = wa; m.app[r0 + 1] = wb; }
+                    __syncwarp();
+                }
+                res = warp_max(res);
+            } else {
             for (int c = 0; c < nc; c++) {                   // normal rows
-                const double* rowp = rows + (size_t)c * RR_ROW_STRIDE;
-                const double J = rowp[lane], rr = rowp[32 + lane], rhs = rowp[64], inv = rowp[65];
-                const double s = warp_sum(J * dv);
-                double app = m.app[c];
-                double delta = rhs - s * inv;
-                const double sum = app + delta;
-                if (sum < 0.0) { delta = 0.0 - app; app = 0.0; }
-                else if (sum > 1e10) { delta = 1e10 - app; app = 1e10; }
-                else app = sum;
-                __syncwarp();
-                if (lane == 0) m.app[c] = app;
-                dv += rr * delta;
-                const double r = delta * rowp[67];
-                res = fmax(res, r * r);
-                __syncwarp();
-            }
-            for (int c = 0; c < nc; c++) {                   // friction pairs with the implicit cone
-                const int r0 = RR_MAX_CONTACTS + 2 * c;
-                const double* ra = rows + (size_t)r0 * RR_ROW_STRIDE; const double* rb = ra + RR_ROW_STRIDE;
-                const double Ja = ra[lane], rra = ra[32 + lane], Jb = rb[lane], rrb = rb[32 + lane];
-                const double inva = ra[65], invb = rb[65];
-                const double lim = ra[66] * m.app[c];
-                double sa_, sb_; warp_sum2(Ja * dv, Jb * dv, sa_, sb_);
-                const double appa = m.app[r0], appb = m.app[r0 + 1];
-                double wa = appa + (ra[64] - sa_ * inva), wb = appb + (rb[64] - sb_ * invb);
-                const double len2 = wa * wa + wb * wb;
-                if (len2 > lim * lim) { const double sc = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= sc; wb *= sc; }
-                const double da = wa - appa, db = wb - appb;
-                __syncwarp();
-                if (lane == 0) { m.app[r0] = wa; m.app[r0 + 1] = wb; }
-                dv += rra * da; dv += rrb * db;
-                const double qa = da * ra[67], qb = db * rb[67];
-                res = fmax(res, fmax(qa * qa, qb * qb));
-                __syncwarp();
+                    const double* rowp = rows + (size_t)c * RR_ROW_STRIDE;
+                    const double J = rowp[lane], rr = rowp[32 + lane], rhs = rowp[64], inv = rowp[65];
+                    const double s = warp_sum(J * dv);
+                    double app = m.app[c];
+                    double delta = rhs - s * inv;
+                    const double sum = app + delta;
+                    if (sum < 0.0) { delta = 0.0 - app; app = 0.0; }
+                    else if (sum > 1e10) { delta = 1e10 - app; app = 1e10; }
+                    else app = sum;
+                    __syncwarp();
+                    if (lane == 0) m.app[c] = app;
+                    dv += rr * delta;
+                    const double r = delta * rowp[67];
+                    res = fmax(res, r * r);
+                    __syncwarp();
+                }
+                for (int c = 0; c < nc; c++) {                   // friction pairs with the implicit cone
+                    const int r0 = RR_MAX_CONTACTS + 2 * c;
+                    const double* ra = rows + (size_t)r0 * RR_ROW_STRIDE; const double* rb = ra + RR_ROW_STRIDE;
+                    const double Ja = ra[lane], rra = ra[32 + lane], Jb = rb[lane], rrb = rb[32 + lane];
+                    const double inva = ra[65], invb = rb[65];
+                    const double lim = ra[66] * m.app[c];
+                    double sa_, sb_; warp_sum2(Ja * dv, Jb * dv, sa_, sb_);
+                    const double appa = m.app[r0], appb = m.app[r0 + 1];
+                    double wa = appa + (ra[64] - sa_ * inva), wb = appb + (rb[64] - sb_ * invb);
+                    const double len2 = wa * wa + wb * wb;
+                    if (len2 > lim * lim) { const double sc = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= sc; wb *= sc; }
+                    const double da = wa - appa, db = wb - appb;
+                    __syncwarp();
+                    if (lane == 0) { m.app[r0] = wa; m.app[r0 + 1] = wb; }
+                    dv += rra * da; dv += rrb * db;
+                    const double qa = da * ra[67], qb = db * rb[67];
+                    res = fmax(res, fmax(qa * qa, qb * qb));
+                    __syncwarp();
+                }
             }
             iters = it + 1;
             if (res <= cf.residual_threshold) break;
