@@ -187,3 +187,26 @@ class _Still:
 
     def step(self, obs, reward, done):
         return {'joint_command': self.z, 'render': False}
+
+
+def test_goal_generation_roundtrip(tmp_path):
+    """generate_goals on the batched sim -> reference file format -> REALRobotEnv.set_goal / evaluateGoal."""
+    from real_robots_b200.generate_goals import generate_goals, save_goals
+    goals = generate_goals(3, n_objects=1, challenge='2D', seed=5, batch=8)
+    assert len(goals) == 3
+    for g in goals:
+        assert set(g.initial_state) == {'cube'} and g.initial_state['cube'].shape == (7,) and g.challenge == '2D'
+        assert g.retina.shape == (240, 320, 3) and g.mask.shape == (240, 320) and (g.mask == 2).any()
+        assert np.linalg.norm(g.initial_state['cube'][:3] - g.final_state['cube'][:3]) >= 0.10      # min_start_goal_dist
+        assert 0.30 < g.initial_state['cube'][2] < 0.33 and 0.30 < g.final_state['cube'][2] < 0.33  # settled on the table
+    path = str(tmp_path / "goals")
+    save_goals(goals, path)
+    env = real_robots.make('REALRobot2020-R1J1-v0')
+    env.set_goals_dataset_path(path + ".npz")
+    env.reset()
+    obs = env.set_goal()
+    assert env.goal_idx == 0 and (obs['goal'] == goals[0].retina).all() and obs['goal_positions']['cube'].shape == (3,)
+    assert np.allclose(env.get_obj_pose('cube')[:3], goals[0].initial_state['cube'][:3], atol=1e-9)
+    ch, score = env.evaluateGoal()
+    assert ch == '2D' and 0 < score < 0.3
+    env.close()
