@@ -251,7 +251,8 @@ def run_ours(args):
                        "pre_roll": "%d untimed physics steps so that objects rest on the table (contacts active)" % args.settle,
                        "l2": "outputs larger than L2 (%.2f GB written per step per GPU)" % (args.envs * IMG_BYTES / 1e9)},
             "roofline": {"kernel": "k_raster", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": args.traffic, "peak_source": peak_src,
+                         "frac": achieved / peak if peak else None, "traffic": (args.traffic * args.envs / 4096 if args.traffic else None),
+                         "algorithmic_bytes": args.envs * IMG_BYTES, "peak_source": peak_src,
                          "ms_per_launch": raster_ms, "launches": r_n,
                          "physics_kernel": {"kernel": "k_step", "ms_per_launch": s_ms / max(s_n, 1),
                                             "achieved_gbs": args.envs * STATE_BYTES / (s_ms / max(s_n, 1) * 1e-3) / 1e9 if s_ms > 0 else None}},
@@ -281,7 +282,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--settle", type=int, default=60, help="untimed physics-only pre-roll steps before the warm-up")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
-    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per k_raster launch from an ncu --set full capture")
+    ap.add_argument("--traffic", type=float, default=5.52e9,
+                    help="dram bytes (read + write) per 4096-env k_raster launch from the ncu capture in profiles/r01_ncu_full_summary.json")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

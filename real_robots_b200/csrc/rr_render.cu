@@ -38,6 +38,9 @@ __constant__ RenderConst c_render;
 #endif
 //           // in-strip bounding-box pixels up to which a triangle is rasterised by its own lane
 #define BIGQ 512
+#ifndef PRECULL_AREA
+#define PRECULL_AREA 4           // bounding boxes up to this many pixels are coverage-tested in the geometry phase
+#endif
 #ifndef HUGE_GROUP
 #define HUGE_GROUP 256         // threads that share one huge triangle
 #endif
@@ -425,6 +428,21 @@ __device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned sho
     if (!S.any) return;
     Edge E; edge_setup(S, E);
     if (E.degenerate) return;                               // bc_screen = (-1,1,1) everywhere: nothing is ever drawn
+#if PRECULL_AREA > 0
+    {   // most robot triangles are sub-pixel: classify their few candidate pixels now and drop the triangle when none
+        // can be covered — fewer records keeps the scratch inside L2
+        const int bw = S.x1 - S.x0 + 1, bh = S.y1 - S.y0 + 1;
+        if (bw * bh <= PRECULL_AREA) {
+            bool any = false;
+            for (int py = S.y0; py <= S.y1; py++)
+                for (int px = S.x0; px <= S.x1; px++) {
+                    float ux, uy; bary_u(S, E, (float)px, (float)py, ux, uy);
+                    any |= coverage_class(ux, uy, E.uz) != 0;
+                }
+            if (!any) return;
+        }
+    }
+#endif
     const int slot = agg_inc(nrec);
     if (slot >= REC_MAX) return;
     Recip R; recip_setup(S, E, R);
@@ -688,12 +706,12 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 const size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
                 if (rgb) {
                     unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3);
-                    p[0] = (col[0] & 0xffffffu) | (col[1] << 24);
-                    p[1] = ((col[1] >> 8) & 0xffffu) | (col[2] << 16);
-                    p[2] = ((col[2] >> 16) & 0xffu) | (col[3] << 8);
+                    __stcs(p, (col[0] & 0xffffffu) | (col[1] << 24));
+                    __stcs(p + 1, ((col[1] >> 8) & 0xffffu) | (col[2] << 16));
+                    __stcs(p + 2, ((col[2] >> 16) & 0xffu) | (col[3] << 8));
                 }
-                if (depth) *reinterpret_cast<float4*>(depth + o) = make_float4(dep[0], dep[1], dep[2], dep[3]);
-                if (seg) *reinterpret_cast<int4*>(seg + o) = make_int4(sg[0], sg[1], sg[2], sg[3]);
+                if (depth) __stcs(reinterpret_cast<float4*>(depth + o), make_float4(dep[0], dep[1], dep[2], dep[3]));
+                if (seg) __stcs(reinterpret_cast<int4*>(seg + o), make_int4(sg[0], sg[1], sg[2], sg[3]));
             }
             __syncthreads();
         }
