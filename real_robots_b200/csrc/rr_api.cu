@@ -240,7 +240,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_err = "rr_create: no CUDA device (this library has no CPU fallback)"; return -1; }
     if (device < 0 || device >= ndev) { g_create_err = "rr_create: bad device index"; return -1; }
     rr_ctx* ctx = new rr_ctx();
-    ctx->device = device; ctx->N = n_envs; ctx->n_objects = n_objects; ctx->launches = 0; ctx->prof_on = false; ctx->host_compute = nullptr; ctx->host_copy = nullptr; ctx->d_rec_scratch = nullptr; ctx->d_list_scratch = nullptr; ctx->d_work_counter = nullptr; ctx->d_tri_shape = nullptr; ctx->raster_grid = 0;
+    ctx->device = device; ctx->N = n_envs; ctx->n_objects = n_objects; ctx->launches = 0; ctx->prof_on = false; ctx->host_compute = nullptr; ctx->host_copy = nullptr; ctx->d_rec_scratch = nullptr; ctx->d_list_scratch = nullptr; ctx->d_work_counter = nullptr; ctx->d_tri_shape = nullptr; ctx->raster_grid = 0; ctx->d_planes = nullptr; ctx->d_cull_scratch = nullptr;
     ctx->d_cmd = nullptr; ctx->d_mask = nullptr; ctx->d_joint = ctx->d_touch = ctx->d_objpose = nullptr;
     ctx->d_rgb = nullptr; ctx->d_depth = nullptr; ctx->d_seg = nullptr; ctx->img_capacity = 0; ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0;
     if (cfg) ctx->cfg = *cfg; else rr_config_default(&ctx->cfg);
@@ -260,7 +260,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
     alloc((void**)&st.q, 11 * N * 8); alloc((void**)&st.qd, 11 * N * 8); alloc((void**)&st.target, 11 * N * 8);
     alloc((void**)&st.obj, 39 * N * 8); alloc((void**)&st.touch, 4 * N * 8); alloc((void**)&st.link_frames, 16 * 12 * N * 8);
-    alloc((void**)&st.render_mats, N * RR_NSHAPES * 40 * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.timestep, N * 8);
+    alloc((void**)&st.render_mats, N * RR_NSHAPES * RR_MAT_STRIDE * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.timestep, N * 8);
     alloc((void**)&ctx->d_cmd, N * 9 * 8); alloc((void**)&ctx->d_mask, N); alloc((void**)&ctx->d_joint, N * 9 * 8);
     alloc((void**)&ctx->d_touch, N * 4 * 8); alloc((void**)&ctx->d_objpose, N * 3 * 7 * 8);
     for (int k = 0; k < 2; k++) {
@@ -283,7 +283,7 @@ int rr_destroy(rr_ctx* ctx) {
     void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.timestep,
                     st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.rows,
                     ctx->d_cmd, ctx->d_mask, ctx->d_joint, ctx->d_touch, ctx->d_objpose, ctx->d_rgb, ctx->d_depth, ctx->d_seg,
-                    ctx->d_tris, ctx->d_tex, ctx->d_hull_verts, ctx->d_rec_scratch, ctx->d_list_scratch, ctx->d_work_counter, ctx->d_tri_shape};
+                    ctx->d_tris, ctx->d_tex, ctx->d_hull_verts, ctx->d_rec_scratch, ctx->d_list_scratch, ctx->d_work_counter, ctx->d_tri_shape, ctx->d_planes, ctx->d_cull_scratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;

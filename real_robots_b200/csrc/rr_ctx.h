@@ -13,6 +13,7 @@
 #define RR_H RR_EYE_H
 #define RR_FRAME_STRIDE (RR_NSHAPES * 12)
 #define RR_MAX_TEX 16
+#define RR_MAT_STRIDE 44       // floats per (env, shape) in render_mats
 #define RR_MAX_PAIRS 96          // candidate collision pairs (92 for 3 objects)
 #define RR_MAX_MANIFOLDS 24      // cached manifolds per env (<= 32: one lane per slot)
 #define RR_PT_STRIDE 17          // doubles per contact point: localA3 localB3 normalB3 dist impulse worldA3 worldB3
@@ -87,6 +88,7 @@ struct rr_ctx {
     int man_parity;            // which manifold buffer holds the current contacts
     int n_tris;
     void* d_rec_scratch; void* d_list_scratch; int* d_work_counter; uint8_t* d_tri_shape; int raster_grid;   // persistent rasteriser
+    void* d_planes; void* d_cull_scratch;   // model-space triangle planes (conservative back-face pre-test), per-CTA survivor lists
     // staging for the host-buffer path
     double* d_cmd; uint8_t* d_mask; double* d_joint; double* d_touch; double* d_objpose;
     uint8_t* d_rgb; float* d_depth; int32_t* d_seg;

@@ -20,6 +20,7 @@
 #include <cfloat>
 
 __constant__ RenderConst c_render;
+__constant__ float c_cull_hmax;      // largest 'smallest altitude' over all triangles (see build_planes)
 
 #ifndef STRIP_ROWS
 #define STRIP_ROWS 40
@@ -32,14 +33,16 @@ __constant__ RenderConst c_render;
 #define RBLOCKS 2
 #endif
 //            // resident CTAs per SM (shared memory bound)
-#define MAT_STRIDE 40          // floats per (env, shape): pmv[16] model[12] invT[9] ylo yhi flag
+#define MAT_STRIDE RR_MAT_STRIDE   // floats per (env, shape): pmv[16] model[12] invT[9] ylo yhi flag cam_model[3] cull_bound
 #ifndef SMALL_AREA
 #define SMALL_AREA 16
 #endif
 //           // in-strip bounding-box pixels up to which a triangle is rasterised by its own lane
-#define BIGQ 512
 #ifndef PRECULL_AREA
 #define PRECULL_AREA 4           // bounding boxes up to this many pixels are coverage-tested in the geometry phase
+#endif
+#ifndef HUGE_FIRST
+#define HUGE_FIRST 1
 #endif
 #ifndef HUGE_GROUP
 #define HUGE_GROUP 256         // threads that share one huge triangle
@@ -48,6 +51,19 @@ __constant__ RenderConst c_render;
 #define HUGE_AREA 256
 #endif
 //         // in-strip bounding-box pixels above which the whole CTA rasterises the triangle
+
+#ifdef RR_STATS   // tuning build only (scripts/raster_stats.py): event counters, read back with rr_debug_raster_stats
+__device__ unsigned long long g_stats[16];
+#define STAT(i, n) atomicAdd(&g_stats[i], (unsigned long long)(n))
+extern "C" int rr_debug_raster_stats(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_stats, sizeof(g_stats)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_stats, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define STAT(i, n)
+#endif
 
 // --------------------------------------------------------------------------------------------- float helpers
 __device__ __forceinline__ float dot4r(const float* a, const float* b) { float r = 0.f; r += a[3] * b[3]; r += a[2] * b[2]; r += a[1] * b[1]; r += a[0] * b[0]; return r; }
@@ -146,6 +162,25 @@ __global__ void k_render_setup(DevState st, const double* __restrict__ frames, f
     }
     if (all_front) { ylo = mn - 2.f; yhi = mx + 2.f; }
     out[37] = ylo; out[38] = yhi; out[39] = (active && !all_behind) ? 1.f : 0.f;
+    // Camera position in model coordinates and the distance bound of the conservative back-face pre-test (k_raster,
+    // geometry pass 1).  The pre-test is only trusted for a rigid model matrix; otherwise the bound is infinite and every
+    // triangle takes the exact test.
+    double R[3][3], t[3], orth = 0.0;
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R[i][j] = (double)model[i][j]; t[i] = (double)model[i][3]; }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        double d = R[0][i] * R[0][j] + R[1][i] * R[1][j] + R[2][i] * R[2][j] - (i == j ? 1.0 : 0.0);
+        orth = fmax(orth, fabs(d));
+    }
+    double cm[3], cn = 0.0, rad = 0.0;
+    for (int j = 0; j < 3; j++) {
+        cm[j] = R[0][j] * (c_render.camP[0] - t[0]) + R[1][j] * (c_render.camP[1] - t[1]) + R[2][j] * (c_render.camP[2] - t[2]);
+        cn += cm[j] * cm[j];
+        const double a = fmax(fabs((double)sh.aabb_min[j]), fabs((double)sh.aabb_max[j]));
+        rad += a * a;
+    }
+    out[40] = (float)cm[0]; out[41] = (float)cm[1]; out[42] = (float)cm[2];
+    const double bound = (sqrt(cn) + sqrt(rad) + (double)c_cull_hmax) * 1.001;
+    out[43] = (orth < 1e-5 && bound == bound) ? (float)bound : FLT_MAX;
 }
 
 // --------------------------------------------------------------------------------------------- triangle setup
@@ -183,6 +218,17 @@ __device__ __forceinline__ bool tri_vertex(const float* __restrict__ M, const fl
     double Nx = e1[1] * e2[2] - e1[2] * e2[1], Ny = e1[2] * e2[0] - e1[0] * e2[2], Nz = e1[0] * e2[1] - e1[1] * e2[0];
     double dd = (v0[0] - c_render.camP[0]) * Nx + (v0[1] - c_render.camP[1]) * Ny + (v0[2] - c_render.camP[2]) * Nz;
     return !(dd >= 0);
+}
+
+// clip coordinates only (triangles the pre-test has already classified as front-facing)
+__device__ __forceinline__ void tri_clip(const float* __restrict__ M, const float* __restrict__ tv, Tri& T) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tv + 8 * j));
+        float px = a.x * 1.f, py = a.y * 1.f, pz = a.z * 1.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) T.c[k][j] = dot4r(M + 4 * k, px, py, pz, 1.f);
+    }
 }
 
 __device__ __forceinline__ void screen_setup(const float c[4][3], Screen& S) {
@@ -351,40 +397,61 @@ __device__ __noinline__ int clip_near(const float tri[4][3], float out[3][4][3])
     return nt;
 }
 
-__device__ __forceinline__ void raster_one(unsigned long long* keys, const Screen& S, const Edge& E, const Recip& R, const float* clipz,
-                                           unsigned int keylo, bool planes, int row0, int px, int py) {
-    float ux, uy; bary_u(S, E, (float)px, (float)py, ux, uy);
-    const int cls = coverage_class(ux, uy, E.uz);
-    if (cls == 0) return;
-    float bs[3], bc[3];
-    if (cls == 1 && R.tight) frag_bar_in(S, E, R, ux, uy, bc);
-    else {
-        frag_bar_r(S, E, R, px, py, bs, bc);
-        if (cls == 2 && (bs[0] < 0 || bs[1] < 0 || bs[2] < 0)) return;
-    }
-    const float fd = -1.f * dot3r(clipz[0], clipz[1], clipz[2], bc);
-    if (!(fd >= -1e30f)) return;                                  // z-buffer cleared to -1e30 (also drops NaN)
-    if (planes && (fd < -c_render.farPlane || fd > -c_render.nearPlane)) return;
-    const unsigned long long key = ((unsigned long long)order_bits(fd) << 32) | keylo;
-    unsigned long long* slot = &keys[(py - row0) * RR_W + px];
-    if (*reinterpret_cast<volatile unsigned long long*>(slot) < key) atomicMax(slot, key);
+// Upper bound (as order-preserving bits) of every fragment depth the triangle can produce: fd = -(clipz . bc) with
+// bc >= 0 and sum(bc) = 1 up to a few ulp, so fd <= max(-clipz) + 1e-5 max|clipz|.  0xffffffff = no bound.
+__device__ __forceinline__ unsigned int depth_bound_bits(const Recip& R, const float* clipz) {
+    if (!R.tight) return 0xffffffffu;
+    const float zm = fmaxf(fmaxf(-clipz[0], -clipz[1]), -clipz[2]);
+    const float am = fmaxf(fmaxf(fabsf(clipz[0]), fabsf(clipz[1])), fabsf(clipz[2]));
+    const float b = zm + (am * 1e-5f + 1e-30f);
+    return (b == b) ? order_bits(b) : 0xffffffffu;
 }
+
+// Rasterise the part of the bounding box inside the strip; this thread takes pixels start, start + stride, ...
+// Two nested loops so that the lanes of a warp re-converge before the expensive part: the inner loop advances to the
+// thread's next pixel that is (a) covered and (b) not already behind the z-buffer by the triangle's depth bound; the
+// outer body then computes the exact barycentrics / depth with as many lanes active as have found such a pixel.
 __device__ __forceinline__ void raster_pixels(unsigned long long* keys, const Screen& S, const Edge& E, const Recip& R, const float* clipz,
                                               unsigned int keylo, bool planes, int row0, int start, int stride) {
     const int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
     if (ya > yb) return;
-    if (stride == 1) {
-        for (int py = ya; py <= yb; py++)
-            for (int px = S.x0; px <= S.x1; px++) raster_one(keys, S, E, R, clipz, keylo, planes, row0, px, py);
-        return;
-    }
     const int wdt = S.x1 - S.x0 + 1, n = wdt * (yb - ya + 1);
     const int sy = start / wdt, dy = stride / wdt;
     int x = S.x0 + (start - sy * wdt), y = ya + sy;
     const int dx = stride - dy * wdt;
-    for (int i = start; i < n; i += stride) {
-        raster_one(keys, S, E, R, clipz, keylo, planes, row0, x, y);
-        x += dx; y += dy; if (x > S.x1) { x -= wdt; y++; }
+    const unsigned int zb = depth_bound_bits(R, clipz);
+    int i = start;
+    for (;;) {
+        float ux = 0.f, uy = 0.f;
+        int cls = 0, px = 0, py = 0;
+        while (i < n) {
+            px = x; py = y;
+            i += stride; x += dx; y += dy; if (x > S.x1) { x -= wdt; y++; }
+            bary_u(S, E, (float)px, (float)py, ux, uy);
+            cls = coverage_class(ux, uy, E.uz);
+            STAT(6, 1);
+            if (cls) {
+                STAT(7, 1);
+                const unsigned int cur = reinterpret_cast<volatile unsigned int*>(&keys[(py - row0) * RR_W + px])[1];
+                if (cur <= zb) break;
+                STAT(8, 1);
+                cls = 0;
+            }
+        }
+        if (cls == 0) return;
+        float bs[3], bc[3];
+        if (cls == 1 && R.tight) frag_bar_in(S, E, R, ux, uy, bc);
+        else {
+            frag_bar_r(S, E, R, px, py, bs, bc);
+            if (cls == 2 && (bs[0] < 0 || bs[1] < 0 || bs[2] < 0)) continue;
+        }
+        const float fd = -1.f * dot3r(clipz[0], clipz[1], clipz[2], bc);
+        if (!(fd >= -1e30f)) continue;                                // z-buffer cleared to -1e30 (also drops NaN)
+        if (planes && (fd < -c_render.farPlane || fd > -c_render.nearPlane)) continue;
+        const unsigned long long key = ((unsigned long long)order_bits(fd) << 32) | keylo;
+        unsigned long long* slot = &keys[(py - row0) * RR_W + px];
+        STAT(9, 1);
+        if (*reinterpret_cast<volatile unsigned long long*>(slot) < key) { STAT(10, 1); atomicMax(slot, key); }
     }
 }
 
@@ -409,6 +476,7 @@ __device__ __forceinline__ void texel_fetch(int tex, const uint8_t* __restrict__
 struct __align__(16) Rec { unsigned int bx, by, keylo, flags; float p2[3][2]; float w[3]; float z[3]; float yuz; float yw[3]; };
 static_assert(sizeof(Rec) == 80, "record must be 80 bytes");
 #define REC_MAX 24576          // records per env (17 578 triangles + clipped pieces), < 2^15
+#define CULL_MAX 32768          // survivor list entries per CTA (triangle index < 2^15, bit 15 = uncertain)
 #define REC_CLIPPED 1u         // piece of a near-plane-clipped triangle: no near/far discard, shading from the original triangle
 #define REC_OK 2u              // reciprocal operands inside the guarded range
 #define REC_TIGHT 4u           // ... and inside the tighter range of the unguarded fast path
@@ -423,7 +491,7 @@ __device__ __forceinline__ int agg_inc(int* ctr) {      // warp-aggregated atomi
     return base + __popc(m & ((1u << lane) - 1u));
 }
 
-__device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist,
+__device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist, int* nbig,
                                             const Screen& S, const float* z, unsigned int gt, unsigned int flags) {
     if (!S.any) return;
     Edge E; edge_setup(S, E);
@@ -445,6 +513,7 @@ __device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned sho
 #endif
     const int slot = agg_inc(nrec);
     if (slot >= REC_MAX) return;
+    STAT(2, 1);
     Recip R; recip_setup(S, E, R);
     Rec r;
     r.bx = (unsigned)S.x0 | ((unsigned)S.x1 << 16); r.by = (unsigned)S.y0 | ((unsigned)S.y1 << 16);
@@ -458,24 +527,29 @@ __device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned sho
 #pragma unroll
     for (int k = 0; k < 5; k++) dst[k] = src[k];
     const int s0 = S.y0 / STRIP_ROWS, s1 = S.y1 / STRIP_ROWS;
+    const int bw = S.x1 - S.x0 + 1;
     for (int st = s0; st <= s1; st++) {
-        // lanes of the warp may be appending to different strips: aggregate per counter
-        const unsigned grp = __match_any_sync(__activemask(), st);
+        // a strip's list grows upwards from entry 0; its huge triangles (shared by the whole CTA) grow downwards from the end
+        const int ya = max(S.y0, st * STRIP_ROWS), yb = min(S.y1, st * STRIP_ROWS + STRIP_ROWS - 1);
+        const int big = (bw * (yb - ya + 1) > HUGE_AREA) ? 1 : 0;
+        STAT(big ? 5 : (bw * (yb - ya + 1) > SMALL_AREA ? 4 : 3), 1);
+        // lanes of the warp may be appending to different counters: aggregate per counter
+        const unsigned grp = __match_any_sync(__activemask(), st * 2 + big);
         const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
         int base = 0;
-        if (lane == leader) base = atomicAdd(&nlist[st], __popc(grp));
+        if (lane == leader) base = atomicAdd(big ? &nbig[st] : &nlist[st], __popc(grp));
         base = __shfl_sync(grp, base, leader);
         const int pos = base + __popc(grp & ((1u << lane) - 1u));
-        lists[(size_t)st * REC_MAX + pos] = (unsigned short)slot;
+        lists[(size_t)st * REC_MAX + (big ? REC_MAX - 1 - pos : pos)] = (unsigned short)slot;
     }
 }
 
-__device__ __noinline__ void emit_clipped(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist, const Tri& T, unsigned int gt) {
+__device__ __noinline__ void emit_clipped(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist, int* nbig, const Tri& T, unsigned int gt) {
     float out[3][4][3];
     const int nc = clip_near(T.c, out);
     for (int c = 0; c < nc; c++) {
         Screen S; screen_setup(out[c], S);
-        emit_record(recs, lists, nrec, nlist, S, out[c][2], gt, REC_CLIPPED);
+        emit_record(recs, lists, nrec, nlist, nbig, S, out[c][2], gt, REC_CLIPPED);
     }
 }
 
@@ -556,6 +630,25 @@ __device__ __noinline__ unsigned int shade_clipped(const float* __restrict__ M, 
     return shade_bar(M, sh, tv, texdata, bar);
 }
 
+// colour of the winning fragment of pixel (x, y): barycentrics from the winner's record, then the fragment shader
+__device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape,
+                                                    const uint8_t* __restrict__ texdata, const Rec* __restrict__ recs, unsigned int lo, int x, int y, int& s_out) {
+    const int gt = (int)(lo >> 15) - 1, ri = (int)(lo & 0x7fffu);
+    const int s = tri_shape[gt];
+    s_out = s;
+    const ShapeRenderConst& sh = c_render.shape[s];
+    const float* tv = tris + (size_t)gt * 24;
+    const Rec rec = load_rec(recs + ri);
+    STAT(11, 1);
+    if (rec.flags & REC_CLIPPED) return shade_clipped(M + s * MAT_STRIDE, sh, tv, texdata, x, y);
+    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(rec, S, E, R, cz);
+    float bs[3], bar[3];
+    float ux, uy; bary_u(S, E, (float)x, (float)y, ux, uy);
+    if (R.tight && coverage_class(ux, uy, E.uz) == 1) frag_bar_in(S, E, R, ux, uy, bar);
+    else frag_bar_r(S, E, R, x, y, bs, bar);
+    return shade_bar(M + s * MAT_STRIDE, sh, tv, texdata, bar);
+}
+
 // Persistent kernel: each CTA takes envs from a global work counter.  Per env:
 //   geometry : one triangle per thread — vertex shader, back-face cull, near-plane clip, viewport, bounding box, edge and
 //              reciprocal set-up; survivors become 80-byte records in the CTA's private scratch (rewritten every env, so
@@ -565,24 +658,27 @@ __device__ __noinline__ unsigned int shade_clipped(const float* __restrict__ M, 
 //              on (depth bits, triangle index); resolve A: one fragment shader per covered pixel (lane per pixel),
 //              resolve B: pack and write RGB / depth / mask rows with 12/16/16-byte stores.
 __global__ void __launch_bounds__(RTHREADS, RBLOCKS)
-k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const uint8_t* __restrict__ texdata,
-         const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch, int* __restrict__ work_counter,
+k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const float4* __restrict__ planes, int n_tris,
+         const uint8_t* __restrict__ texdata, const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch,
+         unsigned short* __restrict__ cull_scratch, int* __restrict__ work_counter,
          uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* M = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);
-    int* bigq = reinterpret_cast<int*>(M + RR_NSHAPES * MAT_STRIDE);
-    __shared__ int s_env, s_nrec, s_bign, s_chunk, s_nlist[NSTRIPS];
+    __shared__ int s_env, s_nrec, s_ncull, s_chunk, s_nlist[NSTRIPS], s_nbig[NSTRIPS];
     const int tid = threadIdx.x, lane = tid & 31;
     Rec* recs = rec_scratch + (size_t)blockIdx.x * REC_MAX;
     unsigned short* lists = list_scratch + (size_t)blockIdx.x * NSTRIPS * REC_MAX;
+    unsigned short* cull = cull_scratch + (size_t)blockIdx.x * CULL_MAX;
     const float nearP = c_render.depthNear, farP = c_render.depthFar;
     const float bg_depth = (float)((double)(farP * (nearP + 1e30f)) / (2. * (double)farP * (double)nearP + (double)(farP * 1e30f) - (double)(nearP * 1e30f)));
+    // the key buffer is zero whenever a strip starts: cleared here once, then by the resolve pass that consumes it
+    for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = 0ull;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_env = atomicAdd(work_counter, 1); s_nrec = 0; }
-        if (tid < NSTRIPS) s_nlist[tid] = 0;
+        if (tid == 0) { s_env = atomicAdd(work_counter, 1); s_nrec = 0; s_ncull = 0; s_chunk = 0; }
+        if (tid < NSTRIPS) { s_nlist[tid] = 0; s_nbig[tid] = 0; }
         __syncthreads();
         if (s_env >= N) break;
         const int e = env_begin + s_env;
@@ -599,31 +695,74 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         }
         for (int i = tid; i < RR_NSHAPES * MAT_STRIDE; i += RTHREADS) M[i] = mats[(size_t)e * RR_NSHAPES * MAT_STRIDE + i];
         __syncthreads();
-        // ---- geometry phase
-        for (int s = 0; s < RR_NSHAPES; s++) {
-            const float* Ms = M + s * MAT_STRIDE;
-            if (Ms[39] == 0.f) continue;
-            const ShapeRenderConst& sh = c_render.shape[s];
-            for (int t = tid; t < sh.tri_count; t += RTHREADS) {
-                const unsigned int gt = sh.tri_start + t;
+        // ---- geometry pass 1: conservative back-face classification in MODEL space, survivors compacted.
+        // planes[t] = (unit normal, offset) of triangle t scaled by (smallest altitude / 1e-5); Ms[40..42] = camera in model
+        // coordinates; Ms[43] bounds |camera - any vertex| + altitude.  |sd| > Ms[43] means the camera is further from the
+        // triangle's plane than any rounding of the fp32 world coordinates can move that plane, so the exact fp64 test of
+        // tri_vertex() would decide the same way; everything else is marked uncertain (bit 15) and takes the exact test.
+        for (int base = 0; base < n_tris; base += RTHREADS) {
+            const int gt = base + tid;
+            int code = -1;
+            if (gt < n_tris) {
+                const float* Ms = M + tri_shape[gt] * MAT_STRIDE;
+                if (Ms[39] != 0.f) {
+                    const float4 pl = __ldg(planes + gt);
+                    const float sd = pl.x * Ms[40] + pl.y * Ms[41] + pl.z * Ms[42] - pl.w;
+                    STAT(0, 1);
+                    if (sd > Ms[43]) code = gt;
+                    else if (!(sd < -Ms[43])) code = gt | 0x8000;
+#ifdef RR_STATS
+                    else { Tri T2; if (tri_vertex(Ms, tris + (size_t)gt * 24, T2)) STAT(13, 1); }   // pre-test said back, exact says front: must stay 0
+#endif
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, code >= 0);
+            if (m) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_ncull, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+                if (code >= 0) cull[pos] = (unsigned short)code;
+            }
+        }
+        __syncthreads();
+        // ---- geometry pass 2: vertex shader, (exact cull for the uncertain ones), clip, viewport, set-up, records
+        {
+            const int ncull = s_ncull;
+            for (int i = tid; i < ncull; i += RTHREADS) {
+                const unsigned int code = cull[i];
+                const unsigned int gt = code & 0x7fffu;
+                const float* Ms = M + tri_shape[gt] * MAT_STRIDE;
                 const float* tv = tris + (size_t)gt * 24;
                 Tri T;
-                if (!tri_vertex(Ms, tv, T)) continue;
+                if (code & 0x8000u) { STAT(15, 1); if (!tri_vertex(Ms, tv, T)) continue; }
+                else {
+                    tri_clip(Ms, tv, T);
+#ifdef RR_STATS
+                    { Tri T2; if (!tri_vertex(Ms, tv, T2)) STAT(14, 1); }       // pre-test said front, exact test says back: must stay 0
+#endif
+                }
+                STAT(1, 1);
                 const bool front = (T.c[3][0] >= 0 && T.c[3][1] >= 0 && T.c[3][2] >= 0);
-                if (front) { Screen S; screen_setup(T.c, S); emit_record(recs, lists, &s_nrec, s_nlist, S, T.c[2], gt, 0u); }
-                else if (!(T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0)) emit_clipped(recs, lists, &s_nrec, s_nlist, T, gt);
+                if (front) { Screen S; screen_setup(T.c, S); emit_record(recs, lists, &s_nrec, s_nlist, s_nbig, S, T.c[2], gt, 0u); }
+                else if (!(T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0)) emit_clipped(recs, lists, &s_nrec, s_nlist, s_nbig, T, gt);
             }
         }
         __threadfence_block();
         __syncthreads();
-        // ---- strips
+        // ---- strips (three barriers each: raster | shade | store + clear)
         for (int strip = 0; strip < NSTRIPS; strip++) {
             const int row0 = strip * STRIP_ROWS;
-            const int nlist = min(s_nlist[strip], REC_MAX);
+            const int nlist = min(s_nlist[strip], REC_MAX), nbig = min(s_nbig[strip], REC_MAX);
             const unsigned short* list = lists + (size_t)strip * REC_MAX;
-            for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = 0ull;
-            if (tid == 0) { s_bign = 0; s_chunk = 0; }
-            __syncthreads();
+#if HUGE_FIRST
+            // ---- huge triangles: every thread takes pixels tid, tid + HUGE_GROUP, ... of the records of its group
+            for (int b = tid / HUGE_GROUP; b < nbig; b += RTHREADS / HUGE_GROUP) {
+                const Rec br = load_rec(recs + list[REC_MAX - 1 - b]);
+                Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
+                raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, tid % HUGE_GROUP, HUGE_GROUP);
+            }
+#endif
+            // ---- small and medium triangles: warps pull 32-record chunks of the strip's list
             for (;;) {
                 int rb = 0;
                 if (lane == 0) rb = atomicAdd(&s_chunk, 32);
@@ -638,10 +777,6 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                     const int ya = max(y0, row0), yb = min(y1, row0 + STRIP_ROWS - 1);
                     const int area = (x1 - x0 + 1) * (yb - ya + 1);
                     state = area <= SMALL_AREA ? 1 : 2;
-                    if (area > HUGE_AREA) {
-                        int slot = atomicAdd(&s_bign, 1);
-                        if (slot < BIGQ) { bigq[slot] = ridx; state = 0; }
-                    }
                 }
                 unsigned med = __ballot_sync(0xffffffffu, state == 2);
                 while (med) {
@@ -656,46 +791,37 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                     raster_pixels(keys, S, E, R, cz, rec.keylo, !(rec.flags & REC_CLIPPED), row0, 0, 1);
                 }
             }
-            __syncthreads();
-            {   // huge triangles: groups of HUGE_GROUP threads take the queued records round-robin
-                const int nb = min(s_bign, BIGQ);
-                const int grp = tid / HUGE_GROUP, gt_ = tid % HUGE_GROUP;
-                for (int b = grp; b < nb; b += RTHREADS / HUGE_GROUP) {
-                    const Rec br = load_rec(recs + bigq[b]);
-                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
-                    raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, gt_, HUGE_GROUP);
-                }
+#if !HUGE_FIRST
+            // ---- huge triangles last (they are mostly the table: the depth bound then rejects what the robot already covers)
+            for (int b = tid / HUGE_GROUP; b < nbig; b += RTHREADS / HUGE_GROUP) {
+                const Rec br = load_rec(recs + list[REC_MAX - 1 - b]);
+                Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
+                raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, tid % HUGE_GROUP, HUGE_GROUP);
             }
+#endif
             __syncthreads();
+            if (tid == 0) s_chunk = 0;
             // ---- resolve A: lane per pixel; the winner's colour replaces the low key word: 1 << 31 | shape << 24 | rgb
             for (int p = tid; p < STRIP_ROWS * RR_W; p += RTHREADS) {
                 const unsigned long long key = keys[p];
                 if (key == 0ull) continue;
                 const int r = p / RR_W, x = p - r * RR_W;
-                const unsigned int lo = (unsigned int)(key & 0xffffffffu);
-                const int gt = (int)(lo >> 15) - 1, ri = (int)(lo & 0x7fffu);
-                const int s = tri_shape[gt];
-                const ShapeRenderConst& sh = c_render.shape[s];
-                const float* tv = tris + (size_t)gt * 24;
-                const Rec rec = load_rec(recs + ri);
-                unsigned int col;
-                if (rec.flags & REC_CLIPPED) col = shade_clipped(M + s * MAT_STRIDE, sh, tv, texdata, x, row0 + r);
-                else {
-                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(rec, S, E, R, cz);
-                    float bs[3], bar[3];
-                    frag_bar_r(S, E, R, x, row0 + r, bs, bar);
-                    col = shade_bar(M + s * MAT_STRIDE, sh, tv, texdata, bar);
-                }
+                int s;
+                const unsigned int col = shade_pixel(M, tris, tri_shape, texdata, recs, (unsigned int)(key & 0xffffffffu), x, row0 + r, s);
                 keys[p] = (key & 0xffffffff00000000ull) | 0x80000000ull | ((unsigned long long)s << 24) | (unsigned long long)(col & 0xffffffu);
             }
             __syncthreads();
-            // ---- resolve B: 4 consecutive pixels per thread-iteration, vector stores, vertical flip folded in
+            // ---- resolve B: 4 consecutive pixels per thread-iteration, vector stores, vertical flip folded in; clears the keys
             for (int i = tid; i < STRIP_ROWS * RR_W / 4; i += RTHREADS) {
                 const int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
                 unsigned int col[4]; float dep[4]; int sg[4];
+                ulonglong2* kp = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
+                const ulonglong2 ka = kp[0], kb = kp[1];
+                kp[0] = make_ulonglong2(0ull, 0ull); kp[1] = make_ulonglong2(0ull, 0ull);
+                const unsigned long long k4[4] = {ka.x, ka.y, kb.x, kb.y};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const unsigned long long key = keys[r * RR_W + 4 * x4 + k];
+                    const unsigned long long key = k4[k];
                     if (key == 0ull) { col[k] = 0xffffffu; sg[k] = -1; dep[k] = bg_depth; continue; }
                     const unsigned int lo = (unsigned int)(key & 0xffffffffu);
                     col[k] = lo & 0xffffffu;
@@ -721,8 +847,44 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
 // --------------------------------------------------------------------------------------------- host side
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return -1; } } while (0)
 
-static const size_t RASTER_SMEM = (size_t)STRIP_ROWS * RR_W * 8 + RR_NSHAPES * MAT_STRIDE * 4 + BIGQ * 4;
+static const size_t RASTER_SMEM = (size_t)STRIP_ROWS * RR_W * 8 + RR_NSHAPES * MAT_STRIDE * 4;
 static double* g_static_frames[16] = {0};
+
+// Per-triangle model-space plane for the conservative back-face pre-test: unit normal n (orientation of e1 x e2) and
+// offset n.v0, both scaled by h / 1e-5 where h is the triangle's smallest altitude.  A vertex rounding error d moves
+// the plane seen from distance D by at most d (1 + 2 D / h); fp32 world coordinates carry d <= 1.2e-6, so a camera
+// whose scaled plane distance exceeds D + h (the bound k_render_setup stores) is on the same side for the exact test.
+static cudaError_t build_planes(rr_ctx* ctx) {
+    const int T = ctx->n_tris;
+    std::vector<float> tv((size_t)T * 24);
+    cudaError_t e = cudaMemcpy(tv.data(), ctx->d_tris, tv.size() * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    std::vector<float> pl((size_t)T * 4, 0.f);
+    double hmax = 0.0;
+    for (int t = 0; t < T; t++) {
+        double v[3][3];
+        for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) v[j][k] = (double)tv[(size_t)t * 24 + 8 * j + k];
+        double e1[3], e2[3], e3[3];
+        for (int k = 0; k < 3; k++) { e1[k] = v[1][k] - v[0][k]; e2[k] = v[2][k] - v[0][k]; e3[k] = v[2][k] - v[1][k]; }
+        const double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        const double a2 = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        const double l1 = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]), l2 = std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+        const double l3 = std::sqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
+        const double lmax = std::max(l1, std::max(l2, l3));
+        if (!(a2 > 0.0) || !(lmax > 0.0)) continue;                 // degenerate: zero plane => always "uncertain"
+        const double h = a2 / lmax, sc = h / 1e-5 / a2;
+        if (!(h > 1e-9) || !std::isfinite(sc)) continue;
+        hmax = std::max(hmax, h);
+        for (int k = 0; k < 3; k++) pl[(size_t)t * 4 + k] = (float)(n[k] * sc);
+        pl[(size_t)t * 4 + 3] = (float)((n[0] * v[0][0] + n[1] * v[0][1] + n[2] * v[0][2]) * sc);
+    }
+    const float hm = (float)hmax;
+    e = cudaMemcpyToSymbol(c_cull_hmax, &hm, sizeof(float));
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&ctx->d_planes, pl.size() * sizeof(float));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(ctx->d_planes, pl.data(), pl.size() * sizeof(float), cudaMemcpyHostToDevice);
+}
 
 int rrk_render_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_render, &ctx->render, sizeof(RenderConst)));
@@ -742,6 +904,9 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
             for (int t = 0; t < ctx->render.shape[sidx].tri_count; t++) ts[ctx->render.shape[sidx].tri_start + t] = (uint8_t)sidx;
         CK(cudaMalloc(&ctx->d_tri_shape, ts.size()));
         CK(cudaMemcpy(ctx->d_tri_shape, ts.data(), ts.size(), cudaMemcpyHostToDevice));
+        if (ctx->n_tris >= 0x8000) { ctx->err = "k_raster: triangle index does not fit 15 bits"; return -1; }
+        CK(build_planes(ctx));
+        CK(cudaMalloc(&ctx->d_cull_scratch, (size_t)ctx->raster_grid * CULL_MAX * sizeof(unsigned short)));
     }
     // static frames (robot base, table) as doubles
     double sf[RR_NSHAPES * 12];
@@ -773,8 +938,9 @@ int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uin
     {
         ProfScope ps(ctx, 2, s);
         int grid = ctx->raster_grid < env_count ? ctx->raster_grid : env_count;
-        k_raster<<<grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, ctx->d_tex, mask,
-                                                     (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, ctx->d_work_counter, rgb, depth, seg,
+        k_raster<<<grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris,
+                                                     ctx->d_tex, mask, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch,
+                                                     (unsigned short*)ctx->d_cull_scratch, ctx->d_work_counter, rgb, depth, seg,
                                                      env_begin, env_count);
     }
     ctx->launches++;
