@@ -7,14 +7,15 @@
 // Pipeline per env (all fp32, same operation order as TinyRenderer's vec/mat templates, no FMA contraction):
 //   k_render_setup : one thread per (env, shape): model / projection*view*model / inverse-transpose matrices and a
 //                    conservative screen-row range of the shape.
-//   k_raster       : one CTA per (env, strip of STRIP_ROWS raster rows).  A 64-bit key per pixel lives in shared
-//                    memory: (order-preserving depth bits << 32) | (triangle index + 1).  Threads walk the triangles
-//                    of the shapes that can touch the strip, set them up (vertex shader, back-face cull, near-plane
-//                    clip, viewport, bounding box) and atomicMax the key of every covered pixel — the z-test
-//                    "later triangle wins ties" of the sequential renderer is exactly max over (depth, index).
-//                    Large triangles are deferred to a queue and rasterised by the whole CTA.  After a barrier the
-//                    CTA resolves: one fragment-shader evaluation per pixel for the winning triangle, then
-//                    coalesced 12/16/16-byte stores of RGB, depth and mask rows (vertical flip folded in).
+//   k_raster       : persistent CTAs pull envs from a global counter.  Geometry runs once per env (conservative
+//                    model-space back-face pre-test, then vertex shader / exact cull / near-plane clip / viewport /
+//                    set-up for the survivors) and leaves 80-byte records plus per-strip work lists in an L2-resident
+//                    scratch.  The image is then produced in strips of STRIP_ROWS raster rows: a 64-bit key per pixel
+//                    in shared memory = (order-preserving depth bits << 32) | (triangle + 1) << 15 | record, and
+//                    atomicMax of the key of every covered pixel — the z-test "later triangle wins ties" of the
+//                    sequential renderer is exactly max over (depth, index).  After a barrier the winners are shaded
+//                    (one fragment-shader evaluation per pixel) and RGB / depth / mask rows leave in packed
+//                    12/16/16-byte streaming stores (vertical flip folded in).
 // Images are written once; meshes (1.7 MB) and textures (10 MB) are shared by all envs and stay L2 resident.
 #include "rr_ctx.h"
 #include <cfloat>
@@ -40,9 +41,6 @@ __constant__ float c_cull_hmax;      // largest 'smallest altitude' over all tri
 //           // in-strip bounding-box pixels up to which a triangle is rasterised by its own lane
 #ifndef PRECULL_AREA
 #define PRECULL_AREA 4           // bounding boxes up to this many pixels are coverage-tested in the geometry phase
-#endif
-#ifndef HUGE_FIRST
-#define HUGE_FIRST 1
 #endif
 #ifndef HUGE_GROUP
 #define HUGE_GROUP 256         // threads that share one huge triangle
@@ -491,7 +489,7 @@ __device__ __forceinline__ int agg_inc(int* ctr) {      // warp-aggregated atomi
     return base + __popc(m & ((1u << lane) - 1u));
 }
 
-__device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist, int* nbig,
+__device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist,
                                             const Screen& S, const float* z, unsigned int gt, unsigned int flags) {
     if (!S.any) return;
     Edge E; edge_setup(S, E);
@@ -529,27 +527,30 @@ __device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned sho
     const int s0 = S.y0 / STRIP_ROWS, s1 = S.y1 / STRIP_ROWS;
     const int bw = S.x1 - S.x0 + 1;
     for (int st = s0; st <= s1; st++) {
-        // a strip's list grows upwards from entry 0; its huge triangles (shared by the whole CTA) grow downwards from the end
+        // per strip three work lists by in-strip bounding-box size: small (own lane) grows upwards from entry 0 of the
+        // strip's first array, huge (shared by HUGE_GROUP threads) downwards from its end; medium (one warp) fills the second
         const int ya = max(S.y0, st * STRIP_ROWS), yb = min(S.y1, st * STRIP_ROWS + STRIP_ROWS - 1);
-        const int big = (bw * (yb - ya + 1) > HUGE_AREA) ? 1 : 0;
-        STAT(big ? 5 : (bw * (yb - ya + 1) > SMALL_AREA ? 4 : 3), 1);
+        const int area = bw * (yb - ya + 1);
+        const int cls = area > HUGE_AREA ? 2 : (area > SMALL_AREA ? 1 : 0);
+        STAT(3 + cls, 1);
         // lanes of the warp may be appending to different counters: aggregate per counter
-        const unsigned grp = __match_any_sync(__activemask(), st * 2 + big);
+        const unsigned grp = __match_any_sync(__activemask(), st * 4 + cls);
         const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
         int base = 0;
-        if (lane == leader) base = atomicAdd(big ? &nbig[st] : &nlist[st], __popc(grp));
+        if (lane == leader) base = atomicAdd(&nlist[cls * NSTRIPS + st], __popc(grp));
         base = __shfl_sync(grp, base, leader);
         const int pos = base + __popc(grp & ((1u << lane) - 1u));
-        lists[(size_t)st * REC_MAX + (big ? REC_MAX - 1 - pos : pos)] = (unsigned short)slot;
+        unsigned short* l = lists + (size_t)st * 2 * REC_MAX;
+        l[cls == 0 ? pos : (cls == 2 ? REC_MAX - 1 - pos : REC_MAX + pos)] = (unsigned short)slot;
     }
 }
 
-__device__ __noinline__ void emit_clipped(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist, int* nbig, const Tri& T, unsigned int gt) {
+__device__ __noinline__ void emit_clipped(Rec* __restrict__ recs, unsigned short* __restrict__ lists, int* nrec, int* nlist, const Tri& T, unsigned int gt) {
     float out[3][4][3];
     const int nc = clip_near(T.c, out);
     for (int c = 0; c < nc; c++) {
         Screen S; screen_setup(out[c], S);
-        emit_record(recs, lists, nrec, nlist, nbig, S, out[c][2], gt, REC_CLIPPED);
+        emit_record(recs, lists, nrec, nlist, S, out[c][2], gt, REC_CLIPPED);
     }
 }
 
@@ -650,13 +651,17 @@ __device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M,
 }
 
 // Persistent kernel: each CTA takes envs from a global work counter.  Per env:
-//   geometry : one triangle per thread — vertex shader, back-face cull, near-plane clip, viewport, bounding box, edge and
-//              reciprocal set-up; survivors become 80-byte records in the CTA's private scratch (rewritten every env, so
-//              it stays in L2) and their indices are appended to the list of every strip their bounding box touches;
-//   per strip of STRIP_ROWS raster rows: clear the 64-bit key buffer in shared memory; warps pull 32-record chunks of the
-//              strip's list and rasterise them (small boxes: own lane; medium: whole warp; huge: whole CTA) with atomicMax
-//              on (depth bits, triangle index); resolve A: one fragment shader per covered pixel (lane per pixel),
-//              resolve B: pack and write RGB / depth / mask rows with 12/16/16-byte stores.
+//   geometry pass 1: one triangle per thread, model-space plane test against the camera: clearly back-facing triangles are
+//              dropped, the rest compacted into a survivor list (bit 15 marks "too close to call");
+//   geometry pass 2: survivors only — vertex shader, exact fp64 back-face test where pass 1 could not decide, near-plane
+//              clip, viewport, bounding box, edge and reciprocal set-up, coverage pre-test of tiny boxes; what is left
+//              becomes 80-byte records in the CTA's private scratch and is appended, per strip its box touches, to one
+//              of three work lists by in-strip box size (small / medium / huge);
+//   per strip (2 barriers): raster — huge records by groups of HUGE_GROUP threads, then medium records one per warp, then
+//              small records one per lane in 32-record chunks, all self-scheduled through shared counters so that the
+//              coarse items are handed out first; atomicMax on (depth bits, triangle index) with a depth-bound
+//              rejection against the current key.  resolve — warps pull groups of 128 pixels: fragment shader for the
+//              winners (lane per pixel), then packed row stores; the keys are cleared on the way out.
 __global__ void __launch_bounds__(RTHREADS, RBLOCKS)
 k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const float4* __restrict__ planes, int n_tris,
          const uint8_t* __restrict__ texdata, const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch,
@@ -665,10 +670,10 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* M = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);
-    __shared__ int s_env, s_nrec, s_ncull, s_chunk, s_nlist[NSTRIPS], s_nbig[NSTRIPS];
+    __shared__ int s_env, s_nrec, s_ncull, s_chunk, s_medc, s_rgrp, s_nlist[3 * NSTRIPS];   // s_nlist[class][strip]
     const int tid = threadIdx.x, lane = tid & 31;
     Rec* recs = rec_scratch + (size_t)blockIdx.x * REC_MAX;
-    unsigned short* lists = list_scratch + (size_t)blockIdx.x * NSTRIPS * REC_MAX;
+    unsigned short* lists = list_scratch + (size_t)blockIdx.x * NSTRIPS * 2 * REC_MAX;
     unsigned short* cull = cull_scratch + (size_t)blockIdx.x * CULL_MAX;
     const float nearP = c_render.depthNear, farP = c_render.depthFar;
     const float bg_depth = (float)((double)(farP * (nearP + 1e30f)) / (2. * (double)farP * (double)nearP + (double)(farP * 1e30f) - (double)(nearP * 1e30f)));
@@ -677,8 +682,8 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_env = atomicAdd(work_counter, 1); s_nrec = 0; s_ncull = 0; s_chunk = 0; }
-        if (tid < NSTRIPS) { s_nlist[tid] = 0; s_nbig[tid] = 0; }
+        if (tid == 0) { s_env = atomicAdd(work_counter, 1); s_nrec = 0; s_ncull = 0; s_chunk = 0; s_medc = 0; s_rgrp = 0; }
+        if (tid < 3 * NSTRIPS) s_nlist[tid] = 0;
         __syncthreads();
         if (s_env >= N) break;
         const int e = env_begin + s_env;
@@ -743,76 +748,70 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 }
                 STAT(1, 1);
                 const bool front = (T.c[3][0] >= 0 && T.c[3][1] >= 0 && T.c[3][2] >= 0);
-                if (front) { Screen S; screen_setup(T.c, S); emit_record(recs, lists, &s_nrec, s_nlist, s_nbig, S, T.c[2], gt, 0u); }
-                else if (!(T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0)) emit_clipped(recs, lists, &s_nrec, s_nlist, s_nbig, T, gt);
+                if (front) { Screen S; screen_setup(T.c, S); emit_record(recs, lists, &s_nrec, s_nlist, S, T.c[2], gt, 0u); }
+                else if (!(T.c[3][0] < 0 && T.c[3][1] < 0 && T.c[3][2] < 0)) emit_clipped(recs, lists, &s_nrec, s_nlist, T, gt);
             }
         }
         __threadfence_block();
         __syncthreads();
-        // ---- strips (three barriers each: raster | shade | store + clear)
+        // ---- strips (two barriers each: raster | shade + store + clear), both phases self-scheduled
         for (int strip = 0; strip < NSTRIPS; strip++) {
             const int row0 = strip * STRIP_ROWS;
-            const int nlist = min(s_nlist[strip], REC_MAX), nbig = min(s_nbig[strip], REC_MAX);
-            const unsigned short* list = lists + (size_t)strip * REC_MAX;
-#if HUGE_FIRST
-            // ---- huge triangles: every thread takes pixels tid, tid + HUGE_GROUP, ... of the records of its group
+            const int nsmall = min(s_nlist[strip], REC_MAX), nmed = min(s_nlist[NSTRIPS + strip], REC_MAX), nbig = min(s_nlist[2 * NSTRIPS + strip], REC_MAX);
+            const unsigned short* list = lists + (size_t)strip * 2 * REC_MAX;
+            if (tid == 0) s_rgrp = 0;
+            // ---- huge triangles first (mostly the table): groups of HUGE_GROUP threads share a record
             for (int b = tid / HUGE_GROUP; b < nbig; b += RTHREADS / HUGE_GROUP) {
-                const Rec br = load_rec(recs + list[REC_MAX - 1 - b]);
+                const unsigned int ridx = list[REC_MAX - 1 - b];
+                const Rec br = load_rec(recs + ridx);
                 Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
                 raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, tid % HUGE_GROUP, HUGE_GROUP);
             }
-#endif
-            // ---- small and medium triangles: warps pull 32-record chunks of the strip's list
+            // ---- medium triangles: one record per warp at a time (the coarse items go before the fine ones)
+            for (;;) {
+                int mi = 0;
+                if (lane == 0) mi = atomicAdd(&s_medc, 1);
+                mi = __shfl_sync(0xffffffffu, mi, 0);
+                if (mi >= nmed) break;
+                const unsigned int ridx = list[REC_MAX + mi];
+                const Rec br = load_rec(recs + ridx);
+                Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
+                raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, lane, 32);
+            }
+            // ---- small triangles: warps pull 32-record chunks, one record per lane
             for (;;) {
                 int rb = 0;
                 if (lane == 0) rb = atomicAdd(&s_chunk, 32);
                 rb = __shfl_sync(0xffffffffu, rb, 0);
-                if (rb >= nlist) break;
-                int state = 0, ridx = 0;                 // 0 nothing, 1 own lane, 2 warp-cooperative
-                Rec rec;
-                if (rb + lane < nlist) {
-                    ridx = list[rb + lane];
-                    rec = load_rec(recs + ridx);
-                    const int y0 = rec.by & 0xffff, y1 = rec.by >> 16, x0 = rec.bx & 0xffff, x1 = rec.bx >> 16;
-                    const int ya = max(y0, row0), yb = min(y1, row0 + STRIP_ROWS - 1);
-                    const int area = (x1 - x0 + 1) * (yb - ya + 1);
-                    state = area <= SMALL_AREA ? 1 : 2;
-                }
-                unsigned med = __ballot_sync(0xffffffffu, state == 2);
-                while (med) {
-                    const int src = __ffs(med) - 1; med &= med - 1;
-                    const int bi = __shfl_sync(0xffffffffu, ridx, src);
-                    const Rec br = load_rec(recs + bi);
-                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
-                    raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, lane, 32);
-                }
-                if (state == 1) {
+                if (rb >= nsmall) break;
+                if (rb + lane < nsmall) {
+                    const Rec rec = load_rec(recs + list[rb + lane]);
                     Screen S; Edge E; Recip R; float cz[3]; rec_unpack(rec, S, E, R, cz);
                     raster_pixels(keys, S, E, R, cz, rec.keylo, !(rec.flags & REC_CLIPPED), row0, 0, 1);
                 }
             }
-#if !HUGE_FIRST
-            // ---- huge triangles last (they are mostly the table: the depth bound then rejects what the robot already covers)
-            for (int b = tid / HUGE_GROUP; b < nbig; b += RTHREADS / HUGE_GROUP) {
-                const Rec br = load_rec(recs + list[REC_MAX - 1 - b]);
-                Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
-                raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, tid % HUGE_GROUP, HUGE_GROUP);
-            }
-#endif
             __syncthreads();
-            if (tid == 0) s_chunk = 0;
-            // ---- resolve A: lane per pixel; the winner's colour replaces the low key word: 1 << 31 | shape << 24 | rgb
-            for (int p = tid; p < STRIP_ROWS * RR_W; p += RTHREADS) {
-                const unsigned long long key = keys[p];
-                if (key == 0ull) continue;
-                const int r = p / RR_W, x = p - r * RR_W;
-                int s;
-                const unsigned int col = shade_pixel(M, tris, tri_shape, texdata, recs, (unsigned int)(key & 0xffffffffu), x, row0 + r, s);
-                keys[p] = (key & 0xffffffff00000000ull) | 0x80000000ull | ((unsigned long long)s << 24) | (unsigned long long)(col & 0xffffffu);
-            }
-            __syncthreads();
-            // ---- resolve B: 4 consecutive pixels per thread-iteration, vector stores, vertical flip folded in; clears the keys
-            for (int i = tid; i < STRIP_ROWS * RR_W / 4; i += RTHREADS) {
+            if (tid == 0) { s_chunk = 0; s_medc = 0; }
+            // ---- resolve: warps pull groups of 128 consecutive pixels.  A: lane per pixel (4 rounds), the winner's colour
+            // replaces the low key word (1 << 31 | shape << 24 | rgb); B: 4 consecutive pixels per lane, packed 12/16/16-byte
+            // stores with the vertical flip folded in, and the keys are cleared for the next strip.
+            for (;;) {
+                int g = 0;
+                if (lane == 0) g = atomicAdd(&s_rgrp, 1);
+                g = __shfl_sync(0xffffffffu, g, 0);
+                if (g >= STRIP_ROWS * RR_W / 128) break;
+#pragma unroll 1
+                for (int j = 0; j < 4; j++) {
+                    const int p = g * 128 + j * 32 + lane;
+                    const unsigned long long key = keys[p];
+                    if (key == 0ull) continue;
+                    const int r = p / RR_W, x = p - r * RR_W;
+                    int s;
+                    const unsigned int col = shade_pixel(M, tris, tri_shape, texdata, recs, (unsigned int)(key & 0xffffffffu), x, row0 + r, s);
+                    keys[p] = (key & 0xffffffff00000000ull) | 0x80000000ull | ((unsigned long long)s << 24) | (unsigned long long)(col & 0xffffffu);
+                }
+                __syncwarp();
+                const int i = g * 32 + lane;
                 const int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
                 unsigned int col[4]; float dep[4]; int sg[4];
                 ulonglong2* kp = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
@@ -898,7 +897,7 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
         if (ctx->raster_grid > ctx->N) ctx->raster_grid = ctx->N;
         CK(cudaMalloc(&ctx->d_rec_scratch, (size_t)ctx->raster_grid * REC_MAX * sizeof(Rec)));
         CK(cudaMalloc(&ctx->d_work_counter, sizeof(int)));
-        CK(cudaMalloc(&ctx->d_list_scratch, (size_t)ctx->raster_grid * NSTRIPS * REC_MAX * sizeof(unsigned short)));
+        CK(cudaMalloc(&ctx->d_list_scratch, (size_t)ctx->raster_grid * NSTRIPS * 2 * REC_MAX * sizeof(unsigned short)));
         std::vector<uint8_t> ts(ctx->n_tris);
         for (int sidx = 0; sidx < RR_NSHAPES; sidx++)
             for (int t = 0; t < ctx->render.shape[sidx].tri_count; t++) ts[ctx->render.shape[sidx].tri_start + t] = (uint8_t)sidx;
