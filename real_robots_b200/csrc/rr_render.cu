@@ -414,7 +414,12 @@ __device__ __forceinline__ void raster_pixels(unsigned long long* keys, const Sc
     const int ya = max(S.y0, row0), yb = min(S.y1, row0 + STRIP_ROWS - 1);
     if (ya > yb) return;
     const int wdt = S.x1 - S.x0 + 1, n = wdt * (yb - ya + 1);
-    const int sy = start / wdt, dy = stride / wdt;
+    int sy = 0, dy = 0;
+    if (stride != 1) {
+        // (k + 0.5) / wdt is at least 0.5 / 320 away from an integer, so the float quotient truncates to the exact k / wdt
+        const float rw = __frcp_rn((float)wdt);
+        sy = (int)(((float)start + 0.5f) * rw); dy = (int)(((float)stride + 0.5f) * rw);
+    } else dy = (wdt == 1) ? 1 : 0;
     int x = S.x0 + (start - sy * wdt), y = ya + sy;
     const int dx = stride - dy * wdt;
     const unsigned int zb = depth_bound_bits(R, clipz);
