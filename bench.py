@@ -254,7 +254,8 @@ def run_ours(args):
                          "frac": achieved / peak if peak else None, "traffic": (args.traffic * args.envs / 4096 if args.traffic else None),
                          "algorithmic_bytes": args.envs * IMG_BYTES, "peak_source": peak_src,
                          "ms_per_launch": raster_ms, "launches": r_n,
-                         "physics_kernel": {"kernel": "k_step", "ms_per_launch": s_ms / max(s_n, 1),
+                         "kernels_ms_per_step": {k: (v[0] / max(v[1], 1)) for k, v in prof.items()},
+                         "physics_kernel": {"kernel": "k_step_dyn + k_step_solve", "ms_per_launch": s_ms / max(s_n, 1),
                                             "achieved_gbs": args.envs * STATE_BYTES / (s_ms / max(s_n, 1) * 1e-3) / 1e9 if s_ms > 0 else None}},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "gpu_launches": launches,

@@ -13,6 +13,7 @@
 #define RR_H RR_EYE_H
 #define RR_FRAME_STRIDE (RR_NSHAPES * 12)
 #define RR_MAX_TEX 16
+#define RR_HANDOFF_DOUBLES 576   // >= the persistent head of WarpMem (static_assert in rr_physics.cu)
 #define RR_MAT_STRIDE 44       // floats per (env, shape) in render_mats
 #define RR_MAX_PAIRS 96          // candidate collision pairs (92 for 3 objects)
 #define RR_MAX_MANIFOLDS 24      // cached manifolds per env (<= 32: one lane per slot)
@@ -69,6 +70,7 @@ struct DevState {
     int*    man_hdr[2];   // [N][RR_MAX_MANIFOLDS][2]  (pair index or -1, point count), double buffered
     double* man_pts[2];   // [N][RR_MAX_MANIFOLDS][4][RR_PT_STRIDE]
     double* rows;         // [N][3*RR_MAX_CONTACTS][RR_ROW_STRIDE] solver row scratch
+    double* handoff;      // [N][RR_HANDOFF_DOUBLES] per-env solver state passed from k_step_dyn to k_step_solve
 };
 
 struct rr_ctx {

@@ -11,17 +11,36 @@
 // pybullet's double-precision build.  Global state is structure-of-arrays [field][env] so the warps of a block
 // touch consecutive addresses.  No tensor cores: nothing here is a dense contraction.
 #include "rr_ctx.h"
+#include <cstddef>
 
 __constant__ RobotConst c_robot;
 
 #define WPB 4                 // envs (warps) per block
+#ifndef SOLVE_MIN_BLOCKS
+#define SOLVE_MIN_BLOCKS 6
+#endif
 #define FULL 0xffffffffu
 
 struct WarpMem {
+    // ---- solver state: produced by k_step_dyn, handed to k_step_solve through DevState::handoff (PERSIST_DOUBLES doubles)
+    double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
+    double Minv[RR_NDOF][RR_NDOF];
+    // non-contact rows (limits then motors)
+    double r_rhs[32], r_inv[32], r_rinv[32], r_lo[32], r_hi[32], r_app[32], r_sign[32];
+    double app[3 * RR_MAX_CONTACTS];                    // applied impulses: normals [0,MAXC), friction pairs after
+    double objreg[RR_MAX_OBJECTS][13];                  // free bodies after the unconstrained update (pos3 quat4 lin3 ang3)
+    int r_dof[32];
+    int n_rows;
+    int ocnt[RR_MAX_OBJECTS];
+    int simple;                                         // every contact is object-vs-static: objects solve independently
+    int nc, overflow, pad_;
+    unsigned char olist[RR_MAX_OBJECTS][RR_MAX_CONTACTS];   // per object: its contact indices, in solver order
+    // ---- kinematics workspace (both kernels, not handed over)
     double Rpc[RR_NL][9];     // parent -> link rotation
     double rvec[RR_NL][3];    // parent COM -> link COM, link frame
     double Rw[RR_NL][9];      // world_from_link
     double pw[RR_NL][3];      // link COM, world
+    // ---- dynamics workspace (k_step_dyn only)
     double v[RR_NL][6];       // spatial velocity (ang, lin) in link frame
     double c[RR_NL][6];       // Coriolis acceleration
     double p[RR_NL][6];       // zero-acceleration force
@@ -31,21 +50,16 @@ struct WarpMem {
     double Y[RR_NL];
     double acc[RR_NL][6];
     double X[36], T[36], Ia[36], pa[6], Ic[6];
-    double Minv[RR_NDOF][RR_NDOF];
-    double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF], tau[RR_NDOF], qdd[RR_NDOF];
-    // non-contact rows (limits then motors)
-    double r_rhs[32], r_inv[32], r_rinv[32], r_lo[32], r_hi[32], r_app[32], r_sign[32];
-    int r_dof[32];
-    int n_rows;
-    // contacts
+    double tau[RR_NDOF], qdd[RR_NDOF];
     double dof_axis[RR_NDOF][3], dof_piv[RR_NDOF][3];   // world joint axis / pivot per dof
     double opos[RR_MAX_OBJECTS][3], ovel[RR_MAX_OBJECTS][6], oIinv[RR_MAX_OBJECTS][9], oinvm[RR_MAX_OBJECTS];
     double Jtmp[32];
-    double app[3 * RR_MAX_CONTACTS];                    // applied impulses: normals [0,MAXC), friction pairs after
-    unsigned char olist[RR_MAX_OBJECTS][RR_MAX_CONTACTS];   // per object: its contact indices, in solver order
-    int ocnt[RR_MAX_OBJECTS];
-    int simple;                                         // every contact is object-vs-static: objects solve independently
 };
+#define PERSIST_BYTES (offsetof(WarpMem, Rpc))
+#define PERSIST_DOUBLES (PERSIST_BYTES / 8)
+#define SOLVE_SMEM_BYTES (offsetof(WarpMem, v))       // k_step_solve and k_fk carry only the head of the struct
+static_assert(PERSIST_BYTES % 8 == 0 && PERSIST_DOUBLES <= RR_HANDOFF_DOUBLES, "handoff buffer too small");
+static_assert(offsetof(WarpMem, Rpc) % 8 == 0 && offsetof(WarpMem, v) % 8 == 0, "WarpMem alignment");
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
@@ -416,7 +430,11 @@ __device__ __forceinline__ void store_frames(const WarpMem& m, const DevState& s
     }
 }
 
-__global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __restrict__ cmd, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
+// One env step is two kernels.  k_step_dyn: action prologue, kinematics, ABA, M^-1, constraint rows -> DevState::handoff
+// and the global row scratch.  k_step_solve: PGS, integration, final kinematics, observations.  The solver is a chain
+// of dependent fp64 operations whose only remedy is more resident warps; it needs a third of the dynamics' shared memory,
+// so on its own it runs at more than twice the occupancy.
+__global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double* __restrict__ cmd, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpMem& m = reinterpret_cast<WarpMem*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -639,6 +657,48 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
         }
     }
     __syncwarp();
+    // ---- hand over to k_step_solve
+    if (has_obj) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { m.objreg[lane][k] = ob.pos[k]; m.objreg[lane][7 + k] = ob.lin[k]; m.objreg[lane][10 + k] = ob.ang[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) m.objreg[lane][3 + k] = ob.quat[k];
+    }
+    if (lane == 0) { m.nc = nc; m.overflow = overflow; }
+    __syncwarp();
+    {
+        const double* src = reinterpret_cast<const double*>(&m);
+        double* dst = st.handoff + (size_t)e * RR_HANDOFF_DOUBLES;
+        for (int k = lane; k < (int)PERSIST_DOUBLES; k += 32) dst[k] = src[k];
+    }
+}
+
+__global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpMem& m = *reinterpret_cast<WarpMem*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (e >= st.N) return;
+    const int N = st.N;
+    const double dt = cf.dt;
+    {
+        double* dst = reinterpret_cast<double*>(&m);
+        const double* src = st.handoff + (size_t)e * RR_HANDOFF_DOUBLES;
+        for (int k = lane; k < (int)PERSIST_DOUBLES; k += 32) dst[k] = src[k];
+    }
+    __syncwarp();
+    ObjReg ob;
+    const bool has_obj = lane < n_objects;
+    if (has_obj) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ob.pos[k] = m.objreg[lane][k]; ob.lin[k] = m.objreg[lane][7 + k]; ob.ang[k] = m.objreg[lane][10 + k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) ob.quat[k] = m.objreg[lane][3 + k];
+    }
+    const int nc = m.nc, overflow = m.overflow;
+    int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
+    double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
+    double* rows = st.rows + (size_t)e * 3 * RR_MAX_CONTACTS * RR_ROW_STRIDE;
     // ---- projected Gauss-Seidel.  dv in owner layout: lane k < 11 owns the arm dof k, lane 11+6o+c the object component.
     double dv = 0.0;
     int iters = 0; double res = 0.0;
@@ -834,7 +894,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step(DevState st, const double* __
 // FK only (after reset / set_state): refresh link_frames
 __global__ void __launch_bounds__(WPB * 32) k_fk(DevState st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpMem& m = reinterpret_cast<WarpMem*>(smem_raw)[threadIdx.x >> 5];
+    WarpMem& m = *reinterpret_cast<WarpMem*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (e >= st.N) return;
@@ -979,14 +1039,15 @@ __global__ void k_shape_frames(DevState st, double* __restrict__ frames, int n_o
 
 int rrk_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_robot, &ctx->robot, sizeof(RobotConst)));
-    CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
-    CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
+    CK(cudaFuncSetAttribute(k_step_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
+    CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * WPB)));
+    CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * WPB)));
     return 0;
 }
 static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 
 static int launch_fk(rr_ctx* ctx, cudaStream_t s) {
-    k_fk<<<nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s>>>(ctx->st);
+    k_fk<<<nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s>>>(ctx->st);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1031,8 +1092,9 @@ int rrk_get_state(rr_ctx* ctx, double* q, double* qd, double* obj, cudaStream_t 
 int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
     if (ctx->cfg.enable_contacts && rrk_collide(ctx, s) != 0) return -1;
     ProfScope ps(ctx, 0, s);
-    k_step<<<nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s>>>(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
-    ctx->launches++;
+    k_step_dyn<<<nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s>>>(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
+    k_step_solve<<<nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s>>>(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
+    ctx->launches += 2;
     CK(cudaGetLastError());
     return 0;
 }

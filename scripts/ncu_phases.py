@@ -34,7 +34,10 @@ src = open(srcfile).read().splitlines()
 label, fn = {}, "?"
 for i, text in enumerate(src, 1):
     m = re.match(r"^(?:template.*>\s*)?(?:static\s+)?(?:__device__|__global__)[^(]*?(\w+)\s*\(", text)
-    if m:
+    mk = re.search(r"\b(k_\w+)\s*\(", text) if text.startswith("__global__") else None
+    if mk:
+        fn = mk.group(1)
+    elif m:
         fn = m.group(1)
     elif re.match(r"^k_\w+\(", text):
         fn = text.split("(")[0]
