@@ -56,6 +56,9 @@ struct ColMem {
     int eh[2 * EPA_MAXF][2];
     // manifold staging
     double pt[4][RR_PT_STRIDE];
+    // GJK simplex (w, a, b per vertex) and its barycentric weights: indexed dynamically, so it lives here rather than in
+    // per-thread local memory; every lane holds and writes identical values
+    double gs[4][9], glam[4];
 };
 
 // cooperative support vertex: first maximum of v . (R^T d) in vertex order
@@ -128,43 +131,58 @@ __device__ bool closest_tetra(const V3* p, double* lam, int* mask) {
     return outside_any;
 }
 
-struct GjkResult { int status; double dist; V3 n, pa, pb; SupPt simplex[4]; int ns; };
+struct GjkResult { int status; double dist; V3 n, pa, pb; int ns; };      // the simplex itself stays in ColMem::gs
 
-__device__ void gjk(const Hull& A, const Hull& B, GjkResult& r, int lane) {
+__device__ __forceinline__ V3 gs_w(const ColMem& m, int k) { return mk(m.gs[k][0], m.gs[k][1], m.gs[k][2]); }
+__device__ __forceinline__ V3 gs_a(const ColMem& m, int k) { return mk(m.gs[k][3], m.gs[k][4], m.gs[k][5]); }
+__device__ __forceinline__ V3 gs_b(const ColMem& m, int k) { return mk(m.gs[k][6], m.gs[k][7], m.gs[k][8]); }
+__device__ __forceinline__ void gs_store(ColMem& m, int k, const SupPt& s) {
+    m.gs[k][0] = s.w.x; m.gs[k][1] = s.w.y; m.gs[k][2] = s.w.z; m.gs[k][3] = s.a.x; m.gs[k][4] = s.a.y; m.gs[k][5] = s.a.z;
+    m.gs[k][6] = s.b.x; m.gs[k][7] = s.b.y; m.gs[k][8] = s.b.z;
+}
+
+__device__ void gjk(const Hull& A, const Hull& B, ColMem& m, GjkResult& r, int lane) {
     r.status = 0; r.ns = 0; r.dist = 0;
     V3 v = A.p - B.p;
     if (dot(v, v) < 1e-12) v = mk(1, 0, 0);
-    SupPt S[4]; int ns = 0;
-    double lam[4] = {0, 0, 0, 0};
+    int ns = 0;
+    double* lam = m.glam;
+    __syncwarp();
     for (int it = 0; it < 64; it++) {
         SupPt w = support(A, B, -v, lane);
         double vv = dot(v, v);
         if (ns > 0 && vv - dot(v, w.w) <= 1e-10 * vv) break;
         bool dup = false;
-        for (int k = 0; k < ns; k++) { V3 d = S[k].w - w.w; if (dot(d, d) < 1e-24) dup = true; }
+        for (int k = 0; k < ns; k++) { V3 d = gs_w(m, k) - w.w; if (dot(d, d) < 1e-24) dup = true; }
         if (dup) break;
-        S[ns++] = w;
+        gs_store(m, ns, w); ns++;
         int mask = 0;
         if (ns == 1) { lam[0] = 1; mask = 1; }
-        else if (ns == 2) closest_segment(S[0].w, S[1].w, lam, &mask);
-        else if (ns == 3) closest_triangle(S[0].w, S[1].w, S[2].w, lam, &mask);
+        else if (ns == 2) closest_segment(gs_w(m, 0), gs_w(m, 1), lam, &mask);
+        else if (ns == 3) closest_triangle(gs_w(m, 0), gs_w(m, 1), gs_w(m, 2), lam, &mask);
         else {
-            V3 P[4] = {S[0].w, S[1].w, S[2].w, S[3].w};
-            if (!closest_tetra(P, lam, &mask)) { r.status = 1; r.ns = 4; for (int k = 0; k < 4; k++) r.simplex[k] = S[k]; return; }
+            V3 P[4] = {gs_w(m, 0), gs_w(m, 1), gs_w(m, 2), gs_w(m, 3)};
+            if (!closest_tetra(P, lam, &mask)) { r.status = 1; r.ns = 4; return; }
         }
-        SupPt T[4]; double tl[4]; int nt = 0;
-        for (int k = 0; k < ns; k++) if (mask & (1 << k)) { T[nt] = S[k]; tl[nt] = lam[k]; nt++; }
+        int nt = 0;
+        for (int k = 0; k < ns; k++) if (mask & (1 << k)) {             // keep the vertices of the closest feature, in order
+            if (nt != k) {
+#pragma unroll
+                for (int c = 0; c < 9; c++) m.gs[nt][c] = m.gs[k][c];
+                lam[nt] = lam[k];
+            }
+            nt++;
+        }
         ns = nt;
         V3 nv = mk(0, 0, 0);
-        for (int k = 0; k < ns; k++) { S[k] = T[k]; lam[k] = tl[k]; nv = nv + S[k].w * lam[k]; }
+        for (int k = 0; k < ns; k++) nv = nv + gs_w(m, k) * lam[k];
         v = nv;
-        if (dot(v, v) < 1e-20) { r.status = 1; r.ns = ns; for (int k = 0; k < ns; k++) r.simplex[k] = S[k]; return; }
+        if (dot(v, v) < 1e-20) { r.status = 1; r.ns = ns; return; }
     }
     V3 pa = mk(0, 0, 0), pb = mk(0, 0, 0);
-    for (int k = 0; k < ns; k++) { pa = pa + S[k].a * lam[k]; pb = pb + S[k].b * lam[k]; }
+    for (int k = 0; k < ns; k++) { pa = pa + gs_a(m, k) * lam[k]; pb = pb + gs_b(m, k) * lam[k]; }
     double d = sqrt(dot(v, v));
     r.dist = d; r.n = v * (1.0 / d); r.pa = pa; r.pb = pb; r.ns = ns;
-    for (int k = 0; k < ns; k++) r.simplex[k] = S[k];
 }
 
 __device__ __forceinline__ double det3(V3 a, V3 b, V3 c) { return dot(a, cross(b, c)); }
@@ -272,13 +290,15 @@ __device__ bool epa(const Hull& A, const Hull& B, ColMem& m, SupPt* S, int ns, d
 }
 
 __device__ bool closest_points(const Hull& A, const Hull& B, ColMem& m, double& dist, V3& n, V3& pa, V3& pb, int lane) {
-    GjkResult g; gjk(A, B, g, lane);
+    GjkResult g; gjk(A, B, m, g, lane);
     if (g.status == 0) {
         if (!(g.dist > 0)) return false;
         dist = g.dist; n = g.n; pa = g.pa; pb = g.pb; return true;
     }
     double depth; V3 en, ea, eb;
-    if (!epa(A, B, m, g.simplex, g.ns, depth, en, ea, eb, lane)) return false;
+    SupPt S4[4];
+    for (int k = 0; k < 4; k++) { S4[k].w = gs_w(m, k); S4[k].a = gs_a(m, k); S4[k].b = gs_b(m, k); }
+    if (!epa(A, B, m, S4, g.ns, depth, en, ea, eb, lane)) return false;
     dist = -depth; n = -en; pa = ea; pb = eb;
     return true;
 }
@@ -306,7 +326,10 @@ __device__ int sort_cached_points(const ColMem& m, V3 pn, double pdist) {
     return mi;
 }
 
-__global__ void __launch_bounds__(CWPB * 32)
+#ifndef COLLIDE_MIN_BLOCKS
+#define COLLIDE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(CWPB * 32, COLLIDE_MIN_BLOCKS)
 k_collide(DevState st, const double* __restrict__ hull_verts, const int* __restrict__ man_hdr_in, const double* __restrict__ man_pts_in,
           int* __restrict__ man_hdr_out, double* __restrict__ man_pts_out, rr_config cf, int n_objects) {
     __shared__ ColMem smem[CWPB];
