@@ -31,6 +31,9 @@ struct CollideConst {
 };
 __constant__ CollideConst c_col;
 
+#ifndef HS_INLINE
+#define HS_INLINE __forceinline__
+#endif
 struct V3 { double x, y, z; };
 __device__ __forceinline__ V3 mk(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -62,17 +65,23 @@ struct ColMem {
 };
 
 // cooperative support vertex: first maximum of v . (R^T d) in vertex order
-__device__ __forceinline__ V3 hull_support(const Hull& h, V3 d, int lane) {
+__device__ HS_INLINE V3 hull_support(const Hull& h, V3 d, int lane) {
     V3 dl = mulRt(h.R, d);
     double best = -DBL_MAX; int idx = 0x7fffffff;
     for (int i = lane; i < h.n; i += 32) {
         double s = h.v[3 * i] * dl.x + h.v[3 * i + 1] * dl.y + h.v[3 * i + 2] * dl.z;
         if (s > best) { best = s; idx = i; }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        double ob = __shfl_xor_sync(FULL, best, off); int oi = __shfl_xor_sync(FULL, idx, off);
-        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    {   // warp arg-max with "lowest index wins ties": the value through an order-preserving 64-bit key and two 32-bit
+        // redux steps, then the lowest index among the lanes that hold the maximum (every lane's idx is already the
+        // first maximum of its own strided subset)
+        const long long bits = __double_as_longlong(best + 0.0);                       // -0 -> +0: equal values, equal keys
+        const unsigned long long key = bits < 0 ? ~(unsigned long long)bits : ((unsigned long long)bits | 0x8000000000000000ull);
+        const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)key;
+        const unsigned int mhi = __reduce_max_sync(FULL, hi);
+        const unsigned int mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+        const bool win = hi == mhi && lo == mlo;
+        idx = (int)__reduce_min_sync(FULL, win ? (unsigned int)idx : 0xffffffffu);
     }
     V3 vl = mk(h.v[3 * idx], h.v[3 * idx + 1], h.v[3 * idx + 2]);
     return mulR(h.R, vl) + h.p;
