@@ -117,11 +117,14 @@ def oracle_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_run(steps_per_worker, workers):
+def cpu_run(steps_per_worker, workers, pool=None):
     import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(workers) as pool:
-        times = pool.map(oracle_worker, [(1234 + w, steps_per_worker, 3) for w in range(workers)])
+    jobs = [(1234 + w, steps_per_worker, 3) for w in range(workers)]
+    if pool is None:
+        with mp.get_context("spawn").Pool(workers) as p:
+            times = p.map(oracle_worker, jobs, chunksize=1)
+    else:
+        times = pool.map(oracle_worker, jobs, chunksize=1)
     wall = max(times)
     return workers * steps_per_worker / wall, wall
 
@@ -136,13 +139,15 @@ def run_reference(args):
     orc.build()
     cores = os.cpu_count() or 1
     per_step = 25                       # env-steps per worker per bench "step" (bounded sample)
+    import multiprocessing as mp
     vals = []
-    for _ in range(args.warmup):
-        cpu_run(5, cores)
     t_all = 0.0
-    for _ in range(args.steps):
-        v, wall = cpu_run(per_step, cores)
-        vals.append(v); t_all += wall
+    with mp.get_context("spawn").Pool(cores) as pool:      # one worker process per host core, reused by every bench step
+        for _ in range(args.warmup):
+            cpu_run(5, cores, pool)
+        for _ in range(args.steps):
+            v, wall = cpu_run(per_step, cores, pool)
+            vals.append(v); t_all += wall
     value = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -276,14 +281,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--settle", type=int, default=60, help="untimed physics-only pre-roll steps before the warm-up")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
-    ap.add_argument("--traffic", type=float, default=5.52e9,
+    ap.add_argument("--traffic", type=float, default=5.69e9,
                     help="dram bytes (read + write) per 4096-env k_raster launch from the ncu capture in profiles/r01_ncu_full_summary.json")
     args = ap.parse_args()
     if args.impl == "reference":
