@@ -287,6 +287,11 @@ int rr_destroy(rr_ctx* ctx) {
                     ctx->d_tris, ctx->d_tex, ctx->d_hull_verts, ctx->d_rec_scratch, ctx->d_list_scratch, ctx->d_work_counter, ctx->d_tri_shape, ctx->d_planes, ctx->d_cull_scratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->host_compute) {
+        for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->host_ev[i]);
+        cudaStreamDestroy(ctx->host_compute); cudaStreamDestroy(ctx->host_copy);
+    }
+    for (int k = 0; k < RR_PROFILE_KINDS; k++) for (cudaEvent_t e : ctx->prof_ev[k]) cudaEventDestroy(e);
     delete ctx;
     return 0;
 }

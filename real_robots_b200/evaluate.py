@@ -32,8 +32,10 @@ class EvaluationService:
         self.setup_evaluation_state()
         self.setup_scores()
         self.video = video
-        if video:
-            raise NotImplementedError("video recording needs the reference's OpenGL debug camera (out of scope, DESIGN.md)")
+        self.videomaker = None
+        if video:                                                           # evaluate.py:69-71: video = (intrinsic, extrinsic, debug)
+            from .videomaker import VideoMaker
+            self.videomaker = VideoMaker(self.env, *video)
 
     def setup_gym_env(self, environment, action_type, n_objects):           # evaluate.py:148-177
         if environment in ["R1", "R2"]:
@@ -95,11 +97,17 @@ class EvaluationService:
             reward, done, steps = 0, False, 0
             self.evaluation_state["state"] = self.evaluation_state["intrinsic_phase_state"] = "INTRINSIC_PHASE_IN_PROGRESS"
             self.controller.start_intrinsic_phase()
+            if self.videomaker:
+                self.videomaker.start_intrinsic()
             while not done:
                 action = self.controller.step(observation, reward, done)
                 observation, reward, done, _ = self.env.step(action)
                 steps += 1
                 self.evaluation_state["current_intrinsic_timestep"] = steps
+                if self.videomaker:
+                    self.videomaker.update_intrinsic(steps)
+            if self.videomaker:
+                self.videomaker.end_intrinsic()
             self.evaluation_state["state"] = self.evaluation_state["intrinsic_phase_state"] = "INTRINSIC_PHASE_COMPLETE"
             self.controller.end_intrinsic_phase(observation, reward, done)
         else:
@@ -111,12 +119,18 @@ class EvaluationService:
         reward, done = 0, False
         observation = self.env.set_goal()
         self.controller.start_extrinsic_trial()
+        if self.videomaker:
+            self.videomaker.start_trial(observation, trial_number)
         steps = 0
         while not done:
             action = self.controller.step(observation, reward, done)
             observation, reward, done, _ = self.env.step(action)
             steps += 1
             self.evaluation_state["progress_in_current_extrinsic_trial"] = float(steps) / self.extrinsic_timesteps
+            if self.videomaker:
+                self.videomaker.extrinsic_trial(observation, action, steps, self.build_score_object() if self.scores else None)
+        if self.videomaker:
+            self.videomaker.end_trial()
         self.add_scores(*self.env.evaluateGoal())
         self.evaluation_state["num_extrinsic_trials_complete"] = trial_number + 1
         self.controller.end_extrinsic_trial(observation, reward, done)

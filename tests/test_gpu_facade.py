@@ -210,3 +210,37 @@ def test_goal_generation_roundtrip(tmp_path):
     ch, score = env.evaluateGoal()
     assert ch == '2D' and 0 < score < 0.3
     env.close()
+
+
+def test_videomaker_writes_frames(tmp_path, monkeypatch):
+    """VideoMaker (videomaker.py:11-190) filmed through rr_render_camera: files named like the reference's, one frame
+    every 8 simulation steps, robot visible from the video camera (distance 1, yaw 90, pitch -45, fov 90)."""
+    import cv2
+    from real_robots.videomaker import VideoMaker, Frames
+    monkeypatch.chdir(tmp_path)
+    env = real_robots.make('REALRobot2020-R1J1-v0')
+    env.intrinsic_timesteps, env.extrinsic_trials = 40, 1
+    obs = env.reset()
+    vm = VideoMaker(env, Frames([0, 40]), Frames(0), debug=True)
+    frame = vm.camera.render(env)
+    assert frame.shape == (240, 320, 3) and frame.dtype == np.uint8
+    assert (frame != 255).any(axis=2).mean() > 0.2            # table and robot fill a good part of the view
+    vm.start_intrinsic()
+    for t in range(1, 41):
+        obs, _, _, _ = env.step({'joint_command': np.zeros(9), 'render': t == 40})
+        vm.update_intrinsic(t)
+    vm.end_intrinsic()
+    vm.start_trial({'goal': obs['retina'], 'retina': obs['retina']}, 0)
+    for t in range(1, 17):
+        vm.extrinsic_trial(obs, None, t, {'score_total': 0.5, 'score_2D': 0.5, 'score_2.5D': 0, 'score_3D': 0})
+    vm.end_trial()
+    assert len(vm.files) == 2 and vm.files[0].endswith("-intrinsic.avi") and vm.files[1].endswith("-trial-0.avi")
+    counts = []
+    for f in vm.files:
+        cap = cv2.VideoCapture(f)
+        n = 0
+        while cap.read()[0]:
+            n += 1
+        counts.append(n)
+    assert counts == [5, 2]
+    env.close()
