@@ -59,9 +59,8 @@ struct ColMem {
     int eh[2 * EPA_MAXF][2];
     // manifold staging
     double pt[4][RR_PT_STRIDE];
-    // GJK simplex (w, a, b per vertex) and its barycentric weights: indexed dynamically, so it lives here rather than in
-    // per-thread local memory; every lane holds and writes identical values
-    double gs[4][9], glam[4];
+    // GJK simplex (w, a, b per vertex): indexed dynamically, so it lives here rather than in per-thread local memory
+    double gs[4][9];
 };
 
 // cooperative support vertex: first maximum of v . (R^T d) in vertex order
@@ -90,13 +89,13 @@ __device__ __forceinline__ SupPt support(const Hull& A, const Hull& B, V3 d, int
     SupPt s; s.a = hull_support(A, d, lane); s.b = hull_support(B, -d, lane); s.w = s.a - s.b; return s;
 }
 
-__device__ void closest_segment(V3 a, V3 b, double* lam, int* mask) {
+__device__ __forceinline__ void closest_segment(V3 a, V3 b, double* lam, int* mask) {
     V3 ab = b - a; double t = -dot(a, ab), den = dot(ab, ab);
     if (t <= 0 || den <= 0) { lam[0] = 1; lam[1] = 0; *mask = 1; return; }
     if (t >= den) { lam[0] = 0; lam[1] = 1; *mask = 2; return; }
     t /= den; lam[0] = 1 - t; lam[1] = t; *mask = 3;
 }
-__device__ void closest_triangle(V3 a, V3 b, V3 c, double* lam, int* mask) {
+__device__ __forceinline__ void closest_triangle(V3 a, V3 b, V3 c, double* lam, int* mask) {
     V3 ab = b - a, ac = c - a, ap = -a;
     double d1 = dot(ab, ap), d2 = dot(ac, ap);
     if (d1 <= 0 && d2 <= 0) { lam[0] = 1; lam[1] = lam[2] = 0; *mask = 1; return; }
@@ -114,12 +113,17 @@ __device__ void closest_triangle(V3 a, V3 b, V3 c, double* lam, int* mask) {
     double v = vb * denom, w = vc * denom;
     lam[0] = 1 - v - w; lam[1] = v; lam[2] = w; *mask = 7;
 }
-__device__ bool closest_tetra(const V3* p, double* lam, int* mask) {
+__device__ __forceinline__ void lam_set(double* lam, int idx, double v) {       // lam[idx] = v without dynamic register indexing
+#pragma unroll
+    for (int t = 0; t < 4; t++) if (t == idx) lam[t] = v;
+}
+__device__ bool closest_tetra(const double (*P)[9], double* lam, int* mask) {     // P: the simplex rows in shared memory (w first)
     const int F[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 3, 2}};
     const int O[4] = {3, 1, 2, 0};
     double best = DBL_MAX; bool outside_any = false;
     for (int f = 0; f < 4; f++) {
-        V3 a = p[F[f][0]], b = p[F[f][1]], c = p[F[f][2]], d = p[O[f]];
+        const int i0 = F[f][0], i1 = F[f][1], i2 = F[f][2], io = O[f];
+        V3 a = mk(P[i0][0], P[i0][1], P[i0][2]), b = mk(P[i1][0], P[i1][1], P[i1][2]), c = mk(P[i2][0], P[i2][1], P[i2][2]), d = mk(P[io][0], P[io][1], P[io][2]);
         V3 n = cross(b - a, c - a);
         double sp = dot(-a, n), sd = dot(d - a, n);
         bool outside = (sp * sd < 0) || (sd == 0);
@@ -131,10 +135,10 @@ __device__ bool closest_tetra(const V3* p, double* lam, int* mask) {
         double d2 = dot(q, q);
         if (d2 < best) {
             best = d2;
+#pragma unroll
             for (int k = 0; k < 4; k++) lam[k] = 0;
-            int mk_ = 0;
-            for (int k = 0; k < 3; k++) { lam[F[f][k]] = l3[k]; if (m3 & (1 << k)) mk_ |= 1 << F[f][k]; }
-            *mask = mk_;
+            lam_set(lam, i0, l3[0]); lam_set(lam, i1, l3[1]); lam_set(lam, i2, l3[2]);
+            *mask = ((m3 & 1) ? 1 << i0 : 0) | ((m3 & 2) ? 1 << i1 : 0) | ((m3 & 4) ? 1 << i2 : 0);
         }
     }
     return outside_any;
@@ -145,9 +149,14 @@ struct GjkResult { int status; double dist; V3 n, pa, pb; int ns; };      // the
 __device__ __forceinline__ V3 gs_w(const ColMem& m, int k) { return mk(m.gs[k][0], m.gs[k][1], m.gs[k][2]); }
 __device__ __forceinline__ V3 gs_a(const ColMem& m, int k) { return mk(m.gs[k][3], m.gs[k][4], m.gs[k][5]); }
 __device__ __forceinline__ V3 gs_b(const ColMem& m, int k) { return mk(m.gs[k][6], m.gs[k][7], m.gs[k][8]); }
-__device__ __forceinline__ void gs_store(ColMem& m, int k, const SupPt& s) {
-    m.gs[k][0] = s.w.x; m.gs[k][1] = s.w.y; m.gs[k][2] = s.w.z; m.gs[k][3] = s.a.x; m.gs[k][4] = s.a.y; m.gs[k][5] = s.a.z;
-    m.gs[k][6] = s.b.x; m.gs[k][7] = s.b.y; m.gs[k][8] = s.b.z;
+// the simplex is written by lane 0 only (every lane holds the same values) and read by all lanes after a __syncwarp
+__device__ __forceinline__ void gs_store(ColMem& m, int k, const SupPt& s, int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        m.gs[k][0] = s.w.x; m.gs[k][1] = s.w.y; m.gs[k][2] = s.w.z; m.gs[k][3] = s.a.x; m.gs[k][4] = s.a.y; m.gs[k][5] = s.a.z;
+        m.gs[k][6] = s.b.x; m.gs[k][7] = s.b.y; m.gs[k][8] = s.b.z;
+    }
+    __syncwarp();
 }
 
 __device__ void gjk(const Hull& A, const Hull& B, ColMem& m, GjkResult& r, int lane) {
@@ -155,8 +164,7 @@ __device__ void gjk(const Hull& A, const Hull& B, ColMem& m, GjkResult& r, int l
     V3 v = A.p - B.p;
     if (dot(v, v) < 1e-12) v = mk(1, 0, 0);
     int ns = 0;
-    double* lam = m.glam;
-    __syncwarp();
+    double lam[4] = {0, 0, 0, 0};                 // barycentric weights of the simplex vertices: registers, static indexing only
     for (int it = 0; it < 64; it++) {
         SupPt w = support(A, B, -v, lane);
         double vv = dot(v, v);
@@ -164,32 +172,35 @@ __device__ void gjk(const Hull& A, const Hull& B, ColMem& m, GjkResult& r, int l
         bool dup = false;
         for (int k = 0; k < ns; k++) { V3 d = gs_w(m, k) - w.w; if (dot(d, d) < 1e-24) dup = true; }
         if (dup) break;
-        gs_store(m, ns, w); ns++;
+        gs_store(m, ns, w, lane); ns++;
         int mask = 0;
         if (ns == 1) { lam[0] = 1; mask = 1; }
         else if (ns == 2) closest_segment(gs_w(m, 0), gs_w(m, 1), lam, &mask);
         else if (ns == 3) closest_triangle(gs_w(m, 0), gs_w(m, 1), gs_w(m, 2), lam, &mask);
-        else {
-            V3 P[4] = {gs_w(m, 0), gs_w(m, 1), gs_w(m, 2), gs_w(m, 3)};
-            if (!closest_tetra(P, lam, &mask)) { r.status = 1; r.ns = 4; return; }
-        }
+        else if (!closest_tetra(m.gs, lam, &mask)) { r.status = 1; r.ns = 4; return; }
+        // keep the vertices of the closest feature, in order
         int nt = 0;
-        for (int k = 0; k < ns; k++) if (mask & (1 << k)) {             // keep the vertices of the closest feature, in order
-            if (nt != k) {
+        double nl[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int c = 0; c < 9; c++) m.gs[nt][c] = m.gs[k][c];
-                lam[nt] = lam[k];
+        for (int k = 0; k < 4; k++) if (k < ns && (mask & (1 << k))) {
+            if (nt != k) {                          // warp-uniform
+                __syncwarp();
+                if (lane < 9) m.gs[nt][lane] = m.gs[k][lane];
+                __syncwarp();
             }
+            lam_set(nl, nt, lam[k]);
             nt++;
         }
         ns = nt;
         V3 nv = mk(0, 0, 0);
-        for (int k = 0; k < ns; k++) nv = nv + gs_w(m, k) * lam[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { lam[k] = nl[k]; if (k < ns) nv = nv + gs_w(m, k) * lam[k]; }
         v = nv;
         if (dot(v, v) < 1e-20) { r.status = 1; r.ns = ns; return; }
     }
     V3 pa = mk(0, 0, 0), pb = mk(0, 0, 0);
-    for (int k = 0; k < ns; k++) { pa = pa + gs_a(m, k) * lam[k]; pb = pb + gs_b(m, k) * lam[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (k < ns) { pa = pa + gs_a(m, k) * lam[k]; pb = pb + gs_b(m, k) * lam[k]; }
     double d = sqrt(dot(v, v));
     r.dist = d; r.n = v * (1.0 / d); r.pa = pa; r.pb = pb; r.ns = ns;
 }

@@ -224,7 +224,7 @@ def test_videomaker_writes_frames(tmp_path, monkeypatch):
     vm = VideoMaker(env, Frames([0, 40]), Frames(0), debug=True)
     frame = vm.camera.render(env)
     assert frame.shape == (240, 320, 3) and frame.dtype == np.uint8
-    assert (frame != 255).any(axis=2).mean() > 0.2            # table and robot fill a good part of the view
+    assert (frame != 255).any(axis=2).mean() > 0.1            # table and robot fill a good part of the view
     vm.start_intrinsic()
     for t in range(1, 41):
         obs, _, _, _ = env.step({'joint_command': np.zeros(9), 'render': t == 40})
