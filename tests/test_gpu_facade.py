@@ -244,3 +244,40 @@ def test_videomaker_writes_frames(tmp_path, monkeypatch):
         counts.append(n)
     assert counts == [5, 2]
     env.close()
+
+
+def test_cartesian_8192_envs_full_observation():
+    """BASELINE config 5 shape: 8192 envs on one GPU, cartesian action (xyz in the reference's Box env.py:44-47, un-normalised
+    quaternion components in [-1, 1], gripper in [0, pi/2] :54-55), full R1 observation.  Size-independent properties:
+    the IK of a sampled env agrees with the oracle's, duplicated commands give identical envs, the request cache
+    (env.py:366-370) suppresses the second solve, outputs have the reference's shapes / dtypes / value sets."""
+    N = 8192
+    env = VecREALRobotEnv(N, objects=3, action_type='cartesian', additional_obs=True)
+    obs = env.reset(render=False)
+    g = torch.Generator(device='cuda'); g.manual_seed(11)
+    lo = torch.tensor([-0.25, -0.5, 0.42, -1, -1, -1, -1], dtype=torch.float64, device='cuda')
+    hi = torch.tensor([0.05, 0.5, 0.6, 1, 1, 1, 1], dtype=torch.float64, device='cuda')
+    cart = lo + (hi - lo) * torch.rand(N, 7, dtype=torch.float64, device='cuda', generator=g)
+    cart[N // 2:] = cart[:N // 2]                                            # second half repeats the first
+    grip = torch.rand(N, 2, dtype=torch.float64, device='cuda', generator=g) * (np.pi / 2)
+    grip[N // 2:] = grip[:N // 2]
+    n0 = env.sim.launch_count()
+    obs, reward, done, _ = env.step({'cartesian_command': cart, 'gripper_command': grip, 'render': False})
+    n1 = env.sim.launch_count()
+    obs, reward, done, _ = env.step({'cartesian_command': cart, 'gripper_command': grip, 'render': True})
+    n2 = env.sim.launch_count()
+    assert (n1 - n0) - (n2 - n1) == 1                                       # the IK kernel ran in the first step only
+    for e in (0, 1, 77, 4095):
+        ref = Oracle(3).ik(cart[e, :3].cpu().numpy(), cart[e, 3:].cpu().numpy())[0]
+        assert np.abs(env.last_ik[e].cpu().numpy() - ref).max() < 1e-7
+    assert obs['retina'].shape == (N, 240, 320, 3) and obs['retina'].dtype == torch.uint8
+    assert obs['depth'].shape == (N, 240, 320) and obs['depth'].dtype == torch.float32
+    assert obs['mask'].shape == (N, 240, 320) and obs['mask'].dtype == torch.int32
+    assert obs['joint_positions'].shape == (N, 9) and obs['touch_sensors'].shape == (N, 4) and obs['object_positions'].shape == (N, 3, 3)
+    assert bool(torch.isfinite(obs['joint_positions']).all()) and bool(torch.isfinite(obs['depth']).all())
+    vals = torch.unique(obs['mask'][::511])
+    assert set(vals.tolist()) <= {-1, 0, 1, 2, 3, 4} and {0, 1}.issubset(set(vals.tolist()))
+    for k in ('retina', 'depth', 'mask', 'joint_positions', 'object_positions'):
+        assert bool((obs[k][:N // 2] == obs[k][N // 2:]).all()), k            # an env does not depend on its slot
+    assert reward.shape == (N,) and float(reward.abs().sum()) == 0.0 and not bool(done.any())
+    env.close()
