@@ -805,19 +805,31 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 if (lane == 0) g = atomicAdd(&s_rgrp, 1);
                 g = __shfl_sync(0xffffffffu, g, 0);
                 if (g >= STRIP_ROWS * RR_W / 128) break;
+                bool covered = false;
 #pragma unroll 1
                 for (int j = 0; j < 4; j++) {
                     const int p = g * 128 + j * 32 + lane;
                     const unsigned long long key = keys[p];
                     if (key == 0ull) continue;
+                    covered = true;
                     const int r = p / RR_W, x = p - r * RR_W;
                     int s;
                     const unsigned int col = shade_pixel(M, tris, tri_shape, texdata, recs, (unsigned int)(key & 0xffffffffu), x, row0 + r, s);
                     keys[p] = (key & 0xffffffff00000000ull) | 0x80000000ull | ((unsigned long long)s << 24) | (unsigned long long)(col & 0xffffffu);
                 }
-                __syncwarp();
                 const int i = g * 32 + lane;
                 const int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
+                if (!__any_sync(0xffffffffu, covered)) {          // nothing but background in these 128 pixels (keys already zero)
+                    const size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
+                    if (rgb) {
+                        unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3);
+                        __stcs(p, 0xffffffffu); __stcs(p + 1, 0xffffffffu); __stcs(p + 2, 0xffffffffu);
+                    }
+                    if (depth) __stcs(reinterpret_cast<float4*>(depth + o), make_float4(bg_depth, bg_depth, bg_depth, bg_depth));
+                    if (seg) __stcs(reinterpret_cast<int4*>(seg + o), make_int4(-1, -1, -1, -1));
+                    continue;
+                }
+                __syncwarp();                                     // the colours written above are read by other lanes below
                 unsigned int col[4]; float dep[4]; int sg[4];
                 ulonglong2* kp = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
                 const ulonglong2 ka = kp[0], kb = kp[1];
