@@ -159,6 +159,12 @@ class Oracle:
         self.L.orc_render_frames(C.c_void_p(self.h), _p(frames), _p(view16), _p(proj16), _p(rgb), _p(depth), _p(mask))
         return rgb, depth, mask
 
+    def targets(self):
+        """Motor targets (11 dofs) set by the action prologue of the last step."""
+        t = np.zeros(11)
+        self.L.orc_get_targets(C.c_void_p(self.h), _p(t))
+        return t
+
     def ik(self, pos, quat, max_iter=1000, residual=1e-3):
         p = np.ascontiguousarray(pos, np.float64); q = np.ascontiguousarray(quat, np.float64); o = np.zeros(11)
         rc = self.L.orc_ik(C.c_void_p(self.h), _p(p), _p(q), int(max_iter), C.c_double(residual), _p(o))

@@ -57,6 +57,7 @@ void orc_set_state(void* p, const double* q, const double* qd, const double* obj
     orc_fk(&e);
 }
 void orc_set_targets(void* p, const double* t11) { OrcEnv& e = ((OrcHandle*)p)->env; for (int i = 0; i < ORC_NDOF; i++) e.target[i] = t11[i]; }
+void orc_get_targets(void* p, double* t11) { OrcEnv& e = ((OrcHandle*)p)->env; for (int i = 0; i < ORC_NDOF; i++) t11[i] = e.target[i]; }
 void orc_step(void* p, const double* joint_cmd9) { orc_env_step(&((OrcHandle*)p)->env, joint_cmd9); }
 void orc_step_sim_only(void* p) { orc_step_simulation(&((OrcHandle*)p)->env); }
 void orc_read(void* p, double* joints9, double* touch4) {

@@ -12,7 +12,9 @@
  * setup.py:24-32) — btMultiBodyDynamicsWorld::solveConstraints, btMultiBody::
  * computeAccelerationsArticulatedBodyAlgorithmMultiDof / calcAccelerationDeltasMultiDof,
  * btMultiBodyJointMotor, btMultiBodyJointLimitConstraint, btMultiBodyConstraintSolver.
- * PARITY UNPINNED: written from the published algorithm; no pybullet available to pin against.
+ * PARITY UNPINNED for the Bullet arithmetic: written from the published algorithm; no pybullet available to pin against.
+ * The action prologue and the object-limit teleport of orc_env_step ARE pinned: tests/test_reference_golden.py checks them
+ * against vectors produced by the reference's own env.py / robot.py (tests/golden/make_reference_golden.py).
  */
 #include "orc_env.h"
 #include <algorithm>

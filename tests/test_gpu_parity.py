@@ -343,3 +343,51 @@ def test_bad_arguments_raise():
         BatchedSim(1, 1, not_a_field=3)
     with pytest.raises(RuntimeError):
         BatchedSim(1, 5)
+
+
+def test_cuda_path_against_reference_host_goldens():
+    """tests/golden/reference_host_golden.npz was produced by the reference's own Python code (make_reference_golden.py).
+    The batched kernels must reproduce, one env per golden case: the scores of evaluateGoal (env.py:181-200), the
+    teleport decisions of control_objects_limits (env.py:257-264) and — through one step from the given joint state —
+    the same joint motion as the oracle whose motor targets are pinned to limitActionByJoint + apply_action."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_host_golden.npz"))
+    # scores
+    cur, goal, want = G["score_cur"], G["score_goal"], G["score_value"]
+    n = len(cur)
+    sim = BatchedSim(n, 3)
+    _, _, obj = sim.get_state()
+    obj[:, :, :3] = torch.from_numpy(cur).cuda()
+    sim.set_state(obj=obj.contiguous())
+    got = sim.score(torch.from_numpy(goal).cuda().contiguous()).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-13
+    sim.close()
+    # object limits
+    pos, flags = G["objlimit_pos"], G["objlimit_reset"]
+    init = G["quat_object_poses"][1:, :3]
+    n = len(pos)
+    sim = BatchedSim(n, 3)
+    _, _, obj = sim.get_state()
+    obj[:, :, :3] = torch.from_numpy(pos).cuda()
+    obj[:, :, 3:7] = torch.tensor([0, 0, 0, 1.0], dtype=torch.float64, device='cuda')
+    obj[:, :, 7:] = 0
+    sim.set_state(obj=obj.contiguous())
+    sim.step(torch.zeros(n, 9, dtype=torch.float64, device='cuda'))
+    after = sim.get_state()[2][:, :, :3].cpu().numpy()
+    got = (np.linalg.norm(after - init[None], axis=2) < 5e-3).astype(np.int32)
+    far = np.linalg.norm(pos - init[None], axis=2) > 2e-2
+    assert np.array_equal(got[far], flags[far])
+    sim.close()
+    # action prologue: one step from the golden joint states, CUDA == oracle (whose targets equal the reference's)
+    q, cmd, targets = G["prologue_q"], G["prologue_cmd"], G["prologue_targets"]
+    n = len(q)
+    sim = BatchedSim(n, 3)
+    sim.set_state(q=torch.from_numpy(q).cuda().contiguous(), qd=torch.zeros(n, 11, dtype=torch.float64, device='cuda'))
+    sim.step(torch.from_numpy(cmd).cuda().contiguous())
+    qg = sim.get_state()[0].cpu().numpy()
+    for i in range(0, n, 7):
+        o = Oracle(3)
+        o.set_state(q=q[i], qd=np.zeros(11))
+        o.step(cmd[i])
+        assert np.abs(o.targets() - targets[i]).max() < 1e-15
+        assert np.abs(o.get_state()[0] - qg[i]).max() < 1e-9
+    sim.close()

@@ -1,0 +1,173 @@
+"""CPU tests against tests/golden/reference_host_golden.npz — vectors produced by running the reference's own Python code
+(tests/golden/make_reference_golden.py imports the unmodified package from /root/reference behind inert stand-ins for
+pybullet / gym).  They pin (a) the oracle's action prologue, object-limit teleport and scoring, and (b) the host mirror
+(spaces, plans, request caches, done logic, score aggregation) to the reference; the GPU parity tests then hold the CUDA
+path to the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import real_robots
+from real_robots_b200.envs.env import Goal, REALRobotEnv, macro_plan
+from real_robots_b200.envs.robot import Kuka
+from real_robots_b200.evaluate import build_score_object
+from real_robots_b200.util import euler_to_quat
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_host_golden.npz"))
+META = json.loads(bytes(G["meta_json"]).decode())
+
+
+def fake_ik(coords, orient=None):          # the same stand-in IK the generator gave the reference
+    c = np.asarray(coords, dtype=np.float64)
+    o = np.zeros(4) if orient is None else np.asarray(orient, dtype=np.float64)
+    ph = c @ np.array([1.3, 2.1, 0.7]) + o @ np.array([0.11, 0.23, 0.31, 0.43])
+    return np.sin(np.arange(11) * 0.37 + ph)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle.orc import Oracle
+    return Oracle(3)
+
+
+def test_joint_limits_spaces_and_constants():
+    k = Kuka(True, 3)
+    assert np.array_equal(k.min_joints, G["limits_min"]) and np.array_equal(k.max_joints, G["limits_max"])
+    assert np.array_equal(k.action_space.low, G["limits_min"]) and np.array_equal(k.action_space.high, G["limits_max"])
+    env = real_robots.make('REALRobot2020-R1J3-v0')
+    for name, sp in (("cartesian", env.cartesian_space), ("macro", env.macro_space), ("gripper", env.gripper_space)):
+        assert np.array_equal(np.asarray(sp.low, np.float64), G["spaces_%s_low" % name])
+        assert np.array_equal(np.asarray(sp.high, np.float64), G["spaces_%s_high" % name])
+    assert sorted(env.observation_space.spaces) == META["obs_keys_R1"]
+    assert sorted(real_robots.make('REALRobot2020-R2J1-v0').observation_space.spaces) == META["obs_keys_R2"]
+    for key, (shape, dtype) in META["obs_shapes_R1"].items():
+        sp = env.observation_space.spaces[key]
+        assert list(sp.shape) == shape and str(sp.dtype) == dtype, key
+    assert [int(env.intrinsic_timesteps), int(env.extrinsic_timesteps), int(env.extrinsic_trials)] == META["timesteps"]
+    for n in (1, 2, 3):
+        assert Kuka(True, n).used_objects == META["used_objects"][str(n)]
+    assert list(k.robot_position) == META["robot_position"] and k.contact_threshold == META["contact_threshold"]
+    names = ["table", "cube", "tomato", "mustard"]
+    mine = np.array([list(Kuka.object_poses[n][:3]) + list(euler_to_quat(Kuka.object_poses[n][3:])) for n in names])
+    assert np.abs(mine - G["quat_object_poses"]).max() < 1e-15
+
+
+def test_oracle_action_prologue_matches_reference(oracle):
+    """limitActionByJoint + apply_action (env.py:314-321, robot.py:188-201): the 11 motor targets for 64 (state, command) pairs."""
+    q, cmd, want = G["prologue_q"], G["prologue_cmd"], G["prologue_targets"]
+    for i in range(len(q)):
+        oracle.reset()
+        oracle.set_state(q=q[i], qd=np.zeros(11))
+        oracle.step(cmd[i])
+        assert np.abs(oracle.targets() - want[i]).max() < 1e-15, i
+
+
+def test_oracle_object_limits_match_reference(oracle):
+    """control_objects_limits (env.py:257-264): the same objects are sent back to their initial pose."""
+    pos, want = G["objlimit_pos"], G["objlimit_reset"]
+    init = G["quat_object_poses"][1:, :3]
+    for i in range(len(pos)):
+        oracle.reset()
+        _, _, obj = oracle.get_state()
+        obj[:, :3] = pos[i]
+        obj[:, 3:7] = [0, 0, 0, 1]
+        obj[:, 7:] = 0
+        oracle.set_state(obj=obj)
+        oracle.step(np.zeros(9))
+        _, _, after = oracle.get_state()
+        got = (np.linalg.norm(after[:, :3] - init, axis=1) < 5e-3).astype(np.int32)
+        far = np.linalg.norm(pos[i] - init, axis=1) > 2e-2          # otherwise the check cannot tell
+        assert np.array_equal(got[far], want[i][far]), (i, pos[i], got, want[i])
+
+
+def test_scores_match_reference():
+    cur, goal, want = G["score_cur"], G["score_goal"], G["score_value"]
+    env = real_robots.make('REALRobot2020-R1J3-v0')
+    objs = ["cube", "tomato", "mustard"]
+    for i in range(len(cur)):
+        env.goal = Goal(initial_state={}, final_state={n: np.concatenate([goal[i, o], [0, 0, 0, 1]]) for o, n in enumerate(objs)}, challenge='2D')
+        env.robot.object_bodies = {n: type("B", (), {"get_position": (lambda p: (lambda self: p))(cur[i, o])})() for o, n in enumerate(objs)}
+        ch, s = env.evaluateGoal()
+        assert ch == '2D' and abs(s - want[i]) < 1e-14
+    assert abs(want[0] - 3.0) < 1e-15 and abs(want[1] - 0.75) < 1e-12        # 0.25 per object at 10 cm (env.py:192-194)
+    so = build_score_object({"2D": [0.5, 0.25, 0.75], "3D": [1.0], "2.5D": [0.125]})
+    assert {k: float(v) for k, v in so.items()} == META["scoreobj"]
+    assert {k: float(v) for k, v in build_score_object({"2D": [0.5]}).items()} == META["scoreobj_single"]
+
+
+def test_macro_plans_match_reference_bit_for_bit():
+    calls = []
+
+    def ik9(coords):
+        calls.append(np.array(coords))
+        return fake_ik(coords, euler_to_quat([0, 3.14, -1.57]))[:9]
+    for m, want, ncall in zip(G["plan_macro"], G["plan_rows"], G["plan_ik_calls"]):
+        calls.clear()
+        plan = macro_plan(ik9, m[0], m[1])
+        assert plan.shape == (1000, 9) and np.array_equal(plan, want)
+        assert len(calls) == ncall
+
+
+def test_macro_sequencing_and_cartesian_cache_match_reference():
+    env = real_robots.make('REALRobot2020-R1M1-v0')
+    sent = []
+    env._ik = lambda coords, orient: fake_ik(coords, orient)
+    env.step_joints = lambda a: sent.append(np.array(a["joint_command"]))
+    macros = G["plan_macro"]
+    steps = []
+    for idx in G["macro_seq_action_index"]:
+        env.step_macro({"macro_action": macros[idx], "render": False})
+        steps.append(env.plan_step)
+    assert np.array_equal(np.array(steps), G["macro_seq_plan_step"])
+    assert np.array_equal(np.array(sent[:8]), G["macro_seq_first_rows"]) and np.array_equal(np.array(sent[-3:]), G["macro_seq_last_rows"])
+    env.step_macro({"macro_action": None, "render": True})
+    assert np.all(sent[-1] == 0)
+    # cartesian request cache (env.py:366-370)
+    env = real_robots.make('REALRobot2020-R1C1-v0')
+    calls, sent = [], []
+
+    def ik(coords, orient):
+        calls.append(1)
+        return fake_ik(coords, orient)
+    env._ik = ik
+    env.step_joints = lambda a: sent.append(np.array(a["joint_command"]))
+    counts = []
+    for c, g in zip(G["cart_cmd"], G["cart_grip"]):
+        env.step_cartesian({"cartesian_command": c, "gripper_command": g, "render": False})
+        counts.append(len(calls))
+    assert np.array_equal(np.array(counts), G["cart_ik_calls"]) and np.array_equal(np.array(sent), G["cart_joint_cmd"])
+
+
+def test_done_logic_matches_reference():
+    """step_joints (env.py:345-352) with a stand-in simulator: done after `intrinsic_timesteps` steps without a goal,
+    after `extrinsic_timesteps` with one; reward 0, info {}."""
+    env = real_robots.make('REALRobot2020-R1J1-v0')
+
+    class FakeTensor:
+        def copy_(self, other):
+            return self
+    env._sim = type("S", (), {"step": lambda self, c: None})()
+    env._cmd = FakeTensor()
+    env._torch = type("T", (), {"from_numpy": staticmethod(lambda a: a)})
+    env.get_observation = lambda cam=True: {}
+    env.intrinsic_timesteps, env.extrinsic_timesteps, env.timestep, env.goal_idx = 3, 2, 0, -1
+    dones = []
+    for t in range(3):
+        o, r, d, info = env.step_joints({"joint_command": None if t == 0 else np.zeros(9), "render": t == 1})
+        assert r == 0 and info == {}
+        dones.append(bool(d))
+    env.goal_idx, env.timestep = 0, 0
+    for t in range(2):
+        dones.append(bool(env.step_joints({"joint_command": np.zeros(9), "render": False})[2]))
+    assert dones == META["done_sequence_intrinsic3_then_extrinsic2"]
+    # the order of operations inside one step that the reference executes and rr_step reproduces (env.py:336-342)
+    assert META["step_joints_call_order"] == ["limitActionByJoint", "control_objects_limits", "apply_action", "global_step", "get_observation(False)"]
+    env._sim = None
+
+
+def test_touch_sensor_semantics_of_the_reference():
+    """robot.py:131-163: a sensor reads the LARGEST normal force among its link's contact points closer than 0.1 (strict)."""
+    assert np.array_equal(G["touch_sensors"], [7.25, 0.0, 0.5, 0.0])
+    assert META["touch_contacts"] == {"finger_00": ["cube"], "skin_00": ["cube", "tomato"], "skin_10": ["table"]}
