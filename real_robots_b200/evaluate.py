@@ -69,8 +69,11 @@ class EvaluationService:
 
     def setup_evaluation_state(self):                                       # evaluate.py:100-121
         self.evaluation_state = {"state": "PENDING", "intrinsic_phase_state": "PENDING", "extrinsic_phase_state": "PENDING",
-                                 "current_intrinsic_timestep": 0, "num_extrinsic_trials_complete": 0,
-                                 "progress_in_current_extrinsic_trial": 0, "evaluation_score": {}}
+                                 "max_intrinsic_timesteps": self.intrinsic_timesteps, "max_extrinsic_timesteps": self.extrinsic_timesteps,
+                                 "current_intrinsic_timestep": 0, "max_extrinsic_trials": self.extrinsic_trials,
+                                 "num_extrinsic_trials_complete": 0, "progress_in_current_extrinsic_trial": 0,
+                                 "evaluation_score": {"score": 0, "score_2D": 0, "score_2.5D": 0, "score_3D": 0, "score_total": 0},
+                                 "score": {"score": 0, "score_secondary": 0}}
 
     def sync_evaluation_state(self):
         pass                                                                # aicrowd_api is not a dependency here
@@ -141,8 +144,12 @@ class EvaluationService:
             self.controller.start_extrinsic_phase()
             for trial in range(int(self.extrinsic_trials)):
                 self.run_extrinsic_trial(trial)
-            self.controller.end_extrinsic_phase()
             self.evaluation_state["state"] = self.evaluation_state["extrinsic_phase_state"] = "EXTRINSIC_PHASE_COMPLETE"
+            final = self.build_score_object()
+            self.evaluation_state["score"] = {"score": final["score_total"], "score_secondary": final["score_2D"]}
+            self.evaluation_state["meta"] = self.evaluation_state["evaluation_score"]
+            self.evaluation_state["state"] = "EVALUATION_COMPLETE"                 # evaluate.py:376-388
+            self.controller.end_extrinsic_phase()
         except Exception as e:
             self.evaluation_state["state"] = "ERROR"
             self.evaluation_state["extrinsic_phase_state"] = "EXTRINSIC_PHASE_ERROR"

@@ -91,7 +91,15 @@ def install_stubs():
     mod("gym.envs")
     mod("gym.envs.registration", register=lambda **kw: None)
     gym.make = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("gym.make is not available in the golden generator"))
-    mod("aicrowd_api")
+    events = []
+
+    class AIcrowdEvents:
+        AICROWD_EVENT_INFO, AICROWD_EVENT_ERROR, AICROWD_EVENT_SUCCESS = "INFO", "ERROR", "SUCCESS"
+
+        def register_event(self, event_type, payload):
+            events.append((event_type, payload["state"]))
+    api = mod("aicrowd_api", event_log=events)
+    api.events = mod("aicrowd_api.events", AIcrowdEvents=AIcrowdEvents)
     mod("interval", interval=type("interval", (), {"__init__": lambda self, *a: None, "__len__": lambda self: 0}))
     sys.path.insert(0, REF)
     return pb
@@ -283,6 +291,46 @@ def main():
     svc2 = NS(scores={}, evaluation_state={}, sync_evaluation_state=lambda: None)
     EvaluationService.add_scores(svc2, "2D", 0.5)
     meta["scoreobj_single"] = {k: float(v) for k, v in EvaluationService.build_score_object(svc2).items()}
+
+    # ---- EvaluationService driven end to end with a deterministic stand-in env and a recording controller
+    sys.path.insert(0, HERE)
+    import fake_env
+    import gym
+    from real_robots.policy import BasePolicy
+    log = []
+    fake_env.FakeEnv.log = log
+    made = []
+    gym.make = lambda env_id: (made.append(env_id), fake_env.FakeEnv())[1]
+    svc = EvaluationService(fake_env.make_controller(BasePolicy, log), environment='R1', action_type='macro_action', n_objects=2,
+                            intrinsic_timesteps=3, extrinsic_timesteps=2, extrinsic_trials=4, visualize=True,
+                            goals_dataset_path="goals.npz", video=None)
+    svc.run_intrinsic_phase()
+    so = svc.run_extrinsic_phase()
+    meta["eval_env_id"] = made
+    meta["eval_log"] = log
+    meta["eval_score_object"] = fake_env.plain(so)
+    meta["eval_scores"] = fake_env.plain(svc.scores)
+    meta["eval_state"] = fake_env.plain(svc.evaluation_state)
+    # skipped intrinsic phase
+    log2 = []
+    fake_env.FakeEnv.log = log2
+    svc = EvaluationService(fake_env.make_controller(BasePolicy, log2), 'R2', 'joints', 1, 0, 1, 1, False, "g.npz", None)
+    svc.run_intrinsic_phase()
+    meta["eval_skip_state"] = fake_env.plain(svc.evaluation_state)
+    meta["eval_skip_log"] = list(log2)
+    errors = {}
+    for args in (("R3", "joints", 1), ("R2", "macro_action", 1), ("R1", "bogus", 1), ("R1", "joints", 4), ("R1", "joints", "2")):
+        try:
+            EvaluationService(fake_env.make_controller(BasePolicy, []), *args, 1, 1, 1, False, "g.npz", None)
+            errors[str(args)] = None
+        except Exception as ex:
+            errors[str(args)] = str(ex)
+    try:
+        EvaluationService(object, 'R1', 'joints', 1, 1, 1, 1, False, "g.npz", None)
+        errors["not_a_policy"] = None
+    except Exception as ex:
+        errors["not_a_policy"] = type(ex).__name__
+    meta["eval_errors"] = errors
 
     G["meta_json"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), dtype=np.uint8)
     out = os.path.join(HERE, "reference_host_golden.npz")

@@ -171,3 +171,40 @@ def test_touch_sensor_semantics_of_the_reference():
     """robot.py:131-163: a sensor reads the LARGEST normal force among its link's contact points closer than 0.1 (strict)."""
     assert np.array_equal(G["touch_sensors"], [7.25, 0.0, 0.5, 0.0])
     assert META["touch_contacts"] == {"finger_00": ["cube"], "skin_00": ["cube", "tomato"], "skin_10": ["table"]}
+
+
+def test_evaluation_service_flow_matches_reference(monkeypatch):
+    """The reference's EvaluationService was driven end to end with tests/golden/fake_env.py; this repo's must make the same
+    calls in the same order (controller hooks, env.reset / set_goal / step / evaluateGoal), end in the same
+    evaluation_state and raise on the same bad arguments (evaluate.py:44-71, 148-191, 203-417)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import fake_env
+    import real_robots_b200
+    from real_robots_b200.evaluate import EvaluationService
+    from real_robots_b200.policy import BasePolicy
+    log, made = [], []
+    fake_env.FakeEnv.log = log
+    monkeypatch.setattr(real_robots_b200, "make", lambda env_id: (made.append(env_id), fake_env.FakeEnv())[1])
+    svc = EvaluationService(fake_env.make_controller(BasePolicy, log), environment='R1', action_type='macro_action', n_objects=2,
+                            intrinsic_timesteps=3, extrinsic_timesteps=2, extrinsic_trials=4, visualize=True,
+                            goals_dataset_path="goals.npz", video=None)
+    svc.run_intrinsic_phase()
+    svc.run_extrinsic_phase()
+    assert made == META["eval_env_id"][:1]
+    assert log == META["eval_log"]
+    assert fake_env.plain(svc.scores) == META["eval_scores"]
+    assert fake_env.plain(svc.evaluation_state) == META["eval_state"]
+    log2 = []
+    fake_env.FakeEnv.log = log2
+    svc = EvaluationService(fake_env.make_controller(BasePolicy, log2), 'R2', 'joints', 1, 0, 1, 1, False, "g.npz", None)
+    svc.run_intrinsic_phase()
+    assert fake_env.plain(svc.evaluation_state) == META["eval_skip_state"] and log2 == META["eval_skip_log"]
+    for args, msg in META["eval_errors"].items():
+        if args == "not_a_policy":
+            with pytest.raises(Exception):
+                EvaluationService(object, 'R1', 'joints', 1, 1, 1, 1, False, "g.npz", None)
+            continue
+        with pytest.raises(Exception) as ei:
+            EvaluationService(fake_env.make_controller(BasePolicy, []), *eval(args), 1, 1, 1, False, "g.npz", None)
+        assert str(ei.value) == msg
