@@ -121,7 +121,7 @@ long long rr_launch_count(rr_ctx* ctx);
 
 /* Optional per-kernel device timing (CUDA events on the launch stream) for bench.py's roofline line.
  * rr_profile(ctx, 1) starts recording, rr_profile(ctx, 0) stops; rr_profile_read synchronises the device and
- * returns, per kernel kind (0 = physics step, 1 = render set-up, 2 = rasteriser, 3 = collision), the summed
+ * returns, per kernel kind (0 = physics step = k_step_dyn + k_step_solve, 1 = render set-up, 2 = rasteriser, 3 = collision), the summed
  * duration in ms and the number of launches since profiling was enabled, then clears the counters. */
 #define RR_PROFILE_KINDS 4
 int  rr_profile(rr_ctx* ctx, int enable);
