@@ -31,6 +31,9 @@ struct CollideConst {
 };
 __constant__ CollideConst c_col;
 
+#ifndef EPA_INLINE
+#define EPA_INLINE __noinline__
+#endif
 #ifndef HS_INLINE
 #define HS_INLINE __forceinline__
 #endif
@@ -256,7 +259,7 @@ __device__ bool epa_add_face(ColMem& m, int& nf, int a, int b, int c) {
     return true;
 }
 
-__device__ bool epa(const Hull& A, const Hull& B, ColMem& m, SupPt* S, int ns, double& depth, V3& n, V3& pa, V3& pb, int lane) {
+__device__ EPA_INLINE bool epa(const Hull& A, const Hull& B, ColMem& m, SupPt* S, int ns, double& depth, V3& n, V3& pa, V3& pb, int lane) {
     bool ok = false;
     if (ns == 1) ok = enclose1(A, B, S, lane);
     else if (ns == 2) ok = enclose2(A, B, S, lane);

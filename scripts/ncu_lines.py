@@ -27,6 +27,8 @@ for l in sass.splitlines():
         line_of[int(m.group(1), 16)] = cur
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(csvtxt.splitlines()))
+if len(rows) < 3:
+    sys.exit("no launch of a kernel matching %r in %s" % (kern, rep))
 hdr = rows[1]
 ia, ii, it, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
 base = None

@@ -49,6 +49,8 @@ base_name = os.path.basename(srcfile)
 
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(csvtxt.splitlines()))
+if len(rows) < 3:
+    sys.exit("no launch of a kernel matching %r in %s" % (kern, rep))
 hdr = rows[1]
 ia, ii, it, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
 base, agg, tot_i, tot_s = None, {}, 0, 0
