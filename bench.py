@@ -260,6 +260,10 @@ def run_ours(args):
                          "algorithmic_bytes": args.envs * IMG_BYTES, "peak_source": peak_src,
                          "ms_per_launch": raster_ms, "launches": r_n,
                          "kernels_ms_per_step": {k: (v[0] / max(v[1], 1)) for k, v in prof.items()},
+                         # SURVEY §8(d) secondary rates of the rasteriser: 17 578 scene triangles and 76 800 pixels per env
+                         "secondary": {"triangles_per_s": args.envs * 17578 / (raster_ms * 1e-3) if raster_ms > 0 else None,
+                                       "pixels_per_s": args.envs * 76800 / (raster_ms * 1e-3) if raster_ms > 0 else None,
+                                       "image_write_GBps": achieved},
                          "physics_kernel": {"kernel": "k_step_dyn + k_step_solve", "ms_per_launch": s_ms / max(s_n, 1),
                                             "achieved_gbs": args.envs * STATE_BYTES / (s_ms / max(s_n, 1) * 1e-3) / 1e9 if s_ms > 0 else None}},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
