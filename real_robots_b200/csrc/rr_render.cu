@@ -42,6 +42,9 @@ __constant__ float c_cull_hmax;      // largest 'smallest altitude' over all tri
 #ifndef PRECULL_AREA
 #define PRECULL_AREA 4           // bounding boxes up to this many pixels are coverage-tested in the geometry phase
 #endif
+#ifndef MED_LANES
+#define MED_LANES 8             // lanes that share one medium record
+#endif
 #ifndef HUGE_GROUP
 #define HUGE_GROUP 256         // threads that share one huge triangle
 #endif
@@ -772,16 +775,19 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
                 raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, tid % HUGE_GROUP, HUGE_GROUP);
             }
-            // ---- medium triangles: one record per warp at a time (the coarse items go before the fine ones)
+            // ---- medium triangles: MED_LANES lanes per record, 32 / MED_LANES records per warp at a time (the coarse
+            // items go before the fine ones); sharing a warp between records amortises the per-record set-up
             for (;;) {
                 int mi = 0;
-                if (lane == 0) mi = atomicAdd(&s_medc, 1);
+                if (lane == 0) mi = atomicAdd(&s_medc, 32 / MED_LANES);
                 mi = __shfl_sync(0xffffffffu, mi, 0);
                 if (mi >= nmed) break;
-                const unsigned int ridx = list[REC_MAX + mi];
-                const Rec br = load_rec(recs + ridx);
-                Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
-                raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, lane, 32);
+                const int my = mi + lane / MED_LANES;
+                if (my < nmed) {
+                    const Rec br = load_rec(recs + list[REC_MAX + my]);
+                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
+                    raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, lane % MED_LANES, MED_LANES);
+                }
             }
             // ---- small triangles: warps pull 32-record chunks, one record per lane
             for (;;) {
