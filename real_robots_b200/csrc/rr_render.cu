@@ -768,37 +768,40 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
             const int nsmall = min(s_nlist[strip], REC_MAX), nmed = min(s_nlist[NSTRIPS + strip], REC_MAX), nbig = min(s_nlist[2 * NSTRIPS + strip], REC_MAX);
             const unsigned short* list = lists + (size_t)strip * 2 * REC_MAX;
             if (tid == 0) s_rgrp = 0;
-            // ---- huge triangles first (mostly the table): groups of HUGE_GROUP threads share a record
-            for (int b = tid / HUGE_GROUP; b < nbig; b += RTHREADS / HUGE_GROUP) {
-                const unsigned int ridx = list[REC_MAX - 1 - b];
-                const Rec br = load_rec(recs + ridx);
-                Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
-                raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, tid % HUGE_GROUP, HUGE_GROUP);
-            }
-            // ---- medium triangles: MED_LANES lanes per record, 32 / MED_LANES records per warp at a time (the coarse
-            // items go before the fine ones); sharing a warp between records amortises the per-record set-up
-            for (;;) {
-                int mi = 0;
-                if (lane == 0) mi = atomicAdd(&s_medc, 32 / MED_LANES);
-                mi = __shfl_sync(0xffffffffu, mi, 0);
-                if (mi >= nmed) break;
-                const int my = mi + lane / MED_LANES;
-                if (my < nmed) {
-                    const Rec br = load_rec(recs + list[REC_MAX + my]);
-                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(br, S, E, R, cz);
-                    raster_pixels(keys, S, E, R, cz, br.keylo, !(br.flags & REC_CLIPPED), row0, lane % MED_LANES, MED_LANES);
-                }
-            }
-            // ---- small triangles: warps pull 32-record chunks, one record per lane
-            for (;;) {
-                int rb = 0;
-                if (lane == 0) rb = atomicAdd(&s_chunk, 32);
-                rb = __shfl_sync(0xffffffffu, rb, 0);
-                if (rb >= nsmall) break;
-                if (rb + lane < nsmall) {
-                    const Rec rec = load_rec(recs + list[rb + lane]);
-                    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(rec, S, E, R, cz);
-                    raster_pixels(keys, S, E, R, cz, rec.keylo, !(rec.flags & REC_CLIPPED), row0, 0, 1);
+            // ---- raster: one loop, one inlined copy of the pixel code (the kernel is instruction-cache sensitive).  A warp
+            // works through three phases, coarse items first: 0 = huge boxes (mostly the table) shared by groups of HUGE_GROUP
+            // threads, 1 = medium boxes, MED_LANES lanes per record, pulled 32 / MED_LANES at a time, 2 = small boxes, one
+            // record per lane, pulled in 32-record chunks.
+            {
+                int phase = 0, hb = tid / HUGE_GROUP;
+                for (;;) {
+                    unsigned int ridx = 0; int start = 0, stride = 1; bool valid = false;
+                    if (phase == 0) {
+                        if (hb >= nbig) { phase = 1; continue; }
+                        ridx = list[REC_MAX - 1 - hb]; start = tid % HUGE_GROUP; stride = HUGE_GROUP; valid = true;
+                        hb += RTHREADS / HUGE_GROUP;
+                    } else if (phase == 1) {
+                        int mi = 0;
+                        if (lane == 0) mi = atomicAdd(&s_medc, 32 / MED_LANES);
+                        mi = __shfl_sync(0xffffffffu, mi, 0);
+                        if (mi >= nmed) { phase = 2; continue; }
+                        const int my = mi + lane / MED_LANES;
+                        valid = my < nmed;
+                        if (valid) ridx = list[REC_MAX + my];
+                        start = lane % MED_LANES; stride = MED_LANES;
+                    } else {
+                        int rb = 0;
+                        if (lane == 0) rb = atomicAdd(&s_chunk, 32);
+                        rb = __shfl_sync(0xffffffffu, rb, 0);
+                        if (rb >= nsmall) break;
+                        valid = rb + lane < nsmall;
+                        if (valid) ridx = list[rb + lane];
+                    }
+                    if (valid) {
+                        const Rec rec = load_rec(recs + ridx);
+                        Screen S; Edge E; Recip R; float cz[3]; rec_unpack(rec, S, E, R, cz);
+                        raster_pixels(keys, S, E, R, cz, rec.keylo, !(rec.flags & REC_CLIPPED), row0, start, stride);
+                    }
                 }
             }
             __syncthreads();
