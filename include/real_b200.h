@@ -135,7 +135,8 @@ int  rr_profile_read(rr_ctx* ctx, double* ms_total /*[4]*/, long long* launches 
 #define RR_CONTACT_POINT_DOUBLES 17
 int  rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, int* n_pairs_host, void* stream);
 
-/* Per-env diagnostics of the last step: i32[N,4] = rows, iterations, contacts, flags. */
+/* Per-env diagnostics of the last step: i32[N,4] = rows, iterations, contacts, flags (bit 0: the 32-contact cap was hit,
+ * bit 1: every contact was object-vs-static, so the solver took its object-parallel path). */
 int  rr_diag(rr_ctx* ctx, int32_t* out, void* stream);
 
 #ifdef __cplusplus

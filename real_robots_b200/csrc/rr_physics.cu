@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
     }
     if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
     if (lane == 0) {
-        st.diag[4 * e] = m.n_rows + 3 * nc; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow;
+        st.diag[4 * e] = m.n_rows + 3 * nc; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (m.simple ? 2 : 0);   // bit 0: contact cap hit, bit 1: object-parallel solver path
         st.timestep[e] += 1;
     }
 }

@@ -15,7 +15,7 @@ torch.cuda.synchronize()
 prof = sim.profile_read()
 q = sim.read_state()
 chk = float(q[0].sum()) + float(q[2].sum())
-d = sim.diag().double().mean(dim=0).tolist()
+dg = sim.diag(); d = dg.double().mean(dim=0).tolist(); d[3] = float(((dg[:, 3] & 2) != 0).double().mean())
 print("%s: dyn+solve %.3f ms, collide %.3f ms  checksum %.12f  diag(rows, iters, contacts, overflow) %s" % (
     os.path.basename(os.environ.get("RR_LIB", "default")), prof["step"][0] / max(prof["step"][1], 1),
     prof["collide"][0] / max(prof["collide"][1], 1), chk, ["%.2f" % x for x in d]))
