@@ -391,3 +391,33 @@ def test_cuda_path_against_reference_host_goldens():
         assert np.abs(o.targets() - targets[i]).max() < 1e-15
         assert np.abs(o.get_state()[0] - qg[i]).max() < 1e-9
     sim.close()
+
+
+def test_long_random_rollout_stays_physical():
+    """1024 envs, 1500 steps of the vectorised random policy (cli.py:12-20): nothing blows up.  Joint positions stay inside
+    the URDF limits (+ the 0.1 rad the limit rows allow while they act), objects stay in the workspace or are sent back
+    by control_objects_limits, velocities stay below Bullet's clamp, the contact cap is never hit, touch >= 0."""
+    import bench
+    N, T = 1024, 1500
+    sim = BatchedSim(N, 3)
+    acts = bench.random_policy_actions(torch, 300, N, torch.device("cuda"), 7)
+    worst_flags = torch.zeros(N, dtype=torch.int32, device="cuda")
+    for t in range(T):
+        sim.step(acts[t % 300])
+        if t % 100 == 99:
+            worst_flags |= sim.diag()[:, 3] & 1
+    q, qd, obj = sim.get_state()
+    joints, touch, _ = sim.read_state()
+    assert bool(torch.isfinite(q).all()) and bool(torch.isfinite(qd).all()) and bool(torch.isfinite(obj).all())
+    # arm and proximal finger joints have URDF limits; the distal finger joints are declared with lower > upper, which
+    # Bullet reads as "unlimited" — only their motors hold them, so contact can push them further
+    # (limits are solver rows with ERP 0.2, not hard stops: a finger jammed against the table gives way by a few tenths of a radian)
+    assert float(q[:, :7].abs().max()) < 0.972 * np.pi + 0.5
+    assert float(q[:, [7, 9]].min()) > -0.5 and float(q[:, [7, 9]].max()) < np.pi / 2 + 0.5 and float(q[:, [8, 10]].abs().max()) < 2 * np.pi
+    assert float(qd.abs().max()) <= 100.0 and float(obj[:, :, 7:].abs().max()) <= 100.0
+    assert float(obj[:, :, 2].min()) > 0.0 and float(obj[:, :, 2].max()) < 2.5 and float(obj[:, :, :2].abs().max()) < 3.0
+    assert float((obj[:, :, 3:7].norm(dim=2) - 1).abs().max()) < 1e-9
+    assert bool((touch >= 0).all()) and int(worst_flags.sum()) == 0
+    rgb, depth, seg = sim.render()
+    assert bool(torch.isfinite(depth).all()) and int(seg.min()) >= -1 and int(seg.max()) <= 4
+    sim.close()
