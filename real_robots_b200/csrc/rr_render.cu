@@ -23,35 +23,33 @@
 __constant__ RenderConst c_render;
 __constant__ float c_cull_hmax;      // largest 'smallest altitude' over all triangles (see build_planes)
 
+// Tunables (all overridable with -D for scripts/build_variant.sh sweeps; the defaults are the measured optimum on B200)
 #ifndef STRIP_ROWS
-#define STRIP_ROWS 40
+#define STRIP_ROWS 40              // raster rows per strip: 40 x 320 x 8 B of keys = 100 KB, two CTAs per SM
 #endif
 #define NSTRIPS (RR_H / STRIP_ROWS)
 #ifndef RTHREADS
-#define RTHREADS 512
+#define RTHREADS 512               // threads per CTA
 #endif
 #ifndef RBLOCKS
-#define RBLOCKS 2
+#define RBLOCKS 2                  // resident CTAs per SM (shared-memory and register bound: 2 x 512 x 64 registers)
 #endif
-//            // resident CTAs per SM (shared memory bound)
 #define MAT_STRIDE RR_MAT_STRIDE   // floats per (env, shape): pmv[16] model[12] invT[9] ylo yhi flag cam_model[3] cull_bound
 #ifndef SMALL_AREA
-#define SMALL_AREA 16
+#define SMALL_AREA 16              // in-strip bounding-box pixels up to which a triangle is rasterised by one lane
 #endif
-//           // in-strip bounding-box pixels up to which a triangle is rasterised by its own lane
 #ifndef PRECULL_AREA
-#define PRECULL_AREA 4           // bounding boxes up to this many pixels are coverage-tested in the geometry phase
+#define PRECULL_AREA 4             // bounding boxes up to this many pixels are coverage-tested in the geometry phase
 #endif
 #ifndef MED_LANES
-#define MED_LANES 8             // lanes that share one medium record
-#endif
-#ifndef HUGE_GROUP
-#define HUGE_GROUP 256         // threads that share one huge triangle
+#define MED_LANES 8                // lanes that share one medium record (32 / MED_LANES records per warp at a time)
 #endif
 #ifndef HUGE_AREA
-#define HUGE_AREA 256
+#define HUGE_AREA 256              // in-strip bounding-box pixels above which HUGE_GROUP threads share the triangle
 #endif
-//         // in-strip bounding-box pixels above which the whole CTA rasterises the triangle
+#ifndef HUGE_GROUP
+#define HUGE_GROUP 256
+#endif
 
 #ifdef RR_STATS   // tuning build only (scripts/raster_stats.py): event counters, read back with rr_debug_raster_stats
 __device__ unsigned long long g_stats[16];
