@@ -50,6 +50,9 @@ __constant__ float c_cull_hmax;      // largest 'smallest altitude' over all tri
 #ifndef HUGE_GROUP
 #define HUGE_GROUP 256
 #endif
+#ifndef REVERSE_ORDER
+#define REVERSE_ORDER 1
+#endif
 
 #ifdef RR_STATS   // tuning build only (scripts/raster_stats.py): event counters, read back with rr_debug_raster_stats
 __device__ unsigned long long g_stats[16];
@@ -712,9 +715,13 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         // triangle's plane than any rounding of the fp32 world coordinates can move that plane, so the exact fp64 test of
         // tri_vertex() would decide the same way; everything else is marked uncertain (bit 15) and takes the exact test.
         for (int base = 0; base < n_tris; base += RTHREADS) {
+#if REVERSE_ORDER
+            const int gt = n_tris - 1 - (base + tid);          // last shapes first: objects and the arm's upper links are nearest the eye
+#else
             const int gt = base + tid;
+#endif
             int code = -1;
-            if (gt < n_tris) {
+            if (gt >= 0 && gt < n_tris) {
                 const float* Ms = M + tri_shape[gt] * MAT_STRIDE;
                 if (Ms[39] != 0.f) {
                     const float4 pl = __ldg(planes + gt);
