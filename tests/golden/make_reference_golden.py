@@ -89,7 +89,8 @@ def install_stubs():
     gym = mod("gym", spaces=shim, Env=object)
     sys.modules["gym.spaces"] = shim
     mod("gym.envs")
-    mod("gym.envs.registration", register=lambda **kw: None)
+    registered = []
+    mod("gym.envs.registration", register=lambda **kw: registered.append(kw), registered=registered)
     gym.make = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("gym.make is not available in the golden generator"))
     events = []
 
@@ -331,6 +332,12 @@ def main():
     except Exception as ex:
         errors["not_a_policy"] = type(ex).__name__
     meta["eval_errors"] = errors
+
+    # ---- registry (real_robots/__init__.py:16-28) and the BasePolicy interface (policy.py)
+    import inspect
+    import gym.envs.registration as reg
+    meta["registry"] = {r["id"]: {"entry_point": r["entry_point"], "kwargs": r["kwargs"]} for r in reg.registered}
+    meta["base_policy"] = {n: str(inspect.signature(f)) for n, f in inspect.getmembers(BasePolicy, inspect.isfunction)}
 
     G["meta_json"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), dtype=np.uint8)
     out = os.path.join(HERE, "reference_host_golden.npz")

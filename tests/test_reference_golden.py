@@ -208,3 +208,20 @@ def test_evaluation_service_flow_matches_reference(monkeypatch):
         with pytest.raises(Exception) as ei:
             EvaluationService(fake_env.make_controller(BasePolicy, []), *eval(args), 1, 1, 1, False, "g.npz", None)
         assert str(ei.value) == msg
+
+
+def test_registry_and_policy_interface_match_reference():
+    """The 18 env ids with their constructor kwargs (real_robots/__init__.py:16-28, recorded from the reference's own
+    register() calls) and the BasePolicy method signatures (policy.py)."""
+    import inspect
+    import real_robots_b200
+    from real_robots_b200.policy import BasePolicy
+    ref = META["registry"]
+    assert sorted(real_robots_b200.REGISTRY) == sorted(ref)
+    for env_id, entry in ref.items():
+        assert real_robots_b200.REGISTRY[env_id] == entry["kwargs"], env_id
+        assert entry["entry_point"] == "real_robots.envs:REALRobotEnv"
+    assert real_robots.envs.REALRobotEnv is REALRobotEnv                       # the entry point resolves under the alias package
+    mine = {n: str(inspect.signature(f)) for n, f in inspect.getmembers(BasePolicy, inspect.isfunction)}
+    for name, sig in META["base_policy"].items():
+        assert mine.get(name) == sig, (name, mine.get(name), sig)
