@@ -84,3 +84,29 @@ def plain(x):
     if isinstance(x, (np.integer, int)):
         return int(x)
     return x
+
+
+# ---- scripted object motion for the settle detector (generate_goals.py:21-68 runEnv)
+def scripted_pose(script, s):
+    """Pose (xyz + quaternion) of the single object after s simulation steps."""
+    p = np.array([0.0, 0.0, 0.4, 0.0, 0.0, 0.0, 1.0])
+    if script == "A":                         # moving for 5 steps
+        p[2] -= 0.01 * min(s, 5)
+    elif script == "B":                       # moving for 40 steps
+        p[2] -= 0.001 * min(s, 40)
+    elif script == "C":                       # at rest, one 2e-4 jolt after step 25
+        p[0] += 2e-4 if s >= 25 else 0.0
+    elif script == "D":                       # q and -q alternate: the same orientation
+        p[3:] *= -1.0 if s % 2 else 1.0
+    elif script == "E":                       # creeping just below the threshold
+        p[1] += 0.9e-4 * s
+    elif script == "F":                       # creeping just above it
+        p[1] += 1.1e-4 * s
+    elif script == "G":                       # orientation drifting by 2e-3 per step for 30 steps
+        a = 1e-3 * min(s, 30)
+        p[3:] = [np.sin(a), 0.0, 0.0, np.cos(a)]
+    return p
+
+
+SCRIPTS = ["A", "B", "C", "D", "E", "F", "G"]
+MAX_TS = [31, 32, 45, 46, 47, 61, 62, 200]

@@ -333,6 +333,25 @@ def main():
         errors["not_a_policy"] = type(ex).__name__
     meta["eval_errors"] = errors
 
+    # ---- settle detector: runEnv (generate_goals.py:21-68) on scripted object motion
+    import contextlib, io
+    from real_robots import generate_goals as ref_gg
+    settle = {}
+    for script in fake_env.SCRIPTS:
+        for max_t in fake_env.MAX_TS:
+            st = NS(s=0)
+            e = NS(robot=NS(used_objects=["table", "cube"]))
+            e.get_obj_pose = lambda obj, st=st, script=script: fake_env.scripted_pose(script, st.s)
+            e.step = lambda action, st=st: (setattr(st, "s", st.s + 1), ({"retina": 0, "mask": 0}, 0, False, {}))[1]
+            with contextlib.redirect_stdout(io.StringIO()):
+                _, pos, failed, t, _ = ref_gg.runEnv(e, max_t=max_t)
+            settle["%s/%d" % (script, max_t)] = [bool(failed), int(t)]
+    meta["settle"] = settle
+    meta["shelf_table_thresholds"] = {obj: [float(z) for z in (0.30, 0.329, 0.331, 0.339, 0.341, 0.394, 0.396, 0.399, 0.401, 0.45)
+                                            if ref_gg.isOnTable(obj, {obj: [0, 0, z]})] +
+                                           [-float(z) for z in (0.30, 0.329, 0.331, 0.339, 0.341, 0.394, 0.396, 0.399, 0.401, 0.45)
+                                            if ref_gg.isOnShelf(obj, {obj: [0, 0, z]})] for obj in ("cube", "tomato", "mustard")}
+
     # ---- registry (real_robots/__init__.py:16-28) and the BasePolicy interface (policy.py)
     import inspect
     import gym.envs.registration as reg

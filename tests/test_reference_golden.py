@@ -225,3 +225,36 @@ def test_registry_and_policy_interface_match_reference():
     mine = {n: str(inspect.signature(f)) for n, f in inspect.getmembers(BasePolicy, inspect.isfunction)}
     for name, sig in META["base_policy"].items():
         assert mine.get(name) == sig, (name, mine.get(name), sig)
+
+
+def test_settle_detector_and_placement_thresholds_match_reference():
+    """generate_goals.runEnv (:21-68) was run on scripted object motions (tests/golden/fake_env.py); the batched settle()
+    must call the same poses still / not still for every script and step budget.  Also isOnTable / isOnShelf (:245-272)."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import fake_env
+    from real_robots_b200 import generate_goals as gg
+    scripts = fake_env.SCRIPTS
+
+    class FakeSim:
+        def __init__(self):
+            self.s = 0
+
+        def step(self, cmd):
+            self.s += 1
+
+        def read_state(self):
+            poses = np.stack([fake_env.scripted_pose(sc, self.s) for sc in scripts])[:, None, :]      # [N, 1 object, 7]
+            return None, None, torch.from_numpy(poses)
+    for max_t in fake_env.MAX_TS:
+        env = type("E", (), {})()
+        env.n_envs, env.device, env.sim = len(scripts), torch.device("cpu"), FakeSim()
+        still, _ = gg.settle(env, max_t=max_t)
+        for i, sc in enumerate(scripts):
+            failed, _t = META["settle"]["%s/%d" % (sc, max_t)]
+            assert bool(still[i]) == (not failed), (sc, max_t)
+    zs = (0.30, 0.329, 0.331, 0.339, 0.341, 0.394, 0.396, 0.399, 0.401, 0.45)
+    for obj, want in META["shelf_table_thresholds"].items():
+        mine = [z for z in zs if z < gg.TABLE_Z[obj]] + [-z for z in zs if z > gg.SHELF_Z[obj]]
+        assert mine == want, obj
