@@ -162,10 +162,11 @@ def main(argv=None):
     ap.add_argument("--file", default=None)
     a = ap.parse_args(argv)
     goals = []
-    for k, (ch, n) in enumerate((('2D', a.n_2d_goals), ('2.5D', a.n_25d_goals), ('3D', a.n_3d_goals))):
+    # generate_goals.py:425-433: 2D and 2.5D goals keep objects 0.25 m apart, 3D goals may touch; start and goal 0.2 m apart
+    for k, (ch, n, sep) in enumerate((('2D', a.n_2d_goals, 0.25), ('2.5D', a.n_25d_goals, 0.25), ('3D', a.n_3d_goals, 0.0))):
         if n > 0:
-            goals += generate_goals(n, a.n_obj, ch, seed=a.seed + k)
-    name = a.file or "goals-REAL2020-s{}-{}-{}-{}-{}".format(a.seed, a.n_2d_goals, a.n_25d_goals, a.n_3d_goals, a.n_obj)
+            goals += generate_goals(n, a.n_obj, ch, seed=a.seed + k, min_start_goal_dist=0.2, min_objects_dist=sep)
+    name = a.file or "goals-REAL2020-s{}-{}-{}-{}-{}.npy".format(a.seed, a.n_2d_goals, a.n_25d_goals, a.n_3d_goals, a.n_obj)
     save_goals(goals, name)
     print("wrote %d goals to %s.npz" % (len(goals), name))
 

@@ -347,6 +347,13 @@ def main():
                 _, pos, failed, t, _ = ref_gg.runEnv(e, max_t=max_t)
             settle["%s/%d" % (script, max_t)] = [bool(failed), int(t)]
     meta["settle"] = settle
+    # generatePosition (:79-108) with the legacy global RNG: x, y, z and (free orientation) the quaternion of 3 Euler draws
+    draws = []
+    fake_p = NS(getQuaternionFromEuler=quat_from_euler)
+    for seed, plane in ((1, None), (2, True), (3, False), (4, True), (5, None)):
+        np.random.seed(seed)
+        draws.append([ref_gg.generatePosition(NS(_p=fake_p), "cube", fixed=False, tablePlane=plane) for _ in range(4)])
+    G["genpos_free"] = np.array(draws)
     meta["shelf_table_thresholds"] = {obj: [float(z) for z in (0.30, 0.329, 0.331, 0.339, 0.341, 0.394, 0.396, 0.399, 0.401, 0.45)
                                             if ref_gg.isOnTable(obj, {obj: [0, 0, z]})] +
                                            [-float(z) for z in (0.30, 0.329, 0.331, 0.339, 0.341, 0.394, 0.396, 0.399, 0.401, 0.45)

@@ -258,3 +258,13 @@ def test_settle_detector_and_placement_thresholds_match_reference():
     for obj, want in META["shelf_table_thresholds"].items():
         mine = [z for z in zs if z < gg.TABLE_Z[obj]] + [-z for z in zs if z > gg.SHELF_Z[obj]]
         assert mine == want, obj
+
+
+def test_generate_position_matches_reference_draw_for_draw():
+    """generatePosition (generate_goals.py:79-108): same legacy-RNG call order, so RandomState(seed) here reproduces the
+    reference under np.random.seed(seed) — x range by table plane, y in [-.45, .45], z = 0.40 / 0.50, free orientation."""
+    from real_robots_b200 import generate_goals as gg
+    for (seed, plane), want in zip(((1, None), (2, True), (3, False), (4, True), (5, None)), G["genpos_free"]):
+        rng = np.random.RandomState(seed)
+        got = np.array([gg.generate_position(rng, "cube", False, plane) for _ in range(4)])
+        assert np.abs(got - want).max() < 1e-15, (seed, plane)
