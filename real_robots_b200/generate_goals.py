@@ -88,13 +88,17 @@ def generate_goals(n_goals, n_objects=1, challenge='2D', seed=2020, device=0, ba
                    min_objects_dist=0.05, max_rounds=20):
     """Returns a list of `Goal` (initial_state / final_state: dict name -> pose7, retina, retina_before, mask, challenge).
 
-    challenge '2D': fixed (base) orientations, objects on the table plane; '2.5D': the goal (or the start) is on the shelf;
-    '3D': free orientations.  (generateGoalREAL2020 :275-365, simplified: the near-objects variants are not reproduced.)"""
+    challenge '2D': fixed (base) orientations, every object drawn on the table plane (objOnTable, :280-285); '2.5D': fixed
+    orientations, x drawn over table and shelf, at least one object on the shelf in the initial or the final state
+    (:314-319, 345-351); '3D': the same with free orientations.  Start and goal of every object are at least
+    `min_start_goal_dist` apart in the table plane (:353-357, xy only).  (generateGoalREAL2020 :275-365; its
+    max_objects_dist = 2 m test is always true on this table and is not reproduced.)"""
     import torch
     from .envs.vec_env import VecREALRobotEnv
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(seed) if not hasattr(seed, "random") else seed
     objects = OBJECTS[:n_objects]
     fixed = challenge != '3D'
+    plane = True if challenge == '2D' else None
     N = batch or max(8, 2 * n_goals)
     env = VecREALRobotEnv(N, device=device, objects=n_objects, action_type='joints', additional_obs=True)
     goals = []
@@ -103,12 +107,9 @@ def generate_goals(n_goals, n_objects=1, challenge='2D', seed=2020, device=0, ba
             break
         states, images = [], []
         for phase in range(2):                       # 0 = initial placement, 1 = goal placement
-            plane = [True] * N                       # True = table plane, False = shelf
-            if challenge == '2.5D':                  # one end of the move is on the shelf
-                plane = [(e % 2 == 0) == (phase == 0) for e in range(N)]
             start = np.zeros((N, n_objects, 7))
             for e in range(N):
-                poses = draw_start_poses(rng, objects, fixed, plane[e], min_objects_dist)
+                poses = draw_start_poses(rng, objects, fixed, plane, min_objects_dist)
                 for o, name in enumerate(objects):
                     start[e, o] = poses[name]
             env.reset(render=False)
@@ -116,29 +117,30 @@ def generate_goals(n_goals, n_objects=1, challenge='2D', seed=2020, device=0, ba
             env.set_object_poses(torch.from_numpy(start).to(env.device))
             still, poses = settle(env)
             rgb, depth, seg = env.sim.render()
-            states.append((still.cpu().numpy(), poses.cpu().numpy(), plane, start))
+            states.append((still.cpu().numpy(), poses.cpu().numpy(), start))
             images.append((rgb.cpu().numpy(), seg.cpu().numpy()))
-        (s0, p0, pl0, st0), (s1, p1, pl1, st1) = states
+        (s0, p0, st0), (s1, p1, st1) = states
         ok = s0 & s1 & (_min_separation(p0) >= min_objects_dist) & (_min_separation(p1) >= min_objects_dist)
-        ok &= (np.linalg.norm(p0[:, :, :3] - p1[:, :, :3], axis=2) >= min_start_goal_dist).all(axis=1)
+        ok &= (np.linalg.norm(p0[:, :, :2] - p1[:, :, :2], axis=2) >= min_start_goal_dist).all(axis=1)
         for e in range(N):
             if not ok[e] or len(goals) >= n_goals:
                 continue
             good = True
-            for o, name in enumerate(objects):
-                for p, plane in ((p0, pl0), (p1, pl1)):
-                    z = p[e, o, 2]
-                    good &= (z < TABLE_Z[name]) if plane[e] else (z > SHELF_Z[name])
-                if fixed:                             # objects must keep their orientation (:186-200)
+            if fixed:                                 # objects must keep their orientation (:186-200)
+                for o in range(n_objects):
                     for p, st in ((p0, st0), (p1, st1)):
                         dq = min(np.linalg.norm(p[e, o, 3:] - st[e, o, 3:]), np.linalg.norm(p[e, o, 3:] + st[e, o, 3:]))
                         good &= dq <= 0.041
+            if challenge != '2D':                     # at least one object on the shelf at one end of the move
+                good &= any(p[e, o, 2] > SHELF_Z[name] for p in (p0, p1) for o, name in enumerate(objects))
             if not good:
                 continue
-            goals.append(Goal(initial_state={n: p0[e, o].copy() for o, n in enumerate(objects)},
-                              final_state={n: p1[e, o].copy() for o, n in enumerate(objects)},
-                              retina_before=images[0][0][e].copy(), retina=images[1][0][e].copy(),
-                              mask=images[1][1][e].copy(), challenge=challenge))
+            g = Goal(initial_state={n: p0[e, o].copy() for o, n in enumerate(objects)},
+                     final_state={n: p1[e, o].copy() for o, n in enumerate(objects)},
+                     retina_before=images[0][0][e].copy(), retina=images[1][0][e].copy(),
+                     mask=images[1][1][e].copy(), challenge=challenge)
+            g.subtype = str(n_objects)                # :359
+            goals.append(g)
     env.close()
     return goals
 

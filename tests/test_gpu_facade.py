@@ -210,6 +210,17 @@ def test_goal_generation_roundtrip(tmp_path):
     ch, score = env.evaluateGoal()
     assert ch == '2D' and 0 < score < 0.3
     env.close()
+    # 2.5D: x is drawn over table and shelf; an accepted goal has an object on the shelf at one end of the move (:314-351)
+    from real_robots_b200.generate_goals import SHELF_Z
+    goals = generate_goals(2, n_objects=2, challenge='2.5D', seed=9, batch=32, min_start_goal_dist=0.2, min_objects_dist=0.25)
+    assert len(goals) == 2
+    for g in goals:
+        assert g.challenge == '2.5D' and g.subtype == '2'
+        assert any(st[n][2] > SHELF_Z[n] for st in (g.initial_state, g.final_state) for n in st)
+        for n in g.initial_state:
+            assert np.linalg.norm(g.initial_state[n][:2] - g.final_state[n][:2]) >= 0.2
+        p = np.array([g.final_state[n][:3] for n in g.final_state])
+        assert np.linalg.norm(p[0] - p[1]) >= 0.25
 
 
 def test_videomaker_writes_frames(tmp_path, monkeypatch):
