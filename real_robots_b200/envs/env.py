@@ -1,9 +1,11 @@
-"""Host-side mirror of real_robots/envs/env.py: Goal, REALRobotEnv (the N = 1 gym facade) and the cameras.
+"""Host-side stand-in for real_robots/envs/env.py: Goal, REALRobotEnv (the N = 1 gym facade) and the eye camera record.
 
-Same method names, argument meaning and error behaviour as the reference (env.py:15-467); every pybullet call
-below the reference's `self._p.*` seam is replaced by a C-ABI call (include/real_b200.h) through BatchedSim.
-The facade is an n_envs = 1 view that copies results to numpy to honour the reference's return types; the
-zero-copy batched interface is envs/vec_env.py.
+The public surface (method and attribute names, argument meaning, return types, error behaviour) is the reference's
+(env.py:15-467) and is checked against vectors recorded from the reference's own code (tests/test_reference_golden.py).
+Nothing below the reference's `self._p.*` seam is Python here: one `rr_step` call does the whole
+limitActionByJoint / control_objects_limits / apply_action / stepSimulation sequence, `rr_render` the retina, `rr_ik` the
+inverse kinematics (include/real_b200.h, through BatchedSim).  The facade is an n_envs = 1 view that copies results to numpy
+to honour the reference's return types; the zero-copy batched interface is envs/vec_env.py.
 """
 import os
 
@@ -13,53 +15,57 @@ from .. import spaces
 from ..util import euler_to_quat
 from .robot import Kuka
 
+# ---- constants of the reference (file:line in the comments)
+CARTESIAN_BOUNDS = ([-0.25, -0.5, 0.40, -1, -1, -1, -1], [0.25, 0.5, 0.60, 1, 1, 1, 1])      # env.py:44-47 xyz + quaternion
+MACRO_BOUNDS = ([[-0.25, -0.5], [-0.25, -0.5]], [[0.05, 0.5], [0.05, 0.5]])                   # env.py:49-52 two table points
+PLAN_ORIENTATION_EULER = [0, 3.14, -1.57]                                                       # env.py:421 gripper pointing down
+PLAN_HIGH_Z, PLAN_LOW_Z, PLAN_SPACING = 0.6, 0.46, 0.05                                         # env.py:425-444
+SCORE_DECAY = -np.log(0.25) / 0.10                                                              # env.py:192: 0.25 at 10 cm
+# action type -> (command keys of the action dict, name of the step method, request-cache attributes reset to None)
+ACTION_TYPES = {
+    'joints': (("joint_command",), "step_joints", ()),
+    'cartesian': (("cartesian_command", "gripper_command"), "step_cartesian", ("requested_coords", "requested_orient", "last_ik")),
+    'macro_action': (("macro_action",), "step_macro", ("requested_action",)),
+}
 
-def DefaultRewardFunc(observation):     # env.py:11-12
+
+def DefaultRewardFunc(observation):     # env.py:11-12: the task has no extrinsic reward
     return 0
 
 
-class Goal:                             # env.py:15-24 (pickled inside goals .npy.npz files)
+class Goal:
+    """env.py:15-24; instances are pickled inside goal files, hence the module path set below."""
+
     def __init__(self, initial_state=None, final_state=None, retina=None,
                  retina_before=None, challenge=None, mask=None):
-        self.initial_state = initial_state
-        self.final_state = final_state
-        self.retina = retina
-        self.retina_before = retina_before
-        self.challenge = challenge
-        self.mask = mask
+        self.initial_state, self.final_state = initial_state, final_state
+        self.retina, self.retina_before = retina, retina_before
+        self.challenge, self.mask = challenge, mask
 
 
 Goal.__module__ = "real_robots.envs.env"     # goal files stay loadable by the reference (generate_goals.py:435, env.py:143-145)
 
 
 def macro_plan(goToPosXY, point_1, point_2):
-    """env.py:410-459 generate_plan: 1000 x 9 joint plan from two table points; goToPosXY(coords) -> 9 joints."""
+    """The 1000 x 9 joint plan of a macro action (env.py:410-459): home2 100 rows, above p1 100, down at p1 50, a 500-row
+    sweep to p2 at table height, above p2 50, home2 100, home 100.  goToPosXY(xyz) -> 9 joint values.
+
+    The sweep visits `pieces` = min(int(|p2 - p1| / 0.05) + 1, 500) equally spaced way-points; way-point i owns the rows from
+    i * (500 // pieces) on, the last one to the end.  The reference also solves the IK of the low point above p2 and never uses
+    it; that solve is skipped here (one IK call fewer per plan, same plan)."""
+    p1, p2 = np.asarray(point_1, dtype=np.float64), np.asarray(point_2, dtype=np.float64)
+    at = lambda p, z: np.append(p, z)                                                           # noqa: E731
     home = np.zeros(9)
     home2 = np.zeros(9)
-    home2[5] = np.pi / 2
-    home2[6] = np.pi / 2
-
-    def interpolate3D(p1, p2, steps):
-        p1 = np.array(p1)
-        p2 = np.array(p2)
-        dist = np.linalg.norm(p2 - p1)
-        pieces = int(dist / 0.05) + 1
-        pieces = min(pieces, steps)
-        coords = np.linspace(p1, p2, pieces + 1)
-        joints = np.zeros((steps, 9))
-        chunk = int(steps / pieces)
-        for i, coord in enumerate(coords[1:]):
-            joints[i * chunk:, :] = goToPosXY(coord)
-        return joints
-
-    point_1_h = goToPosXY(np.hstack([point_1, 0.6]))
-    point_1_l = goToPosXY(np.hstack([point_1, 0.46]))
-    point_2_h = goToPosXY(np.hstack([point_2, 0.6]))
-    point_2_l = goToPosXY(np.hstack([point_2, 0.46]))  # noqa: F841 (computed by the reference too; seeds nothing here)
-    parts = [np.tile(home2, (100, 1)), np.tile(point_1_h, (100, 1)), np.tile(point_1_l, (50, 1)),
-             interpolate3D(np.hstack([point_1, 0.46]), np.hstack([point_2, 0.46]), 500),
-             np.tile(point_2_h, (50, 1)), np.tile(home2, (100, 1)), np.tile(home, (100, 1))]
-    return np.vstack(parts)
+    home2[[5, 6]] = np.pi / 2
+    above_1, down_1, above_2 = goToPosXY(at(p1, PLAN_HIGH_Z)), goToPosXY(at(p1, PLAN_LOW_Z)), goToPosXY(at(p2, PLAN_HIGH_Z))
+    n_rows = 500
+    a, b = at(p1, PLAN_LOW_Z), at(p2, PLAN_LOW_Z)
+    pieces = min(int(np.linalg.norm(b - a) / PLAN_SPACING) + 1, n_rows)
+    solved = np.array([goToPosXY(w) for w in np.linspace(a, b, pieces + 1)[1:]])
+    owner = np.minimum(np.arange(n_rows) // (n_rows // pieces), pieces - 1)
+    blocks = [(home2, 100), (above_1, 100), (down_1, 50), (None, n_rows), (above_2, 50), (home2, 100), (home, 100)]
+    return np.vstack([solved[owner] if row is None else np.tile(row, (count, 1)) for row, count in blocks])
 
 
 class REALRobotEnv:
@@ -71,84 +77,71 @@ class REALRobotEnv:
     metadata = {"render.modes": ["human", "rgb_array"]}
 
     def __init__(self, render=False, objects=3, action_type='joints', additional_obs=True, device=0):
-        self.robot = Kuka(additional_obs, objects)
-        self.isRender = render
-        self._device = device
-        self._sim = None
-        self.joints_space = self.robot.action_space
-        self.cartesian_space = spaces.Box(low=np.array([-0.25, -0.5, 0.40, -1, -1, -1, -1]),
-                                          high=np.array([0.25, 0.5, 0.60, 1, 1, 1, 1]), dtype=float)
-        self.macro_space = spaces.Box(low=np.array([[-0.25, -0.5], [-0.25, -0.5]]),
-                                      high=np.array([[0.05, 0.5], [0.05, 0.5]]), dtype=float)
-        self.gripper_space = spaces.Box(low=0, high=np.pi / 2, shape=(2,), dtype=float)
-        if action_type == 'joints':
-            self.action_space = spaces.Dict({"joint_command": self.joints_space, "render": spaces.MultiBinary(1)})
-            self.step = self.step_joints
-        elif action_type == 'cartesian':
-            self.action_space = spaces.Dict({"cartesian_command": self.cartesian_space, "gripper_command": self.gripper_space,
-                                             "render": spaces.MultiBinary(1)})
-            self.step = self.step_cartesian
-            self.requested_coords = None
-            self.requested_orient = None
-            self.last_ik = None
-        elif action_type == 'macro_action':
-            self.action_space = spaces.Dict({"macro_action": self.macro_space, "render": spaces.MultiBinary(1)})
-            self.step = self.step_macro
-            self.requested_action = None
-        else:
+        if action_type not in ACTION_TYPES:
             raise ValueError("action_type must be one 'joints', 'cartesian' or 'macro_action'")
-        self.action_type = action_type
+        self.robot = Kuka(additional_obs, objects)
+        self.isRender, self.additional_obs, self.action_type = render, additional_obs, action_type
+        self._device, self._sim = device, None
+        # spaces (env.py:42-81)
+        box = lambda bounds: spaces.Box(low=np.array(bounds[0]), high=np.array(bounds[1]), dtype=float)     # noqa: E731
+        self.joints_space = self.robot.action_space
+        self.cartesian_space, self.macro_space = box(CARTESIAN_BOUNDS), box(MACRO_BOUNDS)
+        self.gripper_space = spaces.Box(low=0, high=np.pi / 2, shape=(2,), dtype=float)
+        by_key = {"joint_command": self.joints_space, "cartesian_command": self.cartesian_space,
+                  "gripper_command": self.gripper_space, "macro_action": self.macro_space}
+        keys, step_name, cache_attrs = ACTION_TYPES[action_type]
+        self.action_space = spaces.Dict(dict([(k, by_key[k]) for k in keys] + [("render", spaces.MultiBinary(1))]))
         self.observation_space = self.robot.observation_space
-        self._cam_dist, self._cam_yaw, self._cam_roll, self._cam_pitch = 1.2, 30, 0, -30
+        self.step = getattr(self, step_name)
+        for attr in cache_attrs:
+            setattr(self, attr, None)
+        # debug camera of render('rgb_array') (env.py:83-90) and the eye (env.py:136)
+        self._cam_dist, self._cam_yaw, self._cam_roll, self._cam_pitch, self._cam_pos = 1.2, 30, 0, -30, [0, 0, .4]
         self._render_width, self._render_height = 320, 240
-        self._cam_pos = [0, 0, .4]
         self.eyes = {"eye": EyeCamera([0.01, 0, 1.2], [0, 0, 0])}
         self.reward_func = DefaultRewardFunc
-        S = self.robot.ObsSpaces
-        self.goal = Goal(retina=self.observation_space.spaces[S.GOAL].sample() * 0)
+        # goals (env.py:97-113) and the zero images returned while the camera is off (env.py:114-122)
+        obs = self.observation_space.spaces
+        K = self.robot.ObsSpaces
+        blank = lambda key: obs[key].sample() * 0                                                             # noqa: E731
+        self.goal = Goal(retina=blank(K.GOAL))
+        self.goals, self.goal_idx = None, -1
         from .. import getPackageDataPath
         self.goals_dataset_path = os.path.join(getPackageDataPath(), "goals_dataset.npy.npz")
-        self.goals = None
-        self.goal_idx = -1
-        self.no_retina = self.observation_space.spaces[S.RETINA].sample() * 0
-        self.no_depth = self.observation_space.spaces[S.DEPTH].sample() * 0
-        self.additional_obs = additional_obs
+        self.no_retina, self.no_depth = blank(K.RETINA), blank(K.DEPTH)
         if additional_obs:
+            self.no_mask = blank(K.MASK)
             self.get_observation = self.get_observation_extended
-            self.no_mask = self.observation_space.spaces[S.MASK].sample() * 0
         self.timestep = 0
 
     # ------------------------------------------------------------------ goals (env.py:143-200)
-    def load_goals(self):
-        self.goals = list(np.load(self.goals_dataset_path, allow_pickle=True).items())[0][1]
-
     def set_goals_dataset_path(self, path):
         assert os.path.exists(path), "Non existent path {}".format(path)
         self.goals_dataset_path = path
 
+    def load_goals(self):
+        """The file holds one pickled object array of Goal (np.savez_compressed(path, list_of_goals))."""
+        archive = np.load(self.goals_dataset_path, allow_pickle=True)
+        self.goals = archive[archive.files[0]]
+
     def set_goal(self):
+        """Next goal of the dataset: objects go to its initial poses; its final state keeps positions only."""
         if self.goals is None:
             self.load_goals()
         self.goal_idx += 1
-        self.goal = self.goals[self.goal_idx]
-        for obj in self.goal.initial_state.keys():
-            position = self.goal.initial_state[obj][:3]
-            orientation = self.goal.initial_state[obj][3:]
-            self.robot.object_bodies[obj].reset_pose(position, orientation)
-        for obj in self.goal.final_state.keys():
-            self.goal.final_state[obj] = self.goal.final_state[obj][:3]
+        goal = self.goal = self.goals[self.goal_idx]
+        for name, pose in goal.initial_state.items():
+            self.robot.object_bodies[name].reset_pose(pose[:3], pose[3:])
+        goal.final_state = {name: pose[:3] for name, pose in goal.final_state.items()}
         return self.get_observation()
 
     def evaluateGoal(self):
-        final_state = self.goal.final_state
-        current_state = self.robot.object_bodies
+        """(challenge, sum over goal objects of exp(-ln 4 / 0.1 m x distance to the goal position))."""
+        bodies = self.robot.object_bodies                     # KeyError for unknown objects, as in the reference
         score = 0
-        for obj in final_state.keys():
-            p = np.array(current_state[obj].get_position())      # KeyError for unknown objects, as in the reference
-            p_goal = np.array(final_state[obj][:3])
-            pos_dist = np.linalg.norm(p_goal - p)
-            pos_const = -np.log(0.25) / 0.10                      # score goes down to 0.25 within 10 cm
-            score += np.exp(-pos_const * pos_dist)
+        for name, target in self.goal.final_state.items():
+            offset = np.array(target[:3]) - np.array(bodies[name].get_position())
+            score += np.exp(-SCORE_DECAY * np.linalg.norm(offset))
         return self.goal.challenge, score
 
     # ------------------------------------------------------------------ lifecycle
@@ -197,7 +190,8 @@ class REALRobotEnv:
         return self.robot.object_bodies[name].get_pose()
 
     def get_all_used_objects(self):
-        return {obj: self.robot.object_bodies[obj].get_position() for obj in self.robot.used_objects[1:]}
+        bodies = self.robot.object_bodies
+        return {name: bodies[name].get_position() for name in self.robot.used_objects[1:]}      # [0] is the table
 
     def get_contacts(self):
         return self.robot.get_contacts()
@@ -207,109 +201,84 @@ class REALRobotEnv:
         return rgb[0].cpu().numpy(), seg[0].cpu().numpy(), depth[0].cpu().numpy()
 
     # ------------------------------------------------------------------ observations (env.py:266-312)
-    def get_observation(self, camera_on=True):
-        joints = self.robot.calc_state()
-        sensors = self.robot.get_touch_sensors()
+    def _images(self, camera_on):
         if camera_on:
-            retina, _, depth = self.get_retina()
-        else:
-            retina, depth = self.no_retina, self.no_depth
+            return self.get_retina()
+        return self.no_retina, getattr(self, "no_mask", None), self.no_depth
+
+    def get_observation(self, camera_on=True):
         K = Kuka.ObsSpaces
-        return {K.JOINT_POSITIONS: joints, K.TOUCH_SENSORS: sensors, K.RETINA: retina, K.DEPTH: depth, K.GOAL: self.goal.retina}
+        retina, _, depth = self._images(camera_on)
+        return {K.JOINT_POSITIONS: self.robot.calc_state(), K.TOUCH_SENSORS: self.robot.get_touch_sensors(),
+                K.RETINA: retina, K.DEPTH: depth, K.GOAL: self.goal.retina}
 
     def get_observation_extended(self, camera_on=True):
-        joints = self.robot.calc_state()
-        sensors = self.robot.get_touch_sensors()
-        if camera_on:
-            retina, mask, depth = self.get_retina()
-        else:
-            retina, mask, depth = self.no_retina, self.no_mask, self.no_depth
         K = Kuka.ObsSpaces
-        return {K.JOINT_POSITIONS: joints, K.TOUCH_SENSORS: sensors, K.RETINA: retina, K.DEPTH: depth, K.MASK: mask,
-                K.OBJ_POS: self.get_all_used_objects(), K.GOAL: self.goal.retina, K.GOAL_MASK: self.goal.mask,
-                K.GOAL_POS: self.goal.final_state}
+        retina, mask, depth = self._images(camera_on)
+        return {K.JOINT_POSITIONS: self.robot.calc_state(), K.TOUCH_SENSORS: self.robot.get_touch_sensors(),
+                K.RETINA: retina, K.DEPTH: depth, K.MASK: mask, K.OBJ_POS: self.get_all_used_objects(),
+                K.GOAL: self.goal.retina, K.GOAL_MASK: self.goal.mask, K.GOAL_POS: self.goal.final_state}
 
     # ------------------------------------------------------------------ stepping (env.py:314-467)
     def step(self, action):
         return self.step_joint(action)          # env.py:323-324 (rebound in __init__, exactly as in the reference)
 
+    def _phase_limit(self):
+        """Steps allowed in the current phase: intrinsic until the first goal is set, extrinsic afterwards (env.py:345-352)."""
+        return self.intrinsic_timesteps if self.goal_idx < 0 else self.extrinsic_timesteps
+
     def step_joints(self, action):
-        joint_action = action['joint_command']
-        camera_on = action['render']
-        if joint_action is None:
-            joint_action = np.zeros(9)
-        joint_action = np.asarray(joint_action, dtype=np.float64)
-        assert np.isfinite(joint_action).all()           # robot.py:189
-        assert len(joint_action) == self.robot.num_joints  # robot.py:190
+        command, camera_on = action['joint_command'], action['render']
+        command = np.zeros(9) if command is None else np.asarray(command, dtype=np.float64)
+        assert np.isfinite(command).all()                   # robot.py:189
+        assert len(command) == self.robot.num_joints        # robot.py:190
         # limitActionByJoint, control_objects_limits, apply_action and stepSimulation all run inside rr_step
-        self._cmd.copy_(self._torch.from_numpy(joint_action.reshape(1, 9)))
+        self._cmd.copy_(self._torch.from_numpy(command.reshape(1, 9)))
         self._sim.step(self._cmd)
         observation = self.get_observation(bool(np.any(camera_on)))
-        reward = self.reward_func(observation)
-        done = False
         self.timestep += 1
-        if self.goal_idx < 0:
-            if self.timestep >= self.intrinsic_timesteps:
-                done = True
-        else:
-            if self.timestep >= self.extrinsic_timesteps:
-                done = True
-        return observation, reward, done, {}
+        return observation, self.reward_func(observation), bool(self.timestep >= self._phase_limit()), {}
 
     def _ik(self, coords, orientation):
         t = self._torch
         pq = t.tensor([list(coords) + list(orientation)], dtype=t.float64, device=self._sim.device)
         return self._sim.ik(pq, max_iter=1000, residual=0.001)[0].cpu().numpy()
 
+    def _joint_action(self, joints, action):
+        return self.step_joints({"joint_command": joints, "render": action['render']})
+
     def step_cartesian(self, action):
-        if action['cartesian_command'] is None:
-            joint_action = {"joint_command": np.zeros(9), "render": action['render']}
-        else:
-            coords = action['cartesian_command'][:3]
-            desiredOrientation = action['cartesian_command'][3:]
-            sameCoords = np.all(coords == self.requested_coords)
-            sameOrient = np.all(desiredOrientation == self.requested_orient)
-            if sameCoords and sameOrient:
-                arm_joints = self.last_ik
-            else:
-                arm_joints = self._ik(coords, desiredOrientation)
-                self.last_ik = arm_joints
-                self.requested_coords = coords
-                self.requested_orient = desiredOrientation
-            gripper_joints = action['gripper_command']
-            all_joints = np.hstack([arm_joints[:7], gripper_joints])
-            joint_action = {"joint_command": all_joints, "render": action['render']}
-        return self.step_joints(joint_action)
+        """env.py:358-386: the IK is solved again only when the request differs from the previous one (exact comparison)."""
+        request = action['cartesian_command']
+        if request is None:
+            return self._joint_action(np.zeros(9), action)
+        coords, orient = request[:3], request[3:]
+        if not (np.all(coords == self.requested_coords) and np.all(orient == self.requested_orient)):
+            self.last_ik = self._ik(coords, orient)
+            self.requested_coords, self.requested_orient = coords, orient
+        return self._joint_action(np.hstack([self.last_ik[:7], action['gripper_command']]), action)
 
     def step_macro(self, action):
-        macro_action = action['macro_action']
-        if macro_action is None:
-            joint_action = {"joint_command": np.zeros(9), "render": action['render']}
-        else:
-            sameAction = np.all(macro_action == self.requested_action)
-            joints = None
-            if sameAction:
-                joints = self.next_step()
-            if not sameAction or joints is None:
-                self.requested_action = macro_action
-                self.generate_plan(macro_action)
-                joints = self.next_step()
-            joint_action = {"joint_command": joints, "render": action['render']}
-        return self.step_joints(joint_action)
+        """env.py:388-408: a repeated macro action replays the next row of its plan; a new one, or an exhausted plan, re-plans."""
+        request = action['macro_action']
+        if request is None:
+            return self._joint_action(np.zeros(9), action)
+        row = self.next_step() if np.all(request == self.requested_action) else None
+        if row is None:
+            self.requested_action = request
+            self.generate_plan(request)
+            row = self.next_step()
+        return self._joint_action(row, action)
 
     def generate_plan(self, macro_action):
-        orientation = euler_to_quat([0, 3.14, -1.57])
-
-        def goToPosXY(coords):
-            return self._ik(coords, orientation)[:9]
-        self.planned_actions = macro_plan(goToPosXY, macro_action[0], macro_action[1])
+        down = euler_to_quat(PLAN_ORIENTATION_EULER)
+        self.planned_actions = macro_plan(lambda xyz: self._ik(xyz, down)[:9], macro_action[0], macro_action[1])
         self.plan_step = -1
 
     def next_step(self):
         self.plan_step += 1
-        if self.plan_step < len(self.planned_actions):
-            return self.planned_actions[self.plan_step, :]
-        return None
+        plan = self.planned_actions
+        return plan[self.plan_step, :] if self.plan_step < len(plan) else None
 
 
 class EyeCamera:

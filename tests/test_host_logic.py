@@ -79,13 +79,13 @@ def test_macro_plan_layout():
     assert np.allclose(plan[0], [0, 0, 0, 0, 0, np.pi / 2, np.pi / 2, 0, 0]) and np.allclose(plan[-1], 0)
     dist = np.linalg.norm([0.2, 0.8])
     pieces = int(dist / 0.05) + 1
-    assert len(calls) == 4 + pieces                       # 4 + pieces IK solves
+    assert len(calls) == 3 + pieces                       # 4 + pieces IK solves in the reference, one of them unused
     assert np.allclose(plan[100], 1) and np.allclose(plan[200], 2)
     chunk = 500 // pieces
-    assert np.allclose(plan[250], 5) and np.allclose(plan[250 + chunk], 6)     # first two sweep pieces (IK calls 5 and 6)
-    assert np.allclose(plan[750], 3) and np.allclose(plan[749], 4 + pieces)    # p2 high after the last sweep piece
+    assert np.allclose(plan[250], 4) and np.allclose(plan[250 + chunk], 5)     # first two sweep pieces (IK calls 4 and 5)
+    assert np.allclose(plan[750], 3) and np.allclose(plan[749], 3 + pieces)    # p2 high after the last sweep piece
     assert np.allclose(calls[0], [-0.2, -0.4, 0.6]) and np.allclose(calls[1], [-0.2, -0.4, 0.46])
-    assert np.allclose(calls[4], [-0.2 + 0.2 / pieces, -0.4 + 0.8 / pieces, 0.46])
+    assert np.allclose(calls[3], [-0.2 + 0.2 / pieces, -0.4 + 0.8 / pieces, 0.46])
 
 
 def test_score_object_and_sharding():

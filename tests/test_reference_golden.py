@@ -107,7 +107,7 @@ def test_macro_plans_match_reference_bit_for_bit():
         calls.clear()
         plan = macro_plan(ik9, m[0], m[1])
         assert plan.shape == (1000, 9) and np.array_equal(plan, want)
-        assert len(calls) == ncall
+        assert len(calls) == ncall - 1        # the reference also solves the unused low point above p2 (env.py:447)
 
 
 def test_macro_sequencing_and_cartesian_cache_match_reference():
