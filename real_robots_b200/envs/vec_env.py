@@ -163,3 +163,29 @@ class VecREALRobotEnv:
         """U(low, high) of the joints action Box (cli.RandomPolicy draw)."""
         u = torch.rand(self.n_envs, 9, dtype=torch.float64, device=self.device, generator=generator)
         return self.joints_low + (self.joints_high - self.joints_low) * u
+
+
+def gather_retinas(retina, factor=4, dst=None, group=None):
+    """Policy hand-off after the step path (not in the reference): box-filter the retinas on the device by
+    `factor` (240x320 -> 60x80 for 4) and collect every rank's envs on the learner.
+
+    retina: u8 [n, 240, 320, 3] (CUDA for NCCL over NVLink, CPU for gloo).  Returns u8 [world * n, 240/f, 320/f, 3] on every
+    rank (dst=None, all_gather) or on rank `dst` only (gather; None elsewhere).  Without an initialised process group it is
+    just the down-sampling.  Equal n on all ranks (envs are sharded evenly)."""
+    import torch.distributed as dist
+    n, h, w, c = retina.shape
+    if h % factor or w % factor:
+        raise ValueError("factor must divide 240 and 320")
+    small = retina.reshape(n, h // factor, factor, w // factor, factor, c).to(torch.float32).mean(dim=(2, 4))
+    small = small.round_().clamp_(0, 255).to(torch.uint8).contiguous()
+    if not (dist.is_available() and dist.is_initialized()):
+        return small
+    world = dist.get_world_size(group)
+    if dst is None:
+        parts = [torch.empty_like(small) for _ in range(world)]
+        dist.all_gather(parts, small, group=group)
+        return torch.cat(parts, dim=0)
+    me = dist.get_rank(group)
+    parts = [torch.empty_like(small) for _ in range(world)] if me == dst else None
+    dist.gather(small, parts, dst=dst, group=group)
+    return torch.cat(parts, dim=0) if me == dst else None
