@@ -273,7 +273,7 @@ def run_ours(args):
         if args.cpu_baseline:
             from oracle import orc
             orc.build()
-            n_cpu = 1200
+            n_cpu = 3000                                # ~11 s of single-core CPU work
             wall = oracle_worker((1234, n_cpu, 3))
             line["cpu_baseline"] = {"value": n_cpu / wall, "unit": "env-steps/s", "cores": 1, "kind": "port",
                                     "sample": "1 oracle env x %d env-steps with render (%.1f s)" % (n_cpu, wall)}
