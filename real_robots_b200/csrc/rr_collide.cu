@@ -31,6 +31,15 @@ struct CollideConst {
 };
 __constant__ CollideConst c_col;
 
+#ifndef CT_INLINE
+#define CT_INLINE __forceinline__
+#endif
+#ifndef HS_UNROLL
+#define HS_UNROLL 2
+#endif
+#define RR_DO_PRAGMA(x) _Pragma(#x)
+#define RR_UNROLL(n) RR_DO_PRAGMA(unroll n)
+#define HS_UNROLL_PRAGMA RR_UNROLL(HS_UNROLL)
 #ifndef EPA_INLINE
 #define EPA_INLINE __noinline__
 #endif
@@ -70,6 +79,7 @@ struct ColMem {
 __device__ HS_INLINE V3 hull_support(const Hull& h, V3 d, int lane) {
     V3 dl = mulRt(h.R, d);
     double best = -DBL_MAX; int idx = 0x7fffffff;
+HS_UNROLL_PRAGMA
     for (int i = lane; i < h.n; i += 32) {
         double s = h.v[3 * i] * dl.x + h.v[3 * i + 1] * dl.y + h.v[3 * i + 2] * dl.z;
         if (s > best) { best = s; idx = i; }
@@ -98,7 +108,7 @@ __device__ __forceinline__ void closest_segment(V3 a, V3 b, double* lam, int* ma
     if (t >= den) { lam[0] = 0; lam[1] = 1; *mask = 2; return; }
     t /= den; lam[0] = 1 - t; lam[1] = t; *mask = 3;
 }
-__device__ __forceinline__ void closest_triangle(V3 a, V3 b, V3 c, double* lam, int* mask) {
+__device__ CT_INLINE void closest_triangle(V3 a, V3 b, V3 c, double* lam, int* mask) {
     V3 ab = b - a, ac = c - a, ap = -a;
     double d1 = dot(ab, ap), d2 = dot(ac, ap);
     if (d1 <= 0 && d2 <= 0) { lam[0] = 1; lam[1] = lam[2] = 0; *mask = 1; return; }
