@@ -1,0 +1,52 @@
+"""Throughput of the other BASELINE.json configs on one GPU (documentation numbers; bench.py measures the headline C3).
+C2: joints action, 4096 envs, render off.  C3: render on.  C5: cartesian action, full R1 observation, N/GPU sweep."""
+import os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+import bench
+from real_robots_b200.sim import BatchedSim
+from real_robots_b200.envs.vec_env import VecREALRobotEnv
+
+
+def timed(fn, steps):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(steps):
+        fn(t)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+dev = torch.device("cuda")
+N = 4096
+sim = BatchedSim(N, 3)
+acts = bench.random_policy_actions(torch, 200, N, dev, 1234)
+for t in range(100):
+    sim.step(acts[t])
+ms = timed(lambda t: (sim.step(acts[100 + t % 100]), sim.read_state()), 100)
+print("C2  joints, %5d envs, render off : %7.3f ms/step  %10.0f env-steps/s" % (N, ms, N / ms * 1e3))
+ms = timed(lambda t: (sim.step(acts[100 + t % 100]), sim.read_state(), sim.render()), 50)
+print("C3  joints, %5d envs, render on  : %7.3f ms/step  %10.0f env-steps/s" % (N, ms, N / ms * 1e3))
+sim.close()
+del sim
+for n in (1024, 2048, 4096, 8192):
+    env = VecREALRobotEnv(n, objects=3, action_type='cartesian', additional_obs=True)
+    env.reset(render=False)
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    lo = torch.tensor([-0.25, -0.5, 0.40, -1, -1, -1, -1], dtype=torch.float64, device=dev)
+    hi = torch.tensor([0.25, 0.5, 0.60, 1, 1, 1, 1], dtype=torch.float64, device=dev)
+    cart = lo + (hi - lo) * torch.rand(n, 7, dtype=torch.float64, device=dev, generator=g)
+    grip = torch.rand(n, 2, dtype=torch.float64, device=dev, generator=g) * 1.5707963
+
+    def step(t, cart=cart, grip=grip, env=env, n=n):
+        if t % 20 == 0:                          # p = 0.05 resample, here every 20th step for all envs: a new IK solve
+            cart.copy_(lo + (hi - lo) * torch.rand(n, 7, dtype=torch.float64, device=dev, generator=g))
+        env.step({'cartesian_command': cart, 'gripper_command': grip, 'render': True})
+    for t in range(60):
+        step(t)
+    ms = timed(step, 40)
+    print("C5  cartesian, %5d envs, R1 obs  : %7.3f ms/step  %10.0f env-steps/s" % (n, ms, n / ms * 1e3))
+    env.close()
+    del env
+    torch.cuda.empty_cache()
