@@ -144,6 +144,13 @@ class REALRobotEnv:
             score += np.exp(-SCORE_DECAY * np.linalg.norm(offset))
         return self.goal.challenge, score
 
+    def extrinsicFormula(self, p_goal, p, a_goal, a, w=1):
+        """Unused by the reference's own scoring (env.py:168-179) but part of its surface: weighted position / orientation
+        closeness, 0.25 at 5 cm and at a quaternion distance of 0.3."""
+        near = lambda dist, scale: np.exp(np.log(0.25) / scale * dist)                                        # noqa: E731
+        orient_dist = min(np.linalg.norm(a_goal - a), np.linalg.norm(a_goal + a))
+        return w * near(np.linalg.norm(p_goal - p), 0.05) + (1 - w) * near(orient_dist, 0.30)
+
     # ------------------------------------------------------------------ lifecycle
     def _ensure_sim(self):
         if self._sim is None:

@@ -201,6 +201,13 @@ def main():
         assert ch == '2D'
         scores[i] = s
     G["score_cur"], G["score_goal"], G["score_value"] = cur, goal, scores
+    ef = []
+    for i in range(8):
+        a, b = rng.normal(size=4), rng.normal(size=4)
+        a /= np.linalg.norm(a); b /= np.linalg.norm(b)
+        ef.append(list(cur[i, 0]) + list(goal[i, 0]) + list(a) + list(b) +
+                  [REALRobotEnv.extrinsicFormula(None, goal[i, 0], cur[i, 0], b, a, w) for w in (1, 0.5, 0.0)])
+    G["extrinsic_formula"] = np.array(ef)
 
     # ---- generate_plan with the fake IK
     macros = np.array([[[-0.10, -0.30], [-0.05, 0.20]], [[-0.25, -0.5], [0.05, 0.5]], [[0.0, 0.0], [0.0, 0.0]],

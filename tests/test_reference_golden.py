@@ -268,3 +268,11 @@ def test_generate_position_matches_reference_draw_for_draw():
         rng = np.random.RandomState(seed)
         got = np.array([gg.generate_position(rng, "cube", False, plane) for _ in range(4)])
         assert np.abs(got - want).max() < 1e-15, (seed, plane)
+
+
+def test_extrinsic_formula_matches_reference():
+    env = real_robots.make('REALRobot2020-R1J1-v0')
+    for row in G["extrinsic_formula"]:
+        p, p_goal, a, a_goal, want = row[0:3], row[3:6], row[6:10], row[10:14], row[14:17]
+        got = [env.extrinsicFormula(p_goal, p, a_goal, a, w) for w in (1, 0.5, 0.0)]
+        assert np.abs(np.array(got) - want).max() < 1e-14
