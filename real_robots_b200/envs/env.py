@@ -151,6 +151,30 @@ class REALRobotEnv:
         orient_dist = min(np.linalg.norm(a_goal - a), np.linalg.norm(a_goal + a))
         return w * near(np.linalg.norm(p_goal - p), 0.05) + (1 - w) * near(orient_dist, 0.30)
 
+    # The next two run on the device inside every rr_step; the host versions exist because they are public methods of the
+    # reference (a policy can preview the rate-limited action, a script can force the object check between steps).
+    def limitActionByJoint(self, desired_joints):
+        """env.py:314-321: the request clipped to +-[.2 .2 .2 .2 .2 .3 .3 .1 .1] rad around the current joints."""
+        now = np.asarray(self.robot.calc_state(), dtype=np.float64)
+        reach = np.array([0.2] * 5 + [0.3] * 2 + [0.1] * 2)
+        return now + np.clip(np.asarray(desired_joints, dtype=np.float64) - now, -reach, reach)
+
+    def control_objects_limits(self):
+        """env.py:257-264: objects below the table top level, or beyond the shelf front and below it, go back to their start."""
+        floor = self.robot.object_poses['table'][2]
+        for name in self.robot.used_objects:
+            x, _, z = self.robot.object_bodies[name].get_position()
+            if z < floor or (x > 0.11 and z < 0.29):
+                self.robot.reset_object(name)
+
+    def set_eye(self, name, eye_pos=(0.01, 0, 1.2), target_pos=(0, 0, 0)):     # env.py:124-141
+        self.eyes[name] = EyeCamera(list(eye_pos), list(target_pos))
+
+    def setCamera(self):                                                         # env.py:124-134
+        from ..videomaker import EnvCamera
+        self.envCamera = EnvCamera(distance=self._cam_dist, yaw=self._cam_yaw, pitch=self._cam_pitch, roll=self._cam_roll,
+                                   pos=self._cam_pos, width=self._render_width, height=self._render_height)
+
     # ------------------------------------------------------------------ lifecycle
     def _ensure_sim(self):
         if self._sim is None:
@@ -296,3 +320,10 @@ class EyeCamera:
         self.eyePosition, self.targetPosition, self.upVector = eyePosition, targetPosition, [0, 0, 1]
         self.fov, self.render_width, self.render_height = fov, width, height
         self.pitch_roll = False
+
+    def renderTarget(self, env):
+        """(rgb u8[240,320,3], depth f32[240,320], mask i32[240,320]) of `env` seen from the eye (env.py:536-567)."""
+        rgb, mask, depth = env.get_retina()
+        return rgb, depth, mask
+
+    render = renderTarget

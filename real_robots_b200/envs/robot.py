@@ -51,6 +51,7 @@ class BodyPartView:
 
 
 class Kuka:
+    used_objects = ["table", "orange", "mustard", "cube", "tomato"]     # robot.py:11-16 (class default; set per instance below)
     # robot.py:19-24
     object_poses = {
         "table":   [0.00000, 0.00000, 0.08000, 0.00000, 0.00000, 0.00000],

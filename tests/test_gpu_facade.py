@@ -292,3 +292,19 @@ def test_cartesian_8192_envs_full_observation():
         assert bool((obs[k][:N // 2] == obs[k][N // 2:]).all()), k            # an env does not depend on its slot
     assert reward.shape == (N,) and float(reward.abs().sum()) == 0.0 and not bool(done.any())
     env.close()
+
+
+def test_public_helpers_of_the_reference_surface():
+    """control_objects_limits (env.py:257-264) and EyeCamera.renderTarget (env.py:536-567) as host-callable methods."""
+    env = real_robots.make('REALRobot2020-R1J2-v0')
+    obs = env.reset()
+    env.robot.object_bodies['cube'].reset_pose([0.0, 0.0, 0.02], [0, 0, 0, 1])          # under the table top level
+    env.robot.object_bodies['tomato'].reset_pose([0.2, 0.0, 0.25], [0, 0, 0, 1])        # past the shelf front, below it
+    env.control_objects_limits()
+    assert np.allclose(env.get_obj_pos('cube'), [-0.1, 0.0, 0.45], atol=1e-12)
+    assert np.allclose(env.get_obj_pos('tomato'), [-0.1, -0.3, 0.45], atol=1e-12)
+    rgb, depth, mask = env.eyes['eye'].renderTarget(env)
+    assert rgb.shape == (240, 320, 3) and depth.dtype == np.float32 and mask.dtype == np.int32 and (mask == 2).any()
+    lim = env.limitActionByJoint(np.full(9, 3.0))
+    assert np.allclose(lim, [0.2] * 5 + [0.3] * 2 + [0.1] * 2, atol=1e-12)              # from q = 0
+    env.close()

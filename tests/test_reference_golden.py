@@ -276,3 +276,20 @@ def test_extrinsic_formula_matches_reference():
         p, p_goal, a, a_goal, want = row[0:3], row[3:6], row[6:10], row[10:14], row[14:17]
         got = [env.extrinsicFormula(p_goal, p, a_goal, a, w) for w in (1, 0.5, 0.0)]
         assert np.abs(np.array(got) - want).max() < 1e-14
+
+
+def test_host_limit_action_matches_reference():
+    """The public host-side limitActionByJoint (env.py:314-321) against the recorded prologue: its output, pushed through the
+    reference's own clip / fan-out (recorded as motor targets), must reproduce the first 7 arm targets wherever the
+    joint-limit clip of apply_action is not active."""
+    env = real_robots.make('REALRobot2020-R1J3-v0')
+    k = Kuka(True, 3)
+    for q, cmd, want in zip(G["prologue_q"], G["prologue_cmd"], G["prologue_targets"]):
+        env.robot.calc_state = lambda q=q: [float(v) for v in q[:8]] + [float(-q[8])]
+        lim = env.limitActionByJoint(cmd)
+        clipped = np.maximum(k.min_joints, np.minimum(lim, k.max_joints))
+        clipped[8] = max(0.0, min(2 * clipped[7], clipped[8]))
+        assert np.array_equal(clipped[:8], want[:8]) and clipped[8] == -want[8] and want[9] == want[7] and want[10] == want[8]
+    env.set_eye("left", [0.1, 0, 1.0], [0, 0, 0])
+    env.setCamera()
+    assert set(env.eyes) == {"eye", "left"} and env.envCamera.dist == 1.2 and env.envCamera.yaw == 30
