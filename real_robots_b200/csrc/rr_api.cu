@@ -240,7 +240,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_err = "rr_create: no CUDA device (this library has no CPU fallback)"; return -1; }
     if (device < 0 || device >= ndev) { g_create_err = "rr_create: bad device index"; return -1; }
     rr_ctx* ctx = new rr_ctx();
-    ctx->device = device; ctx->N = n_envs; ctx->n_objects = n_objects; ctx->launches = 0; ctx->prof_on = false; ctx->host_compute = nullptr; ctx->host_copy = nullptr; ctx->d_rec_scratch = nullptr; ctx->d_list_scratch = nullptr; ctx->d_work_counter = nullptr; ctx->d_tri_shape = nullptr; ctx->raster_grid = 0; ctx->d_planes = nullptr; ctx->d_cull_scratch = nullptr;
+    ctx->device = device; ctx->N = n_envs; ctx->n_objects = n_objects; ctx->launches = 0; ctx->prof_on = false; ctx->host_compute = nullptr; ctx->host_copy = nullptr; ctx->d_rec_scratch = nullptr; ctx->d_list_scratch = nullptr; ctx->d_work_counter = nullptr; ctx->d_tri_shape = nullptr; ctx->raster_grid = 0; ctx->d_planes = nullptr; ctx->d_cull_scratch = nullptr; ctx->h_collide_const = nullptr; ctx->cull_hmax = 0.f;
     ctx->d_cmd = nullptr; ctx->d_mask = nullptr; ctx->d_joint = ctx->d_touch = ctx->d_objpose = nullptr;
     ctx->d_rgb = nullptr; ctx->d_depth = nullptr; ctx->d_seg = nullptr; ctx->img_capacity = 0; ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0;
     if (cfg) ctx->cfg = *cfg; else rr_config_default(&ctx->cfg);
@@ -280,6 +280,8 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
 int rr_destroy(rr_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    rrk_physics_unbind(ctx); rrk_collide_unbind(ctx); rrk_render_unbind(ctx);
     DevState& st = ctx->st;
     void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.timestep,
                     st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.rows, st.handoff,

@@ -13,6 +13,8 @@
 // picks the FIRST maximum, exactly as a sequential scan would.  The EPA polytope lives in shared memory.
 // Manifolds are double-buffered in global memory ([env][slot][...], read from one buffer, written to the other).
 #include "rr_ctx.h"
+#include <cstdlib>
+#include <cstring>
 #include <cfloat>
 
 #define CWPB 4
@@ -516,6 +518,21 @@ k_collide(DevState st, const double* __restrict__ hull_verts, const int* __restr
 // ------------------------------------------------------------------------------------------- host side
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return -1; } } while (0)
 
+static rr_ctx* g_col_owner[64];
+static int bind_collide(rr_ctx* ctx, cudaStream_t s) {
+    rr_ctx*& owner = g_col_owner[ctx->device & 63];
+    if (owner != ctx) {
+        CK(cudaDeviceSynchronize());          // kernels of the previous owner may still be reading the old constants
+        CK(cudaMemcpyToSymbolAsync(c_col, ctx->h_collide_const, sizeof(CollideConst), 0, cudaMemcpyHostToDevice, s));
+        owner = ctx;
+    }
+    return 0;
+}
+void rrk_collide_unbind(rr_ctx* ctx) {
+    if (g_col_owner[ctx->device & 63] == ctx) g_col_owner[ctx->device & 63] = nullptr;
+    free(ctx->h_collide_const); ctx->h_collide_const = nullptr;
+}
+
 int rrk_collide_upload_constants(rr_ctx* ctx) {
     CollideConst C; memset(&C, 0, sizeof C);
     const RobotConst& R = ctx->robot;
@@ -542,10 +559,14 @@ int rrk_collide_upload_constants(rr_ctx* ctx) {
     for (int i = 0; i < n; i++) { ctx->pair_a[i] = C.pair_a[i]; ctx->pair_b[i] = C.pair_b[i]; }
     ctx->n_pairs = n;
     CK(cudaMemcpyToSymbol(c_col, &C, sizeof C));
+    if (!ctx->h_collide_const) ctx->h_collide_const = malloc(sizeof(CollideConst));
+    memcpy(ctx->h_collide_const, &C, sizeof(CollideConst));
+    g_col_owner[ctx->device & 63] = ctx;
     return 0;
 }
 
 int rrk_collide(rr_ctx* ctx, cudaStream_t s) {
+    if (bind_collide(ctx, s)) return -1;
     const int in = ctx->man_parity, out = 1 - in;
     {
         ProfScope ps(ctx, 3, s);

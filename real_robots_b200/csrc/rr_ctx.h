@@ -90,6 +90,7 @@ struct rr_ctx {
     int man_parity;            // which manifold buffer holds the current contacts
     int n_tris;
     void* d_rec_scratch; void* d_list_scratch; int* d_work_counter; uint8_t* d_tri_shape; int raster_grid;   // persistent rasteriser
+    void* h_collide_const; float cull_hmax;   // host copies of per-context __constant__ data that are built on the fly
     void* d_planes; void* d_cull_scratch;   // model-space triangle planes (conservative back-face pre-test), per-CTA survivor lists
     // staging for the host-buffer path
     double* d_cmd; uint8_t* d_mask; double* d_joint; double* d_touch; double* d_objpose;
@@ -121,6 +122,11 @@ struct ProfScope {
 
 // kernels / launchers (defined in the .cu files)
 int rrk_upload_constants(rr_ctx* ctx);
+// __constant__ symbols are per device, contexts are not: every launcher re-binds its translation unit's constants when
+// another context used them last (stream-ordered copy); rrk_*_unbind forgets a context that is being destroyed.
+void rrk_physics_unbind(rr_ctx* ctx);
+void rrk_collide_unbind(rr_ctx* ctx);
+void rrk_render_unbind(rr_ctx* ctx);
 int rrk_reset(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s);
 int rrk_set_object_pose(rr_ctx* ctx, const uint8_t* mask, int obj, const double* pq, cudaStream_t s);
 int rrk_set_state(rr_ctx* ctx, const double* q, const double* qd, const double* obj, cudaStream_t s);

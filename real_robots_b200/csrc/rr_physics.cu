@@ -1037,8 +1037,21 @@ __global__ void k_shape_frames(DevState st, double* __restrict__ frames, int n_o
 // ------------------------------------------------------------------------------------------- host launchers
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return -1; } } while (0)
 
+static rr_ctx* g_phys_owner[64];
+static int bind_physics(rr_ctx* ctx, cudaStream_t s) {
+    rr_ctx*& owner = g_phys_owner[ctx->device & 63];
+    if (owner != ctx) {
+        CK(cudaDeviceSynchronize());          // kernels of the previous owner may still be reading the old constants
+        CK(cudaMemcpyToSymbolAsync(c_robot, &ctx->robot, sizeof(RobotConst), 0, cudaMemcpyHostToDevice, s));
+        owner = ctx;
+    }
+    return 0;
+}
+void rrk_physics_unbind(rr_ctx* ctx) { if (g_phys_owner[ctx->device & 63] == ctx) g_phys_owner[ctx->device & 63] = nullptr; }
+
 int rrk_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_robot, &ctx->robot, sizeof(RobotConst)));
+    g_phys_owner[ctx->device & 63] = ctx;
     CK(cudaFuncSetAttribute(k_step_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
     CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * WPB)));
     CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * WPB)));
@@ -1047,18 +1060,21 @@ int rrk_upload_constants(rr_ctx* ctx) {
 static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 
 static int launch_fk(rr_ctx* ctx, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     k_fk<<<nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s>>>(ctx->st);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_reset(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     k_reset<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, mask, ctx->n_objects, ctx->st.man_hdr[ctx->man_parity]);
     ctx->launches++;
     CK(cudaGetLastError());
     return launch_fk(ctx, s);
 }
 int rrk_set_object_pose(rr_ctx* ctx, const uint8_t* mask, int obj, const double* pq, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     k_set_object_pose<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, mask, obj, pq);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1077,6 +1093,7 @@ int rrk_clear_manifolds(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
     return 0;
 }
 int rrk_set_state(rr_ctx* ctx, const double* q, const double* qd, const double* obj, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     if (rrk_clear_manifolds(ctx, nullptr, s) != 0) return -1;
     k_set_state<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, q, qd, obj);
     ctx->launches++;
@@ -1090,6 +1107,7 @@ int rrk_get_state(rr_ctx* ctx, double* q, double* qd, double* obj, cudaStream_t 
     return 0;
 }
 int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     if (ctx->cfg.enable_contacts && rrk_collide(ctx, s) != 0) return -1;
     ProfScope ps(ctx, 0, s);
     k_step_dyn<<<nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s>>>(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
@@ -1099,24 +1117,28 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
     return 0;
 }
 int rrk_read_state(rr_ctx* ctx, double* joint, double* touch, double* objpose, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     k_read_state<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, joint, touch, objpose, ctx->n_objects);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_link_pose(rr_ctx* ctx, int link, double* out, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     k_link_pose<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, link, out);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     k_score<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, goal, score, ctx->n_objects);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     k_shape_frames<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, frames, ctx->n_objects);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1218,6 +1240,7 @@ __global__ void k_ik(DevState st, const uint8_t* __restrict__ mask, const double
 }
 
 int rrk_ik(rr_ctx* ctx, const uint8_t* mask, const double* pos_quat, double* out, int max_iter, double residual, cudaStream_t s) {
+    if (bind_physics(ctx, s)) return -1;
     k_ik<<<nblk(ctx->N, 64), 64, 0, s>>>(ctx->st, mask, pos_quat, out, max_iter, residual);
     ctx->launches++;
     CK(cudaGetLastError());

@@ -909,6 +909,7 @@ static cudaError_t build_planes(rr_ctx* ctx) {
         pl[(size_t)t * 4 + 3] = (float)((n[0] * v[0][0] + n[1] * v[0][1] + n[2] * v[0][2]) * sc);
     }
     const float hm = (float)hmax;
+    ctx->cull_hmax = hm;
     e = cudaMemcpyToSymbol(c_cull_hmax, &hm, sizeof(float));
     if (e != cudaSuccess) return e;
     e = cudaMalloc(&ctx->d_planes, pl.size() * sizeof(float));
@@ -916,8 +917,22 @@ static cudaError_t build_planes(rr_ctx* ctx) {
     return cudaMemcpy(ctx->d_planes, pl.data(), pl.size() * sizeof(float), cudaMemcpyHostToDevice);
 }
 
+static rr_ctx* g_render_owner[64];
+static int bind_render(rr_ctx* ctx, cudaStream_t s) {
+    rr_ctx*& owner = g_render_owner[ctx->device & 63];
+    if (owner != ctx) {
+        CK(cudaDeviceSynchronize());          // kernels of the previous owner may still be reading the old constants
+        CK(cudaMemcpyToSymbolAsync(c_render, &ctx->render, sizeof(RenderConst), 0, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyToSymbolAsync(c_cull_hmax, &ctx->cull_hmax, sizeof(float), 0, cudaMemcpyHostToDevice, s));
+        owner = ctx;
+    }
+    return 0;
+}
+void rrk_render_unbind(rr_ctx* ctx) { if (g_render_owner[ctx->device & 63] == ctx) g_render_owner[ctx->device & 63] = nullptr; }
+
 int rrk_render_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_render, &ctx->render, sizeof(RenderConst)));
+    g_render_owner[ctx->device & 63] = ctx;
     CK(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RASTER_SMEM));
     {
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
@@ -957,6 +972,7 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
 int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg,
                      int env_begin, int env_count, cudaStream_t s) {
     if (env_count <= 0) return 0;
+    if (bind_render(ctx, s)) return -1;
     int total = env_count * RR_NSHAPES;
     {
         ProfScope ps(ctx, 1, s);
@@ -984,6 +1000,7 @@ int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* 
 // Render with another camera (EnvCamera / render('rgb_array'), reference env.py:221-228, 470-513): the camera part of
 // the constants is swapped in stream order around the two kernels and the eye camera restored afterwards.
 int rrk_render_camera(rr_ctx* ctx, const RenderConst* cam, const uint8_t* mask, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s) {
+    if (bind_render(ctx, s)) return -1;
     CK(cudaMemcpyToSymbolAsync(c_render, cam, sizeof(RenderConst), 0, cudaMemcpyHostToDevice, s));
     int rc = rrk_render(ctx, mask, nullptr, rgb, depth, seg, s);
     CK(cudaMemcpyToSymbolAsync(c_render, &ctx->render, sizeof(RenderConst), 0, cudaMemcpyHostToDevice, s));

@@ -421,3 +421,35 @@ def test_long_random_rollout_stays_physical():
     rgb, depth, seg = sim.render()
     assert bool(torch.isfinite(depth).all()) and int(seg.min()) >= -1 and int(seg.max()) <= 4
     sim.close()
+
+
+def test_two_live_contexts_with_different_object_counts():
+    """__constant__ tables (candidate pairs, shape constants, camera) are per device, contexts are not: two simulators that
+    are alive at the same time and stepped alternately must each behave exactly as when run alone."""
+    def run_alone(n_obj, steps, seed):
+        sim = BatchedSim(8, n_obj)
+        g = torch.Generator(device='cuda'); g.manual_seed(seed)
+        a = (torch.rand(8, 9, dtype=torch.float64, device='cuda', generator=g) * 2 - 1) * 1.5
+        for _ in range(steps):
+            sim.step(a)
+        out = [t.clone() for t in sim.get_state()] + [t.clone() for t in sim.render()]
+        sim.close()
+        return out
+    ref1, ref3 = run_alone(1, 60, 1), run_alone(3, 60, 3)
+    s1, s3 = BatchedSim(8, 1), BatchedSim(8, 3)                  # the 3-object context is created last and owns the constants
+    g1 = torch.Generator(device='cuda'); g1.manual_seed(1)
+    g3 = torch.Generator(device='cuda'); g3.manual_seed(3)
+    a1 = (torch.rand(8, 9, dtype=torch.float64, device='cuda', generator=g1) * 2 - 1) * 1.5
+    a3 = (torch.rand(8, 9, dtype=torch.float64, device='cuda', generator=g3) * 2 - 1) * 1.5
+    for _ in range(60):
+        s1.step(a1)
+        s3.step(a3)
+    got1 = list(s1.get_state()) + list(s1.render())
+    got3 = list(s3.get_state()) + list(s3.render())
+    for got, ref in ((got1, ref1), (got3, ref3)):
+        for x, y in zip(got, ref):
+            assert torch.equal(x, y)
+    s3.close()
+    s1.step(a1)                                                   # the survivor keeps working after the other is destroyed
+    assert bool(torch.isfinite(s1.get_state()[0]).all())
+    s1.close()
