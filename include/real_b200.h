@@ -53,7 +53,8 @@ void rr_config_default(rr_config* cfg);
 int  rr_config_size(void);
 
 /* replaces: gym.make -> REALRobotEnv.__init__ (env.py:36-122) + the URDF/OBJ loading inside reset
- * (robot.py:120-123,165-185,214-226): assets are read once from the compiled blob.  * Several contexts may be alive on one device (e.g. a 1-object and a 3-object scene): the device-wide constant tables are
+ * (robot.py:120-123,165-185,214-226): assets are read once from the compiled blob.
+ * Several contexts may be alive on one device (e.g. a 1-object and a 3-object scene): the device-wide constant tables are
  * re-bound, with a device synchronisation, whenever a call arrives for a context other than the one that used them last. */
 int  rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* asset_blob_path, const rr_config* cfg);
 int  rr_destroy(rr_ctx* ctx);
