@@ -272,6 +272,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     if (e != cudaSuccess) { ctx->err = std::string("rr_create: device allocation failed: ") + cudaGetErrorString(e); return fail(-1); }
     ctx->man_parity = 0;
     if (rrk_reset(ctx, nullptr, 0) != 0) return fail(-1);
+    if (rrk_render_build_static(ctx) != 0) return fail(-1);
     if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "rr_create: initial reset failed"; return fail(-1); }
     *out = ctx;
     return 0;
@@ -286,7 +287,8 @@ int rr_destroy(rr_ctx* ctx) {
     void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.timestep,
                     st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.rows, st.handoff,
                     ctx->d_cmd, ctx->d_mask, ctx->d_joint, ctx->d_touch, ctx->d_objpose, ctx->d_rgb, ctx->d_depth, ctx->d_seg,
-                    ctx->d_tris, ctx->d_tex, ctx->d_hull_verts, ctx->d_rec_scratch, ctx->d_list_scratch, ctx->d_work_counter, ctx->d_tri_shape, ctx->d_planes, ctx->d_cull_scratch};
+                    ctx->d_tris, ctx->d_tex, ctx->d_hull_verts, ctx->d_rec_scratch, ctx->d_list_scratch, ctx->d_work_counter, ctx->d_tri_shape, ctx->d_planes, ctx->d_cull_scratch,
+                    ctx->d_static_keys, ctx->d_static_col};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->host_compute) {

@@ -92,6 +92,10 @@ struct rr_ctx {
     void* d_rec_scratch; void* d_list_scratch; int* d_work_counter; uint8_t* d_tri_shape; int raster_grid;   // persistent rasteriser
     void* h_collide_const; float cull_hmax;   // host copies of per-context __constant__ data that are built on the fly
     void* d_planes; void* d_cull_scratch;   // model-space triangle planes (conservative back-face pre-test), per-CTA survivor lists
+    // static layer of the eye camera's image (table + robot base never move): raster keys and winner colours per pixel,
+    // built once by k_raster<1> and used as the z-buffer's initial content by k_raster<2> (see rr_render.cu)
+    void* d_static_keys = nullptr; void* d_static_col = nullptr; bool static_ready = false; bool static_enabled = true;
+    unsigned static_bits = 0; int static_skip_front = 0;
     // staging for the host-buffer path
     double* d_cmd; uint8_t* d_mask; double* d_joint; double* d_touch; double* d_objpose;
     uint8_t* d_rgb; float* d_depth; int32_t* d_seg;
@@ -137,6 +141,7 @@ int rrk_link_pose(rr_ctx* ctx, int link, double* out, cudaStream_t s);
 int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s);
 int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s);
 int rrk_render_upload_constants(rr_ctx* ctx);
+int rrk_render_build_static(rr_ctx* ctx);
 int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames_or_null, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);
 int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg, int env_begin, int env_count, cudaStream_t s);
 int rrk_render_camera(rr_ctx* ctx, const RenderConst* cam, const uint8_t* mask, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);

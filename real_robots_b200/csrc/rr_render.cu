@@ -671,11 +671,20 @@ __device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M,
 //              coarse items are handed out first; atomicMax on (depth bits, triangle index) with a depth-bound
 //              rejection against the current key.  resolve — warps pull groups of 128 pixels: fragment shader for the
 //              winners (lane per pixel), then packed row stores; the keys are cleared on the way out.
+//
+// MODE 0: every shape is rasterised for every env.  The table and the robot base never move and the eye camera is fixed, so
+// their part of the image is the same in every env and every step: MODE 1 rasterises only those static shapes (one CTA,
+// one env) and leaves, per pixel, the winning raster key (record bits = 0x7fff as the "static" marker) in static_keys and
+// the winner's shaded colour word in static_col; MODE 2 starts every strip's z-buffer from static_keys instead of zero,
+// rasterises only the moving shapes on top and, for pixels a static key still owns at resolve time, takes the colour from
+// static_col.  max over (depth, triangle index) is associative, so the image is bit-identical to MODE 0's.
+template <int MODE>
 __global__ void __launch_bounds__(RTHREADS, RBLOCKS)
 k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const float4* __restrict__ planes, int n_tris,
          const uint8_t* __restrict__ texdata, const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch,
          unsigned short* __restrict__ cull_scratch, int* __restrict__ work_counter,
-         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N) {
+         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N,
+         unsigned long long* __restrict__ static_keys, unsigned int* __restrict__ static_col, unsigned int static_bits, int skip_front) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* M = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);
@@ -687,7 +696,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
     const float nearP = c_render.depthNear, farP = c_render.depthFar;
     const float bg_depth = (float)((double)(farP * (nearP + 1e30f)) / (2. * (double)farP * (double)nearP + (double)(farP * 1e30f) - (double)(nearP * 1e30f)));
     // the key buffer is zero whenever a strip starts: cleared here once, then by the resolve pass that consumes it
-    for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = 0ull;
+    for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = (MODE == 2) ? static_keys[i] : 0ull;
 
     for (;;) {
         __syncthreads();
@@ -714,16 +723,21 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         // coordinates; Ms[43] bounds |camera - any vertex| + altitude.  |sd| > Ms[43] means the camera is further from the
         // triangle's plane than any rounding of the fp32 world coordinates can move that plane, so the exact fp64 test of
         // tri_vertex() would decide the same way; everything else is marked uncertain (bit 15) and takes the exact test.
-        for (int base = 0; base < n_tris; base += RTHREADS) {
+        const int n_scan = (MODE == 2) ? n_tris - skip_front : n_tris;    // MODE 2: the leading static shapes are not even scanned
+        for (int base = 0; base < n_scan; base += RTHREADS) {
 #if REVERSE_ORDER
             const int gt = n_tris - 1 - (base + tid);          // last shapes first: objects and the arm's upper links are nearest the eye
 #else
-            const int gt = base + tid;
+            const int gt = (n_tris - n_scan) + base + tid;
 #endif
             int code = -1;
-            if (gt >= 0 && gt < n_tris) {
-                const float* Ms = M + tri_shape[gt] * MAT_STRIDE;
-                if (Ms[39] != 0.f) {
+            if (base + tid < n_scan) {
+                const int sidx = tri_shape[gt];
+                const float* Ms = M + sidx * MAT_STRIDE;
+                bool act = Ms[39] != 0.f;
+                if (MODE == 1) act = act && ((static_bits >> sidx) & 1u);
+                if (MODE == 2) act = act && !((static_bits >> sidx) & 1u);
+                if (act) {
                     const float4 pl = __ldg(planes + gt);
                     const float sd = pl.x * Ms[40] + pl.y * Ms[41] + pl.z * Ms[42] - pl.w;
                     STAT(0, 1);
@@ -824,16 +838,29 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 for (int j = 0; j < 4; j++) {
                     const int p = g * 128 + j * 32 + lane;
                     const unsigned long long key = keys[p];
+                    if (MODE == 1) { static_keys[row0 * RR_W + p] = key ? (key | 0x7fffull) : 0ull; if (key == 0ull) static_col[row0 * RR_W + p] = 0u; }
                     if (key == 0ull) continue;
                     covered = true;
+                    if (MODE == 2 && (key & 0x7fffull) == 0x7fffull) {           // a static key survived: its colour was shaded once
+                        keys[p] = (key & 0xffffffff00000000ull) | (unsigned long long)__ldg(static_col + row0 * RR_W + p);
+                        continue;
+                    }
                     const int r = p / RR_W, x = p - r * RR_W;
                     int s;
                     const unsigned int col = shade_pixel(M, tris, tri_shape, texdata, recs, (unsigned int)(key & 0xffffffffu), x, row0 + r, s);
-                    keys[p] = (key & 0xffffffff00000000ull) | 0x80000000ull | ((unsigned long long)s << 24) | (unsigned long long)(col & 0xffffffu);
+                    const unsigned int low = 0x80000000u | ((unsigned int)s << 24) | (col & 0xffffffu);
+                    if (MODE == 1) static_col[row0 * RR_W + p] = low;
+                    keys[p] = (key & 0xffffffff00000000ull) | (unsigned long long)low;
                 }
                 const int i = g * 32 + lane;
                 const int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
+                // MODE 2: the keys this lane consumes are replaced by the static keys of the same pixels of the next strip
+                const ulonglong2* nk = reinterpret_cast<const ulonglong2*>(static_keys + (size_t)((strip + 1 == NSTRIPS ? 0 : row0 + STRIP_ROWS) + r) * RR_W + 4 * x4);
                 if (!__any_sync(0xffffffffu, covered)) {          // nothing but background in these 128 pixels (keys already zero)
+                    if (MODE == 2) {
+                        ulonglong2* kq = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
+                        kq[0] = __ldg(nk); kq[1] = __ldg(nk + 1);
+                    }
                     const size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
                     if (rgb) {
                         unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3);
@@ -847,7 +874,8 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 unsigned int col[4]; float dep[4]; int sg[4];
                 ulonglong2* kp = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
                 const ulonglong2 ka = kp[0], kb = kp[1];
-                kp[0] = make_ulonglong2(0ull, 0ull); kp[1] = make_ulonglong2(0ull, 0ull);
+                if (MODE == 2) { kp[0] = __ldg(nk); kp[1] = __ldg(nk + 1); }
+                else { kp[0] = make_ulonglong2(0ull, 0ull); kp[1] = make_ulonglong2(0ull, 0ull); }
                 const unsigned long long k4[4] = {ka.x, ka.y, kb.x, kb.y};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -933,11 +961,16 @@ void rrk_render_unbind(rr_ctx* ctx) { if (g_render_owner[ctx->device & 63] == ct
 int rrk_render_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_render, &ctx->render, sizeof(RenderConst)));
     g_render_owner[ctx->device & 63] = ctx;
-    CK(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RASTER_SMEM));
+    CK(cudaFuncSetAttribute(k_raster<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RASTER_SMEM));
+    CK(cudaFuncSetAttribute(k_raster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RASTER_SMEM));
+    CK(cudaFuncSetAttribute(k_raster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RASTER_SMEM));
     {
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raster, RTHREADS, RASTER_SMEM));
+        int per_sm0 = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, k_raster<0>, RTHREADS, RASTER_SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raster<2>, RTHREADS, RASTER_SMEM));
+        if (per_sm0 < per_sm) per_sm = per_sm0;
         if (per_sm < 1) { ctx->err = "k_raster does not fit on this device"; return -1; }
         ctx->raster_grid = prop.multiProcessorCount * per_sm;           // persistent: one wave of CTAs, envs pulled from a counter
         if (ctx->raster_grid > ctx->N) ctx->raster_grid = ctx->N;
@@ -952,6 +985,19 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
         if (ctx->n_tris >= 0x8000) { ctx->err = "k_raster: triangle index does not fit 15 bits"; return -1; }
         CK(build_planes(ctx));
         CK(cudaMalloc(&ctx->d_cull_scratch, (size_t)ctx->raster_grid * CULL_MAX * sizeof(unsigned short)));
+        // static layer: the robot base and the table (bodies whose frames come from static_frames below)
+        ctx->static_bits = 0; ctx->static_skip_front = 0; ctx->static_ready = false;
+        bool leading = true;
+        for (int sidx = 0; sidx < RR_NSHAPES; sidx++) {
+            const bool stat = (ctx->robot.shape_body[sidx] == 0 && ctx->robot.shape_link[sidx] < 0) || ctx->robot.shape_body[sidx] == 1;
+            if (stat) ctx->static_bits |= 1u << sidx;
+            if (stat && leading && ctx->render.shape[sidx].tri_start == ctx->static_skip_front) ctx->static_skip_front += ctx->render.shape[sidx].tri_count;
+            else leading = false;
+        }
+        const char* sl = getenv("RR_STATIC_LAYER");                  // RR_STATIC_LAYER=0: rasterise every shape for every env (A/B measurements)
+        ctx->static_enabled = !(sl && sl[0] == '0');
+        CK(cudaMalloc(&ctx->d_static_keys, (size_t)RR_W * RR_H * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->d_static_col, (size_t)RR_W * RR_H * sizeof(unsigned int)));
     }
     // static frames (robot base, table) as doubles
     double sf[RR_NSHAPES * 12];
@@ -969,8 +1015,8 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
     return 0;
 }
 
-int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg,
-                     int env_begin, int env_count, cudaStream_t s) {
+static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg,
+                        int env_begin, int env_count, bool eye_camera, cudaStream_t s) {
     if (env_count <= 0) return 0;
     if (bind_render(ctx, s)) return -1;
     int total = env_count * RR_NSHAPES;
@@ -980,18 +1026,47 @@ int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uin
     }
     ctx->launches++;
     CK(cudaGetLastError());
+    // the static layer applies to the simulated scene seen by the eye camera; caller-supplied frames (rr_render_frames) and
+    // other cameras (rr_render_camera) rasterise everything
+    const bool use_static = ctx->static_enabled && ctx->static_ready && eye_camera && frames == nullptr;
+    unsigned long long* sk = (unsigned long long*)ctx->d_static_keys; unsigned int* sc = (unsigned int*)ctx->d_static_col;
+#define RASTER_ARGS(RGB, DEP, SEG, MASK, NENV) ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris, \
+        ctx->d_tex, MASK, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, (unsigned short*)ctx->d_cull_scratch, \
+        ctx->d_work_counter, RGB, DEP, SEG, env_begin, NENV, sk, sc, ctx->static_bits, ctx->static_skip_front
     CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), s));
     {
         ProfScope ps(ctx, 2, s);
         int grid = ctx->raster_grid < env_count ? ctx->raster_grid : env_count;
-        k_raster<<<grid, RTHREADS, RASTER_SMEM, s>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris,
-                                                     ctx->d_tex, mask, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch,
-                                                     (unsigned short*)ctx->d_cull_scratch, ctx->d_work_counter, rgb, depth, seg,
-                                                     env_begin, env_count);
+        if (use_static) k_raster<2><<<grid, RTHREADS, RASTER_SMEM, s>>>(RASTER_ARGS(rgb, depth, seg, mask, env_count));
+        else k_raster<0><<<grid, RTHREADS, RASTER_SMEM, s>>>(RASTER_ARGS(rgb, depth, seg, mask, env_count));
     }
+#undef RASTER_ARGS
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+// Once per context (rr_create, after the first reset): matrices of env 0, then the static shapes of that env — their
+// matrices are the same in every env — into d_static_keys / d_static_col.  Synchronous, so that every later launch on
+// any stream sees the finished layer.
+int rrk_render_build_static(rr_ctx* ctx) {
+    if (!ctx->static_enabled || ctx->static_ready) return 0;
+    if (bind_render(ctx, 0)) return -1;
+    k_render_setup<<<1, 128, 0, 0>>>(ctx->st, nullptr, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device], 0, 1);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), 0));
+    k_raster<1><<<1, RTHREADS, RASTER_SMEM, 0>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris,
+        ctx->d_tex, nullptr, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, (unsigned short*)ctx->d_cull_scratch,
+        ctx->d_work_counter, nullptr, nullptr, nullptr, 0, 1, (unsigned long long*)ctx->d_static_keys, (unsigned int*)ctx->d_static_col,
+        ctx->static_bits, ctx->static_skip_front);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    ctx->launches += 2;
+    ctx->static_ready = true;
+    return 0;
+}
+int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg,
+                     int env_begin, int env_count, cudaStream_t s) {
+    return render_range(ctx, mask, frames, rgb, depth, seg, env_begin, env_count, true, s);
 }
 int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s) {
     return rrk_render_range(ctx, mask, frames, rgb, depth, seg, 0, ctx->N, s);
@@ -1002,7 +1077,7 @@ int rrk_render(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* 
 int rrk_render_camera(rr_ctx* ctx, const RenderConst* cam, const uint8_t* mask, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s) {
     if (bind_render(ctx, s)) return -1;
     CK(cudaMemcpyToSymbolAsync(c_render, cam, sizeof(RenderConst), 0, cudaMemcpyHostToDevice, s));
-    int rc = rrk_render(ctx, mask, nullptr, rgb, depth, seg, s);
+    int rc = render_range(ctx, mask, nullptr, rgb, depth, seg, 0, ctx->N, false, s);
     CK(cudaMemcpyToSymbolAsync(c_render, &ctx->render, sizeof(RenderConst), 0, cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));          // `cam` lives on the caller's stack
     return rc;

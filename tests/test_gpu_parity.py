@@ -453,3 +453,37 @@ def test_two_live_contexts_with_different_object_counts():
     s1.step(a1)                                                   # the survivor keeps working after the other is destroyed
     assert bool(torch.isfinite(s1.get_state()[0]).all())
     s1.close()
+
+
+@pytest.mark.parametrize("n_objects", [3, 1])
+def test_static_layer_is_bit_identical_to_rasterising_everything(n_objects, monkeypatch):
+    """rr_render starts every env's z-buffer from the pre-rasterised table + robot base (k_raster<2>, rr_render.cu); a
+    context created with RR_STATIC_LAYER=0 rasterises every shape for every env (k_raster<0>, the path rr_render_frames and
+    the oracle-parity test use).  Same states -> all three images must be identical bit for bit, including objects that
+    intersect the table, the home pose (near-plane clipping), render-off envs and chunked ranges (rr_step_host)."""
+    N = 40
+    rng = np.random.default_rng(17)
+    q = rng.uniform(-1.8, 1.8, (N, 11)); q[:, 7:] = rng.uniform(0, 1.2, (N, 4)) * [1, -1, 1, -1]
+    q[0] = 0.0
+    obj = np.zeros((N, 3, 13)); obj[:, :, 6] = 1.0
+    for e in range(N):
+        for o in range(3):
+            obj[e, o, :3] = [rng.uniform(-0.3, 0.1), rng.uniform(-0.45, 0.45), rng.uniform(0.18, 0.6)]   # some cut the table top
+            qq = rng.normal(size=4); obj[e, o, 3:7] = qq / np.linalg.norm(qq)
+    mask = torch.ones(N, dtype=torch.uint8, device="cuda"); mask[5] = 0; mask[N - 1] = 0
+    monkeypatch.setenv("RR_STATIC_LAYER", "0")
+    plain = BatchedSim(N, n_objects)
+    monkeypatch.delenv("RR_STATIC_LAYER")
+    layered = BatchedSim(N, n_objects)
+    outs = []
+    for sim in (plain, layered):
+        sim.set_state(dev(q), dev(np.zeros((N, 11))), dev(obj))
+        sim.step(dev(q[:, :9] * 0))                                  # one step: link frames of the new state, objects start to move
+        first = [t.clone() for t in sim.render(mask=mask)]
+        second = [t.clone() for t in sim.render()]                   # and again with everything on (the layer is reused)
+        host = sim.step_host(np.zeros((N, 9)), render_mask=np.ones(N, np.uint8))
+        outs.append(first + second + [torch.from_numpy(host[k]).cuda() for k in ("retina", "depth", "mask")])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert int(outs[1][2].max()) == 1 + n_objects and int((outs[1][5] == 1).sum()) > 1000 * N   # the table is in the picture
+    plain.close(); layered.close()
