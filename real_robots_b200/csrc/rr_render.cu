@@ -678,13 +678,19 @@ __device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M,
 // the winner's shaded colour word in static_col; MODE 2 starts every strip's z-buffer from static_keys instead of zero,
 // rasterises only the moving shapes on top and, for pixels a static key still owns at resolve time, takes the colour from
 // static_col.  max over (depth, triangle index) is associative, so the image is bit-identical to MODE 0's.
+struct StaticLayer {
+    unsigned long long* keys; unsigned int* col;                    // [240][320] in raster-row order
+    const uint8_t* rgb; const float* depth; const int32_t* seg;    // the finished static image in output layout (MODE 1 writes it as env 0)
+    unsigned int bits; int skip_front;                              // bit s: shape s is static; triangles [0, skip_front) all belong to static shapes
+};
 template <int MODE>
 __global__ void __launch_bounds__(RTHREADS, RBLOCKS)
 k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const float4* __restrict__ planes, int n_tris,
          const uint8_t* __restrict__ texdata, const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch,
          unsigned short* __restrict__ cull_scratch, int* __restrict__ work_counter,
-         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N,
-         unsigned long long* __restrict__ static_keys, unsigned int* __restrict__ static_col, unsigned int static_bits, int skip_front) {
+         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N, const StaticLayer SL) {
+    unsigned long long* __restrict__ static_keys = SL.keys; unsigned int* __restrict__ static_col = SL.col;
+    const unsigned int static_bits = SL.bits; const int skip_front = SL.skip_front;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* M = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);
@@ -833,7 +839,33 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 if (lane == 0) g = atomicAdd(&s_rgrp, 1);
                 g = __shfl_sync(0xffffffffu, g, 0);
                 if (g >= STRIP_ROWS * RR_W / 128) break;
-                bool covered = false;
+                bool covered = false, moving = false;
+                if (MODE == 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const unsigned long long key = keys[g * 128 + j * 32 + lane];
+                        covered |= key != 0ull; moving |= key != 0ull && (key & 0x7fffull) != 0x7fffull;
+                    }
+                    if (!__any_sync(0xffffffffu, moving) && __any_sync(0xffffffffu, covered)) {
+                        // no moving shape won a pixel of this group: the finished static image is the answer
+                        const int i = g * 32 + lane;
+                        const int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
+                        const size_t po = (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4, o = img + po;
+                        if (rgb) {
+                            const unsigned int* q = reinterpret_cast<const unsigned int*>(SL.rgb + po * 3);
+                            unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3);
+                            const unsigned int a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+                            __stcs(p, a); __stcs(p + 1, b); __stcs(p + 2, c);
+                        }
+                        if (depth) __stcs(reinterpret_cast<float4*>(depth + o), __ldg(reinterpret_cast<const float4*>(SL.depth + po)));
+                        if (seg) __stcs(reinterpret_cast<int4*>(seg + o), __ldg(reinterpret_cast<const int4*>(SL.seg + po)));
+                        const ulonglong2* nk = reinterpret_cast<const ulonglong2*>(static_keys + (size_t)((strip + 1 == NSTRIPS ? 0 : row0 + STRIP_ROWS) + r) * RR_W + 4 * x4);
+                        ulonglong2* kq = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
+                        kq[0] = __ldg(nk); kq[1] = __ldg(nk + 1);
+                        continue;
+                    }
+                    covered = false;
+                }
 #pragma unroll 1
                 for (int j = 0; j < 4; j++) {
                     const int p = g * 128 + j * 32 + lane;
@@ -998,6 +1030,7 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
         ctx->static_enabled = !(sl && sl[0] == '0');
         CK(cudaMalloc(&ctx->d_static_keys, (size_t)RR_W * RR_H * sizeof(unsigned long long)));
         CK(cudaMalloc(&ctx->d_static_col, (size_t)RR_W * RR_H * sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->d_static_img, (size_t)RR_W * RR_H * 12));      // rgb (3 B, padded to 4) | depth f32 | seg i32
     }
     // static frames (robot base, table) as doubles
     double sf[RR_NSHAPES * 12];
@@ -1015,6 +1048,14 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
     return 0;
 }
 
+static StaticLayer static_layer(rr_ctx* ctx) {
+    StaticLayer SL;
+    SL.keys = (unsigned long long*)ctx->d_static_keys; SL.col = (unsigned int*)ctx->d_static_col;
+    SL.rgb = (const uint8_t*)ctx->d_static_img; SL.depth = (const float*)((const uint8_t*)ctx->d_static_img + (size_t)RR_W * RR_H * 4);
+    SL.seg = (const int32_t*)((const uint8_t*)ctx->d_static_img + (size_t)RR_W * RR_H * 8);
+    SL.bits = ctx->static_bits; SL.skip_front = ctx->static_skip_front;
+    return SL;
+}
 static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uint8_t* rgb, float* depth, int32_t* seg,
                         int env_begin, int env_count, bool eye_camera, cudaStream_t s) {
     if (env_count <= 0) return 0;
@@ -1029,10 +1070,10 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
     // the static layer applies to the simulated scene seen by the eye camera; caller-supplied frames (rr_render_frames) and
     // other cameras (rr_render_camera) rasterise everything
     const bool use_static = ctx->static_enabled && ctx->static_ready && eye_camera && frames == nullptr;
-    unsigned long long* sk = (unsigned long long*)ctx->d_static_keys; unsigned int* sc = (unsigned int*)ctx->d_static_col;
+    const StaticLayer SL = static_layer(ctx);
 #define RASTER_ARGS(RGB, DEP, SEG, MASK, NENV) ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris, \
         ctx->d_tex, MASK, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, (unsigned short*)ctx->d_cull_scratch, \
-        ctx->d_work_counter, RGB, DEP, SEG, env_begin, NENV, sk, sc, ctx->static_bits, ctx->static_skip_front
+        ctx->d_work_counter, RGB, DEP, SEG, env_begin, NENV, SL
     CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), s));
     {
         ProfScope ps(ctx, 2, s);
@@ -1051,13 +1092,13 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
 int rrk_render_build_static(rr_ctx* ctx) {
     if (!ctx->static_enabled || ctx->static_ready) return 0;
     if (bind_render(ctx, 0)) return -1;
+    const StaticLayer SL = static_layer(ctx);
     k_render_setup<<<1, 128, 0, 0>>>(ctx->st, nullptr, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device], 0, 1);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), 0));
     k_raster<1><<<1, RTHREADS, RASTER_SMEM, 0>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris,
         ctx->d_tex, nullptr, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, (unsigned short*)ctx->d_cull_scratch,
-        ctx->d_work_counter, nullptr, nullptr, nullptr, 0, 1, (unsigned long long*)ctx->d_static_keys, (unsigned int*)ctx->d_static_col,
-        ctx->static_bits, ctx->static_skip_front);
+        ctx->d_work_counter, const_cast<uint8_t*>(SL.rgb), const_cast<float*>(SL.depth), const_cast<int32_t*>(SL.seg), 0, 1, SL);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     ctx->launches += 2;
