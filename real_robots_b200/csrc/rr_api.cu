@@ -288,7 +288,7 @@ int rr_destroy(rr_ctx* ctx) {
                     st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.rows, st.handoff,
                     ctx->d_cmd, ctx->d_mask, ctx->d_joint, ctx->d_touch, ctx->d_objpose, ctx->d_rgb, ctx->d_depth, ctx->d_seg,
                     ctx->d_tris, ctx->d_tex, ctx->d_hull_verts, ctx->d_rec_scratch, ctx->d_list_scratch, ctx->d_work_counter, ctx->d_tri_shape, ctx->d_planes, ctx->d_cull_scratch,
-                    ctx->d_static_keys, ctx->d_static_col, ctx->d_static_img};
+                    ctx->d_static_keys, ctx->d_static_img};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->host_compute) {

@@ -92,9 +92,9 @@ struct rr_ctx {
     void* d_rec_scratch; void* d_list_scratch; int* d_work_counter; uint8_t* d_tri_shape; int raster_grid;   // persistent rasteriser
     void* h_collide_const; float cull_hmax;   // host copies of per-context __constant__ data that are built on the fly
     void* d_planes; void* d_cull_scratch;   // model-space triangle planes (conservative back-face pre-test), per-CTA survivor lists
-    // static layer of the eye camera's image (table + robot base never move): raster keys and winner colours per pixel,
+    // static layer of the eye camera's image (table + robot base never move): raster keys per pixel and the finished static image,
     // built once by k_raster<1> and used as the z-buffer's initial content by k_raster<2> (see rr_render.cu)
-    void* d_static_keys = nullptr; void* d_static_col = nullptr; void* d_static_img = nullptr; bool static_ready = false; bool static_enabled = true;
+    void* d_static_keys = nullptr; void* d_static_img = nullptr; bool static_ready = false; bool static_enabled = true;
     unsigned static_bits = 0; int static_skip_front = 0;
     // staging for the host-buffer path
     double* d_cmd; uint8_t* d_mask; double* d_joint; double* d_touch; double* d_objpose;

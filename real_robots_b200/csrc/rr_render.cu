@@ -674,12 +674,12 @@ __device__ __forceinline__ unsigned int shade_pixel(const float* __restrict__ M,
 //
 // MODE 0: every shape is rasterised for every env.  The table and the robot base never move and the eye camera is fixed, so
 // their part of the image is the same in every env and every step: MODE 1 rasterises only those static shapes (one CTA,
-// one env) and leaves, per pixel, the winning raster key (record bits = 0x7fff as the "static" marker) in static_keys and
-// the winner's shaded colour word in static_col; MODE 2 starts every strip's z-buffer from static_keys instead of zero,
-// rasterises only the moving shapes on top and, for pixels a static key still owns at resolve time, takes the colour from
-// static_col.  max over (depth, triangle index) is associative, so the image is bit-identical to MODE 0's.
+// one env, at rr_create) and leaves, per pixel, the winning raster key (record bits = 0x7fff as the "static" marker) in
+// SL.keys and the finished static image in SL.rgb / depth / seg; MODE 2 starts every strip's z-buffer from SL.keys instead
+// of zero, rasterises only the moving shapes on top and, for pixels a static key still owns at resolve time, copies the
+// finished static pixel.  max over (depth, triangle index) is associative, so the image is bit-identical to MODE 0's.
 struct StaticLayer {
-    unsigned long long* keys; unsigned int* col;                    // [240][320] in raster-row order
+    unsigned long long* keys;                                       // [240][320] in raster-row order
     const uint8_t* rgb; const float* depth; const int32_t* seg;    // the finished static image in output layout (MODE 1 writes it as env 0)
     unsigned int bits; int skip_front;                              // bit s: shape s is static; triangles [0, skip_front) all belong to static shapes
 };
@@ -689,7 +689,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
          const uint8_t* __restrict__ texdata, const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch,
          unsigned short* __restrict__ cull_scratch, int* __restrict__ work_counter,
          uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N, const StaticLayer SL) {
-    unsigned long long* __restrict__ static_keys = SL.keys; unsigned int* __restrict__ static_col = SL.col;
+    unsigned long long* __restrict__ static_keys = SL.keys;
     const unsigned int static_bits = SL.bits; const int skip_front = SL.skip_front;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -870,19 +870,15 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 for (int j = 0; j < 4; j++) {
                     const int p = g * 128 + j * 32 + lane;
                     const unsigned long long key = keys[p];
-                    if (MODE == 1) { static_keys[row0 * RR_W + p] = key ? (key | 0x7fffull) : 0ull; if (key == 0ull) static_col[row0 * RR_W + p] = 0u; }
+                    if (MODE == 1) static_keys[row0 * RR_W + p] = key ? (key | 0x7fffull) : 0ull;
                     if (key == 0ull) continue;
                     covered = true;
-                    if (MODE == 2 && (key & 0x7fffull) == 0x7fffull) {           // a static key survived: its colour was shaded once
-                        keys[p] = (key & 0xffffffff00000000ull) | (unsigned long long)__ldg(static_col + row0 * RR_W + p);
-                        continue;
-                    }
+                    if (MODE == 2 && (key & 0x7fffull) == 0x7fffull) continue;   // a static key survived: pass B takes the finished static pixel
                     const int r = p / RR_W, x = p - r * RR_W;
                     int s;
                     const unsigned int col = shade_pixel(M, tris, tri_shape, texdata, recs, (unsigned int)(key & 0xffffffffu), x, row0 + r, s);
-                    const unsigned int low = 0x80000000u | ((unsigned int)s << 24) | (col & 0xffffffu);
-                    if (MODE == 1) static_col[row0 * RR_W + p] = low;
-                    keys[p] = (key & 0xffffffff00000000ull) | (unsigned long long)low;
+                    // bit 31 marks a resolved key (a raster key's low word is (triangle + 1) << 15 | record < 2^30)
+                    keys[p] = (key & 0xffffffff00000000ull) | 0x80000000ull | ((unsigned long long)s << 24) | (unsigned long long)(col & 0xffffffu);
                 }
                 const int i = g * 32 + lane;
                 const int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
@@ -909,17 +905,28 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 if (MODE == 2) { kp[0] = __ldg(nk); kp[1] = __ldg(nk + 1); }
                 else { kp[0] = make_ulonglong2(0ull, 0ull); kp[1] = make_ulonglong2(0ull, 0ull); }
                 const unsigned long long k4[4] = {ka.x, ka.y, kb.x, kb.y};
+                const size_t po = (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
+                unsigned int scol[4] = {0u, 0u, 0u, 0u}; float4 sdep = make_float4(0.f, 0.f, 0.f, 0.f); int4 sseg = make_int4(0, 0, 0, 0);
+                if (MODE == 2 && ((ka.x | ka.y | kb.x | kb.y) & 0x7fffull) == 0x7fffull) {     // (necessary, not sufficient: harmless extra loads)
+                    const unsigned int* q = reinterpret_cast<const unsigned int*>(SL.rgb + po * 3);
+                    const unsigned int a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+                    scol[0] = a & 0xffffffu; scol[1] = (a >> 24) | ((b & 0xffffu) << 8); scol[2] = (b >> 16) | ((c & 0xffu) << 16); scol[3] = c >> 8;
+                    if (depth) sdep = __ldg(reinterpret_cast<const float4*>(SL.depth + po));
+                    if (seg) sseg = __ldg(reinterpret_cast<const int4*>(SL.seg + po));
+                }
+                const float sdep4[4] = {sdep.x, sdep.y, sdep.z, sdep.w}; const int sseg4[4] = {sseg.x, sseg.y, sseg.z, sseg.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const unsigned long long key = k4[k];
                     if (key == 0ull) { col[k] = 0xffffffu; sg[k] = -1; dep[k] = bg_depth; continue; }
+                    if (MODE == 2 && !(key & 0x80000000ull)) { col[k] = scol[k]; sg[k] = sseg4[k]; dep[k] = sdep4[k]; continue; }   // static pixel
                     const unsigned int lo = (unsigned int)(key & 0xffffffffu);
                     col[k] = lo & 0xffffffu;
                     sg[k] = c_render.shape[(lo >> 24) & 31].objectAndLink & 0xffffff;
                     const float z_c = -unorder_bits((unsigned int)(key >> 32));
                     dep[k] = (float)((double)(farP * (nearP + z_c)) / (2. * (double)farP * (double)nearP + (double)(farP * z_c) - (double)(nearP * z_c)));
                 }
-                const size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;
+                const size_t o = img + po;
                 if (rgb) {
                     unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3);
                     __stcs(p, (col[0] & 0xffffffu) | (col[1] << 24));
@@ -1029,7 +1036,6 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
         const char* sl = getenv("RR_STATIC_LAYER");                  // RR_STATIC_LAYER=0: rasterise every shape for every env (A/B measurements)
         ctx->static_enabled = !(sl && sl[0] == '0');
         CK(cudaMalloc(&ctx->d_static_keys, (size_t)RR_W * RR_H * sizeof(unsigned long long)));
-        CK(cudaMalloc(&ctx->d_static_col, (size_t)RR_W * RR_H * sizeof(unsigned int)));
         CK(cudaMalloc(&ctx->d_static_img, (size_t)RR_W * RR_H * 12));      // rgb (3 B, padded to 4) | depth f32 | seg i32
     }
     // static frames (robot base, table) as doubles
@@ -1050,7 +1056,7 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
 
 static StaticLayer static_layer(rr_ctx* ctx) {
     StaticLayer SL;
-    SL.keys = (unsigned long long*)ctx->d_static_keys; SL.col = (unsigned int*)ctx->d_static_col;
+    SL.keys = (unsigned long long*)ctx->d_static_keys;
     SL.rgb = (const uint8_t*)ctx->d_static_img; SL.depth = (const float*)((const uint8_t*)ctx->d_static_img + (size_t)RR_W * RR_H * 4);
     SL.seg = (const int32_t*)((const uint8_t*)ctx->d_static_img + (size_t)RR_W * RR_H * 8);
     SL.bits = ctx->static_bits; SL.skip_front = ctx->static_skip_front;
@@ -1087,7 +1093,7 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
     return 0;
 }
 // Once per context (rr_create, after the first reset): matrices of env 0, then the static shapes of that env — their
-// matrices are the same in every env — into d_static_keys / d_static_col.  Synchronous, so that every later launch on
+// matrices are the same in every env — into d_static_keys / d_static_img.  Synchronous, so that every later launch on
 // any stream sees the finished layer.
 int rrk_render_build_static(rr_ctx* ctx) {
     if (!ctx->static_enabled || ctx->static_ready) return 0;
