@@ -50,23 +50,26 @@ def test_native_library_is_what_runs():
 
 
 def test_contact_free_trajectory_parity():
-    """300 steps, contacts off (free-falling objects are teleported home, env.py:257-264): |dq| <= 1e-6 drift bound,
-    in practice ~1e-13."""
-    N = 24
+    """1000-step contact-free trajectories (north_star's drift case; contacts off, free-falling objects are teleported
+    home, env.py:257-264) under the random policy.  Stated drift bound: |dq| <= 1e-6, |dqd| <= 1e-5, object pose <= 1e-6 at
+    every 100th step and at the end; in practice ~1e-12."""
+    N = 16
     rng = np.random.default_rng(0)
     sim = BatchedSim(N, 3, enable_contacts=0)
     orcs = [Oracle(3, enable_contacts=0) for _ in range(N)]
-    worst_step = 0.0
-    for a in policy(rng, N, 300):
+    worst = 0.0
+    for t, a in enumerate(policy(rng, N, 1000)):
         sim.step(dev(a))
         for e in range(N):
             orcs[e].step(a[e])
-    q, qd, obj = [t.cpu().numpy() for t in sim.get_state()]
-    oq = np.array([o.get_state()[0] for o in orcs])
-    oqd = np.array([o.get_state()[1] for o in orcs])
-    oobj = np.array([o.get_state()[2] for o in orcs])
-    assert np.abs(q - oq).max() < 1e-6 and np.abs(qd - oqd).max() < 1e-5 and np.abs(obj - oobj).max() < 1e-6
-    worst_step = max(worst_step, np.abs(q - oq).max())
+        if (t + 1) % 100 == 0:
+            q, qd, obj = [x.cpu().numpy() for x in sim.get_state()]
+            oq = np.array([o.get_state()[0] for o in orcs])
+            oqd = np.array([o.get_state()[1] for o in orcs])
+            oobj = np.array([o.get_state()[2] for o in orcs])
+            assert np.abs(q - oq).max() < 1e-6 and np.abs(qd - oqd).max() < 1e-5 and np.abs(obj - oobj).max() < 1e-6, "step %d" % (t + 1)
+            worst = max(worst, np.abs(q - oq).max())
+    print("contact-free 1000 steps: worst |dq| = %.3e" % worst)
     j, t, op = [x.cpu().numpy() for x in sim.read_state()]
     assert np.allclose(j, np.array([o.read()[0] for o in orcs]), atol=1e-6)
     assert (t == 0).all()
