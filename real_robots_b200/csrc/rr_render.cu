@@ -53,6 +53,9 @@ __constant__ float c_cull_hmax;      // largest 'smallest altitude' over all tri
 #ifndef REVERSE_ORDER
 #define REVERSE_ORDER 1
 #endif
+#ifndef GEO_PREFETCH
+#define GEO_PREFETCH 1             // geometry passes load the next round's indices / planes one round ahead
+#endif
 
 #ifdef RR_STATS   // tuning build only (scripts/raster_stats.py): event counters, read back with rr_debug_raster_stats
 __device__ unsigned long long g_stats[16];
@@ -730,21 +733,38 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         // triangle's plane than any rounding of the fp32 world coordinates can move that plane, so the exact fp64 test of
         // tri_vertex() would decide the same way; everything else is marked uncertain (bit 15) and takes the exact test.
         const int n_scan = (MODE == 2) ? n_tris - skip_front : n_tris;    // MODE 2: the leading static shapes are not even scanned
-        for (int base = 0; base < n_scan; base += RTHREADS) {
 #if REVERSE_ORDER
-            const int gt = n_tris - 1 - (base + tid);          // last shapes first: objects and the arm's upper links are nearest the eye
+#define PASS1_TRI(i) (n_tris - 1 - (i))                        // last shapes first: objects and the arm's upper links are nearest the eye
 #else
-            const int gt = (n_tris - n_scan) + base + tid;
+#define PASS1_TRI(i) ((n_tris - n_scan) + (i))
+#endif
+#if GEO_PREFETCH      // the shape id and the plane of the next round are in flight while this round is classified
+        int sidx_n = 0; float4 pl_n = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < n_scan) { sidx_n = __ldg(tri_shape + PASS1_TRI(tid)); pl_n = __ldg(planes + PASS1_TRI(tid)); }
+#endif
+        for (int base = 0; base < n_scan; base += RTHREADS) {
+            const int gt = PASS1_TRI(base + tid);
+#if GEO_PREFETCH
+            const int sidx_c = sidx_n; const float4 pl_c = pl_n;
+            if (base + RTHREADS + tid < n_scan) { sidx_n = __ldg(tri_shape + PASS1_TRI(base + RTHREADS + tid)); pl_n = __ldg(planes + PASS1_TRI(base + RTHREADS + tid)); }
 #endif
             int code = -1;
             if (base + tid < n_scan) {
+#if GEO_PREFETCH
+                const int sidx = sidx_c;
+#else
                 const int sidx = tri_shape[gt];
+#endif
                 const float* Ms = M + sidx * MAT_STRIDE;
                 bool act = Ms[39] != 0.f;
                 if (MODE == 1) act = act && ((static_bits >> sidx) & 1u);
                 if (MODE == 2) act = act && !((static_bits >> sidx) & 1u);
                 if (act) {
+#if GEO_PREFETCH
+                    const float4 pl = pl_c;
+#else
                     const float4 pl = __ldg(planes + gt);
+#endif
                     const float sd = pl.x * Ms[40] + pl.y * Ms[41] + pl.z * Ms[42] - pl.w;
                     STAT(0, 1);
                     if (sd > Ms[43]) code = gt;
@@ -766,8 +786,16 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         // ---- geometry pass 2: vertex shader, (exact cull for the uncertain ones), clip, viewport, set-up, records
         {
             const int ncull = s_ncull;
+#if GEO_PREFETCH
+            unsigned int code_n = tid < ncull ? cull[tid] : 0u;
+#endif
             for (int i = tid; i < ncull; i += RTHREADS) {
+#if GEO_PREFETCH
+                const unsigned int code = code_n;
+                if (i + RTHREADS < ncull) code_n = cull[i + RTHREADS];
+#else
                 const unsigned int code = cull[i];
+#endif
                 const unsigned int gt = code & 0x7fffu;
                 const float* Ms = M + tri_shape[gt] * MAT_STRIDE;
                 const float* tv = tris + (size_t)gt * 24;
