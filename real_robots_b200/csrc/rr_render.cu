@@ -956,6 +956,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                         if (seg) __stcs(reinterpret_cast<int4*>(seg + o), __ldg(reinterpret_cast<const int4*>(SL.seg + po)));
                         const ulonglong2* nk = reinterpret_cast<const ulonglong2*>(static_keys + (size_t)((strip + 1 == NSTRIPS ? 0 : row0 + STRIP_ROWS) + r) * RR_W + 4 * x4);
                         ulonglong2* kq = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
+                        __syncwarp();                             // the keys replaced here were read by other lanes above
                         kq[0] = __ldg(nk); kq[1] = __ldg(nk + 1);
                         continue;
                     }
@@ -982,6 +983,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 if (!__any_sync(0xffffffffu, covered)) {          // nothing but background in these 128 pixels (keys already zero)
                     if (MODE == 2) {
                         ulonglong2* kq = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
+                        __syncwarp();
                         kq[0] = __ldg(nk); kq[1] = __ldg(nk + 1);
                     }
                     const size_t o = img + (size_t)(RR_H - 1 - (row0 + r)) * RR_W + 4 * x4;

@@ -16,6 +16,9 @@ sim.render(mask=torch.tensor([1, 0, 1, 0, 1, 1], dtype=torch.uint8, device="cuda
 pq = torch.tensor([[-0.1, 0.0, 0.5, 0.7, 0.7, 0, 0]] * N, dtype=torch.float64, device="cuda")
 sim.ik(pq, 200, 1e-3)
 sim.step_host(a.cpu().numpy(), np.ones(N, np.uint8))
+sim.render_frames(sim.shape_frames())                       # every shape rasterised (k_raster<0>); rr_render uses the static layer (k_raster<2>)
+from real_robots_b200.cameras import view_from_yaw_pitch_roll, projection_fov
+sim.render_camera(view_from_yaw_pitch_roll([0, 0, 0.4], 1.2, 30, -30, 0), projection_fov(80, 320 / 240, 0.1, 100.0))   # other-camera path
 sim.contacts(); sim.shape_frames(); sim.link_pose(7); sim.reset()
 torch.cuda.synchronize()
 print("sanitize run ok")
