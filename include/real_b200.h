@@ -85,7 +85,10 @@ int  rr_read_state(rr_ctx* ctx, double* joint_pos, double* touch, double* obj_po
 
 /* replaces: get_retina -> EyeCamera.renderTarget -> getCameraImage/TinyRenderer (env.py:249-255,536-567).
  * env_mask u8[N] = per-env 'render' flag (NULL = all); masked-out envs get the reference's cached zero
- * arrays (env.py:114-122,273-275).  rgb u8[N,240,320,3]; depth f32[N,240,320]; mask i32[N,240,320] or NULL. */
+ * arrays (env.py:114-122,273-275).  rgb u8[N,240,320,3]; depth f32[N,240,320]; mask i32[N,240,320] or NULL.
+ * The table and the robot base (fixed bodies seen by a fixed camera) are rasterised once in rr_create and every env's
+ * z-buffer starts from that layer; the images are bit-identical to rasterising every shape (what rr_render_frames and
+ * rr_render_camera do, and what rr_render does when the environment variable RR_STATIC_LAYER=0 is set at rr_create). */
 int  rr_render(rr_ctx* ctx, const uint8_t* env_mask, uint8_t* rgb, float* depth, int32_t* mask, void* stream);
 
 /* replaces: REALRobotEnv.render('rgb_array') -> EnvCamera.render (env.py:221-228, 470-513): same rasteriser with a
