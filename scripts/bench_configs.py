@@ -19,6 +19,28 @@ def timed(fn, steps):
 
 
 dev = torch.device("cuda")
+
+# C1: the reference's own configuration through the drop-in gym surface — one env, joints action, random policy
+# (cli.RandomPolicy: p = 0.05 resample), 1000 steps with the 240x320 retina, numpy observations on the host
+import numpy as np
+import real_robots
+env = real_robots.make('REALRobot2020-R2J3-v0')
+obs = env.reset()
+rng = np.random.default_rng(1234)
+a = env.action_space['joint_command'].sample() if hasattr(env.action_space, '__getitem__') else rng.uniform(-1, 1, 9)
+for render in (True, False):
+    for t in range(50):
+        env.step({'joint_command': a, 'render': render})
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for t in range(1000):
+        if rng.random() < 0.05:
+            a = env.action_space['joint_command'].sample()
+        obs, _, done, _ = env.step({'joint_command': a, 'render': render})
+    dt = time.perf_counter() - t0
+    print("C1  REALRobot2020-R2J3-v0, 1 env, render %-5s: %7.3f ms/step  %10.0f env-steps/s  (gym facade, numpy obs, wall clock)" % (render, dt, 1000 / dt))
+assert obs['retina'].shape == (240, 320, 3)
+env.close()
+
 N = 4096
 sim = BatchedSim(N, 3)
 acts = bench.random_policy_actions(torch, 200, N, dev, 1234)
