@@ -141,7 +141,10 @@ int  rr_profile_read(rr_ctx* ctx, double* ms_total /*[4]*/, long long* launches 
 int  rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, int* n_pairs_host, void* stream);
 
 /* Per-env diagnostics of the last step: i32[N,4] = rows, iterations, contacts, flags (bit 0: the 32-contact cap was hit,
- * bit 1: every contact was object-vs-static, so the solver took its object-parallel path). */
+ * bit 1: every contact was object-vs-static, so the solver took its object-parallel path; bit 2: a NaN / infinite joint
+ * command arrived — where the reference asserts np.isfinite(a).all() (robot.py:189) a batched step cannot raise per env, the
+ * command acts as a full +-max step and never reaches the state; bit 3: the state had become non-finite and the env was put
+ * back into its initial state, as rr_reset would). */
 int  rr_diag(rr_ctx* ctx, int32_t* out, void* stream);
 
 #ifdef __cplusplus

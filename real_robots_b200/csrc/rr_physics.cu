@@ -33,7 +33,7 @@ struct WarpMem {
     int n_rows;
     int ocnt[RR_MAX_OBJECTS];
     int simple;                                         // every contact is object-vs-static: objects solve independently
-    int nc, overflow, pad_;
+    int nc, overflow, fault;                            // fault bit 0: a non-finite joint command arrived this step
     unsigned char olist[RR_MAX_OBJECTS][RR_MAX_CONTACTS];   // per object: its contact indices, in solver order
     // ---- kinematics workspace (both kernels, not handed over)
     double Rpc[RR_NL][9];     // parent -> link rotation
@@ -448,11 +448,16 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
     // ---- action prologue (env.py:314-321, robot.py:188-201): lanes 0..8
     {
         double a = 0.0;
+        bool badcmd = false;
         if (lane < RR_NUM_JOINTS) {
             const double PI = 3.141592653589793;
             double cur = (lane < 8) ? m.q[lane] : -m.q[8];
             double md = (lane < 5) ? 0.2 : (lane < 7 ? 0.3 : 0.1);
-            double diff = fmin(md, cmd[(size_t)e * RR_NUM_JOINTS + lane] - cur);
+            const double want = cmd[(size_t)e * RR_NUM_JOINTS + lane];
+            // the reference asserts np.isfinite(a).all() (robot.py:189); a batched step cannot raise per env: fmin / fmax turn a NaN
+            // or infinite command into a full +-max step (never into a NaN target) and the env is flagged in rr_diag
+            badcmd = !isfinite(want);
+            double diff = fmin(md, want - cur);
             diff = fmax(-md, diff);
             a = cur + diff;
             double lo = -PI * 0.944, hi = PI * 0.944;
@@ -461,6 +466,8 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
             if (lane >= 7) { lo = 0.0; hi = PI / 2; }
             a = fmax(lo, fmin(a, hi));
         }
+        const bool anybad = __any_sync(FULL, badcmd);
+        if (lane == 0) m.fault = anybad ? 1 : 0;
         double a7 = __shfl_sync(FULL, a, 7);
         if (lane == 8) a = fmax(0.0, fmin(2 * a7, a));
         double a8 = __shfl_sync(FULL, a, 8);
@@ -866,6 +873,31 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
         }
     }
     if (has_obj) obj_integrate(ob, dt);
+    // ---- failure detection: a non-finite state cannot recover by itself (and the reference has nothing to say about it);
+    // the env is put back into its initial state as rr_reset would, keeps stepping, and is flagged in rr_diag (bit 3)
+    int fault = m.fault;
+    {
+        bool bad = lane < RR_NDOF && !(isfinite(m.q[lane]) && isfinite(m.qd[lane]));
+        if (has_obj) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) bad |= !(isfinite(ob.pos[k]) && isfinite(ob.lin[k]) && isfinite(ob.ang[k]));
+#pragma unroll
+            for (int k = 0; k < 4; k++) bad |= !isfinite(ob.quat[k]);
+        }
+        if (__any_sync(FULL, bad)) {
+            fault |= 2;
+            if (lane < RR_NDOF) { m.q[lane] = 0.0; m.qd[lane] = 0.0; m.target[lane] = 0.0; }
+            if (has_obj) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { ob.pos[k] = c_robot.obj_init[lane][k]; ob.lin[k] = 0.0; ob.ang[k] = 0.0; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) ob.quat[k] = c_robot.obj_init[lane][3 + k];
+            }
+            for (int slot = lane; slot < RR_MAX_MANIFOLDS; slot += 32) { hdr[2 * slot] = -1; hdr[2 * slot + 1] = 0; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) touch[k] = 0.0;
+        }
+    }
     __syncwarp();
     // ---- epilogue: final kinematics, state write-back, observations
     fk_local(m, lane);
@@ -886,7 +918,7 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
     }
     if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
     if (lane == 0) {
-        st.diag[4 * e] = m.n_rows + 3 * nc; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (m.simple ? 2 : 0);   // bit 0: contact cap hit, bit 1: object-parallel solver path
+        st.diag[4 * e] = m.n_rows + 3 * nc; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (m.simple ? 2 : 0) | (fault << 2);   // bit 0: contact cap hit, bit 1: object-parallel solver path, bits 2-3: faults
         st.timestep[e] += 1;
     }
 }

@@ -159,6 +159,11 @@ class VecREALRobotEnv:
     def evaluate_goal(self, goal_xyz):
         return self.sim.score(goal_xyz.contiguous())
 
+    def fault_flags(self):
+        """Per-env failure flags of the last step (BatchedSim.faults): a batched env cannot raise for one env the way
+        Kuka.apply_action's assert does (robot.py:189), so non-finite commands / states are flagged instead."""
+        return self.sim.faults()
+
     def sample_random_actions(self, generator=None):
         """U(low, high) of the joints action Box (cli.RandomPolicy draw)."""
         u = torch.rand(self.n_envs, 9, dtype=torch.float64, device=self.device, generator=generator)

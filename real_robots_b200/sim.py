@@ -178,6 +178,11 @@ class BatchedSim:
         self._ck(self.lib.rr_diag(self.ctx, _ptr(out), self._stream()), "rr_diag")
         return out
 
+    def faults(self):
+        """i32[N]: bit 0 = a non-finite joint command arrived in the last step (it acted as a full +-max step; the reference
+        asserts instead, robot.py:189), bit 1 = the state had become non-finite and the env was re-initialised."""
+        return (self.diag()[:, 3] >> 2) & 3
+
     def profile(self, enable=True):
         self._ck(self.lib.rr_profile(self.ctx, 1 if enable else 0), "rr_profile")
 

@@ -490,3 +490,43 @@ def test_static_layer_is_bit_identical_to_rasterising_everything(n_objects, monk
         assert torch.equal(a, b)
     assert int(outs[1][2].max()) == 1 + n_objects and int((outs[1][5] == 1).sum()) > 1000 * N   # the table is in the picture
     plain.close(); layered.close()
+
+
+def test_fault_flags_non_finite_commands_and_states():
+    """Failure detection of the batched step.  The reference asserts np.isfinite(a).all() (robot.py:189); a batched step cannot
+    raise for one env, so a NaN / infinite command acts as a full +-max step (never reaches the state) and is flagged, and an
+    env whose state has become non-finite is re-initialised as rr_reset would and flagged.  Other envs are not affected."""
+    N = 8
+    rng = np.random.default_rng(23)
+    a = rng.uniform(LO, HI, size=(N, 9))
+    bad = a.copy(); bad[2, 3] = np.nan; bad[5, 0] = np.inf; bad[6, 8] = -np.inf
+    big = a.copy(); big[2, 3] = 1e300; big[5, 0] = 1e300; big[6, 8] = -1e300
+    sim, ref = BatchedSim(N, 3), BatchedSim(N, 3)
+    for _ in range(25):
+        sim.step(dev(bad)); ref.step(dev(big))
+    f = sim.faults().cpu().numpy()
+    assert (f[[2, 5, 6]] == 1).all() and (np.delete(f, [2, 5, 6]) == 0).all() and (ref.faults() == 0).all()
+    for x, y in zip(sim.get_state(), ref.get_state()):
+        assert bool(torch.isfinite(x).all()) and torch.equal(x, y)          # NaN / inf behave exactly like a huge finite command
+    # a non-finite state: env 1 is re-initialised, everybody else carries on untouched
+    q, qd, obj = [t.clone() for t in sim.get_state()]
+    q[1, 4] = float("nan"); obj[3, 1, 7] = float("inf")
+    sim.set_state(q, qd, obj)
+    sim.step(dev(a)); ref.step(dev(a))
+    f = sim.faults().cpu().numpy()
+    assert f[1] == 2 and f[3] == 2 and (np.delete(f, [1, 3]) == 0).all()
+    q2, qd2, obj2 = sim.get_state()
+    rq, rqd, robj = ref.get_state()
+    assert bool(torch.isfinite(q2).all()) and bool(torch.isfinite(qd2).all()) and bool(torch.isfinite(obj2).all())
+    keep = [e for e in range(N) if e not in (1, 3)]
+    assert torch.equal(q2[keep], rq[keep]) and torch.equal(obj2[keep], robj[keep])
+    fresh = BatchedSim(1, 3)
+    fq, fqd, fobj = fresh.get_state()
+    for e in (1, 3):
+        assert torch.equal(q2[e], fq[0]) and torch.equal(qd2[e], fqd[0]) and torch.equal(obj2[e], fobj[0])
+    rgb, depth, seg = sim.render()
+    assert bool(torch.isfinite(depth).all())
+    sim.step(dev(a))
+    assert int(sim.faults().sum()) == 0                                      # flags describe the last step only
+    for s_ in (sim, ref, fresh):
+        s_.close()
