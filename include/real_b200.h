@@ -140,6 +140,12 @@ int  rr_profile_read(rr_ctx* ctx, double* ms_total /*[4]*/, long long* launches 
 #define RR_CONTACT_POINT_DOUBLES 17
 int  rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, int* n_pairs_host, void* stream);
 
+/* checkpoint hook: write the persistent contact manifolds back (same layout as rr_contacts returns them).  The manifolds —
+ * contact points with their accumulated normal impulses, i.e. the solver's warm start — are the only state of the path besides
+ * (q, qd, obj); rr_set_state clears them, so a resume is rr_set_state followed by rr_set_contacts and then continues bit for
+ * bit.  (Not in the reference, which has no checkpoint of the simulation: SURVEY section 5.) */
+int  rr_set_contacts(rr_ctx* ctx, const int32_t* hdr, const double* pts, void* stream);
+
 /* Per-env diagnostics of the last step: i32[N,4] = rows, iterations, contacts, flags (bit 0: the 32-contact cap was hit,
  * bit 1: every contact was object-vs-static, so the solver took its object-parallel path; bit 2: a NaN / infinite joint
  * command arrived — where the reference asserts np.isfinite(a).all() (robot.py:189) a batched step cannot raise per env, the

@@ -53,6 +53,7 @@ SYMBOLS = {
     "rr_launch_count": (C.c_longlong, [_VP]),
     "rr_diag": (_I, [_VP, _VP, _VP]),
     "rr_contacts": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "rr_set_contacts": (_I, [_VP, _VP, _VP, _VP]),
     "rr_profile": (_I, [_VP, _I]),
     "rr_profile_read": (_I, [_VP, _VP, _VP]),
 }

@@ -356,6 +356,16 @@ int rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, int
     if (n_pairs_host) *n_pairs_host = ctx->n_pairs;
     return 0;
 }
+int rr_set_contacts(rr_ctx* ctx, const int32_t* hdr, const double* pts, void* stream) {
+    ARG(hdr != nullptr && pts != nullptr, "rr_set_contacts: hdr / pts is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int p = ctx->man_parity;
+    const size_t N = (size_t)ctx->N;
+    cudaError_t e = cudaMemcpyAsync(ctx->st.man_hdr[p], hdr, N * RR_MAX_MANIFOLDS * 2 * 4, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->st.man_pts[p], pts, N * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE * 8, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) { ctx->err = std::string("rr_set_contacts: ") + cudaGetErrorString(e); return -1; }
+    return 0;
+}
 int rr_profile(rr_ctx* ctx, int enable) {
     for (int k = 0; k < RR_PROFILE_KINDS; k++) { for (cudaEvent_t e : ctx->prof_ev[k]) cudaEventDestroy(e); ctx->prof_ev[k].clear(); }
     ctx->prof_on = enable != 0;

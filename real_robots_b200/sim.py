@@ -173,6 +173,28 @@ class BatchedSim:
         self._ck(self.lib.rr_contacts(self.ctx, _ptr(hdr), _ptr(pts), pairs.ctypes.data_as(C.c_void_p), C.byref(n), self._stream()), "rr_contacts")
         return hdr, pts, pairs[:n.value]
 
+    def set_contacts(self, hdr, pts):
+        """Write the persistent manifolds back (layout of contacts()); call after set_state, which clears them."""
+        self._chk(hdr, (self.n_envs, 24, 2), torch.int32, "hdr")
+        self._chk(pts, (self.n_envs, 24, 4, 17), torch.float64, "pts")
+        self._ck(self.lib.rr_set_contacts(self.ctx, _ptr(hdr), _ptr(pts), self._stream()), "rr_set_contacts")
+
+    # checkpoint / resume of the simulation state (not in the reference, SURVEY section 5): (q, qd, obj) and the contact
+    # manifolds with their warm-start impulses are everything a step depends on, so a resumed run continues bit for bit
+    def state_dict(self):
+        q, qd, obj = self.get_state()
+        hdr, pts, _ = self.contacts()
+        return {"n_envs": self.n_envs, "n_objects": self.n_objects, "q": q.cpu(), "qd": qd.cpu(), "obj": obj.cpu(),
+                "contact_hdr": hdr.cpu(), "contact_pts": pts.cpu()}
+
+    def load_state_dict(self, sd):
+        if int(sd["n_envs"]) != self.n_envs or int(sd["n_objects"]) != self.n_objects:
+            raise ValueError("state_dict is for %d envs / %d objects, this simulator has %d / %d"
+                             % (sd["n_envs"], sd["n_objects"], self.n_envs, self.n_objects))
+        dev = self.device
+        self.set_state(sd["q"].to(dev).contiguous(), sd["qd"].to(dev).contiguous(), sd["obj"].to(dev).contiguous())
+        self.set_contacts(sd["contact_hdr"].to(dev).contiguous(), sd["contact_pts"].to(dev).contiguous())
+
     def diag(self):
         out = torch.empty(self.n_envs, 4, dtype=torch.int32, device=self.device)
         self._ck(self.lib.rr_diag(self.ctx, _ptr(out), self._stream()), "rr_diag")
