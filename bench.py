@@ -29,6 +29,25 @@ STATE_BYTES = 3824                            # BASELINE.md §4 physics bytes pe
 METRIC = "env_steps_per_sec_with_retina_4096_envs_per_gpu"
 
 
+_JSON_OUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: anything native libraries print to fd 1 on the way (the NCCL version
+    banner at communicator creation) is sent to stderr, and the line goes to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -160,7 +179,7 @@ def run_reference(args):
                          "sample": "%d processes x %d env-steps with render per bench step (oracle port; pybullet not installable)" % (cores, per_step)},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def bind_to_gpu_numa(local):
@@ -306,7 +325,7 @@ def run_ours(args):
             wall = oracle_worker((1234, n_cpu, 3))
             line["cpu_baseline"] = {"value": n_cpu / wall, "unit": "env-steps/s", "cores": 1, "kind": "port",
                                     "sample": "1 oracle env x %d env-steps with render (%.1f s)" % (n_cpu, wall)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -324,6 +343,7 @@ def main():
     ap.add_argument("--traffic", type=float, default=4.85e9,
                     help="dram bytes (read + write) per 4096-env k_raster launch from the ncu capture in profiles/r01c_ncu_full_summary.json (0.47 GB read + 4.38 GB written)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
