@@ -8,7 +8,6 @@ import math
 
 import torch
 
-from .. import _lib as L
 from ..sim import BatchedSim
 from ..util import euler_to_quat
 from .robot import Kuka

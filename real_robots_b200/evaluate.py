@@ -10,12 +10,6 @@ import numpy as np
 
 from .policy import BasePolicy
 
-try:                                    # pragma: no cover
-    from tqdm import tqdm
-except Exception:                       # pragma: no cover
-    def tqdm(it=None, **kw):
-        return it
-
 
 class EvaluationService:
     def __init__(self, Controller, environment='R1', action_type='macro_action', n_objects=1,
