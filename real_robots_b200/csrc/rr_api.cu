@@ -24,13 +24,18 @@ struct Blob {
         if (got != (size_t)n || n < 16 || memcmp(raw.data(), "RRB200\0\0", 8) != 0) { err = "asset blob: bad magic / short read"; return false; }
         uint32_t ver, cnt; memcpy(&ver, raw.data() + 8, 4); memcpy(&cnt, raw.data() + 12, 4);
         if (ver != 1) { err = "asset blob: unsupported version"; return false; }
+        if ((uint64_t)cnt > ((uint64_t)n - 16) / 112) { err = "asset blob: entry table out of range"; return false; }
+        static const uint64_t item[5] = {1, 4, 4, 8, 8};      // u8 i32 f32 f64 i64
         for (uint32_t i = 0; i < cnt; i++) {
             const uint8_t* e = raw.data() + 16 + 112 * (size_t)i;
             char nm[49]; memcpy(nm, e, 48); nm[48] = 0;
             Entry en; uint32_t dt, nd; memcpy(&dt, e + 48, 4); memcpy(&nd, e + 52, 4);
             en.dtype = (int)dt; en.ndim = (int)nd; memcpy(en.shape, e + 56, 32);
             uint64_t off; memcpy(&off, e + 88, 8); memcpy(&en.nbytes, e + 96, 8);
-            if (off + en.nbytes > (uint64_t)n) { err = "asset blob: entry out of range"; return false; }
+            if (off > (uint64_t)n || en.nbytes > (uint64_t)n - off) { err = "asset blob: entry out of range"; return false; }
+            uint64_t count = 1;
+            for (uint32_t d = 0; d < nd && d < 4; d++) count *= en.shape[d];
+            if (dt > 4 || nd > 4 || count * item[dt > 4 ? 0 : dt] != en.nbytes) { err = std::string("asset blob: inconsistent entry ") + nm; return false; }
             en.data = raw.data() + off;
             ent[nm] = en;
         }
@@ -244,7 +249,8 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     ctx->d_cmd = nullptr; ctx->d_mask = nullptr; ctx->d_joint = ctx->d_touch = ctx->d_objpose = nullptr;
     ctx->d_rgb = nullptr; ctx->d_depth = nullptr; ctx->d_seg = nullptr; ctx->img_capacity = 0; ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0;
     if (cfg) ctx->cfg = *cfg; else rr_config_default(&ctx->cfg);
-    auto fail = [&](int rc) { g_create_err = ctx->err; delete ctx; return rc; };
+    // error path: release whatever was allocated and drop the constant-memory ownership records that point at ctx
+    auto fail = [&](int rc) { g_create_err = ctx->err; rr_destroy(ctx); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(-1); }
     Blob b;
     if (!b.load(blob_path, ctx->err)) return fail(-1);

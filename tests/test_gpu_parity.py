@@ -348,6 +348,36 @@ def test_bad_arguments_raise():
         BatchedSim(1, 5)
 
 
+def test_failed_create_leaves_the_library_usable(tmp_path):
+    """A context that fails half-way through rr_create (corrupted asset blob: truncated, inconsistent entry, missing
+    entry) reports an error, releases what it held, and does not disturb contexts created before or after it."""
+    from real_robots_b200 import _lib as L
+    raw = bytearray(open(L.DEFAULT_BLOB, "rb").read())
+    before = BatchedSim(3, 2)
+    cmd = torch.full((3, 9), 0.1, dtype=torch.float64, device="cuda")
+    before.step(cmd)
+    ref = before.get_state()[0].clone()
+
+    cases = {"truncated": bytes(raw[:len(raw) // 2]), "not_a_blob": b"nope" * 64}
+    bad = bytearray(raw); bad[16 + 96:16 + 104] = (1 << 40).to_bytes(8, "little")          # first entry: nbytes beyond the file
+    cases["entry_out_of_range"] = bytes(bad)
+    bad = bytearray(raw); bad[16 + 56:16 + 64] = (7).to_bytes(8, "little")                  # first entry: shape[0] != nbytes / itemsize
+    cases["inconsistent_entry"] = bytes(bad)
+    bad = bytearray(raw); bad[16:16 + 5] = b"xxxxx"                                         # first entry renamed -> missing
+    cases["missing_entry"] = bytes(bad)
+    for name, data in cases.items():
+        path = tmp_path / (name + ".rrb")
+        path.write_bytes(data)
+        with pytest.raises(RuntimeError, match="asset blob"):
+            BatchedSim(2, 3, blob=str(path))
+
+    after = BatchedSim(3, 2)                       # same size / object count as `before`: must give the same trajectory
+    after.step(cmd)
+    assert torch.equal(after.get_state()[0], ref)
+    before.step(cmd); after.step(cmd)
+    assert torch.equal(after.get_state()[0], before.get_state()[0])
+
+
 def test_cuda_path_against_reference_host_goldens():
     """tests/golden/reference_host_golden.npz was produced by the reference's own Python code (make_reference_golden.py).
     The batched kernels must reproduce, one env per golden case: the scores of evaluateGoal (env.py:181-200), the
