@@ -272,3 +272,24 @@ def test_resting_contact_impulses_carry_the_weight(blob):
         assert np.allclose(d[sel, 6:9], [0, 0, 1], atol=1e-9)
         assert abs(d[sel, 10].sum() - m * 9.81 * 0.005) < 1e-9 and (d[sel, 10] >= 0).all()
     assert np.abs(o.get_state()[2][:, 7:13]).max() < 1e-4
+
+
+def test_motor_rows_converge_to_the_analytic_velocity():
+    """POSITION_CONTROL as a constraint row: the unsaturated solution is qd' = kp (target - q) / dt
+    + (1 - kd) qd for every motor, whatever the dynamics.  PGS on the oracle's rows (J, M^-1 J^T, rhs built from ABA
+    quantities) must converge to exactly that; with Bullet's 50 iterations it is still 0.5 rad/s away in this case,
+    which is the reference's behaviour if App. C-1 holds, not an error."""
+    rng = np.random.default_rng(0)
+    q0 = rng.uniform(-0.5, 0.5, 11); q0[7:] = [0.3, -0.2, 0.3, -0.2]
+    qd0 = rng.uniform(-0.5, 0.5, 11)
+    cmd = np.array([0.1, -0.2, 0.15, 0.3, -0.1, 0.2, 0.1, 0.4, 0.3])
+    err = {}
+    for iters in (50, 500, 5000):
+        o = Oracle(3, enable_contacts=0, solver_iterations=iters, residual_threshold=0.0)
+        o.set_state(q=q0, qd=qd0)
+        o.step(cmd)
+        q1, qd1, _ = o.get_state()
+        desired = 0.1 * (o.targets() - q0) / 0.005                       # kp = 0.1, kd = 1 (pybullet defaults)
+        err[iters] = np.abs(qd1 - desired).max()
+        assert np.allclose(q1, q0 + 0.005 * qd1, atol=1e-15)             # semi-implicit Euler
+    assert err[5000] < 1e-12 and err[500] < 1e-5 and 0.05 < err[50] < 1.0
