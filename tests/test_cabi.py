@@ -58,3 +58,25 @@ def test_bad_arguments_are_rejected(lib):
     ctx = C.c_void_p()
     assert lib.rr_create(C.byref(ctx), 0, 0, 3, L.DEFAULT_BLOB.encode(), None) != 0
     assert lib.rr_create(C.byref(ctx), 0, 4, 7, L.DEFAULT_BLOB.encode(), None) != 0
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/real_b200.h must be consumable by a C compiler (the boundary is a C ABI, no C++ / torch types), and a C
+    program using every entry point must link against libreal_b200.so."""
+    import re
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    hdr = os.path.join(root, "include", "real_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    names = sorted(set(re.findall(r"\b(rr_[a-z_]+)\s*\(", open(hdr).read())))
+    src = tmp_path / "link.c"
+    src.write_text('#include "real_b200.h"\n#include <stdio.h>\nint main(void) {\n  void* p[] = {%s};\n'
+                   '  printf("%%d\\n", (int)(sizeof p / sizeof p[0]));\n  return rr_config_size() > 0 ? 0 : 1;\n}\n'
+                   % ", ".join("(void*)%s" % n for n in names))
+    exe = tmp_path / "link"
+    libdir = os.path.join(root, "real_robots_b200")
+    subprocess.check_call(["gcc", "-std=gnu99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libreal_b200.so", "-Wl,-rpath," + libdir,
+                           "-Wl,-rpath,/usr/local/cuda/lib64"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and int(out.stdout) == len(names) >= 25
