@@ -137,13 +137,19 @@ class VecREALRobotEnv:
         max_pieces = int(pieces[need].max().item())
         chunk = (500 // pieces)
         iks = []
+        piecesf = pieces.to(torch.float64)
         for i in range(max_pieces):
-            frac = ((i + 1) / pieces.to(torch.float64)).clamp(max=1.0)
-            coord = at(p1 + (p2 - p1) * frac[:, None], 0.46)
+            # np.linspace(p1, p2, pieces + 1)[i + 1] bit for bit: (i + 1) / pieces as a correctly rounded tensor / tensor
+            # division (python scalar / tensor is scalar * reciprocal: one ulp off for some i), times delta, plus start;
+            # the end point is p2 itself
+            frac = torch.full_like(piecesf, float(i + 1)) / piecesf
+            way = torch.where((pieces <= i + 1)[:, None], p2, (p2 - p1) * frac[:, None] + p1)
+            coord = at(way, 0.46)
             iks.append(self._ik_xyz(coord, need & (pieces > i)))
         iks = torch.stack(iks, dim=1)                                        # [N, max_pieces, 9]
         rows = torch.arange(500, device=dev)[None, :]
         idx = torch.minimum(rows // chunk[:, None], (pieces - 1)[:, None])     # joints[i*chunk:] = ik_i  (last wins)
+        idx = idx.clamp(max=max_pieces - 1)      # envs that keep their plan may have more pieces than were solved
         sweep = torch.gather(iks, 1, idx[:, :, None].expand(N, 500, 9))
         plan = torch.cat([home2.expand(N, 100, 9), p1h[:, None].expand(N, 100, 9), p1l[:, None].expand(N, 50, 9), sweep,
                           p2h[:, None].expand(N, 50, 9), home2.expand(N, 100, 9), home.expand(N, 100, 9)], dim=1)

@@ -293,3 +293,99 @@ def test_host_limit_action_matches_reference():
     env.set_eye("left", [0.1, 0, 1.0], [0, 0, 0])
     env.setCamera()
     assert set(env.eyes) == {"eye", "left"} and env.envCamera.dist == 1.2 and env.envCamera.yaw == 30
+
+
+def test_vectorised_macro_plans_match_reference_bit_for_bit():
+    """VecREALRobotEnv._generate_plans (torch, one plan per env, every IK request batched) against the reference's
+    generate_plan rows (env.py:410-459) with the same stand-in IK — on CPU tensors, no simulator behind it."""
+    torch = pytest.importorskip("torch")
+    from real_robots_b200.envs.vec_env import VecREALRobotEnv
+    macros = np.asarray(G["plan_macro"], dtype=np.float64)
+    n = len(macros)
+    quat = np.array(euler_to_quat([0, 3.14, -1.57]))
+    env = object.__new__(VecREALRobotEnv)
+    env.n_envs, env.device = n, torch.device("cpu")
+    env.plan = torch.zeros(n, 1000, 9, dtype=torch.float64)
+    requests = []
+
+    def ik_xyz(xyz, mask):
+        requests.append(int(mask.sum()))
+        rows = [fake_ik(r, quat)[:9] if m else np.zeros(9) for r, m in zip(xyz.numpy(), mask.numpy())]
+        return torch.tensor(np.array(rows), dtype=torch.float64)
+    env._ik_xyz = ik_xyz
+    env._generate_plans(torch.tensor(macros), torch.ones(n, dtype=torch.bool))
+    got = env.plan.numpy()
+    for k in range(n):
+        assert np.array_equal(got[k], G["plan_rows"][k]), k
+    # one batched request per plan stage: p1 high / p1 low / p2 high, then one per sweep piece of the longest plan
+    assert len(requests) == 3 + int((np.asarray(G["plan_ik_calls"]) - 4).max())
+    # envs that do not need a plan keep theirs
+    env.plan = torch.full((n, 1000, 9), 7.0, dtype=torch.float64)
+    need = torch.zeros(n, dtype=torch.bool); need[0] = True
+    env._generate_plans(torch.tensor(macros), need)
+    assert np.array_equal(env.plan[0].numpy(), G["plan_rows"][0]) and bool((env.plan[1:] == 7.0).all())
+
+
+def _vec_shell(torch, n, action_type):
+    """A VecREALRobotEnv without a simulator: the request caches and plan replay are plain torch code."""
+    from real_robots_b200.envs.vec_env import VecREALRobotEnv
+    env = object.__new__(VecREALRobotEnv)
+    env.n_envs, env.device, env.action_type = n, torch.device("cpu"), action_type
+    if action_type == 'macro_action':
+        env.requested = torch.full((n, 2, 2), float('nan'), dtype=torch.float64)
+        env.plan = torch.zeros(n, 1000, 9, dtype=torch.float64)
+        env.plan_step = torch.full((n,), 1000, dtype=torch.int64)
+    else:
+        env.requested = torch.full((n, 7), float('nan'), dtype=torch.float64)
+        env.last_ik = torch.zeros(n, 11, dtype=torch.float64)
+    return env
+
+
+def test_vectorised_macro_sequencing_matches_reference_per_env():
+    """Two envs replay the reference's macro sequence (env.py:388-408, 462-467), the second one delayed by three steps of
+    another action, so that at most times only one of them re-plans: plan_step and the rows sent must match the reference's
+    for each env independently."""
+    torch = pytest.importorskip("torch")
+    quat = np.array(euler_to_quat([0, 3.14, -1.57]))
+    macros = np.asarray(G["plan_macro"], dtype=np.float64)
+    seq = [int(i) for i in G["macro_seq_action_index"]]
+    lag = 3
+    env = _vec_shell(torch, 2, 'macro_action')
+    env._ik_xyz = lambda xyz, mask: torch.tensor(np.array([fake_ik(r, quat)[:9] if m else np.zeros(9)
+                                                            for r, m in zip(xyz.numpy(), mask.numpy())]), dtype=torch.float64)
+    steps, sent = [[], []], [[], []]
+    for t in range(len(seq) + lag):
+        a0 = macros[seq[t]] if t < len(seq) else macros[5]
+        a1 = macros[seq[t - lag]] if t >= lag else macros[5]
+        row = env._macro(torch.tensor(np.stack([a0, a1])))
+        for e in range(2):
+            steps[e].append(int(env.plan_step[e])); sent[e].append(row[e].numpy().copy())
+    want = np.asarray(G["macro_seq_plan_step"])
+    assert np.array_equal(np.array(steps[0][:len(seq)]), want) and np.array_equal(np.array(steps[1][lag:]), want)
+    for rows in (sent[0][:len(seq)], sent[1][lag:]):
+        assert np.array_equal(np.array(rows[:8]), G["macro_seq_first_rows"]) and np.array_equal(np.array(rows[-3:]), G["macro_seq_last_rows"])
+
+
+def test_vectorised_cartesian_cache_matches_reference():
+    """env.py:358-386 per env: IK only when the 7-vector request changes (exact equality), gripper passed through."""
+    torch = pytest.importorskip("torch")
+
+    class Sim:
+        calls = []
+
+        def ik(self, pq, max_iter, residual, mask=None):
+            assert max_iter == 1000 and residual == 0.001
+            Sim.calls.append(mask.numpy().copy())
+            return torch.tensor(np.array([fake_ik(r[:3], r[3:]) for r in pq.numpy()]), dtype=torch.float64)
+    env = _vec_shell(torch, 2, 'cartesian')
+    env.sim = Sim()
+    cmds, grips = np.asarray(G["cart_cmd"]), np.asarray(G["cart_grip"])
+    out0, out1, n0 = [], [], []
+    for t in range(len(cmds) + 1):                       # env 1 runs the same sequence one step later
+        c0 = cmds[min(t, len(cmds) - 1)]; g0 = grips[min(t, len(cmds) - 1)]
+        c1 = cmds[max(t - 1, 0)]; g1 = grips[max(t - 1, 0)]
+        cmd = env._cartesian(torch.tensor(np.stack([c0, c1])), torch.tensor(np.stack([g0, g1])))
+        out0.append(cmd[0].numpy().copy()); out1.append(cmd[1].numpy().copy())
+        n0.append(sum(int(m[0]) for m in Sim.calls))
+    assert np.array_equal(np.array(out0[:len(cmds)]), G["cart_joint_cmd"]) and np.array_equal(np.array(out1[1:]), G["cart_joint_cmd"])
+    assert np.array_equal(np.array(n0[:len(cmds)]), G["cart_ik_calls"])
