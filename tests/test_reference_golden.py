@@ -389,3 +389,45 @@ def test_vectorised_cartesian_cache_matches_reference():
         n0.append(sum(int(m[0]) for m in Sim.calls))
     assert np.array_equal(np.array(out0[:len(cmds)]), G["cart_joint_cmd"]) and np.array_equal(np.array(out1[1:]), G["cart_joint_cmd"])
     assert np.array_equal(np.array(n0[:len(cmds)]), G["cart_ik_calls"])
+
+
+def test_vectorised_done_logic_and_masked_reset_match_reference():
+    """VecREALRobotEnv.step_joints / reset(mask) with a stand-in simulator: per env, done follows the reference sequence
+    (env.py:345-352) — also for an env that was reset in between — reward 0, info {}."""
+    torch = pytest.importorskip("torch")
+    from real_robots_b200.envs.vec_env import VecREALRobotEnv
+    n = 3
+    env = object.__new__(VecREALRobotEnv)
+    env.n_envs, env.device, env.action_type, env.additional_obs = n, torch.device("cpu"), 'joints', False
+    env.timestep = torch.zeros(n, dtype=torch.int64)
+    env.goal_idx = -1
+    env._zero9 = torch.zeros(n, 9, dtype=torch.float64)
+    env._all = torch.ones(n, dtype=torch.uint8)
+    log = []
+
+    class Sim:
+        def step(self, cmd):
+            log.append(("step", cmd.clone()))
+
+        def reset(self, mask):
+            log.append(("reset", None if mask is None else mask.clone()))
+    env.sim = Sim()
+    env._observe = lambda render_mask: {"render": render_mask}
+    env.intrinsic_timesteps, env.extrinsic_timesteps = 3, 2
+    want = META["done_sequence_intrinsic3_then_extrinsic2"]
+    dones = []
+    for t in range(3):
+        obs, r, d, info = env.step({'joint_command': None if t == 0 else torch.ones(n, 9, dtype=torch.float64), 'render': t == 1})
+        assert info == {} and r.shape == (n,) and float(r.abs().max()) == 0.0
+        assert (obs["render"] is None) == (t != 1)                  # render flag False -> no env is rendered
+        dones.append(d.clone())
+        if t == 0:
+            assert float(log[-1][1].abs().max()) == 0.0             # joint_command None -> zero action (env.py:329-330)
+            env.reset(mask=torch.tensor([0, 1, 0], dtype=torch.uint8))   # env 1 starts over after its first step
+    assert [bool(d[0]) for d in dones] == want[:3] and [bool(d[2]) for d in dones] == want[:3]
+    assert [bool(d[1]) for d in dones] == [False, False, False] and env.timestep.tolist() == [3, 2, 3]
+    env.goal_idx = 0
+    env.reset()
+    assert env.timestep.tolist() == [0, 0, 0] and log[-1] == ("reset", None)
+    ext = [bool(env.step({'joint_command': torch.zeros(n, 9, dtype=torch.float64), 'render': False})[2][0]) for _ in range(2)]
+    assert ext == want[3:]
