@@ -108,3 +108,34 @@ def test_evaluation_service_checks():
     with pytest.raises(Exception, match="Sub-Class"):
         EvaluationService(object, environment='R1', action_type='joints', n_objects=1, visualize=False,
                           goals_dataset_path=__file__)
+
+
+def test_random_batched_policy_is_the_vectorised_cli_random_policy():
+    """cli.py:12-20 per env: an action drawn from the joints Box, kept until a p = 0.05 redraw; seeded and reproducible."""
+    import torch
+    from real_robots_b200.envs.robot import Kuka
+    from real_robots_b200.envs.vec_env import VecREALRobotEnv
+    from real_robots_b200.policy import RandomBatchedPolicy
+    n = 2000
+    env = object.__new__(VecREALRobotEnv)
+    env.n_envs, env.device = n, torch.device("cpu")
+    robot = Kuka(True, 3)
+    env.joints_low = torch.tensor(robot.min_joints, dtype=torch.float64)
+    env.joints_high = torch.tensor(robot.max_joints, dtype=torch.float64)
+    pi, pi2 = RandomBatchedPolicy(env, seed=7), RandomBatchedPolicy(env, seed=7)
+    prev = pi.action.clone()
+    changed = 0
+    for _ in range(50):
+        a = pi.step(None, None, None)
+        assert a["render"] is True and a["joint_command"].shape == (n, 9)
+        cmd = a["joint_command"]
+        assert bool((cmd >= env.joints_low).all()) and bool((cmd <= env.joints_high).all())
+        moved = (cmd != prev).any(dim=1)
+        assert bool(((cmd != prev).all(dim=1) == moved).all())        # a redraw replaces the whole 9-vector
+        changed += int(moved.sum())
+        prev = cmd.clone()
+        assert torch.equal(pi2.step(None, None, None)["joint_command"], cmd)
+    rate = changed / (50 * n)
+    assert 0.045 < rate < 0.055, rate
+    spread = (cmd.max(dim=0).values - cmd.min(dim=0).values) / (env.joints_high - env.joints_low)
+    assert bool((spread > 0.95).all())                                 # uniform over the whole Box
