@@ -139,3 +139,31 @@ def test_random_batched_policy_is_the_vectorised_cli_random_policy():
     assert 0.045 < rate < 0.055, rate
     spread = (cmd.max(dim=0).values - cmd.min(dim=0).values) / (env.joints_high - env.joints_low)
     assert bool((spread > 0.95).all())                                 # uniform over the whole Box
+
+
+def test_camera_helpers_against_the_oracle_and_geometry():
+    """cameras.py restates pybullet's computeViewMatrix / computeViewMatrixFromYawPitchRoll / computeProjectionMatrixFOV
+    (env.py:489-500, 543-551) in float32: the eye camera must equal the oracle's matrices bit for bit, and the
+    yaw / pitch camera must sit `distance` from its target, look at it, and follow pybullet's angle conventions."""
+    from oracle.orc import eye_matrices
+    from real_robots_b200 import cameras
+    v, p = eye_matrices()
+    assert (cameras.view_from_positions([0.01, 0, 1.2], [0, 0, 0.08], [0, 0, 1]).view(np.uint32) == v.view(np.uint32)).all()
+    assert (cameras.projection_fov(80, 320.0 / 240, 0.1, 100.0).view(np.uint32) == p.view(np.uint32)).all()
+    for target, dist, yaw, pitch in (([0, 0, .4], 1.2, 30, -30), ([-0.3, 0, .4], 1.0, 90, -45), ([0.1, -0.2, 0.3], 2.0, 0, 0),
+                                     ([0, 0, 0], 0.7, -120, 20)):
+        V = cameras.view_from_yaw_pitch_roll(target, dist, yaw, pitch, 0, 2).reshape(4, 4).T.astype(np.float64)
+        R, t = V[:3, :3], V[:3, 3]
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-6) and abs(np.linalg.det(R) - 1) < 1e-6
+        eye = -R.T @ t
+        assert abs(np.linalg.norm(eye - target) - dist) < 1e-6
+        assert np.allclose(R @ np.asarray(target, float) + t, [0, 0, -dist], atol=1e-6)       # the target is straight ahead
+        # pybullet: yaw 0 / pitch 0 looks along +y from behind the target; positive yaw turns the camera about +z,
+        # negative pitch raises it above the target
+        yr, pr = np.radians(yaw), np.radians(pitch)
+        want = np.asarray(target, float) + dist * np.array([np.sin(yr) * np.cos(pr), -np.cos(yr) * np.cos(pr), -np.sin(pr)])
+        assert np.allclose(eye, want, atol=1e-6), (yaw, pitch, eye, want)
+        up_in_view = R @ np.array([0, 0, 1.0])
+        assert up_in_view[1] > 0 and abs(up_in_view[0]) < 1e-6                                 # world z stays up in the image
+    P = cameras.projection_fov(90, 4 / 3, 0.1, 100.0).reshape(4, 4).T
+    assert abs(P[1, 1] - 1.0) < 1e-6 and abs(P[0, 0] - 0.75) < 1e-6 and P[3, 2] == -1
