@@ -167,3 +167,50 @@ def test_camera_helpers_against_the_oracle_and_geometry():
         assert up_in_view[1] > 0 and abs(up_in_view[0]) < 1e-6                                 # world z stays up in the image
     P = cameras.projection_fov(90, 4 / 3, 0.1, 100.0).reshape(4, 4).T
     assert abs(P[1, 1] - 1.0) < 1e-6 and abs(P[0, 0] - 0.75) < 1e-6 and P[3, 2] == -1
+
+
+def test_videomaker_frame_selection_and_files_without_a_gpu(tmp_path, monkeypatch):
+    """VideoMaker's host logic (videomaker.py:23-130) over a stand-in simulator: default intervals, one frame every 8
+    steps inside the selected frames / trials only, GOAL / START insets pasted, reference-style file names."""
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    from real_robots_b200.videomaker import Frames, VideoMaker
+    monkeypatch.chdir(tmp_path)
+
+    class Sim:
+        calls = 0
+
+        def render_camera(self, view, proj):
+            Sim.calls += 1
+            assert view.shape == (16,) and proj.shape == (16,) and abs(float(proj[5]) - 1.0) < 1e-6     # fov 90
+            return torch.full((1, 240, 320, 3), 200, dtype=torch.uint8), None, None
+    env = type("Env", (), {})()
+    env.intrinsic_timesteps, env.extrinsic_trials, env._sim = 15e6, 50, Sim()
+    vm = VideoMaker(env, True, True)                                    # defaults: first / middle / last minute, 5 trials
+    minute = 60 * 25 * 8
+    assert all(x in vm.intrinsic_frames for x in (0, minute, 7.5e6, 15e6 - minute, 15e6))
+    assert minute + 1 not in vm.intrinsic_frames and 7.5e6 - 1 not in vm.intrinsic_frames
+    assert len(vm.extrinsic_trials) == 5 and sum(t in vm.extrinsic_trials for t in range(50)) == 5
+    assert len(VideoMaker(env, None, False).intrinsic_frames) == 0
+    with pytest.raises(Exception):
+        VideoMaker(env, 3, None)
+    vm = VideoMaker(env, Frames([16, 40]), Frames(2), debug=True)
+    vm.start_intrinsic()
+    for t in range(1, 57):
+        vm.update_intrinsic(t)
+    vm.end_intrinsic()
+    assert Sim.calls == 4                                               # steps 16, 24, 32, 40
+    goal = np.zeros((240, 320, 3), np.uint8)
+    start = np.full((240, 320, 3), 90, np.uint8)
+    for trial in (1, 2):
+        vm.start_trial({'goal': goal, 'retina': start}, trial)
+        for t in range(1, 25):
+            vm.extrinsic_trial(None, None, t, {'score_total': 0.5, 'score_2D': 0.5, 'score_2.5D': 0, 'score_3D': 0})
+        vm.end_trial()
+    assert Sim.calls == 4 + 3                                           # only trial 2 is filmed: steps 8, 16, 24
+    assert len(vm.files) == 2 and vm.files[0].endswith("-intrinsic.avi") and vm.files[1].endswith("-trial-2.avi")
+    assert vm.files[0].startswith("Simulation-%d-y" % vm.seed)
+    cap = cv2.VideoCapture(vm.files[1])
+    ok, frame = cap.read()
+    assert ok and frame.shape == (240, 320, 3)
+    assert frame[10, 310].mean() < 60 and 60 < frame[10, 10].mean() < 130 and frame[200, 160].mean() > 170   # GOAL inset, START inset, scene
