@@ -214,3 +214,64 @@ def test_videomaker_frame_selection_and_files_without_a_gpu(tmp_path, monkeypatc
     ok, frame = cap.read()
     assert ok and frame.shape == (240, 320, 3)
     assert frame[10, 310].mean() < 60 and 60 < frame[10, 10].mean() < 130 and frame[200, 160].mean() > 170   # GOAL inset, START inset, scene
+
+
+def test_goal_generation_constraints_with_a_stand_in_simulator(monkeypatch, tmp_path):
+    """generate_goals (generate_goals.py:275-365) over a stand-in VecREALRobotEnv whose objects drop straight down onto
+    the table (x <= 0.05) or the shelf: accepted goals satisfy the challenge's constraints, rejected candidates never
+    appear, and the file round-trips through REALRobotEnv.load_goals' format."""
+    import torch
+    import real_robots_b200.envs.vec_env as ve
+    from real_robots_b200 import generate_goals as gg
+
+    class Sim:
+        def __init__(self, n, k):
+            self.n, self.k, self.t = n, k, 0
+            self.pose = torch.zeros(n, k, 7, dtype=torch.float64); self.pose[:, :, 6] = 1
+
+        def step(self, cmd):
+            self.t += 1
+            rest = torch.where(self.pose[:, :, 0] <= 0.05, torch.tensor(0.32, dtype=torch.float64), torch.tensor(0.42, dtype=torch.float64))
+            self.pose[:, :, 2] = torch.maximum(self.pose[:, :, 2] - 0.02, rest)        # falls 2 cm a step, then rests
+            self.pose[0, :, 1] += 1e-3                                                 # env 0 never settles
+
+        def read_state(self):
+            return None, None, self.pose
+
+        def render(self):
+            return (torch.zeros(self.n, 240, 320, 3, dtype=torch.uint8), torch.zeros(self.n, 240, 320), torch.zeros(self.n, 240, 320, dtype=torch.int32))
+
+    class Env:
+        def __init__(self, n_envs, device=0, objects=3, **kw):
+            self.n_envs, self.device, self.sim = n_envs, torch.device("cpu"), Sim(n_envs, objects)
+
+        def reset(self, render=True):
+            self.sim.pose[:] = 0; self.sim.pose[:, :, 6] = 1; self.sim.pose[:, :, 2] = 0.45
+
+        def set_object_poses(self, pq):
+            self.sim.pose = pq.clone()
+
+        def close(self):
+            pass
+    monkeypatch.setattr(ve, "VecREALRobotEnv", Env)
+    for challenge, n_obj in (('2D', 3), ('2.5D', 2), ('3D', 1)):
+        goals = gg.generate_goals(6, n_obj, challenge, seed=3, batch=24, min_start_goal_dist=0.2, min_objects_dist=0.1)
+        assert len(goals) == 6
+        for g in goals:
+            assert g.challenge == challenge and g.subtype == str(n_obj) and list(g.initial_state) == gg.OBJECTS[:n_obj]
+            a = np.array([g.initial_state[o] for o in gg.OBJECTS[:n_obj]]); b = np.array([g.final_state[o] for o in gg.OBJECTS[:n_obj]])
+            assert (np.linalg.norm(a[:, :2] - b[:, :2], axis=1) >= 0.2).all()          # start and goal apart in the plane
+            assert gg._min_separation(a[None])[0] >= 0.1 and gg._min_separation(b[None])[0] >= 0.1
+            if challenge == '2D':
+                assert (a[:, 0] <= 0.05).all() and (b[:, 0] <= 0.05).all() and (a[:, 2] < 0.33).all()   # everything on the table
+            else:
+                assert (a[:, 2] > 0.40).any() or (b[:, 2] > 0.40).any()                  # the shelf is involved
+            if challenge != '3D':
+                for o, name in enumerate(gg.OBJECTS[:n_obj]):
+                    q = np.array(gg.euler_to_quat(gg.BASE_ORIENTATION[name]))
+                    assert min(np.linalg.norm(a[o, 3:] - q), np.linalg.norm(a[o, 3:] + q)) < 1e-12
+            assert g.retina.shape == (240, 320, 3) and g.mask.shape == (240, 320)
+    path = str(tmp_path / "goals.npy")
+    gg.save_goals(goals, path)
+    back = np.load(path + ".npz", allow_pickle=True)["arr_0"]
+    assert len(back) == 6 and type(back[0]).__module__ == "real_robots.envs.env" and back[0].challenge == '3D'
