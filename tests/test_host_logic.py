@@ -275,3 +275,35 @@ def test_goal_generation_constraints_with_a_stand_in_simulator(monkeypatch, tmp_
     gg.save_goals(goals, path)
     back = np.load(path + ".npz", allow_pickle=True)["arr_0"]
     assert len(back) == 6 and type(back[0]).__module__ == "real_robots.envs.env" and back[0].challenge == '3D'
+
+
+def test_get_contacts_reads_manifolds_like_the_reference():
+    """Kuka.get_contacts (robot.py:131-150) over synthetic manifolds: robot part -> names of the bodies it touches, only
+    against BASE links of other bodies (contact_list passes linkIndexB = -1), distance filter 0.1, forces =
+    normal impulse / dt, first-seen order."""
+    import torch
+    from real_robots_b200.envs.robot import Kuka, manifest
+    shapes = manifest()["shapes"]
+    idx = {s["name"]: i for i, s in enumerate(shapes)}
+    pairs = np.array([[idx["skin_00"], idx["cube_0"]], [idx["finger_00"], idx["table_upper"]], [idx["skin_01"], idx["table_base"]],
+                      [idx["cube_0"], idx["table_base"]], [idx["skin_00"], idx["tomato"]]], np.int32)
+    hdr = torch.full((1, 24, 2), -1, dtype=torch.int32); hdr[0, :, 1] = 0
+    pts = torch.zeros(1, 24, 4, 17, dtype=torch.float64)
+    for slot, (pi, n) in enumerate([(0, 2), (1, 1), (2, 1), (3, 4), (4, 1)]):
+        hdr[0, slot, 0], hdr[0, slot, 1] = pi, n
+        pts[0, slot, :n, 9] = -0.001
+        pts[0, slot, :n, 10] = 0.01 * (slot + 1)
+    pts[0, 0, 1, 9] = 0.2                                   # second skin_00 / cube point is beyond the 0.1 threshold
+
+    class Sim:
+        cfg = type("C", (), {"dt": 0.005})()
+
+        def contacts(self):
+            return hdr, pts, pairs
+    robot = Kuka(True, 3)
+    robot._bind(Sim())
+    assert robot.get_contacts() == {"skin_00": ["cube", "tomato"], "skin_01": ["table"]}
+    forces = robot.get_contacts(forces=True)
+    assert forces["skin_00"][0][0] == "cube" and abs(forces["skin_00"][0][1] - 0.01 / 0.005) < 1e-12
+    assert forces["skin_00"][1][0] == "tomato" and abs(forces["skin_00"][1][1] - 0.05 / 0.005) < 1e-12
+    assert robot.object_names == {0: "kuka", 1: "table", 2: "cube", 3: "tomato", 4: "mustard"}
