@@ -29,6 +29,12 @@ STATE_BYTES = 3824                            # BASELINE.md §4 physics bytes pe
 METRIC = "env_steps_per_sec_with_retina_4096_envs_per_gpu"
 
 
+def workload(envs):
+    """config.workload of BOTH arms (the reference arm runs a bounded sample of the same workload on the host cores)."""
+    return ("BASELINE configs[2]: REALRobot2020 R1J3 joints action, %d envs/GPU, 3 objects, random policy "
+            "(p=0.05 resample), physics + touch + RGB/depth/mask retina 240x320" % envs)
+
+
 _JSON_OUT = None
 
 
@@ -172,9 +178,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 physics / f32 raster", "data": "synthetic",
-        "config": {"workload": "REALRobot2020-R1J3 joints action, random policy, physics + RGB/depth/mask retina 240x320; CPU arm runs "
-                               "one env per host core, %d env-steps per core per bench step" % per_step,
-                   "n_envs_per_gpu": N_ENVS, "n_objects": N_OBJECTS},
+        "config": {"workload": workload(args.envs), "n_envs_per_gpu": args.envs, "n_objects": N_OBJECTS,
+                   "cpu_sample": "one oracle env per host core, %d env-steps per core per bench step" % per_step},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": "%d processes x %d env-steps with render per bench step (oracle port; pybullet not installable)" % (cores, per_step)},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -295,8 +300,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 physics / f32 raster", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: REALRobot2020 R1J3 joints action, %d envs/GPU, 3 objects, random policy "
-                                   "(p=0.05 resample), physics + touch + RGB/depth/mask retina 240x320" % args.envs,
+            "config": {"workload": workload(args.envs),
                        "n_envs_per_gpu": args.envs, "n_objects": N_OBJECTS, "parallelism": "envs sharded, %d rank(s), no collective" % world, "numa": numa,
                        "static_layer": ("off (RR_STATIC_LAYER=0): every shape rasterised for every env" if os.environ.get("RR_STATIC_LAYER", "1")[:1] == "0" else
                                         "table + robot base rasterised once per context, every env's z-buffer starts from it (images bit-identical "
