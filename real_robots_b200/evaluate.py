@@ -240,9 +240,12 @@ def evaluate_vectorised(policy_factory, goals, n_objects=3, action_type='macro_a
         final[:hi - lo] = torch.from_numpy(np.ascontiguousarray(goals["final"][lo:hi])).to(dev)
     else:
         init[:, :, 6] = 1.0
-    obs = env.reset(render=render)
+    env.reset(render=False)
     env.set_object_poses(init)
     env.goal_positions = final
+    # evaluate.py:282-285: the controller's first observation is the one set_goal() returns, i.e. taken AFTER the objects
+    # were moved to the goal's initial state
+    obs = env._observe(env._all if render else None)
     policy = policy_factory(env)
     reward = torch.zeros(n, dtype=torch.float64, device=dev)
     done = torch.zeros(n, dtype=torch.bool, device=dev)

@@ -93,10 +93,14 @@ class _FakeVecEnv:
         self.extrinsic_timesteps, self.goal_idx, self.goal_positions = 0, -1, None
         self.pos = torch.zeros(n_envs, objects, 3, dtype=torch.float64)
         self.steps = 0
+        self._all = torch.ones(n_envs, dtype=torch.uint8)
         _FakeVecEnv.made.append(self)
 
     def reset(self, mask=None, render=True):
         return {"object_positions": self.pos}
+
+    def _observe(self, render_mask):
+        return {"object_positions": self.pos.clone(), "rendered": render_mask is not None}
 
     def set_object_poses(self, pos_quat, mask=None):
         self.pos = pos_quat[:, :, :3].clone()
@@ -139,11 +143,19 @@ def _eval_worker(rank, world, port, n_goals, q):
     ve.VecREALRobotEnv = _FakeVecEnv
 
     class Push(BatchedPolicy):
+        first = None
+
         def step(self, observation, reward, done):
+            if Push.first is None:        # evaluate.py:285: the first observation already shows the goal's initial placement
+                Push.first = observation["object_positions"].clone()
+                assert observation["rendered"] is False
             return {"shift": torch.tensor([[0.001, 0.0, 0.0]], dtype=torch.float64).expand(self.env.n_envs, 3)}
     challenge = ['2D' if g % 2 == 0 else '3D' for g in range(n_goals)]
     so, scores, vec = evaluate_vectorised(Push, _goals(n_goals), n_objects=2, action_type='joints', extrinsic_timesteps=7,
                                           challenge_of=challenge)
+    lo, hi = shard_range(n_goals, rank, world)
+    if hi > lo:
+        assert np.allclose(Push.first[:hi - lo].numpy(), _goals(n_goals)["initial"][lo:hi, :, :3])
     q.put((rank, vec, scores, {k: float(v) for k, v in so.items()}, _FakeVecEnv.made[-1].n_envs))
     if world > 1:
         dist.destroy_process_group()
