@@ -307,3 +307,17 @@ def test_get_contacts_reads_manifolds_like_the_reference():
     assert forces["skin_00"][0][0] == "cube" and abs(forces["skin_00"][0][1] - 0.01 / 0.005) < 1e-12
     assert forces["skin_00"][1][0] == "tomato" and abs(forces["skin_00"][1][1] - 0.05 / 0.005) < 1e-12
     assert robot.object_names == {0: "kuka", 1: "table", 2: "cube", 3: "tomato", 4: "mustard"}
+
+
+def test_euler_to_quat_is_pybullets_convention():
+    """pybullet.getQuaternionFromEuler([roll, pitch, yaw]) = rotation about fixed x, then y, then z (xyzw): equal to scipy's
+    extrinsic 'xyz' — used for object_poses (robot.py:19-24), the macro plan's gripper orientation (env.py:417) and goals."""
+    from scipy.spatial.transform import Rotation
+    from real_robots_b200.util import euler_to_quat
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        e = rng.uniform(-np.pi, np.pi, 3)
+        q, s = np.array(euler_to_quat(e.tolist())), Rotation.from_euler('xyz', e).as_quat()
+        assert min(np.abs(q - s).max(), np.abs(q + s).max()) < 1e-15
+    assert np.allclose(euler_to_quat([0, 0, 0]), [0, 0, 0, 1])
+    assert np.allclose(euler_to_quat([0, 0, np.pi / 2]), [0, 0, np.sqrt(0.5), np.sqrt(0.5)])
