@@ -133,10 +133,10 @@ int  rr_profile(rr_ctx* ctx, int enable);
 int  rr_profile_read(rr_ctx* ctx, double* ms_total /*[4]*/, long long* launches /*[4]*/);
 
 /* replaces: getContactPoints as used by Kuka.get_contacts (robot.py:131-150): the cached contact manifolds of the
- * last step.  hdr i32[N,24,2] = (candidate pair index or -1, point count); pts f64[N,24,4,17] = per point
+ * last step.  hdr i32[N,32,2] = (candidate pair index or -1, point count); pts f64[N,32,4,17] = per point
  * localA3 localB3 normalOnB3 distance normalImpulse worldA3 worldB3; pairs i32[96,2] = (shapeA, shapeB) per pair index
  * (HOST pointer, may be NULL); returns the number of candidate pairs through n_pairs_host (may be NULL). */
-#define RR_MAX_MANIFOLDS_PER_ENV 24
+#define RR_MAX_MANIFOLDS_PER_ENV 32
 #define RR_CONTACT_POINT_DOUBLES 17
 int  rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, int* n_pairs_host, void* stream);
 
@@ -147,6 +147,7 @@ int  rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, in
 int  rr_set_contacts(rr_ctx* ctx, const int32_t* hdr, const double* pts, void* stream);
 
 /* Per-env diagnostics of the last step: i32[N,4] = rows, iterations, contacts, flags (bit 0: the 32-contact cap was hit,
+ * bit 4: a non-empty contact manifold found none of the 32 manifold slots free and was dropped,
  * bit 1: every contact was object-vs-static, so the solver took its object-parallel path; bit 2: a NaN / infinite joint
  * command arrived — where the reference asserts np.isfinite(a).all() (robot.py:189) a batched step cannot raise per env, the
  * command acts as a full +-max step and never reaches the state; bit 3: the state had become non-finite and the env was put

@@ -133,6 +133,11 @@ class Oracle:
         self.L.orc_diag(C.c_void_p(self.h), C.byref(r), C.byref(i), C.byref(c), C.byref(res))
         return dict(rows=r.value, iterations=i.value, contacts=c.value, residual=res.value)
 
+    def diag2(self):
+        a = C.c_int(); b = C.c_int(); c = C.c_int()
+        self.L.orc_diag2(C.c_void_p(self.h), C.byref(a), C.byref(b), C.byref(c))
+        return dict(overlaps=a.value, manifolds=b.value, manifold_overflow=c.value)
+
     def contacts(self, max_pts=256):
         a = np.zeros(max_pts, np.int32); b = np.zeros(max_pts, np.int32); d = np.zeros((max_pts, 11))
         n = self.L.orc_get_contacts(C.c_void_p(self.h), max_pts, _p(a), _p(b), _p(d))

@@ -78,6 +78,10 @@ void orc_diag(void* p, int* rows, int* iters, int* contacts, double* residual) {
     OrcEnv& e = ((OrcHandle*)p)->env;
     *rows = e.last_rows; *iters = e.last_iterations; *contacts = e.last_contacts; *residual = e.last_residual;
 }
+void orc_diag2(void* p, int* overlaps, int* manifolds, int* manifold_overflow) {
+    OrcEnv& e = ((OrcHandle*)p)->env;
+    *overlaps = e.last_overlaps; *manifolds = e.n_manifolds; *manifold_overflow = e.manifold_overflow;
+}
 int orc_get_contacts(void* p, int max_pts, int* shapeA, int* shapeB, double* data /* [n][11]: worldA3 worldB3 normal3 dist impulse */) {
     OrcEnv& e = ((OrcHandle*)p)->env;
     int n = 0;

@@ -308,7 +308,7 @@ void orc_collide(OrcEnv* e) {
     /* mark: manifolds of pairs whose AABBs no longer overlap are destroyed (broadphase pair removed) */
     OrcManifold old[ORC_MAX_MANIFOLDS]; int nold = e->n_manifolds;
     for (int i = 0; i < nold; i++) old[i] = e->manifolds[i];
-    e->n_manifolds = 0;
+    e->n_manifolds = 0; e->last_overlaps = 0; e->manifold_overflow = 0;
     for (int pi = 0; pi < np; pi++) {
         int a = pairs[pi][0], b = pairs[pi][1];
         bool overlap = amin[a].x <= amax[b].x && amax[a].x >= amin[b].x && amin[a].y <= amax[b].y && amax[a].y >= amin[b].y &&
@@ -356,7 +356,14 @@ void orc_collide(OrcEnv* e) {
             }
             if (drop) { m.pt[i] = m.pt[m.n - 1]; m.n--; }     /* removeContactPoint: swap with last */
         }
-        if (e->n_manifolds < ORC_MAX_MANIFOLDS) e->manifolds[e->n_manifolds++] = m;
+        /* A manifold without points carries no state (a later hit on it finds n = 0, the same as no hit), so only
+         * non-empty manifolds take one of the ORC_MAX_MANIFOLDS slots: AABB overlaps without contact cannot crowd out the
+         * object x table pairs at the end of the pair order.  A non-empty manifold that still finds no slot is flagged. */
+        e->last_overlaps++;
+        if (m.n > 0) {
+            if (e->n_manifolds < ORC_MAX_MANIFOLDS) e->manifolds[e->n_manifolds++] = m;
+            else e->manifold_overflow = 1;
+        }
     }
 }
 

@@ -4,7 +4,7 @@
 #define ORC_ENV_H
 #include "orc_scene.h"
 
-#define ORC_MAX_MANIFOLDS 24
+#define ORC_MAX_MANIFOLDS 32
 #define ORC_MAX_ROWS 1024
 
 struct OrcContactPoint {
@@ -43,6 +43,7 @@ struct OrcEnv {
     double touch[4];
     /* diagnostics of the last step */
     int last_rows, last_iterations, last_contacts;
+    int last_overlaps, manifold_overflow;      /* AABB-overlapping pairs of the last step; a non-empty manifold found no slot */
     double last_residual;
 };
 

@@ -59,6 +59,7 @@ void orc_env_reset(OrcEnv* e) {
     e->n_manifolds = 0;
     for (int i = 0; i < 4; i++) e->touch[i] = 0;
     e->last_rows = e->last_iterations = e->last_contacts = 0; e->last_residual = 0;
+    e->last_overlaps = 0; e->manifold_overflow = 0;
     orc_fk(e);
 }
 

@@ -266,7 +266,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
     alloc((void**)&st.q, 11 * N * 8); alloc((void**)&st.qd, 11 * N * 8); alloc((void**)&st.target, 11 * N * 8);
     alloc((void**)&st.obj, 39 * N * 8); alloc((void**)&st.touch, 4 * N * 8); alloc((void**)&st.link_frames, 16 * 12 * N * 8);
-    alloc((void**)&st.render_mats, N * RR_NSHAPES * RR_MAT_STRIDE * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.timestep, N * 8);
+    alloc((void**)&st.render_mats, N * RR_NSHAPES * RR_MAT_STRIDE * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.col_flags, N * 4); alloc((void**)&st.timestep, N * 8);
     alloc((void**)&ctx->d_cmd, N * 9 * 8); alloc((void**)&ctx->d_mask, N); alloc((void**)&ctx->d_joint, N * 9 * 8);
     alloc((void**)&ctx->d_touch, N * 4 * 8); alloc((void**)&ctx->d_objpose, N * 3 * 7 * 8);
     for (int k = 0; k < 2; k++) {
@@ -290,7 +290,7 @@ int rr_destroy(rr_ctx* ctx) {
     cudaDeviceSynchronize();
     rrk_physics_unbind(ctx); rrk_collide_unbind(ctx); rrk_render_unbind(ctx);
     DevState& st = ctx->st;
-    void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.timestep,
+    void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.col_flags, st.timestep,
                     st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.rows, st.handoff,
                     ctx->d_cmd, ctx->d_mask, ctx->d_joint, ctx->d_touch, ctx->d_objpose, ctx->d_rgb, ctx->d_depth, ctx->d_seg,
                     ctx->d_tris, ctx->d_tex, ctx->d_hull_verts, ctx->d_rec_scratch, ctx->d_list_scratch, ctx->d_work_counter, ctx->d_tri_shape, ctx->d_planes, ctx->d_cull_scratch,

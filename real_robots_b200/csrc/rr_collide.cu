@@ -70,7 +70,8 @@ struct ColMem {
     double Vw[EPA_MAXV][3], Va[EPA_MAXV][3], Vb[EPA_MAXV][3];
     double Fn[EPA_MAXF][3], Fd[EPA_MAXF];
     int Fv[EPA_MAXF][3]; int Falive[EPA_MAXF];
-    int eh[2 * EPA_MAXF][2];
+    int eh[2 * EPA_MAXF][2];      // horizon edges
+    int epa_nf, epa_good;         // counters published by lane 0 after a polytope update
     // manifold staging
     double pt[4][RR_PT_STRIDE];
     // GJK simplex (w, a, b per vertex): indexed dynamically, so it lives here rather than in per-thread local memory
@@ -293,24 +294,33 @@ __device__ EPA_INLINE bool epa(const Hull& A, const Hull& B, ColMem& m, SupPt* S
         SupPt w = support(A, B, bn, lane);
         double wd = dot(w.w, bn) - m.Fd[best];
         if (wd <= 1e-10 || nv >= EPA_MAXV) break;
-        int ne = 0;
-        for (int f = 0; f < nf; f++) {
-            if (!m.Falive[f]) continue;
-            if (dot(ld3(m.Fn[f]), w.w - ld3(m.Vw[m.Fv[f][0]])) > 0) {
-                m.Falive[f] = 0;
-                for (int e = 0; e < 3; e++) {
-                    int a = m.Fv[f][e], b = m.Fv[f][(e + 1) % 3];
-                    bool cancelled = false;
-                    for (int k = 0; k < ne; k++) if (m.eh[k][0] == b && m.eh[k][1] == a) { m.eh[k][0] = m.eh[ne - 1][0]; m.eh[k][1] = m.eh[ne - 1][1]; ne--; cancelled = true; break; }
-                    if (!cancelled) { m.eh[ne][0] = a; m.eh[ne][1] = b; ne++; }
+        // Horizon and re-triangulation mutate the polytope while reading it: lane 0 does it alone (the other lanes would only
+        // repeat the same stores), everybody re-reads the counters after the barrier.
+        __syncwarp();
+        if (lane == 0) {
+            int ne = 0; bool ok2 = true;
+            for (int f = 0; f < nf && ok2; f++) {
+                if (!m.Falive[f]) continue;
+                if (ne + 3 > 2 * EPA_MAXF) { ok2 = false; break; }      // horizon buffer full: stop refining (never seen; memory safety)
+                if (dot(ld3(m.Fn[f]), w.w - ld3(m.Vw[m.Fv[f][0]])) > 0) {
+                    m.Falive[f] = 0;
+                    for (int e = 0; e < 3; e++) {
+                        int a = m.Fv[f][e], b = m.Fv[f][(e + 1) % 3];
+                        bool cancelled = false;
+                        for (int k = 0; k < ne; k++) if (m.eh[k][0] == b && m.eh[k][1] == a) { m.eh[k][0] = m.eh[ne - 1][0]; m.eh[k][1] = m.eh[ne - 1][1]; ne--; cancelled = true; break; }
+                        if (!cancelled) { m.eh[ne][0] = a; m.eh[ne][1] = b; ne++; }
+                    }
                 }
             }
+            const int wi = nv; st3(m.Vw[nv], w.w); st3(m.Va[nv], w.a); st3(m.Vb[nv], w.b);
+            int nf2 = nf;
+            for (int k = 0; k < ne && ok2; k++) if (!epa_add_face(m, nf2, m.eh[k][0], m.eh[k][1], wi)) { ok2 = false; break; }
+            m.epa_nf = nf2; m.epa_good = ok2 ? 1 : 0;
         }
-        int wi = nv; st3(m.Vw[nv], w.w); st3(m.Va[nv], w.a); st3(m.Vb[nv], w.b); nv++;
         __syncwarp();
-        bool good = true;
-        for (int k = 0; k < ne; k++) if (!epa_add_face(m, nf, m.eh[k][0], m.eh[k][1], wi)) { good = false; break; }
-        __syncwarp();
+        nv++;
+        nf = m.epa_nf;
+        const bool good = m.epa_good != 0;
         if (!good) break;
     }
     depth = m.Fd[best]; n = ld3(m.Fn[best]);
@@ -440,7 +450,7 @@ k_collide(DevState st, const double* __restrict__ hull_verts, const int* __restr
     double* pout = man_pts_out + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
     int old_pair = -1, old_n = 0;
     if (lane < RR_MAX_MANIFOLDS) { old_pair = hin[2 * lane]; old_n = hin[2 * lane + 1]; }
-    int nout = 0;
+    int nout = 0, dropped = 0;
     for (int r = 0; r < 3; r++) {
         unsigned bits = ov[r];
         while (bits) {
@@ -504,15 +514,21 @@ k_collide(DevState st, const double* __restrict__ hull_verts, const int* __restr
                     __syncwarp();
                 }
             }
-            if (nout < RR_MAX_MANIFOLDS) {
-                for (int k = lane; k < n * RR_PT_STRIDE; k += 32) pout[(size_t)nout * 4 * RR_PT_STRIDE + k] = m.pt[k / RR_PT_STRIDE][k % RR_PT_STRIDE];
-                if (lane == 0) { hout[2 * nout] = pi; hout[2 * nout + 1] = n; }
-                nout++;
+            // A manifold without points carries no state (a later hit on it finds n = 0, the same as no hit), so only non-empty
+            // manifolds take a slot: AABB overlaps without contact cannot crowd out the object x table pairs at the end of the
+            // pair order.  A non-empty manifold that still finds no slot is flagged (rr_diag flags bit 4).
+            if (n > 0) {
+                if (nout < RR_MAX_MANIFOLDS) {
+                    for (int k = lane; k < n * RR_PT_STRIDE; k += 32) pout[(size_t)nout * 4 * RR_PT_STRIDE + k] = m.pt[k / RR_PT_STRIDE][k % RR_PT_STRIDE];
+                    if (lane == 0) { hout[2 * nout] = pi; hout[2 * nout + 1] = n; }
+                    nout++;
+                } else dropped = 1;
             }
             __syncwarp();
         }
     }
     for (int k = nout + lane; k < RR_MAX_MANIFOLDS; k += 32) { hout[2 * k] = -1; hout[2 * k + 1] = 0; }
+    if (lane == 0) st.col_flags[e] = dropped;
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -570,7 +586,7 @@ int rrk_collide(rr_ctx* ctx, cudaStream_t s) {
     const int in = ctx->man_parity, out = 1 - in;
     {
         ProfScope ps(ctx, 3, s);
-        k_collide<<<(ctx->N + CWPB - 1) / CWPB, CWPB * 32, 0, s>>>(ctx->st, ctx->d_hull_verts, ctx->st.man_hdr[in], ctx->st.man_pts[in],
+        RR_LAUNCH(k_collide, (ctx->N + CWPB - 1) / CWPB, CWPB * 32, 0, s)(ctx->st, ctx->d_hull_verts, ctx->st.man_hdr[in], ctx->st.man_pts[in],
                                                                  ctx->st.man_hdr[out], ctx->st.man_pts[out], ctx->cfg, ctx->n_objects);
     }
     ctx->launches++;
@@ -578,3 +594,24 @@ int rrk_collide(rr_ctx* ctx, cudaStream_t s) {
     ctx->man_parity = out;
     return 0;
 }
+
+#ifdef RR_SIMT_EMU_BUILD
+// test hook of the emulated build (tests/simt): closest points of two scene shapes at explicit frames, one warp
+__global__ void k_debug_closest(const double* __restrict__ hull_verts, int sa, int sb, const double* fa, const double* fb, double margin, double* out) {
+    __shared__ ColMem smem1;
+    ColMem& m = smem1;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) { for (int k = 0; k < 9; k++) { m.R[sa][k] = fa[k]; m.R[sb][k] = fb[k]; } for (int k = 0; k < 3; k++) { m.p[sa][k] = fa[9 + k]; m.p[sb][k] = fb[9 + k]; } }
+    __syncwarp();
+    Hull A{hull_verts + 3 * (size_t)c_col.hull_start[sa], c_col.hull_count[sa], m.R[sa], ld3(m.p[sa])};
+    Hull B{hull_verts + 3 * (size_t)c_col.hull_start[sb], c_col.hull_count[sb], m.R[sb], ld3(m.p[sb])};
+    double d; V3 n, pa, pb;
+    const bool ok = closest_points(A, B, m, d, n, pa, pb, lane);
+    if (lane == 0) { out[0] = d; out[1] = n.x; out[2] = n.y; out[3] = n.z; out[4] = pa.x; out[5] = pa.y; out[6] = pa.z; out[7] = pb.x; out[8] = pb.y; out[9] = pb.z; out[10] = ok ? 1.0 : 0.0; }
+}
+extern "C" int rr_debug_closest(rr_ctx* ctx, int sa, const double* fa12, int sb, const double* fb12, double* out11) {
+    if (bind_collide(ctx, 0)) return -1;
+    RR_LAUNCH(k_debug_closest, 1, 32, 0, 0)(ctx->d_hull_verts, sa, sb, fa12, fb12, ctx->cfg.margin, out11);
+    return 0;
+}
+#endif

@@ -1,6 +1,15 @@
 // Internal context of libreal_b200.so (not part of the C ABI).
 #pragma once
+#ifdef RR_SIMT_EMU_BUILD
+// tests/simt: the same sources compiled with g++ against a SIMT emulator (test infrastructure, never shipped or loaded by the package)
+#include "simt_emu.h"
+#define RR_LAUNCH(kern, grid, block, smem, stream) (simt::Launcher((int)(grid), (int)(block), (size_t)(smem)) << [&](auto&&... a) { kern(a...); })
+#define RR_DYN_SMEM(name) unsigned char* name = simt::g_dyn_smem
+#else
 #include <cuda_runtime.h>
+#define RR_LAUNCH(kern, grid, block, smem, stream) kern<<<(grid), (block), (smem), (stream)>>>
+#define RR_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -16,7 +25,7 @@
 #define RR_HANDOFF_DOUBLES 576   // >= the persistent head of WarpMem (static_assert in rr_physics.cu)
 #define RR_MAT_STRIDE 44       // floats per (env, shape) in render_mats
 #define RR_MAX_PAIRS 96          // candidate collision pairs (92 for 3 objects)
-#define RR_MAX_MANIFOLDS 24      // cached manifolds per env (<= 32: one lane per slot)
+#define RR_MAX_MANIFOLDS RR_MAX_MANIFOLDS_PER_ENV      // cached non-empty manifolds per env (<= 32: one lane per slot)
 #define RR_PT_STRIDE 17          // doubles per contact point: localA3 localB3 normalB3 dist impulse worldA3 worldB3
 #define RR_MAX_CONTACTS 32       // contact points per env that get solver rows
 #define RR_ROW_STRIDE 72         // doubles per solver row in the global row scratch
@@ -66,6 +75,7 @@ struct DevState {
     double* link_frames;  // [16][12][N]  world_from_link R(9) + p(3), COM frames
     float*  render_mats;  // [N][22][40] per-shape matrices for the rasteriser (see rr_render.cu)
     int*    diag;     // [N][4]
+    int*    col_flags;  // [N] written by k_collide (1: a non-empty manifold found no slot), merged into diag by k_step_solve
     long long* timestep;  // [N]
     int*    man_hdr[2];   // [N][RR_MAX_MANIFOLDS][2]  (pair index or -1, point count), double buffered
     double* man_pts[2];   // [N][RR_MAX_MANIFOLDS][4][RR_PT_STRIDE]

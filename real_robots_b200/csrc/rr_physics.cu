@@ -435,7 +435,7 @@ __device__ __forceinline__ void store_frames(const WarpMem& m, const DevState& s
 // of dependent fp64 operations whose only remedy is more resident warps; it needs a third of the dynamics' shared memory,
 // so on its own it runs at more than twice the occupancy.
 __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double* __restrict__ cmd, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RR_DYN_SMEM(smem_raw);
     WarpMem& m = reinterpret_cast<WarpMem*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
 }
 
 __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RR_DYN_SMEM(smem_raw);
     WarpMem& m = *reinterpret_cast<WarpMem*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
@@ -918,14 +918,14 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
     }
     if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
     if (lane == 0) {
-        st.diag[4 * e] = m.n_rows + 3 * nc; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (m.simple ? 2 : 0) | (fault << 2);   // bit 0: contact cap hit, bit 1: object-parallel solver path, bits 2-3: faults
+        st.diag[4 * e] = m.n_rows + 3 * nc; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (m.simple ? 2 : 0) | (fault << 2) | (cf.enable_contacts ? (st.col_flags[e] << 4) : 0);   // bit 0: contact cap hit, bit 1: object-parallel solver path, bits 2-3: faults, bit 4: manifold slots exhausted
         st.timestep[e] += 1;
     }
 }
 
 // FK only (after reset / set_state): refresh link_frames
 __global__ void __launch_bounds__(WPB * 32) k_fk(DevState st) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RR_DYN_SMEM(smem_raw);
     WarpMem& m = *reinterpret_cast<WarpMem*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
@@ -1093,21 +1093,21 @@ static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 
 static int launch_fk(rr_ctx* ctx, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    k_fk<<<nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s>>>(ctx->st);
+    RR_LAUNCH(k_fk, nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s)(ctx->st);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_reset(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    k_reset<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, mask, ctx->n_objects, ctx->st.man_hdr[ctx->man_parity]);
+    RR_LAUNCH(k_reset, nblk(ctx->N, 128), 128, 0, s)(ctx->st, mask, ctx->n_objects, ctx->st.man_hdr[ctx->man_parity]);
     ctx->launches++;
     CK(cudaGetLastError());
     return launch_fk(ctx, s);
 }
 int rrk_set_object_pose(rr_ctx* ctx, const uint8_t* mask, int obj, const double* pq, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    k_set_object_pose<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, mask, obj, pq);
+    RR_LAUNCH(k_set_object_pose, nblk(ctx->N, 128), 128, 0, s)(ctx->st, mask, obj, pq);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1119,7 +1119,7 @@ __global__ void k_clear_manifolds(int N, const uint8_t* __restrict__ mask, int* 
     for (int k = 0; k < RR_MAX_MANIFOLDS; k++) { man_hdr[((size_t)e * RR_MAX_MANIFOLDS + k) * 2] = -1; man_hdr[((size_t)e * RR_MAX_MANIFOLDS + k) * 2 + 1] = 0; }
 }
 int rrk_clear_manifolds(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
-    k_clear_manifolds<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->N, mask, ctx->st.man_hdr[ctx->man_parity]);
+    RR_LAUNCH(k_clear_manifolds, nblk(ctx->N, 128), 128, 0, s)(ctx->N, mask, ctx->st.man_hdr[ctx->man_parity]);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1127,13 +1127,13 @@ int rrk_clear_manifolds(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
 int rrk_set_state(rr_ctx* ctx, const double* q, const double* qd, const double* obj, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
     if (rrk_clear_manifolds(ctx, nullptr, s) != 0) return -1;
-    k_set_state<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, q, qd, obj);
+    RR_LAUNCH(k_set_state, nblk(ctx->N, 128), 128, 0, s)(ctx->st, q, qd, obj);
     ctx->launches++;
     CK(cudaGetLastError());
     return launch_fk(ctx, s);
 }
 int rrk_get_state(rr_ctx* ctx, double* q, double* qd, double* obj, cudaStream_t s) {
-    k_get_state<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, q, qd, obj);
+    RR_LAUNCH(k_get_state, nblk(ctx->N, 128), 128, 0, s)(ctx->st, q, qd, obj);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1142,36 +1142,36 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
     if (ctx->cfg.enable_contacts && rrk_collide(ctx, s) != 0) return -1;
     ProfScope ps(ctx, 0, s);
-    k_step_dyn<<<nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s>>>(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
-    k_step_solve<<<nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s>>>(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
+    RR_LAUNCH(k_step_dyn, nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s)(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
+    RR_LAUNCH(k_step_solve, nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
     ctx->launches += 2;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_read_state(rr_ctx* ctx, double* joint, double* touch, double* objpose, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    k_read_state<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, joint, touch, objpose, ctx->n_objects);
+    RR_LAUNCH(k_read_state, nblk(ctx->N, 128), 128, 0, s)(ctx->st, joint, touch, objpose, ctx->n_objects);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_link_pose(rr_ctx* ctx, int link, double* out, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    k_link_pose<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, link, out);
+    RR_LAUNCH(k_link_pose, nblk(ctx->N, 128), 128, 0, s)(ctx->st, link, out);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    k_score<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, goal, score, ctx->n_objects);
+    RR_LAUNCH(k_score, nblk(ctx->N, 128), 128, 0, s)(ctx->st, goal, score, ctx->n_objects);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    k_shape_frames<<<nblk(ctx->N, 128), 128, 0, s>>>(ctx->st, frames, ctx->n_objects);
+    RR_LAUNCH(k_shape_frames, nblk(ctx->N, 128), 128, 0, s)(ctx->st, frames, ctx->n_objects);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1273,7 +1273,7 @@ __global__ void k_ik(DevState st, const uint8_t* __restrict__ mask, const double
 
 int rrk_ik(rr_ctx* ctx, const uint8_t* mask, const double* pos_quat, double* out, int max_iter, double residual, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    k_ik<<<nblk(ctx->N, 64), 64, 0, s>>>(ctx->st, mask, pos_quat, out, max_iter, residual);
+    RR_LAUNCH(k_ik, nblk(ctx->N, 64), 64, 0, s)(ctx->st, mask, pos_quat, out, max_iter, residual);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

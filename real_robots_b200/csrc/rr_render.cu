@@ -78,6 +78,7 @@ extern "C" int rr_debug_raster_stats(unsigned long long* out, int reset) {
 
 // --------------------------------------------------------------------------------------------- TMA bulk copy + mbarrier
 // (cp.async.bulk: the 1-D form of the TMA engine; SASS UBLKCP + SYNCS)
+#ifndef RR_SIMT_EMU_BUILD
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
@@ -99,6 +100,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+#endif
 
 // --------------------------------------------------------------------------------------------- float helpers
 __device__ __forceinline__ float dot4r(const float* a, const float* b) { float r = 0.f; r += a[3] * b[3]; r += a[2] * b[2]; r += a[1] * b[1]; r += a[0] * b[0]; return r; }
@@ -523,6 +525,9 @@ static_assert(sizeof(Rec) == 80, "record must be 80 bytes");
 #define REC_DEGENERATE 8u      // |u.z| <= 1e-2: TinyRenderer rejects every pixel
 
 __device__ __forceinline__ int agg_inc(int* ctr) {      // warp-aggregated atomic increment of a shared counter
+#ifdef RR_SIMT_EMU_BUILD
+    return atomicAdd(ctr, 1);           // (the emulator runs one thread at a time: no aggregation to do)
+#endif
     const unsigned m = __activemask();
     const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
     int base = 0;
@@ -576,12 +581,16 @@ __device__ __forceinline__ void emit_record(Rec* __restrict__ recs, unsigned sho
         const int cls = area > HUGE_AREA ? 2 : (area > SMALL_AREA ? 1 : 0);
         STAT(3 + cls, 1);
         // lanes of the warp may be appending to different counters: aggregate per counter
+#ifdef RR_SIMT_EMU_BUILD
+        const int pos = atomicAdd(&nlist[cls * NSTRIPS + st], 1);
+#else
         const unsigned grp = __match_any_sync(__activemask(), st * 4 + cls);
         const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
         int base = 0;
         if (lane == leader) base = atomicAdd(&nlist[cls * NSTRIPS + st], __popc(grp));
         base = __shfl_sync(grp, base, leader);
         const int pos = base + __popc(grp & ((1u << lane) - 1u));
+#endif
         unsigned short* l = lists + (size_t)st * 2 * REC_MAX;
         l[cls == 0 ? pos : (cls == 2 ? REC_MAX - 1 - pos : REC_MAX + pos)] = (unsigned short)slot;
     }
@@ -724,7 +733,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
          uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N, const StaticLayer SL) {
     unsigned long long* __restrict__ static_keys = SL.keys;
     const unsigned int static_bits = SL.bits; const int skip_front = SL.skip_front;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RR_DYN_SMEM(smem_raw);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* Mbuf = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);       // two matrix tiles with TMA_MATS
     __shared__ __align__(8) unsigned long long s_mbar[2];
@@ -1166,7 +1175,7 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
     int total = env_count * RR_NSHAPES;
     {
         ProfScope ps(ctx, 1, s);
-        k_render_setup<<<(total + 127) / 128, 128, 0, s>>>(ctx->st, frames, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device], env_begin, env_count);
+        RR_LAUNCH(k_render_setup, (total + 127) / 128, 128, 0, s)(ctx->st, frames, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device], env_begin, env_count);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1181,8 +1190,8 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
     {
         ProfScope ps(ctx, 2, s);
         int grid = ctx->raster_grid < env_count ? ctx->raster_grid : env_count;
-        if (use_static) k_raster<2><<<grid, RTHREADS, RASTER_SMEM, s>>>(RASTER_ARGS(rgb, depth, seg, mask, env_count));
-        else k_raster<0><<<grid, RTHREADS, RASTER_SMEM, s>>>(RASTER_ARGS(rgb, depth, seg, mask, env_count));
+        if (use_static) RR_LAUNCH(k_raster<2>, grid, RTHREADS, RASTER_SMEM, s)(RASTER_ARGS(rgb, depth, seg, mask, env_count));
+        else RR_LAUNCH(k_raster<0>, grid, RTHREADS, RASTER_SMEM, s)(RASTER_ARGS(rgb, depth, seg, mask, env_count));
     }
 #undef RASTER_ARGS
     ctx->launches++;
@@ -1196,10 +1205,10 @@ int rrk_render_build_static(rr_ctx* ctx) {
     if (!ctx->static_enabled || ctx->static_ready) return 0;
     if (bind_render(ctx, 0)) return -1;
     const StaticLayer SL = static_layer(ctx);
-    k_render_setup<<<1, 128, 0, 0>>>(ctx->st, nullptr, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device], 0, 1);
+    RR_LAUNCH(k_render_setup, 1, 128, 0, 0)(ctx->st, nullptr, ctx->st.render_mats, ctx->n_objects, g_static_frames[ctx->device], 0, 1);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), 0));
-    k_raster<1><<<1, RTHREADS, RASTER_SMEM, 0>>>(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris,
+    RR_LAUNCH(k_raster<1>, 1, RTHREADS, RASTER_SMEM, 0)(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris,
         ctx->d_tex, nullptr, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, (unsigned short*)ctx->d_cull_scratch,
         ctx->d_work_counter, const_cast<uint8_t*>(SL.rgb), const_cast<float*>(SL.depth), const_cast<int32_t*>(SL.seg), 0, 1, SL);
     CK(cudaGetLastError());

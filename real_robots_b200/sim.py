@@ -11,6 +11,9 @@ import torch
 from . import _lib as L
 
 
+MAX_MANIFOLDS = 32       # RR_MAX_MANIFOLDS_PER_ENV (include/real_b200.h)
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -164,10 +167,10 @@ class BatchedSim:
         return out
 
     def contacts(self):
-        """-> (hdr i32[N,24,2], pts f64[N,24,4,17], pairs i32[n_pairs,2]) — cached manifolds of the last step."""
+        """-> (hdr i32[N,32,2], pts f64[N,32,4,17], pairs i32[n_pairs,2]) — cached manifolds of the last step."""
         N, dev = self.n_envs, self.device
-        hdr = torch.empty(N, 24, 2, dtype=torch.int32, device=dev)
-        pts = torch.empty(N, 24, 4, 17, dtype=torch.float64, device=dev)
+        hdr = torch.empty(N, MAX_MANIFOLDS, 2, dtype=torch.int32, device=dev)
+        pts = torch.empty(N, MAX_MANIFOLDS, 4, 17, dtype=torch.float64, device=dev)
         pairs = np.zeros((96, 2), np.int32)
         n = C.c_int(0)
         self._ck(self.lib.rr_contacts(self.ctx, _ptr(hdr), _ptr(pts), pairs.ctypes.data_as(C.c_void_p), C.byref(n), self._stream()), "rr_contacts")
@@ -175,8 +178,8 @@ class BatchedSim:
 
     def set_contacts(self, hdr, pts):
         """Write the persistent manifolds back (layout of contacts()); call after set_state, which clears them."""
-        self._chk(hdr, (self.n_envs, 24, 2), torch.int32, "hdr")
-        self._chk(pts, (self.n_envs, 24, 4, 17), torch.float64, "pts")
+        self._chk(hdr, (self.n_envs, MAX_MANIFOLDS, 2), torch.int32, "hdr")
+        self._chk(pts, (self.n_envs, MAX_MANIFOLDS, 4, 17), torch.float64, "pts")
         self._ck(self.lib.rr_set_contacts(self.ctx, _ptr(hdr), _ptr(pts), self._stream()), "rr_set_contacts")
 
     # checkpoint / resume of the simulation state (not in the reference, SURVEY section 5): (q, qd, obj) and the contact

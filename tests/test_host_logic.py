@@ -287,8 +287,8 @@ def test_get_contacts_reads_manifolds_like_the_reference():
     idx = {s["name"]: i for i, s in enumerate(shapes)}
     pairs = np.array([[idx["skin_00"], idx["cube_0"]], [idx["finger_00"], idx["table_upper"]], [idx["skin_01"], idx["table_base"]],
                       [idx["cube_0"], idx["table_base"]], [idx["skin_00"], idx["tomato"]]], np.int32)
-    hdr = torch.full((1, 24, 2), -1, dtype=torch.int32); hdr[0, :, 1] = 0
-    pts = torch.zeros(1, 24, 4, 17, dtype=torch.float64)
+    hdr = torch.full((1, 32, 2), -1, dtype=torch.int32); hdr[0, :, 1] = 0
+    pts = torch.zeros(1, 32, 4, 17, dtype=torch.float64)
     for slot, (pi, n) in enumerate([(0, 2), (1, 1), (2, 1), (3, 4), (4, 1)]):
         hdr[0, slot, 0], hdr[0, slot, 1] = pi, n
         pts[0, slot, :n, 9] = -0.001
