@@ -47,6 +47,7 @@ typedef struct rr_config {
     double margin;              /* 0.001 */
     double restitution_threshold; /* 0.2 */
     double friction_erp;        /* 0.2 */
+    int    torsional_friction;  /* 1: spinning / rolling friction rows (urdf/cube.urdf:6-7, kuka_gripper.urdf:294-295 ...) */
 } rr_config;
 
 void rr_config_default(rr_config* cfg);

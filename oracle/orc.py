@@ -20,7 +20,7 @@ CONFIG_FIELDS = [
     ("motor_kp", C.c_double), ("motor_kd", C.c_double), ("motor_max_force", C.c_double),
     ("limit_max_impulse", C.c_double), ("use_box_inertia", C.c_int), ("gravity", C.c_double),
     ("enable_contacts", C.c_int), ("contact_breaking", C.c_double), ("margin", C.c_double),
-    ("restitution_threshold", C.c_double), ("friction_erp", C.c_double),
+    ("restitution_threshold", C.c_double), ("friction_erp", C.c_double), ("torsional_friction", C.c_int),
 ]
 
 

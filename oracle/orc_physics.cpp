@@ -210,7 +210,7 @@ struct Row {
 };
 
 struct Solver {
-    std::vector<Row> noncontact, normal, friction;
+    std::vector<Row> noncontact, normal, spinning, rolling, friction;
     double dva[ORC_NDOF]; double dvo[ORC_MAXOBJ][6];
 };
 
@@ -403,6 +403,11 @@ static void build_rows(OrcEnv* e, Solver& S) {
         const OrcShape& sA = sc->shapes[mf.shapeA]; const OrcShape& sB = sc->shapes[mf.shapeB];
         double mu = sA.friction * sB.friction;
         double rest = sA.restitution * sB.restitution;
+        /* btManifoldResult::calculateCombinedRollingFriction / ...SpinningFriction: r0*f1 + r1*f0, clamped to +-10 */
+        double roll = std::max(-10.0, std::min(10.0, sA.rolling * sB.friction + sB.rolling * sA.friction));
+        double spin = std::max(-10.0, std::min(10.0, sA.spinning * sB.friction + sB.spinning * sA.friction));
+        if (!cf.torsional_friction) roll = spin = 0.0;
+        int rolling_budget = 4;
         for (int k = 0; k < mf.n; k++) {
             OrcContactPoint& cp = mf.pt[k];
             if (cp.distance > cf.contact_breaking) continue;   /* getProcessingThreshold */
@@ -427,6 +432,27 @@ static void build_rows(OrcEnv* e, Solver& S) {
             V3 t1, t2; plane_space(cp.normalB, t1, t2);
             t1 = normalized(t1); t2 = normalized(t2);
             V3 dirs[2] = {t1, t2};
+            /* torsional friction (btMultiBodyConstraintSolver::convertMultiBodyContact: `rollingFriction` counts 4 points per
+             * manifold; addMultiBodySpinningFrictionConstraint along the normal when the combined spinning friction is > 0,
+             * addMultiBodyTorsionalFrictionConstraint along both lateral directions when the combined rolling friction is > 0).
+             * Rows are angular only, target velocity 0, no warm start, limits +-(coefficient x normal impulse) set per iteration.
+             * Reference data: urdf/cube.urdf:6-7, tomato.urdf:6-7, mustard.urdf:6-7, kuka_gripper.urdf:294-295 (fingers, skins). */
+            if (rolling_budget > 0) {
+                for (int f = 0; f < 3; f++) {
+                    double coef = f == 0 ? spin : roll;
+                    if (!(coef > 0)) continue;
+                    V3 dir = f == 0 ? cp.normalB : dirs[f - 1];
+                    Row tr; row_init(tr); tr.kind = 4 + f; tr.cp = &cp;
+                    fill_side(e, tr, mf.shapeA, cp.worldA, dir, +1.0, true);
+                    fill_side(e, tr, mf.shapeB, cp.worldB, dir, -1.0, true);
+                    tr.friction_index = nidx; tr.mu = coef;
+                    row_finish(e, tr);
+                    tr.rhs = (0.0 - row_relvel(e, tr)) * tr.jacDiagABInv;
+                    tr.lo = -coef; tr.hi = coef;
+                    (f == 0 ? S.spinning : S.rolling).push_back(tr);
+                }
+                rolling_budget--;
+            }
             for (int f = 0; f < 2; f++) {
                 Row fr; row_init(fr); fr.kind = 2 + f; fr.cp = &cp;
                 fill_side(e, fr, mf.shapeA, cp.worldA, dirs[f], +1.0, false);
@@ -458,6 +484,16 @@ static void solve(OrcEnv* e, Solver& S) {
             res = std::max(res, r * r);
         }
         for (size_t j = 0; j < S.normal.size(); j++) { double r = resolve_row(S, S.normal[j]); res = std::max(res, r * r); }
+        for (int pass = 0; pass < 2; pass++) {       /* spinning rows, then rolling rows: generic rows whose limits follow the normal impulse */
+            std::vector<Row>& T = pass == 0 ? S.spinning : S.rolling;
+            for (size_t j = 0; j < T.size(); j++) {
+                double total = S.normal[T[j].friction_index].applied;
+                if (total > 0) {
+                    T[j].lo = -(T[j].mu * total); T[j].hi = T[j].mu * total;
+                    double r = resolve_row(S, T[j]); res = std::max(res, r * r);
+                }
+            }
+        }
         for (size_t j = 0; j + 1 < S.friction.size(); j += 2) {
             Row& a = S.friction[j]; Row& b = S.friction[j + 1];
             double total = S.normal[a.friction_index].applied;
@@ -468,7 +504,7 @@ static void solve(OrcEnv* e, Solver& S) {
         if (res <= cf.residual_threshold) { it++; break; }
     }
     e->last_iterations = it; e->last_residual = res;
-    e->last_rows = (int)(S.noncontact.size() + S.normal.size() + S.friction.size());
+    e->last_rows = (int)(S.noncontact.size() + S.normal.size() + S.spinning.size() + S.rolling.size() + S.friction.size());
     /* write back applied impulses (solveGroupCacheFriendlyFinish) */
     for (size_t j = 0; j < S.normal.size(); j++) S.normal[j].cp->applied_impulse = S.normal[j].applied;
     for (size_t j = 0; j < S.friction.size(); j++) {

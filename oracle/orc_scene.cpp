@@ -71,6 +71,7 @@ void orc_default_config(OrcConfig* c) {
     c->margin = 0.001;
     c->restitution_threshold = 0.2;
     c->friction_erp = 0.2;
+    c->torsional_friction = 1;
 }
 
 static V3 v3at(const double* p, int i) { return V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }

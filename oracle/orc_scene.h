@@ -57,6 +57,7 @@ struct OrcConfig {
     double margin;             /* 0.001 per hull */
     double restitution_threshold; /* 0.2 */
     double friction_erp;       /* 0.2 (unused by multibody friction rows) */
+    int torsional_friction;    /* 1: spinning / rolling friction rows where the URDFs set the coefficients */
 };
 void orc_default_config(OrcConfig* c);
 

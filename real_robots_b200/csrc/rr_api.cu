@@ -228,7 +228,7 @@ void rr_config_default(rr_config* c) {
     c->residual_threshold = 1e-7; c->lin_damping = 0.04; c->ang_damping = 0.04; c->max_coord_vel = 100.0;
     c->motor_kp = 0.1; c->motor_kd = 1.0; c->motor_max_force = 100000.0; c->limit_max_impulse = 100.0;
     c->use_box_inertia = 1; c->gravity = -9.81; c->enable_contacts = 1; c->contact_breaking = 0.02; c->margin = 0.001;
-    c->restitution_threshold = 0.2; c->friction_erp = 0.2;
+    c->restitution_threshold = 0.2; c->friction_erp = 0.2; c->torsional_friction = 1;
 }
 int rr_config_size(void) { return (int)sizeof(rr_config); }
 
