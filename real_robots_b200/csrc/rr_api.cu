@@ -168,9 +168,12 @@ static int fill_constants(rr_ctx* ctx, const Blob& b) {
     }
     const Entry* e_fr = b.get("shape.friction", 3, err); if (!e_fr) return -1;
     const Entry* e_re = b.get("shape.restitution", 3, err); if (!e_re) return -1;
+    const Entry* e_ro = b.get("shape.rolling", 3, err); if (!e_ro) return -1;
+    const Entry* e_sp = b.get("shape.spinning", 3, err); if (!e_sp) return -1;
     for (int s = 0; s < RR_NSHAPES; s++) {
         R.shape_body[s] = ((const int32_t*)e_sb->data)[s]; R.shape_link[s] = ((const int32_t*)e_sl->data)[s];
         R.shape_friction[s] = ((const double*)e_fr->data)[s]; R.shape_restitution[s] = ((const double*)e_re->data)[s];
+        R.shape_rolling[s] = ((const double*)e_ro->data)[s]; R.shape_spinning[s] = ((const double*)e_sp->data)[s];
     }
     for (int i = 0; i < RR_NL; i++) {
         int mask = 0;
@@ -273,7 +276,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
         alloc((void**)&st.man_hdr[k], N * RR_MAX_MANIFOLDS * 2 * 4);
         alloc((void**)&st.man_pts[k], N * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE * 8);
     }
-    alloc((void**)&st.rows, N * 3 * RR_MAX_CONTACTS * RR_ROW_STRIDE * 8);
+    alloc((void**)&st.rows, N * RR_MAX_ROWS * RR_ROW_STRIDE * 8);
     alloc((void**)&st.handoff, N * RR_HANDOFF_DOUBLES * 8);
     if (e != cudaSuccess) { ctx->err = std::string("rr_create: device allocation failed: ") + cudaGetErrorString(e); return fail(-1); }
     ctx->man_parity = 0;

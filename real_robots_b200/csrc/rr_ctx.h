@@ -22,13 +22,23 @@
 #define RR_H RR_EYE_H
 #define RR_FRAME_STRIDE (RR_NSHAPES * 12)
 #define RR_MAX_TEX 16
-#define RR_HANDOFF_DOUBLES 576   // >= the persistent head of WarpMem (static_assert in rr_physics.cu)
+#define RR_HANDOFF_DOUBLES 800   // >= sizeof(SolveMem) / 8 (static_assert in rr_physics.cu)
 #define RR_MAT_STRIDE 44       // floats per (env, shape) in render_mats
 #define RR_MAX_PAIRS 96          // candidate collision pairs (92 for 3 objects)
 #define RR_MAX_MANIFOLDS RR_MAX_MANIFOLDS_PER_ENV      // cached non-empty manifolds per env (<= 32: one lane per slot)
 #define RR_PT_STRIDE 17          // doubles per contact point: localA3 localB3 normalB3 dist impulse worldA3 worldB3
-#define RR_MAX_CONTACTS 32       // contact points per env that get solver rows
-#define RR_ROW_STRIDE 72         // doubles per solver row in the global row scratch
+#define RR_MAX_CONTACTS 48       // contact points per env that get solver rows
+#define RR_ROW_STRIDE 72         // doubles per solver row in the global row scratch: (J, M^-1 J^T) per owner lane [32][2], then 8 scalars
+// Solver row ids.  Single rows (phase A of an iteration): joint limits + motors, contact normals, spinning, rolling; then the
+// rows of the friction pairs (phase B, addressed by contact index).  Single-row ids fit one byte (0xff = idle).
+#define RR_NC_ROWS 24                                        // <= 11 limit rows + 11 motor rows
+#define RID_NORMAL RR_NC_ROWS                                // + c
+#define RID_SPIN (RID_NORMAL + RR_MAX_CONTACTS)              // + c
+#define RID_ROLL (RID_SPIN + RR_MAX_CONTACTS)                // + 2 c + {0, 1}
+#define RR_ROWS_A (RID_ROLL + 2 * RR_MAX_CONTACTS)           // 216 single rows
+#define RID_FRIC RR_ROWS_A                                   // + 2 c + {0, 1}
+#define RR_MAX_ROWS (RID_FRIC + 2 * RR_MAX_CONTACTS)         // 312
+#define RR_IDLE 0xff
 
 // ---- constant robot / scene description (uploaded to __constant__ memory once per process+device)
 struct RobotConst {
@@ -44,7 +54,7 @@ struct RobotConst {
     rr_config cfg;
     int anc[RR_NL];              // bit d set: dof d lies on the path from link to the base (incl. the link's own joint)
     int pair_a[RR_MAX_PAIRS], pair_b[RR_MAX_PAIRS];
-    double shape_friction[RR_NSHAPES], shape_restitution[RR_NSHAPES];
+    double shape_friction[RR_NSHAPES], shape_restitution[RR_NSHAPES], shape_rolling[RR_NSHAPES], shape_spinning[RR_NSHAPES];
 };
 
 struct TexConst { int w, h, uniform; long long offset; };
@@ -79,7 +89,7 @@ struct DevState {
     long long* timestep;  // [N]
     int*    man_hdr[2];   // [N][RR_MAX_MANIFOLDS][2]  (pair index or -1, point count), double buffered
     double* man_pts[2];   // [N][RR_MAX_MANIFOLDS][4][RR_PT_STRIDE]
-    double* rows;         // [N][3*RR_MAX_CONTACTS][RR_ROW_STRIDE] solver row scratch
+    double* rows;         // [N][RR_MAX_ROWS][RR_ROW_STRIDE] solver row scratch (only the rows of live constraints are touched)
     double* handoff;      // [N][RR_HANDOFF_DOUBLES] per-env solver state passed from k_step_dyn to k_step_solve
 };
 

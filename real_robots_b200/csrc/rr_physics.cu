@@ -21,26 +21,49 @@ __constant__ RobotConst c_robot;
 #endif
 #define FULL 0xffffffffu
 
-struct WarpMem {
-    // ---- solver state: produced by k_step_dyn, handed to k_step_solve through DevState::handoff (PERSIST_DOUBLES doubles)
-    double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
-    double Minv[RR_NDOF][RR_NDOF];
-    // non-contact rows (limits then motors)
-    double r_rhs[32], r_inv[32], r_rinv[32], r_lo[32], r_hi[32], r_app[32], r_sign[32];
-    double app[3 * RR_MAX_CONTACTS];                    // applied impulses: normals [0,MAXC), friction pairs after
-    double objreg[RR_MAX_OBJECTS][13];                  // free bodies after the unconstrained update (pos3 quat4 lin3 ang3)
-    int r_dof[32];
-    int n_rows;
-    int ocnt[RR_MAX_OBJECTS];
-    int simple;                                         // every contact is object-vs-static: objects solve independently
-    int nc, overflow, fault;                            // fault bit 0: a non-finite joint command arrived this step
-    unsigned char olist[RR_MAX_OBJECTS][RR_MAX_CONTACTS];   // per object: its contact indices, in solver order
-    // ---- kinematics workspace (both kernels, not handed over)
+// Kinematics workspace (both kernels)
+struct KinWs {
     double Rpc[RR_NL][9];     // parent -> link rotation
     double rvec[RR_NL][3];    // parent COM -> link COM, link frame
     double Rw[RR_NL][9];      // world_from_link
     double pw[RR_NL][3];      // link COM, world
-    // ---- dynamics workspace (k_step_dyn only)
+};
+#define RR_SLOTS_A RR_ROWS_A
+#define RR_SLOTS_B RR_MAX_CONTACTS
+// What k_step_dyn hands to k_step_solve through DevState::handoff: the state after the unconstrained update, the applied
+// impulses (warm start) and the SLOT SCHEDULE of the Gauss-Seidel sweep.  The lanes of a warp form four groups — arm
+// dofs (lanes 0..10) and the three free bodies (lanes 11+6o .. 16+6o) — and a constraint row only touches the groups of the
+// bodies it couples, so rows of disjoint groups commute.  schedA[p][slot][g] names the row group g resolves in that slot of
+// an iteration of parity p (the joint rows run backwards on even iterations), in the order of the sequential sweep
+// restricted to that group; rows of different groups in one slot are resolved by the same instructions at the same time.
+// A row that needs a reduction wider than one group's own (an arm contact row, or a row coupling two groups) is the slot's
+// single `wide` row.  schedB does the same for the friction pairs (entries are contact indices).
+struct SolveTables {
+    unsigned char schedA[2][RR_SLOTS_A][4];
+    unsigned char wideA[2][RR_SLOTS_A];
+    unsigned char schedB[RR_SLOTS_B][4];
+    unsigned char wideB[RR_SLOTS_B];
+    unsigned char r_dof[RR_NC_ROWS];                    // dof of a limit / motor row
+    double app[RR_MAX_ROWS];                            // applied impulses by row id
+};
+struct SolveMem {
+    double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
+    double objreg[RR_MAX_OBJECTS][13];                  // free bodies after the unconstrained update (pos3 quat4 lin3 ang3)
+    int n_slotsA[2], n_slotsB;
+    int n_nc, nc, overflow, fault, simple, n_rows_total, pad_;   // fault bit 0: a non-finite joint command arrived this step
+    union { SolveTables t; KinWs k; } u;                // the epilogue's kinematics reuse the tables' memory once the sweep is over
+};
+// k_step_dyn's own workspace
+struct WarpMem {
+    double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
+    double Minv[RR_NDOF][RR_NDOF];
+    // non-contact rows (limits then motors) while they are being set up
+    double r_rhs[RR_NC_ROWS], r_inv[RR_NC_ROWS], r_rinv[RR_NC_ROWS], r_lo[RR_NC_ROWS], r_hi[RR_NC_ROWS], r_sign[RR_NC_ROWS];
+    int r_dof[RR_NC_ROWS];
+    int n_rows;
+    int fault;
+    unsigned char c_grp[RR_MAX_CONTACTS], c_flags[RR_MAX_CONTACTS];   // per contact: group mask (bit 0 arm, bit 1+o object o); bit 0 spinning row, bit 1 rolling rows, bit 2 wide
+    KinWs k;
     double v[RR_NL][6];       // spatial velocity (ang, lin) in link frame
     double c[RR_NL][6];       // Coriolis acceleration
     double p[RR_NL][6];       // zero-acceleration force
@@ -55,11 +78,10 @@ struct WarpMem {
     double opos[RR_MAX_OBJECTS][3], ovel[RR_MAX_OBJECTS][6], oIinv[RR_MAX_OBJECTS][9], oinvm[RR_MAX_OBJECTS];
     double Jtmp[32];
 };
-#define PERSIST_BYTES (offsetof(WarpMem, Rpc))
-#define PERSIST_DOUBLES (PERSIST_BYTES / 8)
-#define SOLVE_SMEM_BYTES (offsetof(WarpMem, v))       // k_step_solve and k_fk carry only the head of the struct
-static_assert(PERSIST_BYTES % 8 == 0 && PERSIST_DOUBLES <= RR_HANDOFF_DOUBLES, "handoff buffer too small");
-static_assert(offsetof(WarpMem, Rpc) % 8 == 0 && offsetof(WarpMem, v) % 8 == 0, "WarpMem alignment");
+#define SOLVE_SMEM_BYTES (sizeof(SolveMem))
+static_assert(sizeof(SolveMem) % 8 == 0 && sizeof(SolveMem) / 8 <= RR_HANDOFF_DOUBLES, "handoff buffer too small");
+static_assert(sizeof(SolveTables) >= sizeof(KinWs), "the kinematics workspace must fit inside the tables it aliases");
+static_assert(RR_ROWS_A < RR_IDLE, "single-row ids must fit one byte");
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
@@ -84,7 +106,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ------------------------------------------------------------------------------------------- forward kinematics
 // lane i < 16 computes its link's joint transform; then a serial sweep down the tree builds world frames.
-__device__ __forceinline__ void fk_local(WarpMem& m, int lane) {
+__device__ __forceinline__ void fk_local(const double* q, KinWs& m, int lane) {
     if (lane < RR_NL) {
         const int i = lane;
         double R0[9];
@@ -92,7 +114,7 @@ __device__ __forceinline__ void fk_local(WarpMem& m, int lane) {
         for (int k = 0; k < 9; k++) R0[k] = c_robot.rot0[i][k];
         double R[9];
         if (c_robot.jtype[i] == 1) {
-            double th = -m.q[c_robot.dof[i]];
+            double th = -q[c_robot.dof[i]];
             double s, c; sincos(th, &s, &c);
             double ax = c_robot.axis[i][0], ay = c_robot.axis[i][1], az = c_robot.axis[i][2];
             double t = 1.0 - c;
@@ -116,9 +138,10 @@ __device__ __forceinline__ void fk_local(WarpMem& m, int lane) {
     __syncwarp();
 }
 
-// serial sweep: world frames (lanes 0..8 rotation entries, then lanes 0..2 position) and, if with_vel,
+// serial sweep: world frames (lanes 0..8 rotation entries, then lanes 0..2 position) and, if vel is given,
 // spatial velocities (lanes 16..21)
-__device__ __forceinline__ void fk_sweep(WarpMem& m, int lane, bool with_vel) {
+__device__ __forceinline__ void fk_sweep(KinWs& m, int lane, double (*vel)[6], const double* qd) {
+    const bool with_vel = vel != nullptr;
     for (int i = 0; i < RR_NL; i++) {
         const int par = c_robot.parent[i];
         if (lane < 9) {
@@ -132,12 +155,12 @@ __device__ __forceinline__ void fk_sweep(WarpMem& m, int lane, bool with_vel) {
             double wp[3] = {0, 0, 0}, vp[3] = {0, 0, 0};
             if (par >= 0) {
 #pragma unroll
-                for (int a = 0; a < 3; a++) { wp[a] = m.v[par][a]; vp[a] = m.v[par][3 + a]; }
+                for (int a = 0; a < 3; a++) { wp[a] = vel[par][a]; vp[a] = vel[par][3 + a]; }
             }
             double w[3];
 #pragma unroll
             for (int a = 0; a < 3; a++) w[a] = m.Rpc[i][3 * a] * wp[0] + m.Rpc[i][3 * a + 1] * wp[1] + m.Rpc[i][3 * a + 2] * wp[2];
-            double qdj = (c_robot.jtype[i] == 1) ? m.qd[c_robot.dof[i]] : 0.0;
+            double qdj = (c_robot.jtype[i] == 1) ? qd[c_robot.dof[i]] : 0.0;
             double out;
             if (k < 3) out = w[k] + c_robot.S[i][k] * qdj;
             else {
@@ -147,7 +170,7 @@ __device__ __forceinline__ void fk_sweep(WarpMem& m, int lane, bool with_vel) {
                 double wxr = (a == 0) ? (w[1] * r[2] - w[2] * r[1]) : (a == 1) ? (w[2] * r[0] - w[0] * r[2]) : (w[0] * r[1] - w[1] * r[0]);
                 out = Rv + wxr + c_robot.S[i][k] * qdj;
             }
-            m.v[i][k] = out;
+            vel[i][k] = out;
         }
         __syncwarp();
         if (lane < 3) {
@@ -188,9 +211,9 @@ __device__ __forceinline__ void aba_bias(WarpMem& m, int lane, const rr_config& 
         double pa0 = Iw[0] * ka + (w[1] * Iw[2] - w[2] * Iw[1]);
         double pa1 = Iw[1] * ka + (w[2] * Iw[0] - w[0] * Iw[2]);
         double pa2 = Iw[2] * ka + (w[0] * Iw[1] - w[1] * Iw[0]);
-        double pl0 = -(m.Rw[i][6] * fz) + l[0] * mass * kl + (w[1] * l[2] - w[2] * l[1]) * mass;
-        double pl1 = -(m.Rw[i][7] * fz) + l[1] * mass * kl + (w[2] * l[0] - w[0] * l[2]) * mass;
-        double pl2 = -(m.Rw[i][8] * fz) + l[2] * mass * kl + (w[0] * l[1] - w[1] * l[0]) * mass;
+        double pl0 = -(m.k.Rw[i][6] * fz) + l[0] * mass * kl + (w[1] * l[2] - w[2] * l[1]) * mass;
+        double pl1 = -(m.k.Rw[i][7] * fz) + l[1] * mass * kl + (w[2] * l[0] - w[0] * l[2]) * mass;
+        double pl2 = -(m.k.Rw[i][8] * fz) + l[2] * mass * kl + (w[0] * l[1] - w[1] * l[0]) * mass;
         m.p[i][0] = pa0; m.p[i][1] = pa1; m.p[i][2] = pa2; m.p[i][3] = pl0; m.p[i][4] = pl1; m.p[i][5] = pl2;
     }
     for (int e = lane; e < RR_NL * 36; e += 32) {
@@ -222,7 +245,7 @@ __device__ __forceinline__ void aba_backward(WarpMem& m, int lane) {
         // Ic = IA*c (lanes 0..5), h = IA*S (lanes 8..13), X entries (all lanes)
         if (lane < 6) m.Ic[lane] = dot6(&m.IA[i][6 * lane], m.c[i]);
         else if (lane >= 8 && lane < 14) { int k = lane - 8; m.h[i][k] = rev ? dot6(&m.IA[i][6 * k], c_robot.S[i]) : 0.0; }
-        if (par >= 0) for (int e = lane; e < 36; e += 32) m.X[e] = X_entry(m.Rpc[i], m.rvec[i], e / 6, e % 6);
+        if (par >= 0) for (int e = lane; e < 36; e += 32) m.X[e] = X_entry(m.k.Rpc[i], m.k.rvec[i], e / 6, e % 6);
         __syncwarp();
         double invD = 0.0, Y = 0.0;
         if (rev) {
@@ -268,7 +291,7 @@ __device__ __forceinline__ void aba_forward(WarpMem& m, int lane) {
         double a6[6];
         // every lane computes the transformed parent acceleration redundantly (6x6 on 6 values is cheap)
         if (par >= 0) {
-            const double* R = m.Rpc[i]; const double* r = m.rvec[i]; const double* ap = m.acc[par];
+            const double* R = m.k.Rpc[i]; const double* r = m.k.rvec[i]; const double* ap = m.acc[par];
             double w[3];
 #pragma unroll
             for (int a = 0; a < 3; a++) w[a] = R[3 * a] * ap[0] + R[3 * a + 1] * ap[1] + R[3 * a + 2] * ap[2];
@@ -316,7 +339,7 @@ __device__ __forceinline__ void aba_minv(WarpMem& m, int lane) {
             int par = c_robot.parent[i];
             if (par >= 0) {
                 // X^T force transform: f_p = R^T f ; t_p = R^T (t + r x f)
-                const double* R = m.Rpc[i]; const double* r = m.rvec[i];
+                const double* R = m.k.Rpc[i]; const double* r = m.k.rvec[i];
                 double t[3] = {pa[0] + (r[1] * pa[5] - r[2] * pa[4]), pa[1] + (r[2] * pa[3] - r[0] * pa[5]), pa[2] + (r[0] * pa[4] - r[1] * pa[3])};
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
@@ -331,7 +354,7 @@ __device__ __forceinline__ void aba_minv(WarpMem& m, int lane) {
             int par = c_robot.parent[i];
             double a6[6];
             if (par >= 0) {
-                const double* R = m.Rpc[i]; const double* r = m.rvec[i]; const double* ap = pz[par];
+                const double* R = m.k.Rpc[i]; const double* r = m.k.rvec[i]; const double* ap = pz[par];
                 double w[3];
 #pragma unroll
                 for (int a = 0; a < 3; a++) w[a] = R[3 * a] * ap[0] + R[3 * a + 1] * ap[1] + R[3 * a + 2] * ap[2];
@@ -423,17 +446,30 @@ __device__ __forceinline__ void obj_integrate(ObjReg& b, double dt) {
 }
 
 // ------------------------------------------------------------------------------------------- step kernel
-__device__ __forceinline__ void store_frames(const WarpMem& m, const DevState& st, int e, int lane) {
+__device__ __forceinline__ void store_frames(const KinWs& m, const DevState& st, int e, int lane) {
     for (int k = lane; k < RR_NL * 12; k += 32) {
         int i = k / 12, j = k % 12;
         st.link_frames[(size_t)k * st.N + e] = (j < 9) ? m.Rw[i][j] : m.pw[i][j - 9];
     }
 }
 
-// One env step is two kernels.  k_step_dyn: action prologue, kinematics, ABA, M^-1, constraint rows -> DevState::handoff
-// and the global row scratch.  k_step_solve: PGS, integration, final kinematics, observations.  The solver is a chain
-// of dependent fp64 operations whose only remedy is more resident warps; it needs a third of the dynamics' shared memory,
-// so on its own it runs at more than twice the occupancy.
+// lane -> group: 0 = arm dofs (lanes 0..10), 1 + o = free body o (lanes 11 + 6 o .. 16 + 6 o), 4 = idle lanes 29..31
+__device__ __forceinline__ int lane_group(int lane) { return lane < RR_NDOF ? 0 : (lane < 29 ? 1 + (lane - RR_NDOF) / 6 : 4); }
+
+// lane 0: place one row (or friction pair) of group mask gm into the earliest slot all its groups are free in; a wide row also
+// needs a slot without another wide row.  sched[slot][g] / wide[slot] are bytes in the handoff image (global memory).
+__device__ __forceinline__ void sched_place(unsigned char (*sched)[4], unsigned char* wide, int* cur, unsigned int* wide_used, int gm, bool is_wide, int id) {
+    int slot = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) if ((gm >> g) & 1) slot = max(slot, cur[g]);
+    if (is_wide) { while ((wide_used[slot >> 5] >> (slot & 31)) & 1u) slot++; wide_used[slot >> 5] |= 1u << (slot & 31); wide[slot] = (unsigned char)id; }
+#pragma unroll
+    for (int g = 0; g < 4; g++) if ((gm >> g) & 1) { sched[slot][g] = (unsigned char)id; cur[g] = slot + 1; }
+}
+
+// One env step is two kernels.  k_step_dyn: action prologue, kinematics, ABA, M^-1, constraint rows -> the global row scratch,
+// and the slot schedule of the solver sweep -> DevState::handoff.  k_step_solve: PGS, integration, final kinematics,
+// observations.  The solver needs a third of the dynamics' shared memory, so on its own it runs at more than twice the occupancy.
 __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double* __restrict__ cmd, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
     RR_DYN_SMEM(smem_raw);
     WarpMem& m = reinterpret_cast<WarpMem*>(smem_raw)[threadIdx.x >> 5];
@@ -497,8 +533,8 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
     __syncwarp();
 
     // ---- forward dynamics
-    fk_local(m, lane);
-    fk_sweep(m, lane, true);
+    fk_local(m.q, m.k, lane);
+    fk_sweep(m.k, lane, m.v, m.qd);
     if (lane < RR_NDOF) m.tau[lane] = -c_robot.damping[c_robot.link_of_dof[lane]] * m.qd[lane];
     aba_bias(m, lane, cf);
     aba_backward(m, lane);
@@ -507,6 +543,8 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
     if (has_obj) obj_free_update(ob, lane, cf);
     aba_minv(m, lane);
 
+    SolveMem* hand = reinterpret_cast<SolveMem*>(st.handoff + (size_t)e * RR_HANDOFF_DOUBLES);      // the solver's image of this env
+    double* rows = st.rows + (size_t)e * RR_MAX_ROWS * RR_ROW_STRIDE;
     // ---- constraint rows: joint limits (link order) then motors (link order)
     if (lane == 0) {
         int n = 0;
@@ -516,13 +554,13 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
             double pos[2] = {m.q[d] - c_robot.lower[i], c_robot.upper[i] - m.q[d]};
             for (int row = 0; row < 2; row++) {
                 double pen = pos[row];
-                if (pen > 0) continue;
+                if (pen > 0 || n >= RR_NC_ROWS - RR_NDOF) continue;
                 double sgn = row ? -1.0 : 1.0;
                 double dd = m.Minv[d][d];
                 double inv = dd > 0 ? 1.0 / dd : 0.0;
                 double rel = sgn * m.qd[d];
                 m.r_dof[n] = d; m.r_sign[n] = sgn; m.r_inv[n] = inv; m.r_rinv[n] = inv != 0.0 ? 1.0 / inv : 0.0; m.r_lo[n] = 0.0; m.r_hi[n] = cf.limit_max_impulse;
-                m.r_rhs[n] = (-pen * cf.erp / dt - rel) * inv; m.r_app[n] = 0.0;
+                m.r_rhs[n] = (-pen * cf.erp / dt - rel) * inv;
                 n++;
             }
         }
@@ -534,32 +572,38 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
             double desired = cf.motor_kp * stab + cur + cf.motor_kd * (0.0 - cur);
             double maxImp = cf.motor_max_force * dt;
             m.r_dof[n] = d; m.r_sign[n] = 1.0; m.r_inv[n] = inv; m.r_rinv[n] = inv != 0.0 ? 1.0 / inv : 0.0; m.r_lo[n] = -maxImp; m.r_hi[n] = maxImp;
-            m.r_rhs[n] = (desired - cur) * inv; m.r_app[n] = 0.0;
+            m.r_rhs[n] = (desired - cur) * inv;
             n++;
         }
         m.n_rows = n;
     }
     __syncwarp();
-    // ---- contact rows (btMultiBodyConstraintSolver::convertMultiBodyContact): normal + two friction directions per
-    //      manifold point.  A row is a 29-vector in "owner" layout: lanes 0..10 = arm dofs, lane 11+6o+k = component k
-    //      (ang xyz, lin xyz) of object o.  J and M^-1 J^T go to the global row scratch; impulses stay in smem.
+    // ... written out as ordinary rows: J = sgn e_d, M^-1 J^T = sgn * column d of M^-1
+    const int n_nc = m.n_rows;
+    for (int idx = 0; idx < n_nc; idx++) {
+        double* rowp = rows + (size_t)idx * RR_ROW_STRIDE;
+        const int d = m.r_dof[idx]; const double sgn = m.r_sign[idx];
+        if (lane < RR_NDOF) { rowp[2 * lane] = lane == d ? sgn : 0.0; rowp[2 * lane + 1] = m.Minv[lane][d] * sgn; }
+        if (lane == 0) { rowp[64] = m.r_rhs[idx]; rowp[65] = m.r_inv[idx]; rowp[66] = m.r_lo[idx]; rowp[67] = m.r_rinv[idx]; rowp[68] = m.r_hi[idx]; hand->u.t.r_dof[idx] = (unsigned char)d; hand->u.t.app[idx] = 0.0; }
+    }
+    // ---- contact rows (btMultiBodyConstraintSolver::convertMultiBodyContact): per manifold point a normal row, two friction
+    //      directions and, where the combined coefficients are > 0, a spinning row (about the normal) and two rolling rows (about
+    //      the friction directions).  A row is a 29-vector in "owner" layout: lanes 0..10 = arm dofs, lane 11+6o+k = component k
+    //      (ang xyz, lin xyz) of object o.  (J, M^-1 J^T) pairs go to the global row scratch, the applied impulses to the handoff.
     const double vel = (lane < RR_NDOF) ? m.qd[lane] : 0.0;
     double ovel = 0.0;      // object velocity component owned by this lane (lanes 11..28)
-    int nc = 0, overflow = 0;
-    if (lane < RR_MAX_OBJECTS) m.ocnt[lane] = 0;
-    if (lane == 0) m.simple = 1;
-    __syncwarp();
+    int nc = 0, overflow = 0, simple = 1;
     int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
     double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
-    double* rows = st.rows + (size_t)e * 3 * RR_MAX_CONTACTS * RR_ROW_STRIDE;
+    const int mygrp = lane_group(lane);
     if (cf.enable_contacts) {
         if (lane < RR_NDOF) {
             const int i = c_robot.link_of_dof[lane];
-            const double* R = m.Rw[i];
+            const double* R = m.k.Rw[i];
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 m.dof_axis[lane][a] = R[3 * a] * c_robot.axis[i][0] + R[3 * a + 1] * c_robot.axis[i][1] + R[3 * a + 2] * c_robot.axis[i][2];
-                m.dof_piv[lane][a] = m.pw[i][a] - (R[3 * a] * c_robot.evec[i][0] + R[3 * a + 1] * c_robot.evec[i][1] + R[3 * a + 2] * c_robot.evec[i][2]);
+                m.dof_piv[lane][a] = m.k.pw[i][a] - (R[3 * a] * c_robot.evec[i][0] + R[3 * a + 1] * c_robot.evec[i][1] + R[3 * a + 2] * c_robot.evec[i][2]);
             }
         }
         if (has_obj) {
@@ -584,8 +628,15 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
             const int bodyA = c_robot.shape_body[sa], linkA = c_robot.shape_link[sa], bodyB = c_robot.shape_body[sb];
             const bool armA = bodyA == 0 && linkA >= 0;
             const int oA = bodyA >= 2 ? bodyA - 2 : -1, oB = bodyB >= 2 ? bodyB - 2 : -1;
-            const double mu = c_robot.shape_friction[sa] * c_robot.shape_friction[sb];
+            const double fa = c_robot.shape_friction[sa], fb = c_robot.shape_friction[sb];
+            const double mu = fa * fb;
             const double rest = c_robot.shape_restitution[sa] * c_robot.shape_restitution[sb];
+            // btManifoldResult::calculateCombinedRollingFriction / ...SpinningFriction: r0 f1 + r1 f0, clamped to +-10
+            double roll = fmax(-10.0, fmin(10.0, c_robot.shape_rolling[sa] * fb + c_robot.shape_rolling[sb] * fa));
+            double spin = fmax(-10.0, fmin(10.0, c_robot.shape_spinning[sa] * fb + c_robot.shape_spinning[sb] * fa));
+            if (!cf.torsional_friction) { roll = 0.0; spin = 0.0; }
+            const int gm = (armA ? 1 : 0) | (oA >= 0 ? 2 << oA : 0) | (oB >= 0 ? 2 << oB : 0);
+            const bool in_row = (gm >> mygrp) & 1;               // (group 4 = idle lanes: never)
             for (int k = 0; k < npt; k++) {
                 const double* P = pts + ((size_t)slot * 4 + k) * RR_PT_STRIDE;
                 const double dist = P[9];
@@ -606,22 +657,33 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
                     double l1 = 1.0 / sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]), l2 = 1.0 / sqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
                     for (int a = 0; a < 3; a++) { t1[a] *= l1; t2[a] *= l2; }
                 }
-                for (int di = 0; di < 3; di++) {
-                    const double* d = di == 0 ? nB : (di == 1 ? t1 : t2);
+                // di: 0 normal, 1 2 friction, 3 spinning (angular, about the normal), 4 5 rolling (angular, about t1 / t2)
+                for (int di = 0; di < 6; di++) {
+                    if (di == 3 && !(spin > 0)) continue;
+                    if (di >= 4 && !(roll > 0)) break;
+                    const bool angular = di >= 3;
+                    const int dd_ = angular ? di - 3 : di;
+                    const double* d = dd_ == 0 ? nB : (dd_ == 1 ? t1 : t2);
                     double J = 0.0;
                     if (lane < RR_NDOF) {
                         if (armA && ((c_robot.anc[linkA] >> lane) & 1)) {
                             const double* aw = m.dof_axis[lane]; const double* pv = m.dof_piv[lane];
-                            double r0 = wA[0] - pv[0], r1 = wA[1] - pv[1], r2 = wA[2] - pv[2];
-                            J = d[0] * (aw[1] * r2 - aw[2] * r1) + d[1] * (aw[2] * r0 - aw[0] * r2) + d[2] * (aw[0] * r1 - aw[1] * r0);
+                            if (angular) J = d[0] * aw[0] + d[1] * aw[1] + d[2] * aw[2];
+                            else {
+                                double r0 = wA[0] - pv[0], r1 = wA[1] - pv[1], r2 = wA[2] - pv[2];
+                                J = d[0] * (aw[1] * r2 - aw[2] * r1) + d[1] * (aw[2] * r0 - aw[0] * r2) + d[2] * (aw[0] * r1 - aw[1] * r0);
+                            }
                         }
                     } else if (myo >= 0 && (myo == oA || myo == oB)) {
                         const double sg = myo == oA ? 1.0 : -1.0;
-                        const double* w = myo == oA ? wA : wB;
-                        double r0 = w[0] - m.opos[myo][0], r1 = w[1] - m.opos[myo][1], r2 = w[2] - m.opos[myo][2];
-                        double dd0 = d[0] * sg, dd1 = d[1] * sg, dd2 = d[2] * sg;
-                        if (myk == 0) J = r1 * dd2 - r2 * dd1; else if (myk == 1) J = r2 * dd0 - r0 * dd2; else if (myk == 2) J = r0 * dd1 - r1 * dd0;
-                        else J = myk == 3 ? dd0 : (myk == 4 ? dd1 : dd2);
+                        const double dd0 = d[0] * sg, dd1 = d[1] * sg, dd2 = d[2] * sg;
+                        if (angular) J = myk == 0 ? dd0 : (myk == 1 ? dd1 : (myk == 2 ? dd2 : 0.0));
+                        else {
+                            const double* w = myo == oA ? wA : wB;
+                            double r0 = w[0] - m.opos[myo][0], r1 = w[1] - m.opos[myo][1], r2 = w[2] - m.opos[myo][2];
+                            if (myk == 0) J = r1 * dd2 - r2 * dd1; else if (myk == 1) J = r2 * dd0 - r0 * dd2; else if (myk == 2) J = r0 * dd1 - r1 * dd0;
+                            else J = myk == 3 ? dd0 : (myk == 4 ? dd1 : dd2);
+                        }
                     }
                     m.Jtmp[lane] = J;
                     __syncwarp();
@@ -638,7 +700,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
                     const double den = warp_sum(J * rr);
                     const double relv = warp_sum(J * (lane < RR_NDOF ? vel : ovel));
                     const double inv = den > 0 ? 1.0 / den : 0.0;
-                    double rhs, app0 = 0.0;
+                    double rhs, app0 = 0.0, coef = mu;
                     if (di == 0) {
                         double restitution = (fabs(relv) < cf.restitution_threshold) ? 0.0 : rest * -relv;
                         if (restitution <= 0) restitution = 0;
@@ -649,40 +711,84 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
                         rhs = (positional + velocity) * inv;
                         app0 = P[10] * cf.warmstart;
                     } else rhs = (0.0 - relv) * inv;
-                    const int ri = di == 0 ? nc : RR_MAX_CONTACTS + 2 * nc + (di - 1);
+                    if (di == 3) coef = spin; else if (di >= 4) coef = roll;
+                    const int ri = di == 0 ? RID_NORMAL + nc : (di < 3 ? RID_FRIC + 2 * nc + (di - 1) : (di == 3 ? RID_SPIN + nc : RID_ROLL + 2 * nc + (di - 4)));
                     double* rowp = rows + (size_t)ri * RR_ROW_STRIDE;
-                    rowp[lane] = J; rowp[32 + lane] = rr;
-                    if (lane == 0) { rowp[64] = rhs; rowp[65] = inv; rowp[66] = mu; rowp[67] = inv != 0.0 ? 1.0 / inv : 0.0; m.app[ri] = app0; }
+                    if (in_row || di == 0) { rowp[2 * lane] = J; rowp[2 * lane + 1] = rr; }      // (normal rows: every lane, the warm start reads them all)
+                    if (lane == 0) { rowp[64] = rhs; rowp[65] = inv; rowp[66] = coef; rowp[67] = inv != 0.0 ? 1.0 / inv : 0.0; hand->u.t.app[ri] = app0; }
                     __syncwarp();
                 }
                 if (lane == 0) {
-                    if (!armA && oA >= 0 && oB < 0) m.olist[oA][m.ocnt[oA]++] = (unsigned char)nc;
-                    else m.simple = 0;
+                    const bool wide = armA || (gm & (gm - 1)) != 0;
+                    m.c_grp[nc] = (unsigned char)gm;
+                    m.c_flags[nc] = (unsigned char)((spin > 0 ? 1 : 0) | (roll > 0 ? 2 : 0) | (wide ? 4 : 0));
                 }
+                if (armA || oA < 0 || oB >= 0) simple = 0;
                 nc++;
             }
         }
     }
     __syncwarp();
-    // ---- hand over to k_step_solve
+    // ---- slot schedule of one Gauss-Seidel iteration (see SolveTables), for both parities of the joint-row order
+    const int n_single = n_nc + 4 * nc;          // upper bound of the slots of phase A
+    for (int par = 0; par < 2; par++) {
+        unsigned char* sa = &hand->u.t.schedA[par][0][0];
+        for (int k = lane; k < n_single * 4; k += 32) sa[k] = RR_IDLE;
+        for (int k = lane; k < n_single; k += 32) hand->u.t.wideA[par][k] = RR_IDLE;
+    }
+    for (int k = lane; k < nc * 4; k += 32) (&hand->u.t.schedB[0][0])[k] = RR_IDLE;
+    for (int k = lane; k < nc; k += 32) hand->u.t.wideB[k] = RR_IDLE;
+    __syncwarp();
+    if (lane == 0) {
+        for (int par = 0; par < 2; par++) {
+            int cur[4] = {0, 0, 0, 0};
+            unsigned int wide_used[(RR_SLOTS_A + 31) / 32];
+            for (int k = 0; k < (RR_SLOTS_A + 31) / 32; k++) wide_used[k] = 0u;
+            unsigned char (*sched)[4] = hand->u.t.schedA[par]; unsigned char* wide = hand->u.t.wideA[par];
+            for (int j = 0; j < n_nc; j++) sched_place(sched, wide, cur, wide_used, 1, false, par ? j : n_nc - 1 - j);     // it & 1 ? j : n - 1 - j
+            for (int c = 0; c < nc; c++) sched_place(sched, wide, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, RID_NORMAL + c);
+            for (int c = 0; c < nc; c++) if (m.c_flags[c] & 1) sched_place(sched, wide, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, RID_SPIN + c);
+            for (int c = 0; c < nc; c++) if (m.c_flags[c] & 2) {
+                sched_place(sched, wide, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, RID_ROLL + 2 * c);
+                sched_place(sched, wide, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, RID_ROLL + 2 * c + 1);
+            }
+            hand->n_slotsA[par] = max(max(cur[0], cur[1]), max(cur[2], cur[3]));
+        }
+        int cur[4] = {0, 0, 0, 0};
+        unsigned int wide_used[(RR_SLOTS_B + 31) / 32];
+        for (int k = 0; k < (RR_SLOTS_B + 31) / 32; k++) wide_used[k] = 0u;
+        for (int c = 0; c < nc; c++) sched_place(hand->u.t.schedB, hand->u.t.wideB, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, c);
+        hand->n_slotsB = max(max(cur[0], cur[1]), max(cur[2], cur[3]));
+        int total = n_nc;
+        for (int c = 0; c < nc; c++) total += 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
+        hand->n_nc = n_nc; hand->nc = nc; hand->overflow = overflow; hand->fault = m.fault; hand->simple = simple; hand->n_rows_total = total;
+    }
+    // ---- hand the state over
+    if (lane < RR_NDOF) { hand->q[lane] = m.q[lane]; hand->qd[lane] = m.qd[lane]; hand->target[lane] = m.target[lane]; }
     if (has_obj) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) { m.objreg[lane][k] = ob.pos[k]; m.objreg[lane][7 + k] = ob.lin[k]; m.objreg[lane][10 + k] = ob.ang[k]; }
+        for (int k = 0; k < 3; k++) { hand->objreg[lane][k] = ob.pos[k]; hand->objreg[lane][7 + k] = ob.lin[k]; hand->objreg[lane][10 + k] = ob.ang[k]; }
 #pragma unroll
-        for (int k = 0; k < 4; k++) m.objreg[lane][3 + k] = ob.quat[k];
+        for (int k = 0; k < 4; k++) hand->objreg[lane][3 + k] = ob.quat[k];
     }
-    if (lane == 0) { m.nc = nc; m.overflow = overflow; }
-    __syncwarp();
-    {
-        const double* src = reinterpret_cast<const double*>(&m);
-        double* dst = st.handoff + (size_t)e * RR_HANDOFF_DOUBLES;
-        for (int k = lane; k < (int)PERSIST_DOUBLES; k += 32) dst[k] = src[k];
-    }
+}
+
+#ifdef RR_SIMT_EMU_BUILD
+#define RR_PREFETCH_L1(p)
+#else
+#define RR_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
+#endif
+
+// sum of the six products of a lane's own group (an arm lane of a joint row: the product of the row's dof), all lanes at once
+__device__ __forceinline__ double group_sum6(double pr, int s0, int s1, int s2, int s3, int s4, int s5) {
+    const double a = __shfl_sync(FULL, pr, s0), b = __shfl_sync(FULL, pr, s1), c = __shfl_sync(FULL, pr, s2);
+    const double d = __shfl_sync(FULL, pr, s3), e = __shfl_sync(FULL, pr, s4), f = __shfl_sync(FULL, pr, s5);
+    return ((a + b) + (c + d)) + (e + f);
 }
 
 __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
     RR_DYN_SMEM(smem_raw);
-    WarpMem& m = *reinterpret_cast<WarpMem*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
+    SolveMem& m = *reinterpret_cast<SolveMem*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (e >= st.N) return;
@@ -691,7 +797,7 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
     {
         double* dst = reinterpret_cast<double*>(&m);
         const double* src = st.handoff + (size_t)e * RR_HANDOFF_DOUBLES;
-        for (int k = lane; k < (int)PERSIST_DOUBLES; k += 32) dst[k] = src[k];
+        for (int k = lane; k < (int)(sizeof(SolveMem) / 8); k += 32) dst[k] = src[k];
     }
     __syncwarp();
     ObjReg ob;
@@ -702,136 +808,126 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
 #pragma unroll
         for (int k = 0; k < 4; k++) ob.quat[k] = m.objreg[lane][3 + k];
     }
-    const int nc = m.nc, overflow = m.overflow;
+    const int nc = m.nc, overflow = m.overflow, n_nc = m.n_nc, simple = m.simple;
     int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
     double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
-    double* rows = st.rows + (size_t)e * 3 * RR_MAX_CONTACTS * RR_ROW_STRIDE;
+    const double* rows = st.rows + (size_t)e * RR_MAX_ROWS * RR_ROW_STRIDE;
+    SolveTables& T = m.u.t;
     // ---- projected Gauss-Seidel.  dv in owner layout: lane k < 11 owns the arm dof k, lane 11+6o+c the object component.
+    const int grp = lane_group(lane);
+    const int g4 = grp < 4 ? grp : 0;                          // idle lanes read group 0's schedule entry and ignore it
+    const int seg0 = grp == 0 ? 0 : (grp < 4 ? 11 + 6 * (grp - 1) : 31);   // first lane of the own group
+    const bool leader = lane == seg0 && grp < 4;
+    // shuffle sources of the group sum: the six lanes of a free body; for arm lanes the row's dof, then lane 31 (always 0)
+    const int s1 = grp >= 1 && grp < 4 ? seg0 + 1 : 31, s2 = grp >= 1 && grp < 4 ? seg0 + 2 : 31, s3 = grp >= 1 && grp < 4 ? seg0 + 3 : 31;
+    const int s4 = grp >= 1 && grp < 4 ? seg0 + 4 : 31, s5 = grp >= 1 && grp < 4 ? seg0 + 5 : 31;
     double dv = 0.0;
     int iters = 0; double res = 0.0;
+#ifdef RR_SIMT_EMU_BUILD
+    if (lane == 0 && getenv("RR_DUMP_SCHED")) {
+        for (int par = 0; par < 2; par++) { fprintf(stderr, "par %d nA %d:", par, m.n_slotsA[par]); for (int sl = 0; sl < m.n_slotsA[par]; sl++) fprintf(stderr, " [%d %d %d %d|%d]", T.schedA[par][sl][0], T.schedA[par][sl][1], T.schedA[par][sl][2], T.schedA[par][sl][3], T.wideA[par][sl]); fprintf(stderr, "\n"); }
+        fprintf(stderr, "nB %d:", m.n_slotsB); for (int sl = 0; sl < m.n_slotsB; sl++) fprintf(stderr, " [%d %d %d %d|%d]", T.schedB[sl][0], T.schedB[sl][1], T.schedB[sl][2], T.schedB[sl][3], T.wideB[sl]); fprintf(stderr, "\n");
+    }
+#endif
     {
-        const int n = m.n_rows;
         for (int c = 0; c < nc; c++) {                       // warm start (normal rows only)
-            const double a = m.app[c];
-            if (a != 0.0) dv += rows[(size_t)c * RR_ROW_STRIDE + 32 + lane] * a;
+            const double a = T.app[RID_NORMAL + c];
+            if (a != 0.0) dv += rows[(size_t)(RID_NORMAL + c) * RR_ROW_STRIDE + 2 * lane + 1] * a;
         }
         for (int it = 0; it < cf.solver_iterations; it++) {
             res = 0.0;
-            for (int j = 0; j < n; j++) {
-                int idx = (it & 1) ? j : n - 1 - j;
-                int d = m.r_dof[idx];
-                double sgn = m.r_sign[idx], inv = m.r_inv[idx];
-                double dvd = __shfl_sync(FULL, dv, d);
-                double app = m.r_app[idx];
-                double delta = m.r_rhs[idx] - (sgn * dvd) * inv;
-                double sum = app + delta;
-                double lo = m.r_lo[idx], hi = m.r_hi[idx];
+            const int par = it & 1;
+            // ---- phase A: single rows (joint limits + motors, normals, spinning, rolling), one slot at a time
+            const int nA = m.n_slotsA[par];
+            for (int slot = 0; slot < nA; slot++) {
+                const int rid = grp < 4 ? T.schedA[par][slot][g4] : RR_IDLE;
+                const int wrid = T.wideA[par][slot];
+                const bool act = rid != RR_IDLE;
+                const double* rowp = rows + (size_t)(act ? rid : 0) * RR_ROW_STRIDE;
+                if (slot + 2 < nA) {                          // the rows two slots ahead are on their way into L1
+                    const int nr = T.schedA[par][slot + 2][g4];
+                    if (grp < 4 && nr != RR_IDLE) RR_PREFETCH_L1(rows + (size_t)nr * RR_ROW_STRIDE + 2 * lane);
+                }
+                double J = 0.0, rr = 0.0, rhs = 0.0, inv = 0.0, c66 = 0.0, rinv = 0.0, c68 = 0.0, app = 0.0;
+                if (act) {
+                    const double2 jr = *reinterpret_cast<const double2*>(rowp + 2 * lane);
+                    J = jr.x; rr = jr.y; rhs = rowp[64]; inv = rowp[65]; c66 = rowp[66]; rinv = rowp[67]; c68 = rowp[68];
+                    app = T.app[rid];
+                }
+                // limits: joint rows carry [lo, hi]; normals [0, 1e10]; spinning / rolling +-(coefficient x normal impulse), solved
+                // only while that impulse is positive
+                double lo = c66, hi = c68; bool on = act;
+                if (act && rid >= RID_NORMAL) {
+                    if (rid < RID_SPIN) { lo = 0.0; hi = 1e10; }
+                    else {
+                        const int c = rid < RID_ROLL ? rid - RID_SPIN : (rid - RID_ROLL) >> 1;
+                        const double total = T.app[RID_NORMAL + c];
+                        on = total > 0.0;
+                        hi = c66 * total; lo = -hi;
+                    }
+                }
+                const int s0 = (grp == 0 && act && rid < RR_NC_ROWS) ? T.r_dof[rid] : (grp >= 1 && grp < 4 ? seg0 : 31);
+                const double pr = J * dv;
+                double s = group_sum6(pr, s0, s1, s2, s3, s4, s5);
+                if (wrid != RR_IDLE) {                        // (warp-uniform) the slot's wide row sums over all of its lanes
+                    const bool inw = act && rid == wrid;
+                    const double t = warp_sum(inw ? pr : 0.0);
+                    if (inw) s = t;
+                }
+                double delta = rhs - s * inv;
+                const double sum = app + delta;
                 if (sum < lo) { delta = lo - app; app = lo; }
                 else if (sum > hi) { delta = hi - app; app = hi; }
                 else app = sum;
-                __syncwarp();
-                if (lane == 0) m.r_app[idx] = app;
-                if (lane < RR_NDOF) dv += m.Minv[lane][d] * sgn * delta;
-                double r = delta * m.r_rinv[idx];
-                res = fmax(res, r * r);
-                __syncwarp();
-            }
-            if (m.simple) {
-                // Object-parallel sweep: every contact row touches exactly one free object, so the rows of different
-                // objects commute and the Gauss-Seidel order is preserved while lanes 11+6o..16+6o solve object o.
-                const int og = (lane >= 11 && lane < 29) ? (lane - 11) / 6 : -1;
-                const int ob0 = og >= 0 ? 11 + 6 * og : lane;
-                const int maxcnt = max(m.ocnt[0], max(m.ocnt[1], m.ocnt[2]));
-                for (int k = 0; k < maxcnt; k++) {               // normal rows
-                    const bool act = og >= 0 && k < m.ocnt[og];
-                    const int c = act ? m.olist[og][k] : 0;
-                    const double* rowp = rows + (size_t)c * RR_ROW_STRIDE;
-                    const double J = act ? rowp[lane] : 0.0, rr = act ? rowp[32 + lane] : 0.0;
-                    const double pr = J * dv;
-                    double sdot = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 6; j++) sdot += __shfl_sync(FULL, pr, ob0 + (og >= 0 ? j : 0));
-                    double app = 0.0, delta = 0.0;
-                    if (act) {
-                        app = m.app[c];
-                        delta = rowp[64] - sdot * rowp[65];
-                        const double sum = app + delta;
-                        if (sum < 0.0) { delta = 0.0 - app; app = 0.0; }
-                        else if (sum > 1e10) { delta = 1e10 - app; app = 1e10; }
-                        else app = sum;
-                        dv += rr * delta;
-                        const double r = delta * rowp[67];
-                        res = fmax(res, r * r);
-                    }
-                    __syncwarp();
-                    if (act && lane == ob0) m.app[c] = app;
-                    __syncwarp();
-                }
-                for (int k = 0; k < maxcnt; k++) {               // friction pairs with the implicit cone
-                    const bool act = og >= 0 && k < m.ocnt[og];
-                    const int c = act ? m.olist[og][k] : 0;
-                    const int r0 = RR_MAX_CONTACTS + 2 * c;
-                    const double* ra = rows + (size_t)r0 * RR_ROW_STRIDE; const double* rb = ra + RR_ROW_STRIDE;
-                    const double Ja = act ? ra[lane] : 0.0, rra = act ? ra[32 + lane] : 0.0, Jb = act ? rb[lane] : 0.0, rrb = act ? rb[32 + lane] : 0.0;
-                    const double pa = Ja * dv, pb = Jb * dv;
-                    double sa_ = 0.0, sb_ = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 6; j++) { const int src = ob0 + (og >= 0 ? j : 0); sa_ += __shfl_sync(FULL, pa, src); sb_ += __shfl_sync(FULL, pb, src); }
-                    double wa = 0.0, wb = 0.0;
-                    if (act) {
-                        const double lim = ra[66] * m.app[c];
-                        const double appa = m.app[r0], appb = m.app[r0 + 1];
-                        wa = appa + (ra[64] - sa_ * ra[65]); wb = appb + (rb[64] - sb_ * rb[65]);
-                        const double len2 = wa * wa + wb * wb;
-                        if (len2 > lim * lim) { const double sc = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= sc; wb *= sc; }
-                        const double da = wa - appa, db = wb - appb;
-                        dv += rra * da; dv += rrb * db;
-                        const double qa = da * ra[67], qb = db * rb[67];
-                        res = fmax(res, fmax(qa * qa, qb * qb));
-                    }
-                    __syncwarp();
-                    if (act && lane == ob0) { m.app[r0] = wa; m.app[r0 + 1] = wb; }
-                    __syncwarp();
-                }
-                res = warp_max(res);
-            } else {
-            for (int c = 0; c < nc; c++) {                   // normal rows
-                    const double* rowp = rows + (size_t)c * RR_ROW_STRIDE;
-                    const double J = rowp[lane], rr = rowp[32 + lane], rhs = rowp[64], inv = rowp[65];
-                    const double s = warp_sum(J * dv);
-                    double app = m.app[c];
-                    double delta = rhs - s * inv;
-                    const double sum = app + delta;
-                    if (sum < 0.0) { delta = 0.0 - app; app = 0.0; }
-                    else if (sum > 1e10) { delta = 1e10 - app; app = 1e10; }
-                    else app = sum;
-                    __syncwarp();
-                    if (lane == 0) m.app[c] = app;
+                if (on) {
                     dv += rr * delta;
-                    const double r = delta * rowp[67];
+                    const double r = delta * rinv;
                     res = fmax(res, r * r);
-                    __syncwarp();
+                    if (leader) T.app[rid] = app;
                 }
-                for (int c = 0; c < nc; c++) {                   // friction pairs with the implicit cone
-                    const int r0 = RR_MAX_CONTACTS + 2 * c;
-                    const double* ra = rows + (size_t)r0 * RR_ROW_STRIDE; const double* rb = ra + RR_ROW_STRIDE;
-                    const double Ja = ra[lane], rra = ra[32 + lane], Jb = rb[lane], rrb = rb[32 + lane];
-                    const double inva = ra[65], invb = rb[65];
-                    const double lim = ra[66] * m.app[c];
-                    double sa_, sb_; warp_sum2(Ja * dv, Jb * dv, sa_, sb_);
-                    const double appa = m.app[r0], appb = m.app[r0 + 1];
-                    double wa = appa + (ra[64] - sa_ * inva), wb = appb + (rb[64] - sb_ * invb);
-                    const double len2 = wa * wa + wb * wb;
-                    if (len2 > lim * lim) { const double sc = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= sc; wb *= sc; }
-                    const double da = wa - appa, db = wb - appb;
-                    __syncwarp();
-                    if (lane == 0) { m.app[r0] = wa; m.app[r0 + 1] = wb; }
-                    dv += rra * da; dv += rrb * db;
-                    const double qa = da * ra[67], qb = db * rb[67];
-                    res = fmax(res, fmax(qa * qa, qb * qb));
-                    __syncwarp();
-                }
+                __syncwarp();
             }
+            // ---- phase B: friction pairs with the implicit cone
+            const int nB = m.n_slotsB;
+            for (int slot = 0; slot < nB; slot++) {
+                const int c = grp < 4 ? T.schedB[slot][g4] : RR_IDLE;
+                const int wc = T.wideB[slot];
+                const bool act = c != RR_IDLE;
+                const int r0 = RID_FRIC + 2 * (act ? c : 0);
+                const double* ra = rows + (size_t)r0 * RR_ROW_STRIDE; const double* rb = ra + RR_ROW_STRIDE;
+                if (slot + 2 < nB) {
+                    const int nx = T.schedB[slot + 2][g4];
+                    if (grp < 4 && nx != RR_IDLE) { const double* pn = rows + (size_t)(RID_FRIC + 2 * nx) * RR_ROW_STRIDE + 2 * lane; RR_PREFETCH_L1(pn); RR_PREFETCH_L1(pn + RR_ROW_STRIDE); }
+                }
+                double Ja = 0.0, rra = 0.0, Jb = 0.0, rrb = 0.0, rhsa = 0.0, inva = 0.0, rhsb = 0.0, invb = 0.0, rinva = 0.0, rinvb = 0.0, lim = 0.0, appa = 0.0, appb = 0.0;
+                if (act) {
+                    const double2 ja = *reinterpret_cast<const double2*>(ra + 2 * lane), jb = *reinterpret_cast<const double2*>(rb + 2 * lane);
+                    Ja = ja.x; rra = ja.y; Jb = jb.x; rrb = jb.y;
+                    rhsa = ra[64]; inva = ra[65]; rinva = ra[67]; rhsb = rb[64]; invb = rb[65]; rinvb = rb[67];
+                    lim = ra[66] * T.app[RID_NORMAL + c];
+                    appa = T.app[r0]; appb = T.app[r0 + 1];
+                }
+                const int s0 = grp >= 1 && grp < 4 ? seg0 : 31;
+                const double pa = Ja * dv, pb = Jb * dv;
+                double sa_ = group_sum6(pa, s0, s1, s2, s3, s4, s5), sb_ = group_sum6(pb, s0, s1, s2, s3, s4, s5);
+                if (wc != RR_IDLE) {
+                    const bool inw = act && c == wc;
+                    double ta, tb; warp_sum2(inw ? pa : 0.0, inw ? pb : 0.0, ta, tb);
+                    if (inw) { sa_ = ta; sb_ = tb; }
+                }
+                double wa = appa + (rhsa - sa_ * inva), wb = appb + (rhsb - sb_ * invb);
+                const double len2 = wa * wa + wb * wb;
+                if (len2 > lim * lim) { const double sc = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= sc; wb *= sc; }
+                const double da = wa - appa, db = wb - appb;
+                if (act) {
+                    dv += rra * da; dv += rrb * db;
+                    const double qa = da * rinva, qb = db * rinvb;
+                    res = fmax(res, fmax(qa * qa, qb * qb));
+                    if (leader) { T.app[r0] = wa; T.app[r0 + 1] = wb; }
+                }
+                __syncwarp();
+            }
+            res = warp_max(res);
             iters = it + 1;
             if (res <= cf.residual_threshold) break;
         }
@@ -866,7 +962,7 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
             for (int k = 0; k < npt; k++) {
                 double* P = pts + ((size_t)slot * 4 + k) * RR_PT_STRIDE;
                 double imp = P[10];
-                if (!(P[9] > cf.contact_breaking) && c < RR_MAX_CONTACTS) { imp = m.app[c]; if (lane == 0) P[10] = imp; c++; }
+                if (!(P[9] > cf.contact_breaking) && c < RR_MAX_CONTACTS) { imp = T.app[RID_NORMAL + c]; if (lane == 0) P[10] = imp; c++; }
                 if (sens && sensor >= 0 && fabs(P[9]) < 0.1) { const double f = imp / dt; if (!any || f > best) { best = f; any = true; } }
             }
             if (any && sens && sensor >= 0 && best > touch[sensor]) touch[sensor] = best;
@@ -899,10 +995,12 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
         }
     }
     __syncwarp();
-    // ---- epilogue: final kinematics, state write-back, observations
-    fk_local(m, lane);
-    fk_sweep(m, lane, false);
-    store_frames(m, st, e, lane);
+    // ---- epilogue: final kinematics (in the memory of the solver tables, which are dead now), state write-back, observations
+    const int rows_live = m.n_rows_total;
+    __syncwarp();
+    fk_local(m.q, m.u.k, lane);
+    fk_sweep(m.u.k, lane, nullptr, nullptr);
+    store_frames(m.u.k, st, e, lane);
     if (lane < RR_NDOF) {
         st.q[(size_t)lane * N + e] = m.q[lane]; st.qd[(size_t)lane * N + e] = m.qd[lane];
         st.target[(size_t)lane * N + e] = m.target[lane];
@@ -918,23 +1016,24 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
     }
     if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
     if (lane == 0) {
-        st.diag[4 * e] = m.n_rows + 3 * nc; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (m.simple ? 2 : 0) | (fault << 2) | (cf.enable_contacts ? (st.col_flags[e] << 4) : 0);   // bit 0: contact cap hit, bit 1: object-parallel solver path, bits 2-3: faults, bit 4: manifold slots exhausted
+        st.diag[4 * e] = rows_live; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (simple ? 2 : 0) | (fault << 2) | (cf.enable_contacts ? (st.col_flags[e] << 4) : 0);   // bit 0: contact cap hit, bit 1: every contact is object-vs-static, bits 2-3: faults, bit 4: manifold slots exhausted
         st.timestep[e] += 1;
     }
 }
 
 // FK only (after reset / set_state): refresh link_frames
+struct FkMem { double q[RR_NDOF]; KinWs k; };
 __global__ void __launch_bounds__(WPB * 32) k_fk(DevState st) {
     RR_DYN_SMEM(smem_raw);
-    WarpMem& m = *reinterpret_cast<WarpMem*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
+    FkMem& m = *reinterpret_cast<FkMem*>(smem_raw + (size_t)(threadIdx.x >> 5) * sizeof(FkMem));
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (e >= st.N) return;
     if (lane < RR_NDOF) m.q[lane] = st.q[(size_t)lane * st.N + e];
     __syncwarp();
-    fk_local(m, lane);
-    fk_sweep(m, lane, false);
-    store_frames(m, st, e, lane);
+    fk_local(m.q, m.k, lane);
+    fk_sweep(m.k, lane, nullptr, nullptr);
+    store_frames(m.k, st, e, lane);
 }
 
 __global__ void k_reset(DevState st, const uint8_t* __restrict__ mask, int n_objects, int* __restrict__ man_hdr) {
@@ -1086,14 +1185,14 @@ int rrk_upload_constants(rr_ctx* ctx) {
     g_phys_owner[ctx->device & 63] = ctx;
     CK(cudaFuncSetAttribute(k_step_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
     CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * WPB)));
-    CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * WPB)));
+    CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FkMem) * WPB)));
     return 0;
 }
 static inline int nblk(int n, int b) { return (n + b - 1) / b; }
 
 static int launch_fk(rr_ctx* ctx, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    RR_LAUNCH(k_fk, nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s)(ctx->st);
+    RR_LAUNCH(k_fk, nblk(ctx->N, WPB), WPB * 32, sizeof(FkMem) * WPB, s)(ctx->st);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

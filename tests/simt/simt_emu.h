@@ -41,6 +41,8 @@ struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c 
 struct float4 { float x, y, z, w; } __attribute__((aligned(16)));
 struct int4 { int x, y, z, w; } __attribute__((aligned(16)));
 struct uint4 { unsigned x, y, z, w; } __attribute__((aligned(16)));
+struct double2 { double x, y; } __attribute__((aligned(16)));
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 struct ulonglong2 { unsigned long long x, y; } __attribute__((aligned(16)));
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }

@@ -260,36 +260,46 @@ def test_epa_depth_is_the_minimum_support_width(blob):
 
 
 def test_resting_contact_impulses_carry_the_weight(blob):
-    """Statics: the normal impulses of each object's contact points sum to m g dt per step, along +z."""
-    o = Oracle(3)
-    for _ in range(400):
-        o.step_sim_only()
-    a, b, d = o.contacts()                                  # [n][11]: worldA3 worldB3 normal3 dist impulse
-    for shape, m in zip(blob["obj.shape"], blob["obj.mass"]):
-        sel = (a == shape) | (b == shape)
-        assert 3 <= sel.sum() <= 4
-        assert set(b[sel].tolist()) <= set(blob["table.shape"].tolist())
-        assert np.allclose(d[sel, 6:9], [0, 0, 1], atol=1e-9)
-        assert abs(d[sel, 10].sum() - m * 9.81 * 0.005) < 1e-9 and (d[sel, 10] >= 0).all()
-    assert np.abs(o.get_state()[2][:, 7:13]).max() < 1e-4
+    """Statics: the normal impulses of each object's contact points sum to m g dt per step, along +z — to 1e-9 without the
+    torsional rows.  With them (the default) the tomato, which rests on two points of a round hull, keeps creeping at
+    ~5e-4 rad/s (the rolling rows hold against the penetration correction of the unequal contact depths; PGS settles on a
+    blend instead of converging), so there the balance is held to 1e-4 of the weight."""
+    for tf, tol, vmax in ((0, 1e-9, 1e-4), (1, 1e-4 * 9.81 * 0.005, 1e-3)):
+        o = Oracle(3, torsional_friction=tf)
+        for _ in range(400):
+            o.step_sim_only()
+        a, b, d = o.contacts()                                  # [n][11]: worldA3 worldB3 normal3 dist impulse
+        for shape, m in zip(blob["obj.shape"], blob["obj.mass"]):
+            sel = (a == shape) | (b == shape)
+            assert 2 <= sel.sum() <= 4
+            assert set(b[sel].tolist()) <= set(blob["table.shape"].tolist())
+            assert np.allclose(d[sel, 6:9], [0, 0, 1], atol=1e-9)
+            assert abs(d[sel, 10].sum() - m * 9.81 * 0.005) < tol * max(1.0, m) and (d[sel, 10] >= 0).all()
+        assert np.abs(o.get_state()[2][:, 7:13]).max() < vmax
 
 
-def test_motor_rows_converge_to_the_analytic_velocity():
-    """POSITION_CONTROL as a constraint row: the unsaturated solution is qd' = kp (target - q) / dt
-    + (1 - kd) qd for every motor, whatever the dynamics.  PGS on the oracle's rows (J, M^-1 J^T, rhs built from ABA
-    quantities) must converge to exactly that; with Bullet's 50 iterations it is still 0.5 rad/s away in this case,
-    which is the reference's behaviour if App. C-1 holds, not an error."""
-    rng = np.random.default_rng(0)
-    q0 = rng.uniform(-0.5, 0.5, 11); q0[7:] = [0.3, -0.2, 0.3, -0.2]
-    qd0 = rng.uniform(-0.5, 0.5, 11)
-    cmd = np.array([0.1, -0.2, 0.15, 0.3, -0.1, 0.2, 0.1, 0.4, 0.3])
-    err = {}
-    for iters in (50, 500, 5000):
-        o = Oracle(3, enable_contacts=0, solver_iterations=iters, residual_threshold=0.0)
-        o.set_state(q=q0, qd=qd0)
-        o.step(cmd)
-        q1, qd1, _ = o.get_state()
-        desired = 0.1 * (o.targets() - q0) / 0.005                       # kp = 0.1, kd = 1 (pybullet defaults)
-        err[iters] = np.abs(qd1 - desired).max()
-        assert np.allclose(q1, q0 + 0.005 * qd1, atol=1e-15)             # semi-implicit Euler
-    assert err[5000] < 1e-12 and err[500] < 1e-5 and 0.05 < err[50] < 1.0
+def test_spinning_friction_decelerates_at_the_torsional_rate(blob):
+    """Torsional friction rows (urdf/cube.urdf:6-7: spinning_friction 1e-4; Bullet adds one spinning row per manifold point when
+    the combined coefficient spin_obj * friction_table is > 0, limits +-(coefficient x normal impulse)).  A cube spinning flat
+    on the table is braked by lateral friction at its four contact points AND by the spinning rows; Coulomb friction does
+    not depend on the speed, so the difference between a run with and without the torsional rows is the torsional torque
+    alone: coefficient * m * g about the vertical axis, i.e. an extra angular deceleration of coefficient * m * g / I_zz."""
+    runs = {}
+    for tf in (1, 0):
+        o = Oracle(3, torsional_friction=tf)
+        for _ in range(150):
+            o.step(np.zeros(9))
+        q, qd, ob = o.get_state()
+        ob[0, 7:] = 0
+        ob[0, 12] = 25.0                                  # rad/s about z
+        o.set_state(q, qd, ob)
+        w = []
+        for _ in range(10):
+            o.step(np.zeros(9))
+            w.append(o.get_state()[2][0, 12])
+        runs[tf] = np.array(w)
+    assert runs[1][-1] > 10 and runs[0][-1] > 10          # both still spinning: friction is saturated throughout
+    extra = np.diff(runs[0] - runs[1])[1:8].mean()        # extra loss of angular velocity per step with the torsional rows
+    coef = blob["shape.spinning"][19] * blob["shape.friction"][17]      # cube x table_base
+    pred = coef * blob["obj.mass"][0] * 9.81 / blob["obj.inertia"][0][2] * 0.005
+    assert abs(extra - pred) < 0.1 * pred, (extra, pred)
