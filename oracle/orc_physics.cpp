@@ -411,7 +411,7 @@ static void build_rows(OrcEnv* e, Solver& S) {
         for (int k = 0; k < mf.n; k++) {
             OrcContactPoint& cp = mf.pt[k];
             if (cp.distance > cf.contact_breaking) continue;   /* getProcessingThreshold */
-            if (e->last_contacts >= 32) continue;              /* solver row capacity shared with the CUDA kernel */
+            if (e->last_contacts >= 48) continue;              /* solver row capacity shared with the CUDA kernel (RR_MAX_CONTACTS) */
             e->last_contacts++;
             Row r; row_init(r); r.kind = 1; r.cp = &cp;
             fill_side(e, r, mf.shapeA, cp.worldA, cp.normalB, +1.0, false);

@@ -276,8 +276,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
         alloc((void**)&st.man_hdr[k], N * RR_MAX_MANIFOLDS * 2 * 4);
         alloc((void**)&st.man_pts[k], N * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE * 8);
     }
-    alloc((void**)&st.rows, N * RR_MAX_ROWS * RR_ROW_STRIDE * 8);
-    alloc((void**)&st.handoff, N * RR_HANDOFF_DOUBLES * 8);
+    alloc((void**)&st.handoff, N * RR_IMG_DOUBLES * 8);
     if (e != cudaSuccess) { ctx->err = std::string("rr_create: device allocation failed: ") + cudaGetErrorString(e); return fail(-1); }
     ctx->man_parity = 0;
     if (rrk_reset(ctx, nullptr, 0) != 0) return fail(-1);
@@ -294,7 +293,7 @@ int rr_destroy(rr_ctx* ctx) {
     rrk_physics_unbind(ctx); rrk_collide_unbind(ctx); rrk_render_unbind(ctx);
     DevState& st = ctx->st;
     void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.col_flags, st.timestep,
-                    st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.rows, st.handoff,
+                    st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.handoff,
                     ctx->d_cmd, ctx->d_mask, ctx->d_joint, ctx->d_touch, ctx->d_objpose, ctx->d_rgb, ctx->d_depth, ctx->d_seg,
                     ctx->d_tris, ctx->d_tex, ctx->d_hull_verts, ctx->d_rec_scratch, ctx->d_list_scratch, ctx->d_work_counter, ctx->d_tri_shape, ctx->d_planes, ctx->d_cull_scratch,
                     ctx->d_static_keys, ctx->d_static_img};

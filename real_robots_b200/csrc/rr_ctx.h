@@ -22,15 +22,14 @@
 #define RR_H RR_EYE_H
 #define RR_FRAME_STRIDE (RR_NSHAPES * 12)
 #define RR_MAX_TEX 16
-#define RR_HANDOFF_DOUBLES 800   // >= sizeof(SolveMem) / 8 (static_assert in rr_physics.cu)
+#define RR_IMG_DOUBLES 16384     // doubles per env of the solver image in global memory (head + slot schedule + row blocks; static_assert in rr_physics.cu)
 #define RR_MAT_STRIDE 44       // floats per (env, shape) in render_mats
 #define RR_MAX_PAIRS 96          // candidate collision pairs (92 for 3 objects)
 #define RR_MAX_MANIFOLDS RR_MAX_MANIFOLDS_PER_ENV      // cached non-empty manifolds per env (<= 32: one lane per slot)
 #define RR_PT_STRIDE 17          // doubles per contact point: localA3 localB3 normalB3 dist impulse worldA3 worldB3
 #define RR_MAX_CONTACTS 48       // contact points per env that get solver rows
-#define RR_ROW_STRIDE 72         // doubles per solver row in the global row scratch: (J, M^-1 J^T) per owner lane [32][2], then 8 scalars
 // Solver row ids.  Single rows (phase A of an iteration): joint limits + motors, contact normals, spinning, rolling; then the
-// rows of the friction pairs (phase B, addressed by contact index).  Single-row ids fit one byte (0xff = idle).
+// friction pairs (phase B, addressed by contact index).
 #define RR_NC_ROWS 24                                        // <= 11 limit rows + 11 motor rows
 #define RID_NORMAL RR_NC_ROWS                                // + c
 #define RID_SPIN (RID_NORMAL + RR_MAX_CONTACTS)              // + c
@@ -89,8 +88,7 @@ struct DevState {
     long long* timestep;  // [N]
     int*    man_hdr[2];   // [N][RR_MAX_MANIFOLDS][2]  (pair index or -1, point count), double buffered
     double* man_pts[2];   // [N][RR_MAX_MANIFOLDS][4][RR_PT_STRIDE]
-    double* rows;         // [N][RR_MAX_ROWS][RR_ROW_STRIDE] solver row scratch (only the rows of live constraints are touched)
-    double* handoff;      // [N][RR_HANDOFF_DOUBLES] per-env solver state passed from k_step_dyn to k_step_solve
+    double* handoff;      // [N][RR_IMG_DOUBLES] per-env solver image passed from k_step_dyn to k_step_solve (only its used head is touched)
 };
 
 struct rr_ctx {

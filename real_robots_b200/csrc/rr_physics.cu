@@ -16,9 +16,6 @@
 __constant__ RobotConst c_robot;
 
 #define WPB 4                 // envs (warps) per block
-#ifndef SOLVE_MIN_BLOCKS
-#define SOLVE_MIN_BLOCKS 6
-#endif
 #define FULL 0xffffffffu
 
 // Kinematics workspace (both kernels)
@@ -30,29 +27,36 @@ struct KinWs {
 };
 #define RR_SLOTS_A RR_ROWS_A
 #define RR_SLOTS_B RR_MAX_CONTACTS
-// What k_step_dyn hands to k_step_solve through DevState::handoff: the state after the unconstrained update, the applied
-// impulses (warm start) and the SLOT SCHEDULE of the Gauss-Seidel sweep.  The lanes of a warp form four groups — arm
-// dofs (lanes 0..10) and the three free bodies (lanes 11+6o .. 16+6o) — and a constraint row only touches the groups of the
-// bodies it couples, so rows of disjoint groups commute.  schedA[p][slot][g] names the row group g resolves in that slot of
-// an iteration of parity p (the joint rows run backwards on even iterations), in the order of the sequential sweep
-// restricted to that group; rows of different groups in one slot are resolved by the same instructions at the same time.
-// A row that needs a reduction wider than one group's own (an arm contact row, or a row coupling two groups) is the slot's
-// single `wide` row.  schedB does the same for the friction pairs (entries are contact indices).
-struct SolveTables {
-    unsigned char schedA[2][RR_SLOTS_A][4];
-    unsigned char wideA[2][RR_SLOTS_A];
-    unsigned char schedB[RR_SLOTS_B][4];
-    unsigned char wideB[RR_SLOTS_B];
-    unsigned char r_dof[RR_NC_ROWS];                    // dof of a limit / motor row
-    double app[RR_MAX_ROWS];                            // applied impulses by row id
-};
-struct SolveMem {
+// What k_step_dyn hands to k_step_solve through DevState::handoff — the solver IMAGE of an env: a fixed head (state after
+// the unconstrained update), the SLOT SCHEDULE of one Gauss-Seidel iteration, and the constraint rows as compact BLOCKS.
+//
+// The lanes of a warp form four groups — the arm dofs (lanes 0..10) and the three free bodies (lanes 11+6o .. 16+6o) — and a
+// constraint row only touches the groups of the bodies it couples, so rows of disjoint groups commute.  A row is stored
+// once per group it touches, as a block: (J, M^-1 J^T) per lane of the group, then rhs, 1/d, d, lo-or-coefficient, hi, applied
+// impulse.  The schedule says, per slot and group, which block that group resolves (in the order of the sequential sweep
+// restricted to the group; the joint rows run backwards on even iterations, hence two schedules for the single rows); the
+// groups of one slot execute the same instructions at the same time.  A row that needs a reduction wider than one group's
+// own shuffles (an arm contact row, or a row coupling two groups) is the slot's single `wide` row.  Friction pairs (the
+// implicit cone) have their own slots after the single rows.  The solver keeps the image in shared memory (the part that
+// does not fit stays in global memory and is addressed there).
+#define RR_ARM_BLK 28            // doubles: 11 x (J, rr), rhs, inv, rinv, lo | coef, hi, app
+#define RR_OBJ_BLK 18            // doubles:  6 x (J, rr), rhs, inv, rinv, lo | coef, hi, app
+#define ENT_IDLE 0xffffffffu     // schedule entry: bits 0..14 block offset (16-byte units, relative to the first block), bit 15 wide,
+#define ENT_NORMAL 0xfffeu       // bits 16..31: 0xfffe normal row, 0xffe0 | dof joint row, else offset of the same group's normal block
+#define ENT_JOINT 0xffe0u
+struct SolveHead {
     double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
     double objreg[RR_MAX_OBJECTS][13];                  // free bodies after the unconstrained update (pos3 quat4 lin3 ang3)
     int n_slotsA[2], n_slotsB;
-    int n_nc, nc, overflow, fault, simple, n_rows_total, pad_;   // fault bit 0: a non-finite joint command arrived this step
-    union { SolveTables t; KinWs k; } u;                // the epilogue's kinematics reuse the tables' memory once the sweep is over
+    int n_nc, nc, overflow, fault, simple, n_rows_total, n_blk_doubles, pad_[2];   // fault bit 0: a non-finite joint command arrived this step
+    unsigned short nrm_rel[RR_MAX_CONTACTS];            // per contact: its normal row's first block (bit 15: an arm block), for the impulse write-back
 };
+#define HEAD_DOUBLES ((int)(sizeof(SolveHead) / 8))
+#define GSCHED_A(par) (4 * RR_SLOTS_A * (par))                          // word offsets of the schedules in the global image (fixed places)
+#define GSCHED_B (8 * RR_SLOTS_A)
+#define GBLK_BASE (HEAD_DOUBLES + (8 * RR_SLOTS_A + 4 * RR_SLOTS_B) / 2)   // first block, in doubles
+static_assert(sizeof(SolveHead) % 16 == 0, "the schedule words and blocks must stay 16-byte aligned");
+static_assert(GBLK_BASE % 2 == 0 && GBLK_BASE + RR_NC_ROWS * RR_ARM_BLK + RR_MAX_CONTACTS * 6 * (RR_ARM_BLK + RR_OBJ_BLK) <= RR_IMG_DOUBLES, "solver image too small");
 // k_step_dyn's own workspace
 struct WarpMem {
     double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
@@ -63,6 +67,7 @@ struct WarpMem {
     int n_rows;
     int fault;
     unsigned char c_grp[RR_MAX_CONTACTS], c_flags[RR_MAX_CONTACTS];   // per contact: group mask (bit 0 arm, bit 1+o object o); bit 0 spinning row, bit 1 rolling rows, bit 2 wide
+    unsigned short c_base[RR_MAX_CONTACTS];                           // first block of the contact (16-byte units)
     KinWs k;
     double v[RR_NL][6];       // spatial velocity (ang, lin) in link frame
     double c[RR_NL][6];       // Coriolis acceleration
@@ -78,11 +83,6 @@ struct WarpMem {
     double opos[RR_MAX_OBJECTS][3], ovel[RR_MAX_OBJECTS][6], oIinv[RR_MAX_OBJECTS][9], oinvm[RR_MAX_OBJECTS];
     double Jtmp[32];
 };
-#define SOLVE_SMEM_BYTES (sizeof(SolveMem))
-static_assert(sizeof(SolveMem) % 8 == 0 && sizeof(SolveMem) / 8 <= RR_HANDOFF_DOUBLES, "handoff buffer too small");
-static_assert(sizeof(SolveTables) >= sizeof(KinWs), "the kinematics workspace must fit inside the tables it aliases");
-static_assert(RR_ROWS_A < RR_IDLE, "single-row ids must fit one byte");
-
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
@@ -457,14 +457,25 @@ __device__ __forceinline__ void store_frames(const KinWs& m, const DevState& st,
 __device__ __forceinline__ int lane_group(int lane) { return lane < RR_NDOF ? 0 : (lane < 29 ? 1 + (lane - RR_NDOF) / 6 : 4); }
 
 // lane 0: place one row (or friction pair) of group mask gm into the earliest slot all its groups are free in; a wide row also
-// needs a slot without another wide row.  sched[slot][g] / wide[slot] are bytes in the handoff image (global memory).
-__device__ __forceinline__ void sched_place(unsigned char (*sched)[4], unsigned char* wide, int* cur, unsigned int* wide_used, int gm, bool is_wide, int id) {
+// needs a slot without another wide row.  ent[g] = schedule entry of group g for this row; sched = words of the schedule.
+__device__ __forceinline__ void sched_place(unsigned int* sched, int* cur, unsigned int* wide_used, int gm, bool is_wide, const unsigned int* ent) {
     int slot = 0;
 #pragma unroll
     for (int g = 0; g < 4; g++) if ((gm >> g) & 1) slot = max(slot, cur[g]);
-    if (is_wide) { while ((wide_used[slot >> 5] >> (slot & 31)) & 1u) slot++; wide_used[slot >> 5] |= 1u << (slot & 31); wide[slot] = (unsigned char)id; }
+    if (is_wide) { while ((wide_used[slot >> 5] >> (slot & 31)) & 1u) slot++; wide_used[slot >> 5] |= 1u << (slot & 31); }
 #pragma unroll
-    for (int g = 0; g < 4; g++) if ((gm >> g) & 1) { sched[slot][g] = (unsigned char)id; cur[g] = slot + 1; }
+    for (int g = 0; g < 4; g++) if ((gm >> g) & 1) { sched[4 * slot + g] = ent[g] | (is_wide ? 0x8000u : 0u); cur[g] = slot + 1; }
+}
+// entries of contact c's row `rowidx` (0 normal, 1 2 friction, 3.. spinning / rolling) for the groups of gm; blocks of one contact
+// are laid out group by group, `nr` rows each
+__device__ __forceinline__ void contact_entries(unsigned int* ent, int gm, int base16, int nr, int rowidx) {
+    int off = base16;        // 16-byte units
+#pragma unroll
+    for (int g = 0; g < 4; g++) if ((gm >> g) & 1) {
+        const int sz = (g == 0 ? RR_ARM_BLK : RR_OBJ_BLK) / 2;
+        ent[g] = (unsigned int)(off + rowidx * sz) | ((rowidx == 0 ? ENT_NORMAL : (unsigned int)off) << 16);
+        off += nr * sz;
+    }
 }
 
 // One env step is two kernels.  k_step_dyn: action prologue, kinematics, ABA, M^-1, constraint rows -> the global row scratch,
@@ -543,8 +554,15 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
     if (has_obj) obj_free_update(ob, lane, cf);
     aba_minv(m, lane);
 
-    SolveMem* hand = reinterpret_cast<SolveMem*>(st.handoff + (size_t)e * RR_HANDOFF_DOUBLES);      // the solver's image of this env
-    double* rows = st.rows + (size_t)e * RR_MAX_ROWS * RR_ROW_STRIDE;
+    double* img = st.handoff + (size_t)e * RR_IMG_DOUBLES;                      // the solver image of this env
+    SolveHead* hand = reinterpret_cast<SolveHead*>(img);
+    unsigned int* gsched = reinterpret_cast<unsigned int*>(img + HEAD_DOUBLES);
+    double* gblk = img + GBLK_BASE;
+    const int mygrp = lane_group(lane);
+    const int seg0 = mygrp == 0 ? 0 : (mygrp < 4 ? 11 + 6 * (mygrp - 1) : 31);
+    const int myk2 = 2 * (lane - seg0);                                          // offset of this lane's (J, rr) pair inside a block of its group
+    const int mysc = mygrp == 0 ? 2 * RR_NDOF : 12;                              // offset of the scalars
+    const bool leader = mygrp < 4 && lane == seg0;
     // ---- constraint rows: joint limits (link order) then motors (link order)
     if (lane == 0) {
         int n = 0;
@@ -578,24 +596,24 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
         m.n_rows = n;
     }
     __syncwarp();
-    // ... written out as ordinary rows: J = sgn e_d, M^-1 J^T = sgn * column d of M^-1
+    // ... written out as arm blocks: J = sgn e_d, M^-1 J^T = sgn * column d of M^-1
     const int n_nc = m.n_rows;
     for (int idx = 0; idx < n_nc; idx++) {
-        double* rowp = rows + (size_t)idx * RR_ROW_STRIDE;
+        double* blk = gblk + idx * RR_ARM_BLK;
         const int d = m.r_dof[idx]; const double sgn = m.r_sign[idx];
-        if (lane < RR_NDOF) { rowp[2 * lane] = lane == d ? sgn : 0.0; rowp[2 * lane + 1] = m.Minv[lane][d] * sgn; }
-        if (lane == 0) { rowp[64] = m.r_rhs[idx]; rowp[65] = m.r_inv[idx]; rowp[66] = m.r_lo[idx]; rowp[67] = m.r_rinv[idx]; rowp[68] = m.r_hi[idx]; hand->u.t.r_dof[idx] = (unsigned char)d; hand->u.t.app[idx] = 0.0; }
+        if (lane < RR_NDOF) { blk[2 * lane] = lane == d ? sgn : 0.0; blk[2 * lane + 1] = m.Minv[lane][d] * sgn; }
+        if (lane == 0) { blk[22] = m.r_rhs[idx]; blk[23] = m.r_inv[idx]; blk[24] = m.r_rinv[idx]; blk[25] = m.r_lo[idx]; blk[26] = m.r_hi[idx]; blk[27] = 0.0; }
     }
+    int blk_top = n_nc * RR_ARM_BLK;               // doubles used by the blocks so far
     // ---- contact rows (btMultiBodyConstraintSolver::convertMultiBodyContact): per manifold point a normal row, two friction
     //      directions and, where the combined coefficients are > 0, a spinning row (about the normal) and two rolling rows (about
     //      the friction directions).  A row is a 29-vector in "owner" layout: lanes 0..10 = arm dofs, lane 11+6o+k = component k
-    //      (ang xyz, lin xyz) of object o.  (J, M^-1 J^T) pairs go to the global row scratch, the applied impulses to the handoff.
+    //      (ang xyz, lin xyz) of object o; each group the row touches gets a block with its lanes' (J, M^-1 J^T) pairs.
     const double vel = (lane < RR_NDOF) ? m.qd[lane] : 0.0;
     double ovel = 0.0;      // object velocity component owned by this lane (lanes 11..28)
-    int nc = 0, overflow = 0, simple = 1;
+    int nc = 0, overflow = 0, simple = 1, n_rows_total = n_nc;
     int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
     double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
-    const int mygrp = lane_group(lane);
     if (cf.enable_contacts) {
         if (lane < RR_NDOF) {
             const int i = c_robot.link_of_dof[lane];
@@ -636,7 +654,12 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
             double spin = fmax(-10.0, fmin(10.0, c_robot.shape_spinning[sa] * fb + c_robot.shape_spinning[sb] * fa));
             if (!cf.torsional_friction) { roll = 0.0; spin = 0.0; }
             const int gm = (armA ? 1 : 0) | (oA >= 0 ? 2 << oA : 0) | (oB >= 0 ? 2 << oB : 0);
-            const bool in_row = (gm >> mygrp) & 1;               // (group 4 = idle lanes: never)
+            const bool in_row = mygrp < 4 && ((gm >> mygrp) & 1);
+            const int nr = 3 + (spin > 0 ? 1 : 0) + (roll > 0 ? 2 : 0);          // rows of each point of this manifold
+            int csize = 0, mygoff = 0;                                           // doubles per point; offset of this lane's group inside it
+#pragma unroll
+            for (int g = 0; g < 4; g++) if ((gm >> g) & 1) { if (g == mygrp) mygoff = csize; csize += nr * (g == 0 ? RR_ARM_BLK : RR_OBJ_BLK); }
+            const int mysz = mygrp == 0 ? RR_ARM_BLK : RR_OBJ_BLK;
             for (int k = 0; k < npt; k++) {
                 const double* P = pts + ((size_t)slot * 4 + k) * RR_PT_STRIDE;
                 const double dist = P[9];
@@ -658,6 +681,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
                     for (int a = 0; a < 3; a++) { t1[a] *= l1; t2[a] *= l2; }
                 }
                 // di: 0 normal, 1 2 friction, 3 spinning (angular, about the normal), 4 5 rolling (angular, about t1 / t2)
+                int rowidx = 0;
                 for (int di = 0; di < 6; di++) {
                     if (di == 3 && !(spin > 0)) continue;
                     if (di >= 4 && !(roll > 0)) break;
@@ -700,7 +724,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
                     const double den = warp_sum(J * rr);
                     const double relv = warp_sum(J * (lane < RR_NDOF ? vel : ovel));
                     const double inv = den > 0 ? 1.0 / den : 0.0;
-                    double rhs, app0 = 0.0, coef = mu;
+                    double rhs, app0 = 0.0, lo = 0.0, hi = 1e10;         // normal rows: [0, 1e10]; the others: lo = the coefficient, limits follow the normal impulse
                     if (di == 0) {
                         double restitution = (fabs(relv) < cf.restitution_threshold) ? 0.0 : rest * -relv;
                         if (restitution <= 0) restitution = 0;
@@ -710,58 +734,77 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
                         if (pen > 0) velocity -= pen / dt; else positional = -pen * erp / dt;
                         rhs = (positional + velocity) * inv;
                         app0 = P[10] * cf.warmstart;
-                    } else rhs = (0.0 - relv) * inv;
-                    if (di == 3) coef = spin; else if (di >= 4) coef = roll;
-                    const int ri = di == 0 ? RID_NORMAL + nc : (di < 3 ? RID_FRIC + 2 * nc + (di - 1) : (di == 3 ? RID_SPIN + nc : RID_ROLL + 2 * nc + (di - 4)));
-                    double* rowp = rows + (size_t)ri * RR_ROW_STRIDE;
-                    if (in_row || di == 0) { rowp[2 * lane] = J; rowp[2 * lane + 1] = rr; }      // (normal rows: every lane, the warm start reads them all)
-                    if (lane == 0) { rowp[64] = rhs; rowp[65] = inv; rowp[66] = coef; rowp[67] = inv != 0.0 ? 1.0 / inv : 0.0; hand->u.t.app[ri] = app0; }
+                    } else { rhs = (0.0 - relv) * inv; lo = di < 3 ? mu : (di == 3 ? spin : roll); hi = 0.0; }
+                    if (in_row) {
+                        double* blk = gblk + blk_top + mygoff + rowidx * mysz;
+                        blk[myk2] = J; blk[myk2 + 1] = rr;
+                        if (leader) { blk[mysc] = rhs; blk[mysc + 1] = inv; blk[mysc + 2] = inv != 0.0 ? 1.0 / inv : 0.0; blk[mysc + 3] = lo; blk[mysc + 4] = hi; blk[mysc + 5] = app0; }
+                    }
+                    rowidx++;
                     __syncwarp();
                 }
                 if (lane == 0) {
-                    const bool wide = armA || (gm & (gm - 1)) != 0;
+                    const bool wide = (gm & (gm - 1)) != 0;       // the row couples two groups: their lanes meet in one slot
                     m.c_grp[nc] = (unsigned char)gm;
                     m.c_flags[nc] = (unsigned char)((spin > 0 ? 1 : 0) | (roll > 0 ? 2 : 0) | (wide ? 4 : 0));
+                    m.c_base[nc] = (unsigned short)(blk_top / 2);
+                    hand->nrm_rel[nc] = (unsigned short)((blk_top / 2) | (armA ? 0x8000 : 0));
                 }
                 if (armA || oA < 0 || oB >= 0) simple = 0;
+                blk_top += csize;
+                n_rows_total += nr;
                 nc++;
             }
         }
     }
     __syncwarp();
-    // ---- slot schedule of one Gauss-Seidel iteration (see SolveTables), for both parities of the joint-row order
-    const int n_single = n_nc + 4 * nc;          // upper bound of the slots of phase A
-    for (int par = 0; par < 2; par++) {
-        unsigned char* sa = &hand->u.t.schedA[par][0][0];
-        for (int k = lane; k < n_single * 4; k += 32) sa[k] = RR_IDLE;
-        for (int k = lane; k < n_single; k += 32) hand->u.t.wideA[par][k] = RR_IDLE;
-    }
-    for (int k = lane; k < nc * 4; k += 32) (&hand->u.t.schedB[0][0])[k] = RR_IDLE;
-    for (int k = lane; k < nc; k += 32) hand->u.t.wideB[k] = RR_IDLE;
+    // ---- slot schedule of one Gauss-Seidel iteration (see SolveHead), for both parities of the joint-row order
+    const int n_single = n_nc + 4 * nc;          // upper bound of the slots of the single rows
+    for (int k = lane; k < n_single * 4; k += 32) { gsched[GSCHED_A(0) + k] = ENT_IDLE; gsched[GSCHED_A(1) + k] = ENT_IDLE; }
+    for (int k = lane; k < nc * 4; k += 32) gsched[GSCHED_B + k] = ENT_IDLE;
     __syncwarp();
     if (lane == 0) {
+        unsigned int ent[4] = {0u, 0u, 0u, 0u};
         for (int par = 0; par < 2; par++) {
             int cur[4] = {0, 0, 0, 0};
             unsigned int wide_used[(RR_SLOTS_A + 31) / 32];
             for (int k = 0; k < (RR_SLOTS_A + 31) / 32; k++) wide_used[k] = 0u;
-            unsigned char (*sched)[4] = hand->u.t.schedA[par]; unsigned char* wide = hand->u.t.wideA[par];
-            for (int j = 0; j < n_nc; j++) sched_place(sched, wide, cur, wide_used, 1, false, par ? j : n_nc - 1 - j);     // it & 1 ? j : n - 1 - j
-            for (int c = 0; c < nc; c++) sched_place(sched, wide, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, RID_NORMAL + c);
-            for (int c = 0; c < nc; c++) if (m.c_flags[c] & 1) sched_place(sched, wide, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, RID_SPIN + c);
+            unsigned int* sched = gsched + GSCHED_A(par);
+            for (int j = 0; j < n_nc; j++) {
+                const int idx = par ? j : n_nc - 1 - j;                               // it & 1 ? j : n - 1 - j
+                ent[0] = (unsigned int)(idx * (RR_ARM_BLK / 2)) | ((ENT_JOINT | (unsigned int)m.r_dof[idx]) << 16);
+                sched_place(sched, cur, wide_used, 1, false, ent);
+            }
+            for (int c = 0; c < nc; c++) {
+                const int nr = 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
+                contact_entries(ent, m.c_grp[c], m.c_base[c], nr, 0);
+                sched_place(sched, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent);
+            }
+            for (int c = 0; c < nc; c++) if (m.c_flags[c] & 1) {
+                const int nr = 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
+                contact_entries(ent, m.c_grp[c], m.c_base[c], nr, 3);
+                sched_place(sched, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent);
+            }
             for (int c = 0; c < nc; c++) if (m.c_flags[c] & 2) {
-                sched_place(sched, wide, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, RID_ROLL + 2 * c);
-                sched_place(sched, wide, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, RID_ROLL + 2 * c + 1);
+                const int nr = 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
+                for (int r2 = 0; r2 < 2; r2++) {
+                    contact_entries(ent, m.c_grp[c], m.c_base[c], nr, 3 + (m.c_flags[c] & 1) + r2);
+                    sched_place(sched, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent);
+                }
             }
             hand->n_slotsA[par] = max(max(cur[0], cur[1]), max(cur[2], cur[3]));
         }
         int cur[4] = {0, 0, 0, 0};
         unsigned int wide_used[(RR_SLOTS_B + 31) / 32];
         for (int k = 0; k < (RR_SLOTS_B + 31) / 32; k++) wide_used[k] = 0u;
-        for (int c = 0; c < nc; c++) sched_place(hand->u.t.schedB, hand->u.t.wideB, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, c);
+        for (int c = 0; c < nc; c++) {
+            const int nr = 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
+            contact_entries(ent, m.c_grp[c], m.c_base[c], nr, 1);                     // first friction row; the second follows it
+            sched_place(gsched + GSCHED_B, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent);
+        }
         hand->n_slotsB = max(max(cur[0], cur[1]), max(cur[2], cur[3]));
-        int total = n_nc;
-        for (int c = 0; c < nc; c++) total += 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
-        hand->n_nc = n_nc; hand->nc = nc; hand->overflow = overflow; hand->fault = m.fault; hand->simple = simple; hand->n_rows_total = total;
+        hand->n_nc = n_nc; hand->nc = nc; hand->overflow = overflow; hand->fault = m.fault; hand->simple = simple;
+        hand->n_rows_total = n_rows_total; hand->n_blk_doubles = blk_top;
     }
     // ---- hand the state over
     if (lane < RR_NDOF) { hand->q[lane] = m.q[lane]; hand->qd[lane] = m.qd[lane]; hand->target[lane] = m.target[lane]; }
@@ -773,251 +816,341 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
     }
 }
 
-#ifdef RR_SIMT_EMU_BUILD
-#define RR_PREFETCH_L1(p)
-#else
-#define RR_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
+// ------------------------------------------------------------------------------------------- the solver kernel
+// One warp solves SOLVE_E envs at once: lane 4 e' + g resolves the rows of group g (0 = arm, 1 + o = free body o) of the
+// warp's e'-th env, walking that group's column of the slot schedule and reading its blocks from shared memory.  The work
+// of a row is a handful of scalars per group (a dot product over the group's 11 or 6 velocity components, a clamp, an
+// axpy), so the lanes are spent on independent (env, group) streams rather than on the components of one row: ~10 warp
+// instructions per env and slot instead of ~100.  Rows coupling two groups of an env meet in one slot (the schedule
+// guarantees it, at most one such row per env and slot) and exchange their partial sums with one shuffle.
+#ifndef SOLVE_E
+#define SOLVE_E 7                // envs per warp (lanes 4 e' .. 4 e' + 3)
 #endif
+#ifndef SOLVE_ENV_CAP
+#define SOLVE_ENV_CAP 1984       // doubles of (schedule + blocks) per env in shared memory: 7 x 15.5 KB + scratch = 2 blocks per SM
+#endif
+struct SolveScratch { SolveHead head; KinWs kin; double dv[32]; };           // per-env epilogue workspace (one env at a time)
+#define SOLVE_SMEM_BYTES ((size_t)SOLVE_E * SOLVE_ENV_CAP * 8 + sizeof(SolveScratch))
 
-// sum of the six products of a lane's own group (an arm lane of a joint row: the product of the row's dof), all lanes at once
-__device__ __forceinline__ double group_sum6(double pr, int s0, int s1, int s2, int s3, int s4, int s5) {
-    const double a = __shfl_sync(FULL, pr, s0), b = __shfl_sync(FULL, pr, s1), c = __shfl_sync(FULL, pr, s2);
-    const double d = __shfl_sync(FULL, pr, s3), e = __shfl_sync(FULL, pr, s4), f = __shfl_sync(FULL, pr, s5);
-    return ((a + b) + (c + d)) + (e + f);
-}
-
-__global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
-    RR_DYN_SMEM(smem_raw);
-    SolveMem& m = *reinterpret_cast<SolveMem*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
+// The Gauss-Seidel sweeps of the warp's envs.  FAST: every schedule and block of every env of the warp lives in shared memory.
+template <bool FAST>
+__device__ __forceinline__ void pgs_sweep(const bool valid, const int g, double* const sbase, double* const gblk, const int sblk_off, const int n_blk_smem,
+                                          const unsigned int* gsched, const bool sched_smem, const int nA0, const int nA1, const int nB,
+                                          const rr_config& cf, double (&dv)[RR_NDOF], int& iters_out) {
     const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
-    if (e >= st.N) return;
-    const int N = st.N;
-    const double dt = cf.dt;
-    {
-        double* dst = reinterpret_cast<double*>(&m);
-        const double* src = st.handoff + (size_t)e * RR_HANDOFF_DOUBLES;
-        for (int k = lane; k < (int)(sizeof(SolveMem) / 8); k += 32) dst[k] = src[k];
-    }
-    __syncwarp();
-    ObjReg ob;
-    const bool has_obj = lane < n_objects;
-    if (has_obj) {
+    const int dim = g == 0 ? RR_NDOF : 6;                          // velocity components of the own group
+    const int sc = g == 0 ? 2 * RR_NDOF : 12;                      // offset of the scalars inside a block
+    const int sz16 = (g == 0 ? RR_ARM_BLK : RR_OBJ_BLK) / 2;
+    const int lim16 = (n_blk_smem - RR_ARM_BLK) / 2;
+    double* const sblk = sbase + sblk_off;
+    auto BLK = [&](unsigned int off16) -> double* {
+        if (FAST) return sblk + 2 * (int)off16;
+        return (int)off16 <= lim16 ? sblk + 2 * (int)off16 : gblk + 2 * (int)off16;
+    };
+    const unsigned int* ssched = reinterpret_cast<const unsigned int*>(sbase);
+    auto ENT = [&](int base_words, int gbase_words, int slot) -> unsigned int {
+        if (FAST || sched_smem) return ssched[base_words + 4 * slot + g];
+        return gsched[gbase_words + 4 * slot + g];
+    };
+    const int quad = lane & ~3;
 #pragma unroll
-        for (int k = 0; k < 3; k++) { ob.pos[k] = m.objreg[lane][k]; ob.lin[k] = m.objreg[lane][7 + k]; ob.ang[k] = m.objreg[lane][10 + k]; }
-#pragma unroll
-        for (int k = 0; k < 4; k++) ob.quat[k] = m.objreg[lane][3 + k];
-    }
-    const int nc = m.nc, overflow = m.overflow, n_nc = m.n_nc, simple = m.simple;
-    int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
-    double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
-    const double* rows = st.rows + (size_t)e * RR_MAX_ROWS * RR_ROW_STRIDE;
-    SolveTables& T = m.u.t;
-    // ---- projected Gauss-Seidel.  dv in owner layout: lane k < 11 owns the arm dof k, lane 11+6o+c the object component.
-    const int grp = lane_group(lane);
-    const int g4 = grp < 4 ? grp : 0;                          // idle lanes read group 0's schedule entry and ignore it
-    const int seg0 = grp == 0 ? 0 : (grp < 4 ? 11 + 6 * (grp - 1) : 31);   // first lane of the own group
-    const bool leader = lane == seg0 && grp < 4;
-    // shuffle sources of the group sum: the six lanes of a free body; for arm lanes the row's dof, then lane 31 (always 0)
-    const int s1 = grp >= 1 && grp < 4 ? seg0 + 1 : 31, s2 = grp >= 1 && grp < 4 ? seg0 + 2 : 31, s3 = grp >= 1 && grp < 4 ? seg0 + 3 : 31;
-    const int s4 = grp >= 1 && grp < 4 ? seg0 + 4 : 31, s5 = grp >= 1 && grp < 4 ? seg0 + 5 : 31;
-    double dv = 0.0;
-    int iters = 0; double res = 0.0;
-#ifdef RR_SIMT_EMU_BUILD
-    if (lane == 0 && getenv("RR_DUMP_SCHED")) {
-        for (int par = 0; par < 2; par++) { fprintf(stderr, "par %d nA %d:", par, m.n_slotsA[par]); for (int sl = 0; sl < m.n_slotsA[par]; sl++) fprintf(stderr, " [%d %d %d %d|%d]", T.schedA[par][sl][0], T.schedA[par][sl][1], T.schedA[par][sl][2], T.schedA[par][sl][3], T.wideA[par][sl]); fprintf(stderr, "\n"); }
-        fprintf(stderr, "nB %d:", m.n_slotsB); for (int sl = 0; sl < m.n_slotsB; sl++) fprintf(stderr, " [%d %d %d %d|%d]", T.schedB[sl][0], T.schedB[sl][1], T.schedB[sl][2], T.schedB[sl][3], T.wideB[sl]); fprintf(stderr, "\n");
-    }
-#endif
+    for (int k = 0; k < RR_NDOF; k++) dv[k] = 0.0;
+    // warm start: the applied impulses of the normal rows (no other row starts non-zero)
     {
-        for (int c = 0; c < nc; c++) {                       // warm start (normal rows only)
-            const double a = T.app[RID_NORMAL + c];
-            if (a != 0.0) dv += rows[(size_t)(RID_NORMAL + c) * RR_ROW_STRIDE + 2 * lane + 1] * a;
-        }
-        for (int it = 0; it < cf.solver_iterations; it++) {
-            res = 0.0;
-            const int par = it & 1;
-            // ---- phase A: single rows (joint limits + motors, normals, spinning, rolling), one slot at a time
-            const int nA = m.n_slotsA[par];
-            for (int slot = 0; slot < nA; slot++) {
-                const int rid = grp < 4 ? T.schedA[par][slot][g4] : RR_IDLE;
-                const int wrid = T.wideA[par][slot];
-                const bool act = rid != RR_IDLE;
-                const double* rowp = rows + (size_t)(act ? rid : 0) * RR_ROW_STRIDE;
-                if (slot + 2 < nA) {                          // the rows two slots ahead are on their way into L1
-                    const int nr = T.schedA[par][slot + 2][g4];
-                    if (grp < 4 && nr != RR_IDLE) RR_PREFETCH_L1(rows + (size_t)nr * RR_ROW_STRIDE + 2 * lane);
-                }
-                double J = 0.0, rr = 0.0, rhs = 0.0, inv = 0.0, c66 = 0.0, rinv = 0.0, c68 = 0.0, app = 0.0;
-                if (act) {
-                    const double2 jr = *reinterpret_cast<const double2*>(rowp + 2 * lane);
-                    J = jr.x; rr = jr.y; rhs = rowp[64]; inv = rowp[65]; c66 = rowp[66]; rinv = rowp[67]; c68 = rowp[68];
-                    app = T.app[rid];
-                }
-                // limits: joint rows carry [lo, hi]; normals [0, 1e10]; spinning / rolling +-(coefficient x normal impulse), solved
-                // only while that impulse is positive
-                double lo = c66, hi = c68; bool on = act;
-                if (act && rid >= RID_NORMAL) {
-                    if (rid < RID_SPIN) { lo = 0.0; hi = 1e10; }
-                    else {
-                        const int c = rid < RID_ROLL ? rid - RID_SPIN : (rid - RID_ROLL) >> 1;
-                        const double total = T.app[RID_NORMAL + c];
-                        on = total > 0.0;
-                        hi = c66 * total; lo = -hi;
+        const int nmax = (int)__reduce_max_sync(FULL, (unsigned int)(valid ? nA0 : 0));
+        for (int slot = 0; slot < nmax; slot++) {
+            if (valid && slot < nA0) {
+                const unsigned int ent = ENT(0, GSCHED_A(0), slot);
+                if (ent != ENT_IDLE && (ent >> 16) == ENT_NORMAL) {
+                    const double* b = BLK(ent & 0x7fffu);
+                    const double a = b[sc + 5];
+                    if (a != 0.0) {
+#pragma unroll
+                        for (int k = 0; k < RR_NDOF; k++) if (k < dim) dv[k] += b[2 * k + 1] * a;
                     }
                 }
-                const int s0 = (grp == 0 && act && rid < RR_NC_ROWS) ? T.r_dof[rid] : (grp >= 1 && grp < 4 ? seg0 : 31);
-                const double pr = J * dv;
-                double s = group_sum6(pr, s0, s1, s2, s3, s4, s5);
-                if (wrid != RR_IDLE) {                        // (warp-uniform) the slot's wide row sums over all of its lanes
-                    const bool inw = act && rid == wrid;
-                    const double t = warp_sum(inw ? pr : 0.0);
-                    if (inw) s = t;
-                }
-                double delta = rhs - s * inv;
-                const double sum = app + delta;
-                if (sum < lo) { delta = lo - app; app = lo; }
-                else if (sum > hi) { delta = hi - app; app = hi; }
-                else app = sum;
-                if (on) {
-                    dv += rr * delta;
-                    const double r = delta * rinv;
-                    res = fmax(res, r * r);
-                    if (leader) T.app[rid] = app;
-                }
-                __syncwarp();
             }
-            // ---- phase B: friction pairs with the implicit cone
-            const int nB = m.n_slotsB;
-            for (int slot = 0; slot < nB; slot++) {
-                const int c = grp < 4 ? T.schedB[slot][g4] : RR_IDLE;
-                const int wc = T.wideB[slot];
-                const bool act = c != RR_IDLE;
-                const int r0 = RID_FRIC + 2 * (act ? c : 0);
-                const double* ra = rows + (size_t)r0 * RR_ROW_STRIDE; const double* rb = ra + RR_ROW_STRIDE;
-                if (slot + 2 < nB) {
-                    const int nx = T.schedB[slot + 2][g4];
-                    if (grp < 4 && nx != RR_IDLE) { const double* pn = rows + (size_t)(RID_FRIC + 2 * nx) * RR_ROW_STRIDE + 2 * lane; RR_PREFETCH_L1(pn); RR_PREFETCH_L1(pn + RR_ROW_STRIDE); }
-                }
-                double Ja = 0.0, rra = 0.0, Jb = 0.0, rrb = 0.0, rhsa = 0.0, inva = 0.0, rhsb = 0.0, invb = 0.0, rinva = 0.0, rinvb = 0.0, lim = 0.0, appa = 0.0, appb = 0.0;
-                if (act) {
-                    const double2 ja = *reinterpret_cast<const double2*>(ra + 2 * lane), jb = *reinterpret_cast<const double2*>(rb + 2 * lane);
-                    Ja = ja.x; rra = ja.y; Jb = jb.x; rrb = jb.y;
-                    rhsa = ra[64]; inva = ra[65]; rinva = ra[67]; rhsb = rb[64]; invb = rb[65]; rinvb = rb[67];
-                    lim = ra[66] * T.app[RID_NORMAL + c];
-                    appa = T.app[r0]; appb = T.app[r0 + 1];
-                }
-                const int s0 = grp >= 1 && grp < 4 ? seg0 : 31;
-                const double pa = Ja * dv, pb = Jb * dv;
-                double sa_ = group_sum6(pa, s0, s1, s2, s3, s4, s5), sb_ = group_sum6(pb, s0, s1, s2, s3, s4, s5);
-                if (wc != RR_IDLE) {
-                    const bool inw = act && c == wc;
-                    double ta, tb; warp_sum2(inw ? pa : 0.0, inw ? pb : 0.0, ta, tb);
-                    if (inw) { sa_ = ta; sb_ = tb; }
-                }
-                double wa = appa + (rhsa - sa_ * inva), wb = appb + (rhsb - sb_ * invb);
-                const double len2 = wa * wa + wb * wb;
-                if (len2 > lim * lim) { const double sc = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= sc; wb *= sc; }
-                const double da = wa - appa, db = wb - appb;
-                if (act) {
-                    dv += rra * da; dv += rrb * db;
-                    const double qa = da * rinva, qb = db * rinvb;
-                    res = fmax(res, fmax(qa * qa, qb * qb));
-                    if (leader) { T.app[r0] = wa; T.app[r0 + 1] = wb; }
-                }
-                __syncwarp();
-            }
-            res = warp_max(res);
-            iters = it + 1;
-            if (res <= cf.residual_threshold) break;
         }
     }
-    if (lane < RR_NDOF) {
-        m.qd[lane] = clampd(m.qd[lane] + dv, -cf.max_coord_vel, cf.max_coord_vel);
-        m.q[lane] += m.qd[lane] * dt;
-    }
-    {   // hand the object delta-velocities back to the lanes that own the bodies
+    bool live = valid;
+    int iters = 0;
+    for (int it = 0; it < cf.solver_iterations; it++) {
+        if (!__any_sync(FULL, live)) break;
+        double res = 0.0;
+        const int par = it & 1;
+        // ---- phase A: single rows (joint limits + motors, normals, spinning, rolling)
+        const int nA = par ? nA1 : nA0;
+        const int nAmax = (int)__reduce_max_sync(FULL, (unsigned int)(live ? nA : 0));
+        for (int slot = 0; slot < nAmax; slot++) {
+            unsigned int ent = ENT_IDLE;
+            if (live && slot < nA) ent = par ? ENT(4 * nA0, GSCHED_A(1), slot) : ENT(0, GSCHED_A(0), slot);
+            const bool act = ent != ENT_IDLE;
+            const unsigned int kind = ent >> 16;
+            double* b = BLK(act ? (ent & 0x7fffu) : 0u);
+            double J[RR_NDOF], R[RR_NDOF];
+            double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const double da = __shfl_sync(FULL, dv, 11 + 6 * (lane % 3) + k), dl = __shfl_sync(FULL, dv, 14 + 6 * (lane % 3) + k);
-            if (has_obj) {
-                ob.ang[k] = clampd(ob.ang[k] + da, -cf.max_coord_vel, cf.max_coord_vel);
-                ob.lin[k] = clampd(ob.lin[k] + dl, -cf.max_coord_vel, cf.max_coord_vel);
+            for (int k = 0; k < RR_NDOF; k++) {
+                J[k] = 0.0; R[k] = 0.0;
+                if (act && k < dim) { const double2 p = *reinterpret_cast<const double2*>(b + 2 * k); J[k] = p.x; R[k] = p.y; }
+                if (k & 1) s1 += J[k] * dv[k]; else s0 += J[k] * dv[k];
+            }
+            double s = s0 + s1;
+            double rhs = 0.0, inv = 0.0, rinv = 0.0, lo = 0.0, hi = 0.0, app = 0.0;
+            bool on = act;
+            if (act) {
+                const double2 c0 = *reinterpret_cast<const double2*>(b + sc), c1 = *reinterpret_cast<const double2*>(b + sc + 2), c2 = *reinterpret_cast<const double2*>(b + sc + 4);
+                rhs = c0.x; inv = c0.y; rinv = c1.x; lo = c1.y; hi = c2.x; app = c2.y;
+                if (kind < ENT_JOINT) {           // spinning / rolling row: limits +-(coefficient x normal impulse), solved only while that impulse is positive
+                    const double total = BLK(kind)[sc + 5];
+                    on = total > 0.0;
+                    hi = lo * total; lo = -hi;
+                }
+            }
+            {   // a row coupling two groups of the env: the two lanes exchange their partial sums
+                const bool w = act && (ent & 0x8000u);
+                const unsigned int wq = (__ballot_sync(FULL, w) >> quad) & 15u;
+                const unsigned int other = wq & ~(1u << g);
+                const int src = (w && other) ? quad + __ffs(other) - 1 : lane;
+                const double so = __shfl_sync(FULL, s, src);
+                if (w && other) s += so;
+            }
+            double delta = rhs - s * inv;
+            const double sum = app + delta;
+            if (sum < lo) { delta = lo - app; app = lo; }
+            else if (sum > hi) { delta = hi - app; app = hi; }
+            else app = sum;
+            if (on) {
+#pragma unroll
+                for (int k = 0; k < RR_NDOF; k++) dv[k] += R[k] * delta;
+                const double r = delta * rinv;
+                res = fmax(res, r * r);
+                b[sc + 5] = app;
             }
         }
-    }
-    // ---- impulse write-back (warm start of the next step) and gripper touch sensors (robot.py:131-163)
-    double touch[4] = {0.0, 0.0, 0.0, 0.0};
-    if (cf.enable_contacts) {
-        int c = 0;
-        for (int slot = 0; slot < RR_MAX_MANIFOLDS; slot++) {
-            const int pi = hdr[2 * slot];
-            if (pi < 0) break;
-            const int npt = hdr[2 * slot + 1];
-            const int sa = c_robot.pair_a[pi], sb = c_robot.pair_b[pi];
-            const int linkA = c_robot.shape_link[sa];
-            const bool sens = c_robot.shape_body[sa] == 0 && c_robot.shape_body[sb] != 0 && c_robot.shape_link[sb] == -1;
-            const int sensor = linkA == 11 ? 0 : (linkA == 10 ? 1 : (linkA == 15 ? 2 : (linkA == 14 ? 3 : -1)));
-            bool any = false; double best = 0.0;
-            for (int k = 0; k < npt; k++) {
-                double* P = pts + ((size_t)slot * 4 + k) * RR_PT_STRIDE;
-                double imp = P[10];
-                if (!(P[9] > cf.contact_breaking) && c < RR_MAX_CONTACTS) { imp = T.app[RID_NORMAL + c]; if (lane == 0) P[10] = imp; c++; }
-                if (sens && sensor >= 0 && fabs(P[9]) < 0.1) { const double f = imp / dt; if (!any || f > best) { best = f; any = true; } }
+        // ---- phase B: friction pairs with the implicit cone
+        const int nBmax = (int)__reduce_max_sync(FULL, (unsigned int)(live ? nB : 0));
+        for (int slot = 0; slot < nBmax; slot++) {
+            unsigned int ent = ENT_IDLE;
+            if (live && slot < nB) ent = ENT(4 * (nA0 + nA1), GSCHED_B, slot);
+            const bool act = ent != ENT_IDLE;
+            double* ba = BLK(act ? (ent & 0x7fffu) : 0u);
+            double* bb = BLK(act ? (ent & 0x7fffu) + sz16 : 0u);
+            double Ra[RR_NDOF], Rb[RR_NDOF];
+            double sa_ = 0.0, sb_ = 0.0;
+#pragma unroll
+            for (int k = 0; k < RR_NDOF; k++) {
+                Ra[k] = 0.0; Rb[k] = 0.0;
+                if (act && k < dim) {
+                    const double2 pa = *reinterpret_cast<const double2*>(ba + 2 * k), pb = *reinterpret_cast<const double2*>(bb + 2 * k);
+                    Ra[k] = pa.y; Rb[k] = pb.y;
+                    sa_ += pa.x * dv[k]; sb_ += pb.x * dv[k];
+                }
             }
-            if (any && sens && sensor >= 0 && best > touch[sensor]) touch[sensor] = best;
+            double rhsa = 0.0, inva = 0.0, rhsb = 0.0, invb = 0.0, rinva = 0.0, rinvb = 0.0, lim = 0.0, appa = 0.0, appb = 0.0;
+            if (act) {
+                const double2 a0 = *reinterpret_cast<const double2*>(ba + sc), a1 = *reinterpret_cast<const double2*>(ba + sc + 2);
+                const double2 b0 = *reinterpret_cast<const double2*>(bb + sc);
+                rhsa = a0.x; inva = a0.y; rinva = a1.x; rhsb = b0.x; invb = b0.y; rinvb = bb[sc + 2];
+                lim = a1.y * BLK(ent >> 16)[sc + 5];
+                appa = ba[sc + 5]; appb = bb[sc + 5];
+            }
+            {
+                const bool w = act && (ent & 0x8000u);
+                const unsigned int wq = (__ballot_sync(FULL, w) >> quad) & 15u;
+                const unsigned int other = wq & ~(1u << g);
+                const int src = (w && other) ? quad + __ffs(other) - 1 : lane;
+                const double oa = __shfl_sync(FULL, sa_, src), ob_ = __shfl_sync(FULL, sb_, src);
+                if (w && other) { sa_ += oa; sb_ += ob_; }
+            }
+            double wa = appa + (rhsa - sa_ * inva), wb = appb + (rhsb - sb_ * invb);
+            const double len2 = wa * wa + wb * wb;
+            if (len2 > lim * lim) { const double scl = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= scl; wb *= scl; }
+            const double da = wa - appa, db = wb - appb;
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < RR_NDOF; k++) { dv[k] += Ra[k] * da; dv[k] += Rb[k] * db; }
+                const double qa = da * rinva, qb = db * rinvb;
+                res = fmax(res, fmax(qa * qa, qb * qb));
+                ba[sc + 5] = wa; bb[sc + 5] = wb;
+            }
         }
+        // the env's residual: maximum over its four lanes
+        res = fmax(res, __shfl_xor_sync(FULL, res, 1));
+        res = fmax(res, __shfl_xor_sync(FULL, res, 2));
+        if (live) { iters = it + 1; if (res <= cf.residual_threshold) live = false; }
     }
-    if (has_obj) obj_integrate(ob, dt);
-    // ---- failure detection: a non-finite state cannot recover by itself (and the reference has nothing to say about it);
-    // the env is put back into its initial state as rr_reset would, keeps stepping, and is flagged in rr_diag (bit 3)
-    int fault = m.fault;
-    {
-        bool bad = lane < RR_NDOF && !(isfinite(m.q[lane]) && isfinite(m.qd[lane]));
+    iters_out = iters;
+}
+
+__global__ void __launch_bounds__(32, 2) k_step_solve(DevState st, int* __restrict__ man_hdr_all, double* __restrict__ man_pts_all, rr_config cf, int n_objects) {
+    RR_DYN_SMEM(smem_raw);
+    double* const simg_all = reinterpret_cast<double*>(smem_raw);
+    SolveScratch& scr = *reinterpret_cast<SolveScratch*>(smem_raw + (size_t)SOLVE_E * SOLVE_ENV_CAP * 8);
+    const int lane = threadIdx.x & 31;
+    const int N = st.N;
+    const double dt = cf.dt;
+    const int e0 = blockIdx.x * SOLVE_E;
+    const int n_here = min(SOLVE_E, N - e0);
+    if (n_here <= 0) return;
+    // ---- the images of the warp's envs come into shared memory, one env after the other with all lanes: the used part of
+    // the three schedules (compacted), then as many blocks as fit; what does not fit is addressed in global memory
+    int my_nA0 = 0, my_nA1 = 0, my_nB = 0, my_sblk_off = 0, my_nblk_smem = 0; bool my_sched_smem = true, all_fast = true;
+    const int my_e = lane >> 2, my_g = lane & 3;
+    const bool valid = my_e < n_here;
+    for (int k = 0; k < n_here; k++) {
+        const double* gimg = st.handoff + (size_t)(e0 + k) * RR_IMG_DOUBLES;
+        const SolveHead* gh = reinterpret_cast<const SolveHead*>(gimg);
+        double* simg = simg_all + (size_t)k * SOLVE_ENV_CAP;
+        const int nA0 = gh->n_slotsA[0], nA1 = gh->n_slotsA[1], nB = gh->n_slotsB, n_blk = gh->n_blk_doubles;
+        const int n_words = 4 * (nA0 + nA1 + nB);
+        const bool sched_smem = n_words / 2 <= SOLVE_ENV_CAP;
+        const unsigned int* gs = reinterpret_cast<const unsigned int*>(gimg + HEAD_DOUBLES);
+        unsigned int* ss = reinterpret_cast<unsigned int*>(simg);
+        if (sched_smem) {
+            for (int i = lane; i < 4 * nA0; i += 32) ss[i] = gs[GSCHED_A(0) + i];
+            for (int i = lane; i < 4 * nA1; i += 32) ss[4 * nA0 + i] = gs[GSCHED_A(1) + i];
+            for (int i = lane; i < 4 * nB; i += 32) ss[4 * (nA0 + nA1) + i] = gs[GSCHED_B + i];
+        }
+        const int sblk_off = sched_smem ? n_words / 2 : SOLVE_ENV_CAP;
+        const int n_smem = min(n_blk, SOLVE_ENV_CAP - sblk_off);
+        {
+            const double2* src = reinterpret_cast<const double2*>(gimg + GBLK_BASE); double2* dst = reinterpret_cast<double2*>(simg + sblk_off);
+            for (int i = lane; i < n_smem / 2; i += 32) dst[i] = src[i];
+        }
+        all_fast = all_fast && sched_smem && n_smem == n_blk;
+        if (my_e == k) { my_nA0 = nA0; my_nA1 = nA1; my_nB = nB; my_sblk_off = sblk_off; my_nblk_smem = n_smem; my_sched_smem = sched_smem; }
+    }
+    __syncwarp();
+    double* const my_gimg = st.handoff + (size_t)(e0 + (valid ? my_e : 0)) * RR_IMG_DOUBLES;
+    double* const my_simg = simg_all + (size_t)(valid ? my_e : 0) * SOLVE_ENV_CAP;
+    double dv[RR_NDOF];
+    int my_iters = 0;
+    if (all_fast) pgs_sweep<true>(valid, my_g, my_simg, my_gimg + GBLK_BASE, my_sblk_off, my_nblk_smem, reinterpret_cast<const unsigned int*>(my_gimg + HEAD_DOUBLES), my_sched_smem, my_nA0, my_nA1, my_nB, cf, dv, my_iters);
+    else pgs_sweep<false>(valid, my_g, my_simg, my_gimg + GBLK_BASE, my_sblk_off, my_nblk_smem, reinterpret_cast<const unsigned int*>(my_gimg + HEAD_DOUBLES), my_sched_smem, my_nA0, my_nA1, my_nB, cf, dv, my_iters);
+    __syncwarp();
+    // ---- per env, with all lanes: integration, impulse write-back, touch sensors, final kinematics, observations
+    for (int k = 0; k < n_here; k++) {
+        const int e = e0 + k;
+        double* gimg = st.handoff + (size_t)e * RR_IMG_DOUBLES;
+        double* simg = simg_all + (size_t)k * SOLVE_ENV_CAP;
+        __syncwarp();
+        for (int i = lane; i < HEAD_DOUBLES; i += 32) reinterpret_cast<double*>(&scr.head)[i] = gimg[i];
+        // the env's velocity change back into owner layout (lane j < 11: arm dof j, lane 11 + 6 o + c: component c of body o)
+        if (my_e == k) {
+#pragma unroll
+            for (int j = 0; j < RR_NDOF; j++) { if (my_g == 0) scr.dv[j] = dv[j]; else if (j < 6) scr.dv[RR_NDOF + 6 * (my_g - 1) + j] = dv[j]; }
+        }
+        __syncwarp();
+        SolveHead& m = scr.head;
+        const double dvl = lane < 29 ? scr.dv[lane] : 0.0;
+        const int iters = __shfl_sync(FULL, my_iters, 4 * k);
+        const int sblk_off = __shfl_sync(FULL, my_sblk_off, 4 * k), n_blk_smem = __shfl_sync(FULL, my_nblk_smem, 4 * k);
+        const int smem_lim16 = (n_blk_smem - RR_ARM_BLK) / 2;
+        double* const sblk = simg + sblk_off; double* const gblk = gimg + GBLK_BASE;
+#define BLK_PTR(off16) ((int)(off16) <= smem_lim16 ? sblk + 2 * (int)(off16) : gblk + 2 * (int)(off16))
+        ObjReg ob;
+        const bool has_obj = lane < n_objects;
         if (has_obj) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) bad |= !(isfinite(ob.pos[k]) && isfinite(ob.lin[k]) && isfinite(ob.ang[k]));
+            for (int j = 0; j < 3; j++) { ob.pos[j] = m.objreg[lane][j]; ob.lin[j] = m.objreg[lane][7 + j]; ob.ang[j] = m.objreg[lane][10 + j]; }
 #pragma unroll
-            for (int k = 0; k < 4; k++) bad |= !isfinite(ob.quat[k]);
+            for (int j = 0; j < 4; j++) ob.quat[j] = m.objreg[lane][3 + j];
         }
-        if (__any_sync(FULL, bad)) {
-            fault |= 2;
-            if (lane < RR_NDOF) { m.q[lane] = 0.0; m.qd[lane] = 0.0; m.target[lane] = 0.0; }
+        const int nc = m.nc, overflow = m.overflow, simple = m.simple, rows_live = m.n_rows_total;
+        int fault = m.fault;
+        int* hdr = man_hdr_all + (size_t)e * RR_MAX_MANIFOLDS * 2;
+        double* pts = man_pts_all + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
+        if (lane < RR_NDOF) {
+            m.qd[lane] = clampd(m.qd[lane] + dvl, -cf.max_coord_vel, cf.max_coord_vel);
+            m.q[lane] += m.qd[lane] * dt;
+        }
+        {   // hand the object delta-velocities to the lanes that own the bodies
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double da = __shfl_sync(FULL, dvl, 11 + 6 * (lane % 3) + j), dl = __shfl_sync(FULL, dvl, 14 + 6 * (lane % 3) + j);
+                if (has_obj) {
+                    ob.ang[j] = clampd(ob.ang[j] + da, -cf.max_coord_vel, cf.max_coord_vel);
+                    ob.lin[j] = clampd(ob.lin[j] + dl, -cf.max_coord_vel, cf.max_coord_vel);
+                }
+            }
+        }
+        // ---- impulse write-back (warm start of the next step) and gripper touch sensors (robot.py:131-163)
+        double touch[4] = {0.0, 0.0, 0.0, 0.0};
+        if (cf.enable_contacts) {
+            int c = 0;
+            for (int slot = 0; slot < RR_MAX_MANIFOLDS; slot++) {
+                const int pi = hdr[2 * slot];
+                if (pi < 0) break;
+                const int npt = hdr[2 * slot + 1];
+                const int sa = c_robot.pair_a[pi], sb = c_robot.pair_b[pi];
+                const int linkA = c_robot.shape_link[sa];
+                const bool sens = c_robot.shape_body[sa] == 0 && c_robot.shape_body[sb] != 0 && c_robot.shape_link[sb] == -1;
+                const int sensor = linkA == 11 ? 0 : (linkA == 10 ? 1 : (linkA == 15 ? 2 : (linkA == 14 ? 3 : -1)));
+                bool any = false; double best = 0.0;
+                for (int j = 0; j < npt; j++) {
+                    double* P = pts + ((size_t)slot * 4 + j) * RR_PT_STRIDE;
+                    double imp = P[10];
+                    if (!(P[9] > cf.contact_breaking) && c < RR_MAX_CONTACTS) {
+                        const unsigned int nr = m.nrm_rel[c];
+                        imp = BLK_PTR(nr & 0x7fffu)[(nr & 0x8000u) ? 2 * RR_NDOF + 5 : 17];
+                        if (lane == 0) P[10] = imp;
+                        c++;
+                    }
+                    if (sens && sensor >= 0 && fabs(P[9]) < 0.1) { const double f = imp / dt; if (!any || f > best) { best = f; any = true; } }
+                }
+                if (any && sens && sensor >= 0 && best > touch[sensor]) touch[sensor] = best;
+            }
+        }
+#undef BLK_PTR
+        if (has_obj) obj_integrate(ob, dt);
+        // ---- failure detection: a non-finite state cannot recover by itself (and the reference has nothing to say about it);
+        // the env is put back into its initial state as rr_reset would, keeps stepping, and is flagged in rr_diag (bit 3)
+        {
+            bool bad = lane < RR_NDOF && !(isfinite(m.q[lane]) && isfinite(m.qd[lane]));
             if (has_obj) {
 #pragma unroll
-                for (int k = 0; k < 3; k++) { ob.pos[k] = c_robot.obj_init[lane][k]; ob.lin[k] = 0.0; ob.ang[k] = 0.0; }
+                for (int j = 0; j < 3; j++) bad |= !(isfinite(ob.pos[j]) && isfinite(ob.lin[j]) && isfinite(ob.ang[j]));
 #pragma unroll
-                for (int k = 0; k < 4; k++) ob.quat[k] = c_robot.obj_init[lane][3 + k];
+                for (int j = 0; j < 4; j++) bad |= !isfinite(ob.quat[j]);
             }
-            for (int slot = lane; slot < RR_MAX_MANIFOLDS; slot += 32) { hdr[2 * slot] = -1; hdr[2 * slot + 1] = 0; }
+            if (__any_sync(FULL, bad)) {
+                fault |= 2;
+                if (lane < RR_NDOF) { m.q[lane] = 0.0; m.qd[lane] = 0.0; m.target[lane] = 0.0; }
+                if (has_obj) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) touch[k] = 0.0;
+                    for (int j = 0; j < 3; j++) { ob.pos[j] = c_robot.obj_init[lane][j]; ob.lin[j] = 0.0; ob.ang[j] = 0.0; }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) ob.quat[j] = c_robot.obj_init[lane][3 + j];
+                }
+                for (int slot = lane; slot < RR_MAX_MANIFOLDS; slot += 32) { hdr[2 * slot] = -1; hdr[2 * slot + 1] = 0; }
+#pragma unroll
+                for (int j = 0; j < 4; j++) touch[j] = 0.0;
+            }
         }
-    }
-    __syncwarp();
-    // ---- epilogue: final kinematics (in the memory of the solver tables, which are dead now), state write-back, observations
-    const int rows_live = m.n_rows_total;
-    __syncwarp();
-    fk_local(m.q, m.u.k, lane);
-    fk_sweep(m.u.k, lane, nullptr, nullptr);
-    store_frames(m.u.k, st, e, lane);
-    if (lane < RR_NDOF) {
-        st.q[(size_t)lane * N + e] = m.q[lane]; st.qd[(size_t)lane * N + e] = m.qd[lane];
-        st.target[(size_t)lane * N + e] = m.target[lane];
-    }
-    if (has_obj) {
-        double* base = st.obj + (size_t)lane * 13 * N + e;
+        __syncwarp();
+        // ---- final kinematics, state write-back, observations
+        fk_local(m.q, scr.kin, lane);
+        fk_sweep(scr.kin, lane, nullptr, nullptr);
+        store_frames(scr.kin, st, e, lane);
+        if (lane < RR_NDOF) {
+            st.q[(size_t)lane * N + e] = m.q[lane]; st.qd[(size_t)lane * N + e] = m.qd[lane];
+            st.target[(size_t)lane * N + e] = m.target[lane];
+        }
+        if (has_obj) {
+            double* base = st.obj + (size_t)lane * 13 * N + e;
 #pragma unroll
-        for (int k = 0; k < 3; k++) base[(size_t)k * N] = ob.pos[k];
+            for (int j = 0; j < 3; j++) base[(size_t)j * N] = ob.pos[j];
 #pragma unroll
-        for (int k = 0; k < 4; k++) base[(size_t)(3 + k) * N] = ob.quat[k];
+            for (int j = 0; j < 4; j++) base[(size_t)(3 + j) * N] = ob.quat[j];
 #pragma unroll
-        for (int k = 0; k < 3; k++) { base[(size_t)(7 + k) * N] = ob.lin[k]; base[(size_t)(10 + k) * N] = ob.ang[k]; }
-    }
-    if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
-    if (lane == 0) {
-        st.diag[4 * e] = rows_live; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (simple ? 2 : 0) | (fault << 2) | (cf.enable_contacts ? (st.col_flags[e] << 4) : 0);   // bit 0: contact cap hit, bit 1: every contact is object-vs-static, bits 2-3: faults, bit 4: manifold slots exhausted
-        st.timestep[e] += 1;
+            for (int j = 0; j < 3; j++) { base[(size_t)(7 + j) * N] = ob.lin[j]; base[(size_t)(10 + j) * N] = ob.ang[j]; }
+        }
+        if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
+        if (lane == 0) {
+            st.diag[4 * e] = rows_live; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (simple ? 2 : 0) | (fault << 2) | (cf.enable_contacts ? (st.col_flags[e] << 4) : 0);   // bit 0: contact cap hit, bit 1: every contact is object-vs-static, bits 2-3: faults, bit 4: manifold slots exhausted
+            st.timestep[e] += 1;
+        }
     }
 }
 
@@ -1184,7 +1317,7 @@ int rrk_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_robot, &ctx->robot, sizeof(RobotConst)));
     g_phys_owner[ctx->device & 63] = ctx;
     CK(cudaFuncSetAttribute(k_step_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
-    CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * WPB)));
+    CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FkMem) * WPB)));
     return 0;
 }
@@ -1242,7 +1375,7 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
     if (ctx->cfg.enable_contacts && rrk_collide(ctx, s) != 0) return -1;
     ProfScope ps(ctx, 0, s);
     RR_LAUNCH(k_step_dyn, nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s)(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
-    RR_LAUNCH(k_step_solve, nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
+    RR_LAUNCH(k_step_solve, nblk(ctx->N, SOLVE_E), 32, SOLVE_SMEM_BYTES, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
     ctx->launches += 2;
     CK(cudaGetLastError());
     return 0;

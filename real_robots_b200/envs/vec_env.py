@@ -61,14 +61,27 @@ class VecREALRobotEnv:
         joints, touch, objs = self.sim.read_state()
         K = Kuka.ObsSpaces
         obs = {K.JOINT_POSITIONS: joints, K.TOUCH_SENSORS: touch}
-        rgb, depth, seg = self.sim.render(mask=render_mask if render_mask is not None else torch.zeros_like(self._all),
-                                          want_mask=self.additional_obs)
+        if render_mask is None:
+            # render off for every env: the reference returns its cached zero arrays (env.py:114-122, 273-275) and so do we —
+            # one zero image per kind, broadcast over the env axis (read-only views), no kernel launch, no 3.46 GB of zero stores
+            rgb, depth, seg = self._zero_images()
+        else:
+            rgb, depth, seg = self.sim.render(mask=render_mask, want_mask=self.additional_obs)
         obs[K.RETINA], obs[K.DEPTH] = rgb, depth
         if self.additional_obs:
             obs[K.MASK] = seg
             obs[K.OBJ_POS] = objs[:, :, :3]
             obs[K.GOAL_POS] = self.goal_positions
         return obs
+
+    def _zero_images(self):
+        if getattr(self, "_zimg", None) is None:
+            N, dev = self.n_envs, self.device
+            H, W = Kuka.eye_height, Kuka.eye_width
+            self._zimg = (torch.zeros(1, H, W, 3, dtype=torch.uint8, device=dev).expand(N, H, W, 3),
+                          torch.zeros(1, H, W, dtype=torch.float32, device=dev).expand(N, H, W),
+                          torch.zeros(1, H, W, dtype=torch.int32, device=dev).expand(N, H, W))
+        return self._zimg
 
     def _render_mask(self, r):
         if r is None:

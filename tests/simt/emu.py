@@ -19,30 +19,33 @@ _CSRC = os.path.join(_ROOT, "real_robots_b200", "csrc")
 _SO = os.path.join(_HERE, "_build", "libreal_emu.so")
 _SRCS = [os.path.join(_CSRC, f) for f in ("rr_api.cu", "rr_physics.cu", "rr_render.cu", "rr_collide.cu")] + [os.path.join(_HERE, "simt_emu.cpp")]
 _DEPS = _SRCS + [os.path.join(_CSRC, "rr_ctx.h"), os.path.join(_ROOT, "include", "real_b200.h"), os.path.join(_HERE, "simt_emu.h")]
-_lib = None
+_libs = {}
 
 
-def build(force=False):
-    os.makedirs(os.path.dirname(_SO), exist_ok=True)
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in _DEPS):
+def build(flags=(), force=False):
+    """flags: extra -D options (tuning macros of the kernels, e.g. a tiny SOLVE_ENV_CAP to force the solver's global-memory
+    path); every flag set gets its own library."""
+    so = _SO if not flags else _SO.replace(".so", "_" + "_".join(f.strip("-").replace("=", "") for f in flags) + ".so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in _DEPS):
         # -ffp-contract=off mirrors nvcc -fmad=false (rasteriser, narrowphase); the dynamics kernels are compared to 1e-9
         cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DRR_SIMT_EMU_BUILD", "-I" + _HERE,
-               "-Wno-unknown-pragmas", "-x", "c++"] + _SRCS + ["-o", _SO]
+               "-Wno-unknown-pragmas"] + list(flags) + ["-x", "c++"] + _SRCS + ["-o", so]
         subprocess.check_call(cmd)
-    return _SO
+    return so
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        lb = C.CDLL(build())
+def lib(flags=()):
+    key = tuple(flags)
+    if key not in _libs:
+        lb = C.CDLL(build(key))
         for name, (res, args) in L.SYMBOLS.items():
             fn = getattr(lb, name)
             fn.restype = res
             fn.argtypes = args
         assert lb.rr_config_size() == C.sizeof(L.RRConfig)
-        _lib = lb
-    return _lib
+        _libs[key] = lb
+    return _libs[key]
 
 
 def _p(a):
@@ -52,8 +55,8 @@ def _p(a):
 class EmuSim:
     """numpy mirror of real_robots_b200.sim.BatchedSim over the emulated library."""
 
-    def __init__(self, n_envs, n_objects=3, **cfg):
-        self.lib = lib()
+    def __init__(self, n_envs, n_objects=3, build_flags=(), **cfg):
+        self.lib = lib(build_flags)
         self.cfg = L.RRConfig()
         self.lib.rr_config_default(C.byref(self.cfg))
         for k, v in cfg.items():
