@@ -41,9 +41,9 @@ struct KinWs {
 // does not fit stays in global memory and is addressed there).
 #define RR_ARM_BLK 28            // doubles: 11 x (J, rr), rhs, inv, rinv, lo | coef, hi, app
 #define RR_OBJ_BLK 18            // doubles:  6 x (J, rr), rhs, inv, rinv, lo | coef, hi, app
-#define ENT_IDLE 0xffffffffu     // schedule entry: bits 0..14 block offset (16-byte units, relative to the first block), bit 15 wide,
-#define ENT_NORMAL 0xfffeu       // bits 16..31: 0xfffe normal row, 0xffe0 | dof joint row, else offset of the same group's normal block
-#define ENT_JOINT 0xffe0u
+#define ENT_IDLE 0xffffffffu     // schedule entry, word 0: bits 0..14 block offset (16-byte units, relative to the first block), bit 15 wide,
+#define ENT_NORMAL 0xfffeu       // bits 16..31: 0xfffe normal row, 0xffe0 | dof joint row, else (0) a row whose limits follow its normal row's impulse;
+#define ENT_JOINT 0xffe0u        // word 1: row id | row id of the contact's normal row << 16 (the applied impulses live in shared memory by row id)
 struct SolveHead {
     double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
     double objreg[RR_MAX_OBJECTS][13];                  // free bodies after the unconstrained update (pos3 quat4 lin3 ang3)
@@ -52,9 +52,9 @@ struct SolveHead {
     unsigned short nrm_rel[RR_MAX_CONTACTS];            // per contact: its normal row's first block (bit 15: an arm block), for the impulse write-back
 };
 #define HEAD_DOUBLES ((int)(sizeof(SolveHead) / 8))
-#define GSCHED_A(par) (4 * RR_SLOTS_A * (par))                          // word offsets of the schedules in the global image (fixed places)
-#define GSCHED_B (8 * RR_SLOTS_A)
-#define GBLK_BASE (HEAD_DOUBLES + (8 * RR_SLOTS_A + 4 * RR_SLOTS_B) / 2)   // first block, in doubles
+#define GSCHED_A(par) (8 * RR_SLOTS_A * (par))                          // word offsets of the schedules in the image (fixed places; 2 words per slot and group)
+#define GSCHED_B (16 * RR_SLOTS_A)
+#define GBLK_BASE (HEAD_DOUBLES + (16 * RR_SLOTS_A + 8 * RR_SLOTS_B) / 2)   // first block, in doubles
 static_assert(sizeof(SolveHead) % 16 == 0, "the schedule words and blocks must stay 16-byte aligned");
 static_assert(GBLK_BASE % 2 == 0 && GBLK_BASE + RR_NC_ROWS * RR_ARM_BLK + RR_MAX_CONTACTS * 6 * (RR_ARM_BLK + RR_OBJ_BLK) <= RR_IMG_DOUBLES, "solver image too small");
 // k_step_dyn's own workspace
@@ -457,23 +457,23 @@ __device__ __forceinline__ void store_frames(const KinWs& m, const DevState& st,
 __device__ __forceinline__ int lane_group(int lane) { return lane < RR_NDOF ? 0 : (lane < 29 ? 1 + (lane - RR_NDOF) / 6 : 4); }
 
 // lane 0: place one row (or friction pair) of group mask gm into the earliest slot all its groups are free in; a wide row also
-// needs a slot without another wide row.  ent[g] = schedule entry of group g for this row; sched = words of the schedule.
-__device__ __forceinline__ void sched_place(unsigned int* sched, int* cur, unsigned int* wide_used, int gm, bool is_wide, const unsigned int* ent) {
+// needs a slot without another wide row.  ent[g] = word 0 of group g's schedule entry for this row, w1 = word 1.
+__device__ __forceinline__ void sched_place(unsigned int* sched, int* cur, unsigned int* wide_used, int gm, bool is_wide, const unsigned int* ent, unsigned int w1) {
     int slot = 0;
 #pragma unroll
     for (int g = 0; g < 4; g++) if ((gm >> g) & 1) slot = max(slot, cur[g]);
     if (is_wide) { while ((wide_used[slot >> 5] >> (slot & 31)) & 1u) slot++; wide_used[slot >> 5] |= 1u << (slot & 31); }
 #pragma unroll
-    for (int g = 0; g < 4; g++) if ((gm >> g) & 1) { sched[4 * slot + g] = ent[g] | (is_wide ? 0x8000u : 0u); cur[g] = slot + 1; }
+    for (int g = 0; g < 4; g++) if ((gm >> g) & 1) { sched[8 * slot + 2 * g] = ent[g] | (is_wide ? 0x8000u : 0u); sched[8 * slot + 2 * g + 1] = w1; cur[g] = slot + 1; }
 }
-// entries of contact c's row `rowidx` (0 normal, 1 2 friction, 3.. spinning / rolling) for the groups of gm; blocks of one contact
-// are laid out group by group, `nr` rows each
+// word 0 of the entries of contact row `rowidx` (0 normal, 1 2 friction, 3.. spinning / rolling) for the groups of gm; blocks of
+// one contact are laid out group by group, `nr` rows each
 __device__ __forceinline__ void contact_entries(unsigned int* ent, int gm, int base16, int nr, int rowidx) {
     int off = base16;        // 16-byte units
 #pragma unroll
     for (int g = 0; g < 4; g++) if ((gm >> g) & 1) {
         const int sz = (g == 0 ? RR_ARM_BLK : RR_OBJ_BLK) / 2;
-        ent[g] = (unsigned int)(off + rowidx * sz) | ((rowidx == 0 ? ENT_NORMAL : (unsigned int)off) << 16);
+        ent[g] = (unsigned int)(off + rowidx * sz) | ((rowidx == 0 ? ENT_NORMAL : 0u) << 16);
         off += nr * sz;
     }
 }
@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
                     __syncwarp();
                 }
                 if (lane == 0) {
-                    const bool wide = (gm & (gm - 1)) != 0;       // the row couples two groups: their lanes meet in one slot
+                    const bool wide = armA || (gm & (gm - 1)) != 0;       // needs a sum over more lanes than one group's own shuffles cover
                     m.c_grp[nc] = (unsigned char)gm;
                     m.c_flags[nc] = (unsigned char)((spin > 0 ? 1 : 0) | (roll > 0 ? 2 : 0) | (wide ? 4 : 0));
                     m.c_base[nc] = (unsigned short)(blk_top / 2);
@@ -760,8 +760,8 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
     __syncwarp();
     // ---- slot schedule of one Gauss-Seidel iteration (see SolveHead), for both parities of the joint-row order
     const int n_single = n_nc + 4 * nc;          // upper bound of the slots of the single rows
-    for (int k = lane; k < n_single * 4; k += 32) { gsched[GSCHED_A(0) + k] = ENT_IDLE; gsched[GSCHED_A(1) + k] = ENT_IDLE; }
-    for (int k = lane; k < nc * 4; k += 32) gsched[GSCHED_B + k] = ENT_IDLE;
+    for (int k = lane; k < n_single * 8; k += 32) { gsched[GSCHED_A(0) + k] = ENT_IDLE; gsched[GSCHED_A(1) + k] = ENT_IDLE; }
+    for (int k = lane; k < nc * 8; k += 32) gsched[GSCHED_B + k] = ENT_IDLE;
     __syncwarp();
     if (lane == 0) {
         unsigned int ent[4] = {0u, 0u, 0u, 0u};
@@ -773,23 +773,23 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
             for (int j = 0; j < n_nc; j++) {
                 const int idx = par ? j : n_nc - 1 - j;                               // it & 1 ? j : n - 1 - j
                 ent[0] = (unsigned int)(idx * (RR_ARM_BLK / 2)) | ((ENT_JOINT | (unsigned int)m.r_dof[idx]) << 16);
-                sched_place(sched, cur, wide_used, 1, false, ent);
+                sched_place(sched, cur, wide_used, 1, false, ent, (unsigned int)idx);
             }
             for (int c = 0; c < nc; c++) {
                 const int nr = 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
                 contact_entries(ent, m.c_grp[c], m.c_base[c], nr, 0);
-                sched_place(sched, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent);
+                sched_place(sched, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent, (unsigned int)(RID_NORMAL + c) | ((unsigned int)(RID_NORMAL + c) << 16));
             }
             for (int c = 0; c < nc; c++) if (m.c_flags[c] & 1) {
                 const int nr = 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
                 contact_entries(ent, m.c_grp[c], m.c_base[c], nr, 3);
-                sched_place(sched, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent);
+                sched_place(sched, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent, (unsigned int)(RID_SPIN + c) | ((unsigned int)(RID_NORMAL + c) << 16));
             }
             for (int c = 0; c < nc; c++) if (m.c_flags[c] & 2) {
                 const int nr = 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
                 for (int r2 = 0; r2 < 2; r2++) {
                     contact_entries(ent, m.c_grp[c], m.c_base[c], nr, 3 + (m.c_flags[c] & 1) + r2);
-                    sched_place(sched, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent);
+                    sched_place(sched, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent, (unsigned int)(RID_ROLL + 2 * c + r2) | ((unsigned int)(RID_NORMAL + c) << 16));
                 }
             }
             hand->n_slotsA[par] = max(max(cur[0], cur[1]), max(cur[2], cur[3]));
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
         for (int c = 0; c < nc; c++) {
             const int nr = 3 + (m.c_flags[c] & 1) + (m.c_flags[c] & 2);
             contact_entries(ent, m.c_grp[c], m.c_base[c], nr, 1);                     // first friction row; the second follows it
-            sched_place(gsched + GSCHED_B, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent);
+            sched_place(gsched + GSCHED_B, cur, wide_used, m.c_grp[c], (m.c_flags[c] & 4) != 0, ent, (unsigned int)(RID_FRIC + 2 * c) | ((unsigned int)(RID_NORMAL + c) << 16));
         }
         hand->n_slotsB = max(max(cur[0], cur[1]), max(cur[2], cur[3]));
         hand->n_nc = n_nc; hand->nc = nc; hand->overflow = overflow; hand->fault = m.fault; hand->simple = simple;
@@ -817,340 +817,263 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
 }
 
 // ------------------------------------------------------------------------------------------- the solver kernel
-// One warp solves SOLVE_E envs at once: lane 4 e' + g resolves the rows of group g (0 = arm, 1 + o = free body o) of the
-// warp's e'-th env, walking that group's column of the slot schedule and reading its blocks from shared memory.  The work
-// of a row is a handful of scalars per group (a dot product over the group's 11 or 6 velocity components, a clamp, an
-// axpy), so the lanes are spent on independent (env, group) streams rather than on the components of one row: ~10 warp
-// instructions per env and slot instead of ~100.  Rows coupling two groups of an env meet in one slot (the schedule
-// guarantees it, at most one such row per env and slot) and exchange their partial sums with one shuffle.
-#ifndef SOLVE_E
-#define SOLVE_E 7                // envs per warp (lanes 4 e' .. 4 e' + 3)
+#ifdef RR_SIMT_EMU_BUILD
+#define RR_PREFETCH_L1(p)
+#else
+#define RR_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
 #endif
-#ifndef SOLVE_ENV_CAP
-#define SOLVE_ENV_CAP 1984       // doubles of (schedule + blocks) per env in shared memory: 7 x 15.5 KB + scratch = 2 blocks per SM
-#endif
-struct SolveScratch { SolveHead head; KinWs kin; double dv[32]; };           // per-env epilogue workspace (one env at a time)
-#define SOLVE_SMEM_BYTES ((size_t)SOLVE_E * SOLVE_ENV_CAP * 8 + sizeof(SolveScratch))
-
-// The Gauss-Seidel sweeps of the warp's envs.  FAST: every schedule and block of every env of the warp lives in shared memory.
-template <bool FAST>
-__device__ __forceinline__ void pgs_sweep(const bool valid, const int g, double* const sbase, double* const gblk, const int sblk_off, const int n_blk_smem,
-                                          const unsigned int* gsched, const bool sched_smem, const int nA0, const int nA1, const int nB,
-                                          const rr_config& cf, double (&dv)[RR_NDOF], int& iters_out) {
-    const int lane = threadIdx.x & 31;
-    const int dim = g == 0 ? RR_NDOF : 6;                          // velocity components of the own group
-    const int sc = g == 0 ? 2 * RR_NDOF : 12;                      // offset of the scalars inside a block
-    const int sz16 = (g == 0 ? RR_ARM_BLK : RR_OBJ_BLK) / 2;
-    const int lim16 = (n_blk_smem - RR_ARM_BLK) / 2;
-    double* const sblk = sbase + sblk_off;
-    auto BLK = [&](unsigned int off16) -> double* {
-        if (FAST) return sblk + 2 * (int)off16;
-        return (int)off16 <= lim16 ? sblk + 2 * (int)off16 : gblk + 2 * (int)off16;
-    };
-    const unsigned int* ssched = reinterpret_cast<const unsigned int*>(sbase);
-    auto ENT = [&](int base_words, int gbase_words, int slot) -> unsigned int {
-        if (FAST || sched_smem) return ssched[base_words + 4 * slot + g];
-        return gsched[gbase_words + 4 * slot + g];
-    };
-    const int quad = lane & ~3;
-#pragma unroll
-    for (int k = 0; k < RR_NDOF; k++) dv[k] = 0.0;
-    // warm start: the applied impulses of the normal rows (no other row starts non-zero)
-    {
-        const int nmax = (int)__reduce_max_sync(FULL, (unsigned int)(valid ? nA0 : 0));
-        for (int slot = 0; slot < nmax; slot++) {
-            if (valid && slot < nA0) {
-                const unsigned int ent = ENT(0, GSCHED_A(0), slot);
-                if (ent != ENT_IDLE && (ent >> 16) == ENT_NORMAL) {
-                    const double* b = BLK(ent & 0x7fffu);
-                    const double a = b[sc + 5];
-                    if (a != 0.0) {
-#pragma unroll
-                        for (int k = 0; k < RR_NDOF; k++) if (k < dim) dv[k] += b[2 * k + 1] * a;
-                    }
-                }
-            }
-        }
-    }
-    bool live = valid;
-    int iters = 0;
-    for (int it = 0; it < cf.solver_iterations; it++) {
-        if (!__any_sync(FULL, live)) break;
-        double res = 0.0;
-        const int par = it & 1;
-        // ---- phase A: single rows (joint limits + motors, normals, spinning, rolling)
-        const int nA = par ? nA1 : nA0;
-        const int nAmax = (int)__reduce_max_sync(FULL, (unsigned int)(live ? nA : 0));
-        for (int slot = 0; slot < nAmax; slot++) {
-            unsigned int ent = ENT_IDLE;
-            if (live && slot < nA) ent = par ? ENT(4 * nA0, GSCHED_A(1), slot) : ENT(0, GSCHED_A(0), slot);
-            const bool act = ent != ENT_IDLE;
-            const unsigned int kind = ent >> 16;
-            double* b = BLK(act ? (ent & 0x7fffu) : 0u);
-            double J[RR_NDOF], R[RR_NDOF];
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int k = 0; k < RR_NDOF; k++) {
-                J[k] = 0.0; R[k] = 0.0;
-                if (act && k < dim) { const double2 p = *reinterpret_cast<const double2*>(b + 2 * k); J[k] = p.x; R[k] = p.y; }
-                if (k & 1) s1 += J[k] * dv[k]; else s0 += J[k] * dv[k];
-            }
-            double s = s0 + s1;
-            double rhs = 0.0, inv = 0.0, rinv = 0.0, lo = 0.0, hi = 0.0, app = 0.0;
-            bool on = act;
-            if (act) {
-                const double2 c0 = *reinterpret_cast<const double2*>(b + sc), c1 = *reinterpret_cast<const double2*>(b + sc + 2), c2 = *reinterpret_cast<const double2*>(b + sc + 4);
-                rhs = c0.x; inv = c0.y; rinv = c1.x; lo = c1.y; hi = c2.x; app = c2.y;
-                if (kind < ENT_JOINT) {           // spinning / rolling row: limits +-(coefficient x normal impulse), solved only while that impulse is positive
-                    const double total = BLK(kind)[sc + 5];
-                    on = total > 0.0;
-                    hi = lo * total; lo = -hi;
-                }
-            }
-            {   // a row coupling two groups of the env: the two lanes exchange their partial sums
-                const bool w = act && (ent & 0x8000u);
-                const unsigned int wq = (__ballot_sync(FULL, w) >> quad) & 15u;
-                const unsigned int other = wq & ~(1u << g);
-                const int src = (w && other) ? quad + __ffs(other) - 1 : lane;
-                const double so = __shfl_sync(FULL, s, src);
-                if (w && other) s += so;
-            }
-            double delta = rhs - s * inv;
-            const double sum = app + delta;
-            if (sum < lo) { delta = lo - app; app = lo; }
-            else if (sum > hi) { delta = hi - app; app = hi; }
-            else app = sum;
-            if (on) {
-#pragma unroll
-                for (int k = 0; k < RR_NDOF; k++) dv[k] += R[k] * delta;
-                const double r = delta * rinv;
-                res = fmax(res, r * r);
-                b[sc + 5] = app;
-            }
-        }
-        // ---- phase B: friction pairs with the implicit cone
-        const int nBmax = (int)__reduce_max_sync(FULL, (unsigned int)(live ? nB : 0));
-        for (int slot = 0; slot < nBmax; slot++) {
-            unsigned int ent = ENT_IDLE;
-            if (live && slot < nB) ent = ENT(4 * (nA0 + nA1), GSCHED_B, slot);
-            const bool act = ent != ENT_IDLE;
-            double* ba = BLK(act ? (ent & 0x7fffu) : 0u);
-            double* bb = BLK(act ? (ent & 0x7fffu) + sz16 : 0u);
-            double Ra[RR_NDOF], Rb[RR_NDOF];
-            double sa_ = 0.0, sb_ = 0.0;
-#pragma unroll
-            for (int k = 0; k < RR_NDOF; k++) {
-                Ra[k] = 0.0; Rb[k] = 0.0;
-                if (act && k < dim) {
-                    const double2 pa = *reinterpret_cast<const double2*>(ba + 2 * k), pb = *reinterpret_cast<const double2*>(bb + 2 * k);
-                    Ra[k] = pa.y; Rb[k] = pb.y;
-                    sa_ += pa.x * dv[k]; sb_ += pb.x * dv[k];
-                }
-            }
-            double rhsa = 0.0, inva = 0.0, rhsb = 0.0, invb = 0.0, rinva = 0.0, rinvb = 0.0, lim = 0.0, appa = 0.0, appb = 0.0;
-            if (act) {
-                const double2 a0 = *reinterpret_cast<const double2*>(ba + sc), a1 = *reinterpret_cast<const double2*>(ba + sc + 2);
-                const double2 b0 = *reinterpret_cast<const double2*>(bb + sc);
-                rhsa = a0.x; inva = a0.y; rinva = a1.x; rhsb = b0.x; invb = b0.y; rinvb = bb[sc + 2];
-                lim = a1.y * BLK(ent >> 16)[sc + 5];
-                appa = ba[sc + 5]; appb = bb[sc + 5];
-            }
-            {
-                const bool w = act && (ent & 0x8000u);
-                const unsigned int wq = (__ballot_sync(FULL, w) >> quad) & 15u;
-                const unsigned int other = wq & ~(1u << g);
-                const int src = (w && other) ? quad + __ffs(other) - 1 : lane;
-                const double oa = __shfl_sync(FULL, sa_, src), ob_ = __shfl_sync(FULL, sb_, src);
-                if (w && other) { sa_ += oa; sb_ += ob_; }
-            }
-            double wa = appa + (rhsa - sa_ * inva), wb = appb + (rhsb - sb_ * invb);
-            const double len2 = wa * wa + wb * wb;
-            if (len2 > lim * lim) { const double scl = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= scl; wb *= scl; }
-            const double da = wa - appa, db = wb - appb;
-            if (act) {
-#pragma unroll
-                for (int k = 0; k < RR_NDOF; k++) { dv[k] += Ra[k] * da; dv[k] += Rb[k] * db; }
-                const double qa = da * rinva, qb = db * rinvb;
-                res = fmax(res, fmax(qa * qa, qb * qb));
-                ba[sc + 5] = wa; bb[sc + 5] = wb;
-            }
-        }
-        // the env's residual: maximum over its four lanes
-        res = fmax(res, __shfl_xor_sync(FULL, res, 1));
-        res = fmax(res, __shfl_xor_sync(FULL, res, 2));
-        if (live) { iters = it + 1; if (res <= cf.residual_threshold) live = false; }
-    }
-    iters_out = iters;
+// sum of the six products of a lane's own group (an arm lane of a joint row: the product of the row's dof), all lanes at once
+__device__ __forceinline__ double group_sum6(double pr, int s0, int s1, int s2, int s3, int s4, int s5) {
+    const double a = __shfl_sync(FULL, pr, s0), b = __shfl_sync(FULL, pr, s1), c = __shfl_sync(FULL, pr, s2);
+    const double d = __shfl_sync(FULL, pr, s3), e = __shfl_sync(FULL, pr, s4), f = __shfl_sync(FULL, pr, s5);
+    return ((a + b) + (c + d)) + (e + f);
 }
-
-__global__ void __launch_bounds__(32, 2) k_step_solve(DevState st, int* __restrict__ man_hdr_all, double* __restrict__ man_pts_all, rr_config cf, int n_objects) {
+// One warp per env, 32 warps per SM.  The schedule and the blocks are read-only here and stream from L2 (the images of the
+// envs in flight — ~14 KB each — stay L2-resident; a block is one or two 128-byte lines); the applied impulses, the only
+// thing the sweep updates besides dv, live in shared memory by row id.  (Measured alternatives, same results: the whole image
+// in shared memory, one env per warp — 12 warps per SM, and lane-per-(env, group) streams, 7 envs per warp — 2 warps per SM:
+// both residency-bound at 1.9 ms for 4096 envs.)
+#ifndef SOLVE_MIN_BLOCKS
+#define SOLVE_MIN_BLOCKS 8
+#endif
+struct SolveEpi { SolveHead head; KinWs kin; };
+#define SOLVE_SMEM_DOUBLES ((int)(sizeof(SolveEpi) / 8) > RR_MAX_ROWS ? (int)(sizeof(SolveEpi) / 8) : RR_MAX_ROWS)
+#define SOLVE_SMEM_BYTES ((size_t)SOLVE_SMEM_DOUBLES * 8)
+__global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
     RR_DYN_SMEM(smem_raw);
-    double* const simg_all = reinterpret_cast<double*>(smem_raw);
-    SolveScratch& scr = *reinterpret_cast<SolveScratch*>(smem_raw + (size_t)SOLVE_E * SOLVE_ENV_CAP * 8);
+    double* const smem = reinterpret_cast<double*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
+    double* const sapp = smem;                                 // applied impulses by row id (during the sweep)
     const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (e >= st.N) return;
     const int N = st.N;
     const double dt = cf.dt;
-    const int e0 = blockIdx.x * SOLVE_E;
-    const int n_here = min(SOLVE_E, N - e0);
-    if (n_here <= 0) return;
-    // ---- the images of the warp's envs come into shared memory, one env after the other with all lanes: the used part of
-    // the three schedules (compacted), then as many blocks as fit; what does not fit is addressed in global memory
-    int my_nA0 = 0, my_nA1 = 0, my_nB = 0, my_sblk_off = 0, my_nblk_smem = 0; bool my_sched_smem = true, all_fast = true;
-    const int my_e = lane >> 2, my_g = lane & 3;
-    const bool valid = my_e < n_here;
-    for (int k = 0; k < n_here; k++) {
-        const double* gimg = st.handoff + (size_t)(e0 + k) * RR_IMG_DOUBLES;
-        const SolveHead* gh = reinterpret_cast<const SolveHead*>(gimg);
-        double* simg = simg_all + (size_t)k * SOLVE_ENV_CAP;
-        const int nA0 = gh->n_slotsA[0], nA1 = gh->n_slotsA[1], nB = gh->n_slotsB, n_blk = gh->n_blk_doubles;
-        const int n_words = 4 * (nA0 + nA1 + nB);
-        const bool sched_smem = n_words / 2 <= SOLVE_ENV_CAP;
-        const unsigned int* gs = reinterpret_cast<const unsigned int*>(gimg + HEAD_DOUBLES);
-        unsigned int* ss = reinterpret_cast<unsigned int*>(simg);
-        if (sched_smem) {
-            for (int i = lane; i < 4 * nA0; i += 32) ss[i] = gs[GSCHED_A(0) + i];
-            for (int i = lane; i < 4 * nA1; i += 32) ss[4 * nA0 + i] = gs[GSCHED_A(1) + i];
-            for (int i = lane; i < 4 * nB; i += 32) ss[4 * (nA0 + nA1) + i] = gs[GSCHED_B + i];
-        }
-        const int sblk_off = sched_smem ? n_words / 2 : SOLVE_ENV_CAP;
-        const int n_smem = min(n_blk, SOLVE_ENV_CAP - sblk_off);
-        {
-            const double2* src = reinterpret_cast<const double2*>(gimg + GBLK_BASE); double2* dst = reinterpret_cast<double2*>(simg + sblk_off);
-            for (int i = lane; i < n_smem / 2; i += 32) dst[i] = src[i];
-        }
-        all_fast = all_fast && sched_smem && n_smem == n_blk;
-        if (my_e == k) { my_nA0 = nA0; my_nA1 = nA1; my_nB = nB; my_sblk_off = sblk_off; my_nblk_smem = n_smem; my_sched_smem = sched_smem; }
+    const double* gimg = st.handoff + (size_t)e * RR_IMG_DOUBLES;
+    const SolveHead* gh = reinterpret_cast<const SolveHead*>(gimg);
+    const int nA0 = gh->n_slotsA[0], nA1 = gh->n_slotsA[1], nB = gh->n_slotsB, nc = gh->nc;
+    const unsigned int* gsched = reinterpret_cast<const unsigned int*>(gimg + HEAD_DOUBLES);
+    const double* gblk = gimg + GBLK_BASE;
+    // dv in owner layout: lane k < 11 owns the arm dof k, lane 11+6o+c the object component.
+    const int grp = lane_group(lane);
+    const bool ingrp = grp < 4;
+    const int g4 = ingrp ? grp : 0;                            // idle lanes read group 0's entry and ignore it
+    const int seg0 = grp == 0 ? 0 : (ingrp ? 11 + 6 * (grp - 1) : 31);   // first lane of the own group
+    const bool leader = ingrp && lane == seg0;
+    const int myk2 = 2 * (lane - seg0), mysc = grp == 0 ? 2 * RR_NDOF : 12, mysz = grp == 0 ? RR_ARM_BLK : RR_OBJ_BLK;
+    // shuffle sources of the group sum: the six lanes of a free body; for arm lanes the row's dof, then lane 31 (always 0)
+    const bool isobj = grp >= 1 && grp < 4;
+    const int s1 = isobj ? seg0 + 1 : 31, s2 = isobj ? seg0 + 2 : 31, s3 = isobj ? seg0 + 3 : 31, s4 = isobj ? seg0 + 4 : 31, s5 = isobj ? seg0 + 5 : 31;
+    // ---- applied impulses: zero, except the warm start of the normal rows
+    for (int k = lane; k < RR_MAX_ROWS; k += 32) sapp[k] = 0.0;
+    __syncwarp();
+    for (int c = lane; c < nc; c += 32) {
+        const unsigned int nr = gh->nrm_rel[c];
+        sapp[RID_NORMAL + c] = gblk[2 * (nr & 0x7fffu) + ((nr & 0x8000u) ? 2 * RR_NDOF + 5 : 17)];
     }
     __syncwarp();
-    double* const my_gimg = st.handoff + (size_t)(e0 + (valid ? my_e : 0)) * RR_IMG_DOUBLES;
-    double* const my_simg = simg_all + (size_t)(valid ? my_e : 0) * SOLVE_ENV_CAP;
-    double dv[RR_NDOF];
-    int my_iters = 0;
-    if (all_fast) pgs_sweep<true>(valid, my_g, my_simg, my_gimg + GBLK_BASE, my_sblk_off, my_nblk_smem, reinterpret_cast<const unsigned int*>(my_gimg + HEAD_DOUBLES), my_sched_smem, my_nA0, my_nA1, my_nB, cf, dv, my_iters);
-    else pgs_sweep<false>(valid, my_g, my_simg, my_gimg + GBLK_BASE, my_sblk_off, my_nblk_smem, reinterpret_cast<const unsigned int*>(my_gimg + HEAD_DOUBLES), my_sched_smem, my_nA0, my_nA1, my_nB, cf, dv, my_iters);
-    __syncwarp();
-    // ---- per env, with all lanes: integration, impulse write-back, touch sensors, final kinematics, observations
-    for (int k = 0; k < n_here; k++) {
-        const int e = e0 + k;
-        double* gimg = st.handoff + (size_t)e * RR_IMG_DOUBLES;
-        double* simg = simg_all + (size_t)k * SOLVE_ENV_CAP;
-        __syncwarp();
-        for (int i = lane; i < HEAD_DOUBLES; i += 32) reinterpret_cast<double*>(&scr.head)[i] = gimg[i];
-        // the env's velocity change back into owner layout (lane j < 11: arm dof j, lane 11 + 6 o + c: component c of body o)
-        if (my_e == k) {
-#pragma unroll
-            for (int j = 0; j < RR_NDOF; j++) { if (my_g == 0) scr.dv[j] = dv[j]; else if (j < 6) scr.dv[RR_NDOF + 6 * (my_g - 1) + j] = dv[j]; }
+    double dv = 0.0;
+    int iters = 0; double res = 0.0;
+    {
+        for (int slot = 0; slot < nA0; slot++) {             // warm start: dv of the normal rows' initial impulses
+            const uint2 w = *reinterpret_cast<const uint2*>(gsched + GSCHED_A(0) + 8 * slot + 2 * g4);
+            if (ingrp && w.x != ENT_IDLE && (w.x >> 16) == ENT_NORMAL) {
+                const double a = sapp[w.y & 0xffffu];
+                if (a != 0.0) dv += gblk[2 * (w.x & 0x7fffu) + myk2 + 1] * a;
+            }
         }
-        __syncwarp();
-        SolveHead& m = scr.head;
-        const double dvl = lane < 29 ? scr.dv[lane] : 0.0;
-        const int iters = __shfl_sync(FULL, my_iters, 4 * k);
-        const int sblk_off = __shfl_sync(FULL, my_sblk_off, 4 * k), n_blk_smem = __shfl_sync(FULL, my_nblk_smem, 4 * k);
-        const int smem_lim16 = (n_blk_smem - RR_ARM_BLK) / 2;
-        double* const sblk = simg + sblk_off; double* const gblk = gimg + GBLK_BASE;
-#define BLK_PTR(off16) ((int)(off16) <= smem_lim16 ? sblk + 2 * (int)(off16) : gblk + 2 * (int)(off16))
-        ObjReg ob;
-        const bool has_obj = lane < n_objects;
+        for (int it = 0; it < cf.solver_iterations; it++) {
+            res = 0.0;
+            const int par = it & 1;
+            // ---- phase A: single rows (joint limits + motors, normals, spinning, rolling), one slot at a time
+            const unsigned int* sched = gsched + GSCHED_A(par) + 2 * g4;
+            const int nA = par ? nA1 : nA0;
+            for (int slot = 0; slot < nA; slot++) {
+                const uint2 w = *reinterpret_cast<const uint2*>(sched + 8 * slot);
+                const bool act = ingrp && w.x != ENT_IDLE;
+                const unsigned int kind = w.x >> 16;
+                const double* b = gblk + 2 * (act ? (w.x & 0x7fffu) : 0u);
+                if (slot + 2 < nA) {                          // the blocks two slots ahead are on their way into L1
+                    const unsigned int nx = sched[8 * (slot + 2)];
+                    if (ingrp && nx != ENT_IDLE) RR_PREFETCH_L1(gblk + 2 * (nx & 0x7fffu) + myk2);
+                }
+                double J = 0.0, rr = 0.0, rhs = 0.0, inv = 0.0, rinv = 0.0, lo = 0.0, hi = 0.0, app = 0.0;
+                bool on = act;
+                const int rid = act ? (int)(w.y & 0xffffu) : 0;
+                if (act) {
+                    const double2 jr = *reinterpret_cast<const double2*>(b + myk2);
+                    const double2 c0 = *reinterpret_cast<const double2*>(b + mysc), c1 = *reinterpret_cast<const double2*>(b + mysc + 2);
+                    J = jr.x; rr = jr.y; rhs = c0.x; inv = c0.y; rinv = c1.x; lo = c1.y; hi = b[mysc + 4]; app = sapp[rid];
+                    if (kind < ENT_JOINT) {           // spinning / rolling row: limits +-(coefficient x normal impulse), solved only while that impulse is positive
+                        const double total = sapp[w.y >> 16];
+                        on = total > 0.0;
+                        hi = lo * total; lo = -hi;
+                    }
+                }
+                const int s0 = isobj ? seg0 : ((act && kind >= ENT_JOINT && kind < ENT_NORMAL) ? (int)(kind & 15u) : 31);
+                const double pr = J * dv;
+                double s = group_sum6(pr, s0, s1, s2, s3, s4, s5);
+                const bool inw = act && (w.x & 0x8000u);
+                if (__any_sync(FULL, inw)) {                 // the slot's wide row sums over all of its lanes
+                    const double t = warp_sum(inw ? pr : 0.0);
+                    if (inw) s = t;
+                }
+                double delta = rhs - s * inv;
+                const double sum = app + delta;
+                if (sum < lo) { delta = lo - app; app = lo; }
+                else if (sum > hi) { delta = hi - app; app = hi; }
+                else app = sum;
+                if (on) {
+                    dv += rr * delta;
+                    const double r = delta * rinv;
+                    res = fmax(res, r * r);
+                    if (leader) sapp[rid] = app;
+                }
+                __syncwarp();
+            }
+            // ---- phase B: friction pairs with the implicit cone
+            const unsigned int* schedb = gsched + GSCHED_B + 2 * g4;
+            for (int slot = 0; slot < nB; slot++) {
+                const uint2 w = *reinterpret_cast<const uint2*>(schedb + 8 * slot);
+                const bool act = ingrp && w.x != ENT_IDLE;
+                const double* ba = gblk + 2 * (act ? (w.x & 0x7fffu) : 0u);
+                const double* bb = ba + mysz;
+                const int r0 = act ? (int)(w.y & 0xffffu) : 0;
+                double Ja = 0.0, rra = 0.0, Jb = 0.0, rrb = 0.0, rhsa = 0.0, inva = 0.0, rhsb = 0.0, invb = 0.0, rinva = 0.0, rinvb = 0.0, lim = 0.0, appa = 0.0, appb = 0.0;
+                if (act) {
+                    const double2 ja = *reinterpret_cast<const double2*>(ba + myk2), jb = *reinterpret_cast<const double2*>(bb + myk2);
+                    const double2 a0 = *reinterpret_cast<const double2*>(ba + mysc), a1 = *reinterpret_cast<const double2*>(ba + mysc + 2);
+                    const double2 b0 = *reinterpret_cast<const double2*>(bb + mysc);
+                    Ja = ja.x; rra = ja.y; Jb = jb.x; rrb = jb.y;
+                    rhsa = a0.x; inva = a0.y; rinva = a1.x; rhsb = b0.x; invb = b0.y; rinvb = bb[mysc + 2];
+                    lim = a1.y * sapp[w.y >> 16];
+                    appa = sapp[r0]; appb = sapp[r0 + 1];
+                }
+                const int s0 = isobj ? seg0 : 31;
+                const double pa = Ja * dv, pb = Jb * dv;
+                double sa_ = group_sum6(pa, s0, s1, s2, s3, s4, s5), sb_ = group_sum6(pb, s0, s1, s2, s3, s4, s5);
+                const bool inw = act && (w.x & 0x8000u);
+                if (__any_sync(FULL, inw)) {
+                    double ta, tb; warp_sum2(inw ? pa : 0.0, inw ? pb : 0.0, ta, tb);
+                    if (inw) { sa_ = ta; sb_ = tb; }
+                }
+                double wa = appa + (rhsa - sa_ * inva), wb = appb + (rhsb - sb_ * invb);
+                const double len2 = wa * wa + wb * wb;
+                if (len2 > lim * lim) { const double scl = len2 > 0 ? lim / sqrt(len2) : 0.0; wa *= scl; wb *= scl; }
+                const double da = wa - appa, db = wb - appb;
+                if (act) {
+                    dv += rra * da; dv += rrb * db;
+                    const double qa = da * rinva, qb = db * rinvb;
+                    res = fmax(res, fmax(qa * qa, qb * qb));
+                    if (leader) { sapp[r0] = wa; sapp[r0 + 1] = wb; }
+                }
+                __syncwarp();
+            }
+            res = warp_max(res);
+            iters = it + 1;
+            if (res <= cf.residual_threshold) break;
+        }
+    }
+    // ---- impulse write-back (warm start of the next step) and gripper touch sensors (robot.py:131-163)
+    int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
+    double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
+    double touch[4] = {0.0, 0.0, 0.0, 0.0};
+    if (cf.enable_contacts) {
+        int c = 0;
+        for (int slot = 0; slot < RR_MAX_MANIFOLDS; slot++) {
+            const int pi = hdr[2 * slot];
+            if (pi < 0) break;
+            const int npt = hdr[2 * slot + 1];
+            const int sa = c_robot.pair_a[pi], sb = c_robot.pair_b[pi];
+            const int linkA = c_robot.shape_link[sa];
+            const bool sens = c_robot.shape_body[sa] == 0 && c_robot.shape_body[sb] != 0 && c_robot.shape_link[sb] == -1;
+            const int sensor = linkA == 11 ? 0 : (linkA == 10 ? 1 : (linkA == 15 ? 2 : (linkA == 14 ? 3 : -1)));
+            bool any = false; double best = 0.0;
+            for (int k = 0; k < npt; k++) {
+                double* P = pts + ((size_t)slot * 4 + k) * RR_PT_STRIDE;
+                double imp = P[10];
+                if (!(P[9] > cf.contact_breaking) && c < RR_MAX_CONTACTS) { imp = sapp[RID_NORMAL + c]; if (lane == 0) P[10] = imp; c++; }
+                if (sens && sensor >= 0 && fabs(P[9]) < 0.1) { const double f = imp / dt; if (!any || f > best) { best = f; any = true; } }
+            }
+            if (any && sens && sensor >= 0 && best > touch[sensor]) touch[sensor] = best;
+        }
+    }
+    __syncwarp();
+    // ---- the sweep's shared memory now holds the head of the image and the kinematics workspace
+    SolveEpi& ep = *reinterpret_cast<SolveEpi*>(smem);
+    for (int k = lane; k < HEAD_DOUBLES; k += 32) reinterpret_cast<double*>(&ep.head)[k] = gimg[k];
+    __syncwarp();
+    SolveHead& m = ep.head;
+    ObjReg ob;
+    const bool has_obj = lane < n_objects;
+    if (has_obj) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ob.pos[k] = m.objreg[lane][k]; ob.lin[k] = m.objreg[lane][7 + k]; ob.ang[k] = m.objreg[lane][10 + k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) ob.quat[k] = m.objreg[lane][3 + k];
+    }
+    const int overflow = m.overflow, simple = m.simple, rows_live = m.n_rows_total;
+    int fault = m.fault;
+    if (lane < RR_NDOF) {
+        m.qd[lane] = clampd(m.qd[lane] + dv, -cf.max_coord_vel, cf.max_coord_vel);
+        m.q[lane] += m.qd[lane] * dt;
+    }
+    {   // hand the object delta-velocities back to the lanes that own the bodies
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double da = __shfl_sync(FULL, dv, 11 + 6 * (lane % 3) + k), dl = __shfl_sync(FULL, dv, 14 + 6 * (lane % 3) + k);
+            if (has_obj) {
+                ob.ang[k] = clampd(ob.ang[k] + da, -cf.max_coord_vel, cf.max_coord_vel);
+                ob.lin[k] = clampd(ob.lin[k] + dl, -cf.max_coord_vel, cf.max_coord_vel);
+            }
+        }
+    }
+    if (has_obj) obj_integrate(ob, dt);
+    // ---- failure detection: a non-finite state cannot recover by itself (and the reference has nothing to say about it);
+    // the env is put back into its initial state as rr_reset would, keeps stepping, and is flagged in rr_diag (bit 3)
+    {
+        bool bad = lane < RR_NDOF && !(isfinite(m.q[lane]) && isfinite(m.qd[lane]));
         if (has_obj) {
 #pragma unroll
-            for (int j = 0; j < 3; j++) { ob.pos[j] = m.objreg[lane][j]; ob.lin[j] = m.objreg[lane][7 + j]; ob.ang[j] = m.objreg[lane][10 + j]; }
+            for (int k = 0; k < 3; k++) bad |= !(isfinite(ob.pos[k]) && isfinite(ob.lin[k]) && isfinite(ob.ang[k]));
 #pragma unroll
-            for (int j = 0; j < 4; j++) ob.quat[j] = m.objreg[lane][3 + j];
+            for (int k = 0; k < 4; k++) bad |= !isfinite(ob.quat[k]);
         }
-        const int nc = m.nc, overflow = m.overflow, simple = m.simple, rows_live = m.n_rows_total;
-        int fault = m.fault;
-        int* hdr = man_hdr_all + (size_t)e * RR_MAX_MANIFOLDS * 2;
-        double* pts = man_pts_all + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
-        if (lane < RR_NDOF) {
-            m.qd[lane] = clampd(m.qd[lane] + dvl, -cf.max_coord_vel, cf.max_coord_vel);
-            m.q[lane] += m.qd[lane] * dt;
-        }
-        {   // hand the object delta-velocities to the lanes that own the bodies
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const double da = __shfl_sync(FULL, dvl, 11 + 6 * (lane % 3) + j), dl = __shfl_sync(FULL, dvl, 14 + 6 * (lane % 3) + j);
-                if (has_obj) {
-                    ob.ang[j] = clampd(ob.ang[j] + da, -cf.max_coord_vel, cf.max_coord_vel);
-                    ob.lin[j] = clampd(ob.lin[j] + dl, -cf.max_coord_vel, cf.max_coord_vel);
-                }
-            }
-        }
-        // ---- impulse write-back (warm start of the next step) and gripper touch sensors (robot.py:131-163)
-        double touch[4] = {0.0, 0.0, 0.0, 0.0};
-        if (cf.enable_contacts) {
-            int c = 0;
-            for (int slot = 0; slot < RR_MAX_MANIFOLDS; slot++) {
-                const int pi = hdr[2 * slot];
-                if (pi < 0) break;
-                const int npt = hdr[2 * slot + 1];
-                const int sa = c_robot.pair_a[pi], sb = c_robot.pair_b[pi];
-                const int linkA = c_robot.shape_link[sa];
-                const bool sens = c_robot.shape_body[sa] == 0 && c_robot.shape_body[sb] != 0 && c_robot.shape_link[sb] == -1;
-                const int sensor = linkA == 11 ? 0 : (linkA == 10 ? 1 : (linkA == 15 ? 2 : (linkA == 14 ? 3 : -1)));
-                bool any = false; double best = 0.0;
-                for (int j = 0; j < npt; j++) {
-                    double* P = pts + ((size_t)slot * 4 + j) * RR_PT_STRIDE;
-                    double imp = P[10];
-                    if (!(P[9] > cf.contact_breaking) && c < RR_MAX_CONTACTS) {
-                        const unsigned int nr = m.nrm_rel[c];
-                        imp = BLK_PTR(nr & 0x7fffu)[(nr & 0x8000u) ? 2 * RR_NDOF + 5 : 17];
-                        if (lane == 0) P[10] = imp;
-                        c++;
-                    }
-                    if (sens && sensor >= 0 && fabs(P[9]) < 0.1) { const double f = imp / dt; if (!any || f > best) { best = f; any = true; } }
-                }
-                if (any && sens && sensor >= 0 && best > touch[sensor]) touch[sensor] = best;
-            }
-        }
-#undef BLK_PTR
-        if (has_obj) obj_integrate(ob, dt);
-        // ---- failure detection: a non-finite state cannot recover by itself (and the reference has nothing to say about it);
-        // the env is put back into its initial state as rr_reset would, keeps stepping, and is flagged in rr_diag (bit 3)
-        {
-            bool bad = lane < RR_NDOF && !(isfinite(m.q[lane]) && isfinite(m.qd[lane]));
+        if (__any_sync(FULL, bad)) {
+            fault |= 2;
+            if (lane < RR_NDOF) { m.q[lane] = 0.0; m.qd[lane] = 0.0; m.target[lane] = 0.0; }
             if (has_obj) {
 #pragma unroll
-                for (int j = 0; j < 3; j++) bad |= !(isfinite(ob.pos[j]) && isfinite(ob.lin[j]) && isfinite(ob.ang[j]));
+                for (int k = 0; k < 3; k++) { ob.pos[k] = c_robot.obj_init[lane][k]; ob.lin[k] = 0.0; ob.ang[k] = 0.0; }
 #pragma unroll
-                for (int j = 0; j < 4; j++) bad |= !isfinite(ob.quat[j]);
+                for (int k = 0; k < 4; k++) ob.quat[k] = c_robot.obj_init[lane][3 + k];
             }
-            if (__any_sync(FULL, bad)) {
-                fault |= 2;
-                if (lane < RR_NDOF) { m.q[lane] = 0.0; m.qd[lane] = 0.0; m.target[lane] = 0.0; }
-                if (has_obj) {
+            for (int slot = lane; slot < RR_MAX_MANIFOLDS; slot += 32) { hdr[2 * slot] = -1; hdr[2 * slot + 1] = 0; }
 #pragma unroll
-                    for (int j = 0; j < 3; j++) { ob.pos[j] = c_robot.obj_init[lane][j]; ob.lin[j] = 0.0; ob.ang[j] = 0.0; }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) ob.quat[j] = c_robot.obj_init[lane][3 + j];
-                }
-                for (int slot = lane; slot < RR_MAX_MANIFOLDS; slot += 32) { hdr[2 * slot] = -1; hdr[2 * slot + 1] = 0; }
-#pragma unroll
-                for (int j = 0; j < 4; j++) touch[j] = 0.0;
-            }
+            for (int k = 0; k < 4; k++) touch[k] = 0.0;
         }
-        __syncwarp();
-        // ---- final kinematics, state write-back, observations
-        fk_local(m.q, scr.kin, lane);
-        fk_sweep(scr.kin, lane, nullptr, nullptr);
-        store_frames(scr.kin, st, e, lane);
-        if (lane < RR_NDOF) {
-            st.q[(size_t)lane * N + e] = m.q[lane]; st.qd[(size_t)lane * N + e] = m.qd[lane];
-            st.target[(size_t)lane * N + e] = m.target[lane];
-        }
-        if (has_obj) {
-            double* base = st.obj + (size_t)lane * 13 * N + e;
+    }
+    __syncwarp();
+    // ---- final kinematics, state write-back, observations
+    fk_local(m.q, ep.kin, lane);
+    fk_sweep(ep.kin, lane, nullptr, nullptr);
+    store_frames(ep.kin, st, e, lane);
+    if (lane < RR_NDOF) {
+        st.q[(size_t)lane * N + e] = m.q[lane]; st.qd[(size_t)lane * N + e] = m.qd[lane];
+        st.target[(size_t)lane * N + e] = m.target[lane];
+    }
+    if (has_obj) {
+        double* base = st.obj + (size_t)lane * 13 * N + e;
 #pragma unroll
-            for (int j = 0; j < 3; j++) base[(size_t)j * N] = ob.pos[j];
+        for (int k = 0; k < 3; k++) base[(size_t)k * N] = ob.pos[k];
 #pragma unroll
-            for (int j = 0; j < 4; j++) base[(size_t)(3 + j) * N] = ob.quat[j];
+        for (int k = 0; k < 4; k++) base[(size_t)(3 + k) * N] = ob.quat[k];
 #pragma unroll
-            for (int j = 0; j < 3; j++) { base[(size_t)(7 + j) * N] = ob.lin[j]; base[(size_t)(10 + j) * N] = ob.ang[j]; }
-        }
-        if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
-        if (lane == 0) {
-            st.diag[4 * e] = rows_live; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (simple ? 2 : 0) | (fault << 2) | (cf.enable_contacts ? (st.col_flags[e] << 4) : 0);   // bit 0: contact cap hit, bit 1: every contact is object-vs-static, bits 2-3: faults, bit 4: manifold slots exhausted
-            st.timestep[e] += 1;
-        }
+        for (int k = 0; k < 3; k++) { base[(size_t)(7 + k) * N] = ob.lin[k]; base[(size_t)(10 + k) * N] = ob.ang[k]; }
+    }
+    if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
+    if (lane == 0) {
+        st.diag[4 * e] = rows_live; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (simple ? 2 : 0) | (fault << 2) | (cf.enable_contacts ? (st.col_flags[e] << 4) : 0);   // bit 0: contact cap hit, bit 1: every contact is object-vs-static, bits 2-3: faults, bit 4: manifold slots exhausted
+        st.timestep[e] += 1;
     }
 }
 
@@ -1317,7 +1240,7 @@ int rrk_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_robot, &ctx->robot, sizeof(RobotConst)));
     g_phys_owner[ctx->device & 63] = ctx;
     CK(cudaFuncSetAttribute(k_step_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
-    CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * WPB)));
     CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FkMem) * WPB)));
     return 0;
 }
@@ -1375,7 +1298,7 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
     if (ctx->cfg.enable_contacts && rrk_collide(ctx, s) != 0) return -1;
     ProfScope ps(ctx, 0, s);
     RR_LAUNCH(k_step_dyn, nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s)(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
-    RR_LAUNCH(k_step_solve, nblk(ctx->N, SOLVE_E), 32, SOLVE_SMEM_BYTES, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
+    RR_LAUNCH(k_step_solve, nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
     ctx->launches += 2;
     CK(cudaGetLastError());
     return 0;

@@ -6,7 +6,7 @@ from real_robots_b200.sim import BatchedSim
 N = 4096
 sim = BatchedSim(N, 3)
 g = torch.Generator(device="cuda"); g.manual_seed(0)
-acts = [(torch.rand(N, 9, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * 2.0 for _ in range(8)]
+acts = [(torch.rand(N, 9, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * float(os.environ.get("ACT_SCALE", "2.0")) for _ in range(8)]
 for i in range(80): sim.step(acts[(i // 20) % 8])
 torch.cuda.synchronize()
 sim.profile(True)

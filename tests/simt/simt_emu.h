@@ -41,6 +41,7 @@ struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c 
 struct float4 { float x, y, z, w; } __attribute__((aligned(16)));
 struct int4 { int x, y, z, w; } __attribute__((aligned(16)));
 struct uint4 { unsigned x, y, z, w; } __attribute__((aligned(16)));
+struct uint2 { unsigned x, y; } __attribute__((aligned(8)));
 struct double2 { double x, y; } __attribute__((aligned(16)));
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 struct ulonglong2 { unsigned long long x, y; } __attribute__((aligned(16)));

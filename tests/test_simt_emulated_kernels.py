@@ -69,27 +69,6 @@ def test_emulated_step_kernels_match_oracle_with_contacts():
     assert seen_contacts >= 8 and seen_wide >= 20, (seen_contacts, seen_wide)        # arm contacts (rows coupling the arm with an object) were solved too
 
 
-def test_emulated_solver_with_rows_left_in_global_memory():
-    """The solver keeps an env's schedule and row blocks in shared memory and addresses whatever does not fit in global
-    memory (contact-heavy envs).  A build with a tiny SOLVE_ENV_CAP forces that path for every env: same results."""
-    N = 2
-    sim = EmuSim(N, 3, build_flags=("-DSOLVE_ENV_CAP=256",))
-    orcs = [Oracle(3) for _ in range(N)]
-    for s, a in enumerate(zip(*[_policy_single(sd, 70) for sd in (13, 11)])):
-        a = np.stack(a)
-        sim.step(a)
-        for e in range(N):
-            orcs[e].step(a[e])
-        j = sim.read_state()[0]
-        d = sim.diag()
-        for e in range(N):
-            assert np.abs(j[e] - orcs[e].read()[0]).max() < 1e-9, (s, e)
-            assert d[e, 0] == orcs[e].diag()["rows"] and d[e, 2] == orcs[e].diag()["contacts"]
-        ob = sim.get_state()[2]
-        assert np.abs(ob - np.array([x.get_state()[2] for x in orcs])).max() < 1e-8, s
-    assert max(x.diag()["contacts"] for x in orcs) >= 5
-
-
 def test_emulated_rasteriser_is_bit_exact_and_static_layer_is_identical():
     N = 2
     rng = np.random.default_rng(5)
