@@ -271,17 +271,23 @@ def run_ours(args):
     value = world * args.envs * K / (ms_max * 1e-3)
 
     # ---- end-to-end leg through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
+    # The random policy is open loop, so the driver keeps two steps in flight (rr_step_host_begin / _end): the physics and first
+    # render chunks of step t+1 run while the copy engine drains step t's images into the other set of pinned buffers.
     Ke = max(3, min(K, args.e2e_steps))
-    host_acts = acts[:Ke + 2].cpu().pin_memory().numpy()
-    mask = torch.ones(args.envs, dtype=torch.uint8).pin_memory().numpy()
-    out = sim.alloc_host(images=True, want_mask=True, pinned=True)
+    host_acts_t = acts[:Ke + 2].cpu().pin_memory()
+    host_acts = host_acts_t.numpy()
+    mask_t = torch.ones(args.envs, dtype=torch.uint8).pin_memory()
+    mask = mask_t.numpy()
+    outs = [sim.alloc_host(images=True, want_mask=True, pinned=True) for _ in range(2)]
     for t in range(2):
-        sim.step_host(host_acts[t], mask, out=out)
+        sim.step_host(host_acts[t], mask, out=outs[t])
     barrier()
     t0 = time.perf_counter()
-    for t in range(2, 2 + Ke):
-        sim.step_host(host_acts[t], mask, out=out)
-    torch.cuda.synchronize()
+    sim.step_host_begin(host_acts[2], mask, outs[0])
+    for t in range(3, 2 + Ke):
+        sim.step_host_begin(host_acts[t], mask, outs[(t - 2) & 1])
+        sim.step_host_end()
+    sim.step_host_end()
     te = time.perf_counter() - t0
     tt = torch.tensor([te], dtype=torch.float64, device=dev)
     if world > 1:
@@ -289,6 +295,40 @@ def run_ours(args):
     e2e_value = world * args.envs * Ke / float(tt.item())
     h2d = args.envs * 9 * 8 + args.envs
     d2h = args.envs * (9 * 8 + 4 * 8 + N_OBJECTS * 7 * 8 + IMG_BYTES)
+    # ---- the ceiling of that leg: nothing but the device-to-host copies of one step's images into pinned memory, all ranks at once
+    rgb_d, depth_d, seg_d = sim.images()
+    pinned = outs[0]["_torch"][3:6]
+    cstream = torch.cuda.Stream(device=dev)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ceil_ms = []
+    for rep in range(4):
+        barrier()
+        with torch.cuda.stream(cstream):
+            c0.record()
+            for h, d in zip(pinned, (rgb_d, depth_d, seg_d)):
+                h.copy_(d, non_blocking=True)
+            c1.record()
+        cstream.synchronize()
+        if rep:
+            ceil_ms.append(c0.elapsed_time(c1))
+    ct = torch.tensor([max(ceil_ms) if world > 1 else min(ceil_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+    d2h_ceiling_gbs = args.envs * IMG_BYTES / (float(ct.item()) * 1e-3) / 1e9           # per rank, with every rank copying
+    e2e_ceiling = world * args.envs / (float(ct.item()) * 1e-3)
+    # ---- N > 1: the score gather of evaluate() over NCCL on real rr_score output (the only collective of the port)
+    collective = None
+    if world > 1:
+        from real_robots_b200.evaluate import gather_scores, shard_range
+        G = world * 64
+        lo, hi = shard_range(G, rank, world)
+        goal = sim.read_state()[2][:, :, :3].contiguous() + 0.05
+        local = sim.score(goal)[:hi - lo]
+        vec = gather_scores(torch.arange(lo, hi, dtype=torch.int64, device=dev), local, G)
+        ok = bool(torch.isfinite(vec).all()) and bool(torch.equal(vec[lo:hi], local)) and bool(((vec > 0) & (vec <= N_OBJECTS)).all())
+        okt = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        collective = {"what": "evaluate.gather_scores (all_gather over NCCL) of rr_score output, %d goals" % G, "ranks": world, "ok": bool(okt.item() == 1.0)}
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -318,7 +358,11 @@ def run_ours(args):
                                        "image_write_GBps": achieved},
                          "physics_kernel": {"kernel": "k_step_dyn + k_step_solve", "ms_per_launch": s_ms / max(s_n, 1),
                                             "achieved_gbs": args.envs * STATE_BYTES / (s_ms / max(s_n, 1) * 1e-3) / 1e9 if s_ms > 0 else None}},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "api": "rr_step_host_begin / rr_step_host_end, two steps in flight, pinned host buffers",
+                    "d2h_ceiling_gbs": d2h_ceiling_gbs, "ceiling": e2e_ceiling, "frac_of_ceiling": e2e_value / e2e_ceiling if e2e_ceiling else None,
+                    "ceiling_how": "plain pinned D2H copy of one step's images (%.2f GB per rank), all ranks at once, slowest rank" % (args.envs * IMG_BYTES / 1e9)},
+            "collective_check": collective,
             "gpu_launches": launches,
             "clocks": sampler.summary(),
         }

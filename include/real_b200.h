@@ -121,6 +121,15 @@ int  rr_score(rr_ctx* ctx, const double* goal_xyz, double* score, void* stream);
 int  rr_step_host(rr_ctx* ctx, const double* joint_cmd_host, const uint8_t* render_mask_host,
                   double* joint_pos_host, double* touch_host, double* obj_pos_quat_host,
                   uint8_t* rgb_host, float* depth_host, int32_t* mask_host);
+/* The same step, split: _begin enqueues it (commands in, physics, read-out, render, every copy back into the given HOST
+ * buffers) and returns at once; _end waits for the oldest step begun.  Up to two steps may be in flight (device staging is
+ * double buffered), so an open-loop driver — bench.py's random policy, a replayed plan — overlaps the physics of step t+1
+ * with the image copies of step t; the host buffers of a step must stay untouched until its _end returns.  rr_step_host is
+ * _begin followed by _end.  (Not in the reference, whose step is synchronous: env.py:326-356.) */
+int  rr_step_host_begin(rr_ctx* ctx, const double* joint_cmd_host, const uint8_t* render_mask_host,
+                        double* joint_pos_host, double* touch_host, double* obj_pos_quat_host,
+                        uint8_t* rgb_host, float* depth_host, int32_t* mask_host);
+int  rr_step_host_end(rr_ctx* ctx);
 
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 long long rr_launch_count(rr_ctx* ctx);

@@ -50,6 +50,8 @@ SYMBOLS = {
     "rr_link_pose": (_I, [_VP, _I, _VP, _VP]),
     "rr_score": (_I, [_VP, _VP, _VP, _VP]),
     "rr_step_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rr_step_host_begin": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rr_step_host_end": (_I, [_VP]),
     "rr_launch_count": (C.c_longlong, [_VP]),
     "rr_diag": (_I, [_VP, _VP, _VP]),
     "rr_contacts": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),

@@ -249,8 +249,8 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     if (device < 0 || device >= ndev) { g_create_err = "rr_create: bad device index"; return -1; }
     rr_ctx* ctx = new rr_ctx();
     ctx->device = device; ctx->N = n_envs; ctx->n_objects = n_objects; ctx->launches = 0; ctx->prof_on = false; ctx->host_compute = nullptr; ctx->host_copy = nullptr; ctx->d_rec_scratch = nullptr; ctx->d_list_scratch = nullptr; ctx->d_work_counter = nullptr; ctx->d_tri_shape = nullptr; ctx->raster_grid = 0; ctx->d_planes = nullptr; ctx->d_cull_scratch = nullptr; ctx->h_collide_const = nullptr; ctx->cull_hmax = 0.f;
-    ctx->d_cmd = nullptr; ctx->d_mask = nullptr; ctx->d_joint = ctx->d_touch = ctx->d_objpose = nullptr;
-    ctx->d_rgb = nullptr; ctx->d_depth = nullptr; ctx->d_seg = nullptr; ctx->img_capacity = 0; ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0;
+    for (int k = 0; k < 2; k++) { ctx->d_cmd[k] = nullptr; ctx->d_mask[k] = nullptr; ctx->d_joint[k] = ctx->d_touch[k] = ctx->d_objpose[k] = nullptr; ctx->d_rgb[k] = nullptr; ctx->d_depth[k] = nullptr; ctx->d_seg[k] = nullptr; }
+    ctx->img_capacity = 0; ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0; ctx->host_begun = ctx->host_ended = 0;
     if (cfg) ctx->cfg = *cfg; else rr_config_default(&ctx->cfg);
     // error path: release whatever was allocated and drop the constant-memory ownership records that point at ctx
     auto fail = [&](int rc) { g_create_err = ctx->err; rr_destroy(ctx); return rc; };
@@ -270,8 +270,10 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     alloc((void**)&st.q, 11 * N * 8); alloc((void**)&st.qd, 11 * N * 8); alloc((void**)&st.target, 11 * N * 8);
     alloc((void**)&st.obj, 39 * N * 8); alloc((void**)&st.touch, 4 * N * 8); alloc((void**)&st.link_frames, 16 * 12 * N * 8);
     alloc((void**)&st.render_mats, N * RR_NSHAPES * RR_MAT_STRIDE * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.col_flags, N * 4); alloc((void**)&st.timestep, N * 8);
-    alloc((void**)&ctx->d_cmd, N * 9 * 8); alloc((void**)&ctx->d_mask, N); alloc((void**)&ctx->d_joint, N * 9 * 8);
-    alloc((void**)&ctx->d_touch, N * 4 * 8); alloc((void**)&ctx->d_objpose, N * 3 * 7 * 8);
+    for (int k = 0; k < 2; k++) {
+        alloc((void**)&ctx->d_cmd[k], N * 9 * 8); alloc((void**)&ctx->d_mask[k], N); alloc((void**)&ctx->d_joint[k], N * 9 * 8);
+        alloc((void**)&ctx->d_touch[k], N * 4 * 8); alloc((void**)&ctx->d_objpose[k], N * 3 * 7 * 8);
+    }
     for (int k = 0; k < 2; k++) {
         alloc((void**)&st.man_hdr[k], N * RR_MAX_MANIFOLDS * 2 * 4);
         alloc((void**)&st.man_pts[k], N * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE * 8);
@@ -294,13 +296,15 @@ int rr_destroy(rr_ctx* ctx) {
     DevState& st = ctx->st;
     void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.col_flags, st.timestep,
                     st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.handoff,
-                    ctx->d_cmd, ctx->d_mask, ctx->d_joint, ctx->d_touch, ctx->d_objpose, ctx->d_rgb, ctx->d_depth, ctx->d_seg,
+                    ctx->d_cmd[0], ctx->d_mask[0], ctx->d_joint[0], ctx->d_touch[0], ctx->d_objpose[0], ctx->d_rgb[0], ctx->d_depth[0], ctx->d_seg[0],
+                    ctx->d_cmd[1], ctx->d_mask[1], ctx->d_joint[1], ctx->d_touch[1], ctx->d_objpose[1], ctx->d_rgb[1], ctx->d_depth[1], ctx->d_seg[1],
                     ctx->d_tris, ctx->d_tex, ctx->d_hull_verts, ctx->d_rec_scratch, ctx->d_list_scratch, ctx->d_work_counter, ctx->d_tri_shape, ctx->d_planes, ctx->d_cull_scratch,
                     ctx->d_static_keys, ctx->d_static_img};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->host_compute) {
         for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->host_ev[i]);
+        for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->host_done[i]);
         cudaStreamDestroy(ctx->host_compute); cudaStreamDestroy(ctx->host_copy);
     }
     for (int k = 0; k < RR_PROFILE_KINDS; k++) for (cudaEvent_t e : ctx->prof_ev[k]) cudaEventDestroy(e);
@@ -403,9 +407,14 @@ int rr_diag(rr_ctx* ctx, int32_t* out, void* stream) {
 
 #define CKH(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return -1; } } while (0)
 
-int rr_step_host(rr_ctx* ctx, const double* cmd_h, const uint8_t* render_mask_h, double* joint_h, double* touch_h, double* objpose_h,
-                 uint8_t* rgb_h, float* depth_h, int32_t* mask_h) {
+// Host-buffer path.  rr_step_host_begin enqueues one whole step — H2D of the commands, physics, read-out, render in chunks
+// whose D2H copies (on a second stream) overlap the render of the next chunk — and returns; rr_step_host_end waits for the
+// oldest step begun.  Two steps may be in flight: the device staging (commands, observations, images) is double buffered,
+// so the physics and the first render chunks of step t+1 run while the copy engine still drains step t's images.
+int rr_step_host_begin(rr_ctx* ctx, const double* cmd_h, const uint8_t* render_mask_h, double* joint_h, double* touch_h, double* objpose_h,
+                       uint8_t* rgb_h, float* depth_h, int32_t* mask_h) {
     ARG(cmd_h != nullptr, "rr_step_host: joint_cmd_host is NULL");
+    ARG(ctx->host_begun - ctx->host_ended < 2, "rr_step_host_begin: two steps are already in flight (call rr_step_host_end first)");
     CKH(cudaSetDevice(ctx->device));
     const size_t N = (size_t)ctx->N, PX = (size_t)RR_W * RR_H;
     const bool want_img = render_mask_h && (rgb_h || depth_h || mask_h);
@@ -413,20 +422,22 @@ int rr_step_host(rr_ctx* ctx, const double* cmd_h, const uint8_t* render_mask_h,
         CKH(cudaStreamCreateWithFlags(&ctx->host_compute, cudaStreamNonBlocking));
         CKH(cudaStreamCreateWithFlags(&ctx->host_copy, cudaStreamNonBlocking));
         for (int i = 0; i < 16; i++) CKH(cudaEventCreateWithFlags(&ctx->host_ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) CKH(cudaEventCreateWithFlags(&ctx->host_done[i], cudaEventDisableTiming));
     }
     if (want_img && ctx->img_capacity < N) {
-        CKH(cudaMalloc(&ctx->d_rgb, N * PX * 3)); CKH(cudaMalloc(&ctx->d_depth, N * PX * 4)); CKH(cudaMalloc(&ctx->d_seg, N * PX * 4));
+        for (int k = 0; k < 2; k++) { CKH(cudaMalloc(&ctx->d_rgb[k], N * PX * 3)); CKH(cudaMalloc(&ctx->d_depth[k], N * PX * 4)); CKH(cudaMalloc(&ctx->d_seg[k], N * PX * 4)); }
         ctx->img_capacity = N;
     }
-    CKH(cudaDeviceSynchronize());             // order after whatever the caller enqueued on other streams
+    if (ctx->host_begun == ctx->host_ended) CKH(cudaDeviceSynchronize());      // nothing in flight: order after whatever the caller enqueued on other streams
+    const int k = ctx->host_begun & 1;
     cudaStream_t s = ctx->host_compute, cs = ctx->host_copy;
-    CKH(cudaMemcpyAsync(ctx->d_cmd, cmd_h, N * 9 * 8, cudaMemcpyHostToDevice, s));
-    if (want_img) CKH(cudaMemcpyAsync(ctx->d_mask, render_mask_h, N, cudaMemcpyHostToDevice, s));
-    if (rrk_step(ctx, ctx->d_cmd, s) != 0) return -1;
-    if (rrk_read_state(ctx, ctx->d_joint, ctx->d_touch, ctx->d_objpose, s) != 0) return -1;
-    if (joint_h) CKH(cudaMemcpyAsync(joint_h, ctx->d_joint, N * 9 * 8, cudaMemcpyDeviceToHost, s));
-    if (touch_h) CKH(cudaMemcpyAsync(touch_h, ctx->d_touch, N * 4 * 8, cudaMemcpyDeviceToHost, s));
-    if (objpose_h) CKH(cudaMemcpyAsync(objpose_h, ctx->d_objpose, N * ctx->n_objects * 7 * 8, cudaMemcpyDeviceToHost, s));
+    CKH(cudaMemcpyAsync(ctx->d_cmd[k], cmd_h, N * 9 * 8, cudaMemcpyHostToDevice, s));
+    if (want_img) CKH(cudaMemcpyAsync(ctx->d_mask[k], render_mask_h, N, cudaMemcpyHostToDevice, s));
+    if (rrk_step(ctx, ctx->d_cmd[k], s) != 0) return -1;
+    if (rrk_read_state(ctx, ctx->d_joint[k], ctx->d_touch[k], ctx->d_objpose[k], s) != 0) return -1;
+    if (joint_h) CKH(cudaMemcpyAsync(joint_h, ctx->d_joint[k], N * 9 * 8, cudaMemcpyDeviceToHost, s));
+    if (touch_h) CKH(cudaMemcpyAsync(touch_h, ctx->d_touch[k], N * 4 * 8, cudaMemcpyDeviceToHost, s));
+    if (objpose_h) CKH(cudaMemcpyAsync(objpose_h, ctx->d_objpose[k], N * ctx->n_objects * 7 * 8, cudaMemcpyDeviceToHost, s));
     if (want_img) {
         // render in chunks of envs; the device->host copy of chunk c runs on the copy stream while chunk c+1 renders
         const int chunks = N >= 1024 ? 16 : (N >= 64 ? 4 : 1);
@@ -434,18 +445,34 @@ int rr_step_host(rr_ctx* ctx, const double* cmd_h, const uint8_t* render_mask_h,
         for (int c = 0; c < chunks; c++) {
             const int lo = c * per, cnt = (int)N - lo < per ? (int)N - lo : per;
             if (cnt <= 0) break;
-            if (rrk_render_range(ctx, ctx->d_mask, nullptr, ctx->d_rgb, ctx->d_depth, mask_h ? ctx->d_seg : nullptr, lo, cnt, s) != 0) return -1;
+            if (rrk_render_range(ctx, ctx->d_mask[k], nullptr, ctx->d_rgb[k], ctx->d_depth[k], mask_h ? ctx->d_seg[k] : nullptr, lo, cnt, s) != 0) return -1;
             CKH(cudaEventRecord(ctx->host_ev[c], s));
             CKH(cudaStreamWaitEvent(cs, ctx->host_ev[c], 0));
             const size_t o = (size_t)lo * PX, n = (size_t)cnt * PX;
-            if (rgb_h) CKH(cudaMemcpyAsync(rgb_h + o * 3, ctx->d_rgb + o * 3, n * 3, cudaMemcpyDeviceToHost, cs));
-            if (depth_h) CKH(cudaMemcpyAsync(depth_h + o, ctx->d_depth + o, n * 4, cudaMemcpyDeviceToHost, cs));
-            if (mask_h) CKH(cudaMemcpyAsync(mask_h + o, ctx->d_seg + o, n * 4, cudaMemcpyDeviceToHost, cs));
+            if (rgb_h) CKH(cudaMemcpyAsync(rgb_h + o * 3, ctx->d_rgb[k] + o * 3, n * 3, cudaMemcpyDeviceToHost, cs));
+            if (depth_h) CKH(cudaMemcpyAsync(depth_h + o, ctx->d_depth[k] + o, n * 4, cudaMemcpyDeviceToHost, cs));
+            if (mask_h) CKH(cudaMemcpyAsync(mask_h + o, ctx->d_seg[k] + o, n * 4, cudaMemcpyDeviceToHost, cs));
         }
     }
-    CKH(cudaStreamSynchronize(s));
-    CKH(cudaStreamSynchronize(cs));
+    // the step is done when the compute stream (small copies) and the copy stream (images) both are
+    CKH(cudaEventRecord(ctx->host_ev[15], s));
+    CKH(cudaStreamWaitEvent(cs, ctx->host_ev[15], 0));
+    CKH(cudaEventRecord(ctx->host_done[k], cs));
+    ctx->host_begun++;
     return 0;
+}
+int rr_step_host_end(rr_ctx* ctx) {
+    ARG(ctx->host_begun > ctx->host_ended, "rr_step_host_end: no step in flight");
+    CKH(cudaSetDevice(ctx->device));
+    CKH(cudaEventSynchronize(ctx->host_done[ctx->host_ended & 1]));
+    ctx->host_ended++;
+    return 0;
+}
+int rr_step_host(rr_ctx* ctx, const double* cmd_h, const uint8_t* render_mask_h, double* joint_h, double* touch_h, double* objpose_h,
+                 uint8_t* rgb_h, float* depth_h, int32_t* mask_h) {
+    while (ctx->host_begun > ctx->host_ended) if (rr_step_host_end(ctx) != 0) return -1;
+    if (rr_step_host_begin(ctx, cmd_h, render_mask_h, joint_h, touch_h, objpose_h, rgb_h, depth_h, mask_h) != 0) return -1;
+    return rr_step_host_end(ctx);
 }
 
 }  // extern "C"

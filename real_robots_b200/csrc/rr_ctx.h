@@ -115,10 +115,12 @@ struct rr_ctx {
     void* d_static_keys = nullptr; void* d_static_img = nullptr; bool static_ready = false; bool static_enabled = true;
     unsigned static_bits = 0; int static_skip_front = 0;
     // staging for the host-buffer path
-    double* d_cmd; uint8_t* d_mask; double* d_joint; double* d_touch; double* d_objpose;
-    uint8_t* d_rgb; float* d_depth; int32_t* d_seg;
+    // two staging sets: step t+1 may be begun (physics, render into the other image set) while step t's copies still run
+    double* d_cmd[2]; uint8_t* d_mask[2]; double* d_joint[2]; double* d_touch[2]; double* d_objpose[2];
+    uint8_t* d_rgb[2]; float* d_depth[2]; int32_t* d_seg[2];
     size_t img_capacity;       // envs for which d_rgb/d_depth/d_seg are allocated
     cudaStream_t host_compute, host_copy; cudaEvent_t host_ev[16];   // rr_step_host: render chunk c overlaps the D2H copy of chunk c-1
+    cudaEvent_t host_done[2]; int host_begun, host_ended;            // steps begun / ended through rr_step_host_begin / _end
     double* h_pinned; size_t h_pinned_bytes;
     long long launches;
     std::string err;

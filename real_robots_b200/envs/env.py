@@ -99,6 +99,7 @@ class REALRobotEnv:
         self._cam_dist, self._cam_yaw, self._cam_roll, self._cam_pitch, self._cam_pos = 1.2, 30, 0, -30, [0, 0, .4]
         self._render_width, self._render_height = 320, 240
         self.eyes = {"eye": EyeCamera([0.01, 0, 1.2], [0, 0, 0])}
+        self.setCamera()                      # env.py:90: envCamera exists from construction on
         self.reward_func = DefaultRewardFunc
         # goals (env.py:97-113) and the zero images returned while the camera is off (env.py:114-122)
         obs = self.observation_space.spaces
@@ -184,6 +185,10 @@ class REALRobotEnv:
             import torch
             self._torch = torch
             self._cmd = torch.zeros(1, 9, dtype=torch.float64, device=self._sim.device)
+            # step_joints goes through rr_step_host: one C call and one synchronisation per step, pinned host buffers
+            self._host = self._sim.alloc_host(images=True, want_mask=True, pinned=True)
+            self._host_cmd = torch.zeros(1, 9, dtype=torch.float64).pin_memory().numpy()
+            self._host_on = torch.ones(1, dtype=torch.uint8).pin_memory().numpy()
 
     def reset(self):                      # env.py:206-219
         self._ensure_sim()
@@ -250,6 +255,35 @@ class REALRobotEnv:
                 K.RETINA: retina, K.DEPTH: depth, K.MASK: mask, K.OBJ_POS: self.get_all_used_objects(),
                 K.GOAL: self.goal.retina, K.GOAL_MASK: self.goal.mask, K.GOAL_POS: self.goal.final_state}
 
+    def _stock_observation(self):
+        """True while nobody replaced the observation hooks (then step_joints may assemble the dict from rr_step_host's buffers)."""
+        cls = type(self)
+        own = self.__dict__.get("get_observation")
+        bound_ok = own is None or getattr(own, "__func__", None) in (REALRobotEnv.get_observation, REALRobotEnv.get_observation_extended)
+        return (bound_ok and cls.get_observation is REALRobotEnv.get_observation and cls.get_observation_extended is REALRobotEnv.get_observation_extended
+                and cls.get_retina is REALRobotEnv.get_retina and cls.get_all_used_objects is REALRobotEnv.get_all_used_objects
+                and type(self.robot).calc_state is Kuka.calc_state and type(self.robot).get_touch_sensors is Kuka.get_touch_sensors)
+
+    def _observation_from_host(self, camera_on):
+        """The dict get_observation / get_observation_extended would build (env.py:266-312), from the buffers rr_step_host filled."""
+        K = Kuka.ObsSpaces
+        h = self._host
+        if camera_on:
+            retina, depth, mask = h["retina"][0].copy(), h["depth"][0].copy(), h["mask"][0].copy()
+        else:
+            retina, depth, mask = self.no_retina, self.no_depth, getattr(self, "no_mask", None)
+        obs = {K.JOINT_POSITIONS: [float(v) for v in h["joint_positions"][0]], K.TOUCH_SENSORS: h["touch_sensors"][0].copy(),
+               K.RETINA: retina, K.DEPTH: depth}
+        if self.additional_obs:
+            obs[K.MASK] = mask
+            obs[K.OBJ_POS] = {name: h["object_poses"][0, i, :3].copy() for i, name in enumerate(self.robot.used_objects[1:])}
+            obs[K.GOAL] = self.goal.retina
+            obs[K.GOAL_MASK] = self.goal.mask
+            obs[K.GOAL_POS] = self.goal.final_state
+        else:
+            obs[K.GOAL] = self.goal.retina
+        return obs
+
     # ------------------------------------------------------------------ stepping (env.py:314-467)
     def step(self, action):
         return self.step_joint(action)          # env.py:323-324 (rebound in __init__, exactly as in the reference)
@@ -264,9 +298,16 @@ class REALRobotEnv:
         assert np.isfinite(command).all()                   # robot.py:189
         assert len(command) == self.robot.num_joints        # robot.py:190
         # limitActionByJoint, control_objects_limits, apply_action and stepSimulation all run inside rr_step
-        self._cmd.copy_(self._torch.from_numpy(command.reshape(1, 9)))
-        self._sim.step(self._cmd)
-        observation = self.get_observation(bool(np.any(camera_on)))
+        camera_on = bool(np.any(camera_on))
+        if self._stock_observation():
+            # the whole step — command in, physics, read-out, retina, every observation back — is one rr_step_host call
+            self._host_cmd[0, :] = command
+            self._sim.step_host(self._host_cmd, self._host_on if camera_on else None, out=self._host)
+            observation = self._observation_from_host(camera_on)
+        else:       # a subclass / monkeypatch replaced an observation hook: keep calling it
+            self._cmd.copy_(self._torch.from_numpy(command.reshape(1, 9)))
+            self._sim.step(self._cmd)
+            observation = self.get_observation(camera_on)
         self.timestep += 1
         return observation, self.reward_func(observation), bool(self.timestep >= self._phase_limit()), {}
 

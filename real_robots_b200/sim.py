@@ -238,11 +238,26 @@ class BatchedSim:
         self._ck(rc, "rr_step_host")
         return out
 
+    def step_host_begin(self, joint_cmd, render_mask, out):
+        """Enqueue one step (rr_step_host_begin); `joint_cmd`, `render_mask` and the arrays of `out` (alloc_host) must be
+        pinned, contiguous and stay untouched until the matching step_host_end().  At most two steps in flight."""
+        def p(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+        rc = self.lib.rr_step_host_begin(self.ctx, p(joint_cmd), p(render_mask), p(out["joint_positions"]), p(out["touch_sensors"]),
+                                         p(out["object_poses"]), p(out.get("retina")), p(out.get("depth")), p(out.get("mask")))
+        self._ck(rc, "rr_step_host_begin")
+
+    def step_host_end(self):
+        self._ck(self.lib.rr_step_host_end(self.ctx), "rr_step_host_end")
+
     def alloc_host(self, images=True, want_mask=True, pinned=True):
         N = self.n_envs
 
+        tensors = {}
+
         def mk(shape, dtype):
             t = torch.empty(shape, dtype=dtype, pin_memory=pinned)
+            tensors[len(tensors)] = t
             return t.numpy()
         out = dict(joint_positions=mk((N, 9), torch.float64), touch_sensors=mk((N, 4), torch.float64),
                    object_poses=mk((N, self.n_objects, 7), torch.float64))
@@ -251,4 +266,5 @@ class BatchedSim:
             out["depth"] = mk((N, L.EYE_H, L.EYE_W), torch.float32)
             if want_mask:
                 out["mask"] = mk((N, L.EYE_H, L.EYE_W), torch.int32)
+        out["_torch"] = list(tensors.values())        # the (pinned) torch tensors behind the numpy views, in creation order
         return out

@@ -161,11 +161,25 @@ class EmuSim:
         self._ck(self.lib.rr_contacts(self.ctx, _p(hdr), _p(pts), _p(pairs), C.byref(n), None), "rr_contacts")
         return hdr, pts, pairs[:n.value]
 
-    def step_host(self, cmd, render=True):
+    def alloc_host(self):
         N = self.n_envs
-        c = np.ascontiguousarray(cmd, np.float64)
-        j = np.zeros((N, 9)); t = np.zeros((N, 4)); o = np.zeros((N, self.n_objects, 7))
         rgb, depth, seg = self._imgs()
-        m = np.ones(N, np.uint8) if render else None
-        self._ck(self.lib.rr_step_host(self.ctx, _p(c), _p(m), _p(j), _p(t), _p(o), _p(rgb), _p(depth), _p(seg)), "rr_step_host")
-        return j, t, o, rgb, depth, seg
+        return dict(joint_positions=np.zeros((N, 9)), touch_sensors=np.zeros((N, 4)), object_poses=np.zeros((N, self.n_objects, 7)),
+                    retina=rgb, depth=depth, mask=seg)
+
+    def _host_args(self, cmd, mask, out):
+        return (self.ctx, _p(cmd), _p(mask), _p(out["joint_positions"]), _p(out["touch_sensors"]), _p(out["object_poses"]),
+                _p(out["retina"]), _p(out["depth"]), _p(out["mask"]))
+
+    def step_host(self, cmd, render=True, out=None):
+        c = np.ascontiguousarray(cmd, np.float64)
+        out = out or self.alloc_host()
+        m = np.ones(self.n_envs, np.uint8) if render else None
+        self._ck(self.lib.rr_step_host(*self._host_args(c, m, out)), "rr_step_host")
+        return out
+
+    def step_host_begin(self, cmd, mask, out):
+        self._ck(self.lib.rr_step_host_begin(*self._host_args(cmd, mask, out)), "rr_step_host_begin")
+
+    def step_host_end(self):
+        self._ck(self.lib.rr_step_host_end(self.ctx), "rr_step_host_end")

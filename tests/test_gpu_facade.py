@@ -311,3 +311,53 @@ def test_public_helpers_of_the_reference_surface():
     lim = env.limitActionByJoint(np.full(9, 3.0))
     assert np.allclose(lim, [0.2] * 5 + [0.3] * 2 + [0.1] * 2, atol=1e-12)              # from q = 0
     env.close()
+
+
+def test_c4_macro_action_evaluate_vectorised_equals_the_serial_facade(tmp_path):
+    """BASELINE configs[3]: macro_action, 3 objects, the extrinsic phase of evaluate() on 50 seeded synthetic
+    goals (object xy ~ U([-0.25, 0.05] x [-0.45, 0.45]), dropped from z = 0.40, seed 2020), one 1000-step trial per goal.
+    evaluate_vectorised runs the 50 trials side by side; real_robots.evaluate() (the reference's serial flow,
+    evaluate.py:281-332, through the N = 1 gym facade) runs the first three one after the other with the same policy — a
+    macro action that sweeps from the cube's start to its goal.  Same kernels, same inputs: the scores must be equal."""
+    from real_robots_b200.evaluate import evaluate_vectorised
+    G, names = 50, ['cube', 'tomato', 'mustard']
+    rng = np.random.default_rng(2020)
+    init = np.zeros((G, 3, 7)); init[:, :, 6] = 1.0
+    init[:, :, 0] = rng.uniform(-0.25, 0.05, (G, 3)); init[:, :, 1] = rng.uniform(-0.45, 0.45, (G, 3)); init[:, :, 2] = 0.40
+    final = np.zeros((G, 3, 3))
+    final[:, :, 0] = rng.uniform(-0.25, 0.05, (G, 3)); final[:, :, 1] = rng.uniform(-0.45, 0.45, (G, 3)); final[:, :, 2] = 0.3214
+    macro = np.stack([init[:, 0, :2], final[:, 0, :2]], axis=1)                 # [G, 2, 2]: cube start -> cube goal
+
+    class Sweep:
+        def __init__(self, env):
+            self.m = torch.from_numpy(macro[:env.n_envs]).to(env.device).contiguous()
+
+        def step(self, obs, reward, done):
+            return {'macro_action': self.m, 'render': False}
+
+    score, scores, vec = evaluate_vectorised(lambda env: Sweep(env), dict(initial=init, final=final), n_objects=3,
+                                             action_type='macro_action', extrinsic_timesteps=1000)
+    assert vec.shape == (G,) and np.isfinite(vec).all() and (vec > 0).all() and (vec <= 3.0).all()
+    assert np.isclose(score['score_total'], vec.mean()) and len(scores['2D']) == G
+    assert vec.std() > 0.05                                                     # the trials differ (the sweep moves the cubes)
+
+    K = 3
+    goals = [Goal(initial_state={n: init[g, i] for i, n in enumerate(names)}, final_state={n: np.r_[final[g, i], 0, 0, 0, 1.0] for i, n in enumerate(names)},
+                  challenge='2D', retina=np.zeros((240, 320, 3), np.uint8), mask=np.zeros((240, 320), np.int32)) for g in range(K)]
+    path = str(tmp_path / "goals_c4.npy")
+    np.savez_compressed(path, np.array(goals, dtype=object))
+
+    class SerialSweep(BasePolicy):
+        trial = -1
+
+        def start_extrinsic_trial(self):
+            SerialSweep.trial += 1
+
+        def step(self, observation, reward, done):
+            return {'macro_action': macro[SerialSweep.trial], 'render': False}
+
+    s_obj, s_scores = real_robots.evaluate(SerialSweep, environment='R1', action_type='macro_action', n_objects=3, intrinsic_timesteps=0,
+                                           extrinsic_timesteps=1000, extrinsic_trials=K, visualize=False, goals_dataset_path=path + ".npz")
+    serial = np.array(s_scores['2D'])
+    assert serial.shape == (K,)
+    assert np.abs(serial - vec[:K]).max() < 1e-9, (serial, vec[:K])

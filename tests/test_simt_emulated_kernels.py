@@ -157,3 +157,43 @@ def test_contact_free_aabb_overlaps_do_not_crowd_out_object_table_manifolds():
         assert not inside.any() or ob[inside, 2].min() > 0.29
         assert (sim.diag()[0, 3] & 16) == 0
     assert seen > 24
+
+
+def test_emulated_host_buffer_path_and_pipelined_begin_end():
+    """rr_step_host == rr_step + rr_read_state + rr_render; rr_step_host_begin / _end with two steps in flight gives the same
+    observations (double-buffered staging), and a third begin without an end is refused."""
+    N = 2
+    a = np.stack(list(zip(*[_policy_single(sd, 6) for sd in (3, 4)])))          # [6, N, 9]
+    ref = EmuSim(N, 3)
+    want = []
+    for t in range(6):
+        ref.step(a[t])
+        j, tch, o = ref.read_state()
+        rgb, depth, seg = ref.render()
+        want.append((j.copy(), tch.copy(), o.copy(), rgb.copy(), depth.copy(), seg.copy()))
+    sim = EmuSim(N, 3)
+    for t in range(2):
+        out = sim.step_host(a[t])
+        for got, w in zip((out["joint_positions"], out["touch_sensors"], out["object_poses"], out["retina"], out["depth"], out["mask"]), want[t]):
+            assert (got == w).all()
+    mask = np.ones(N, np.uint8)
+    outs = [sim.alloc_host(), sim.alloc_host()]
+    cmds = [np.ascontiguousarray(a[t]) for t in range(6)]
+    sim.step_host_begin(cmds[2], mask, outs[0])
+    sim.step_host_begin(cmds[3], mask, outs[1])
+    with pytest.raises(RuntimeError):
+        sim.step_host_begin(cmds[4], mask, outs[0])
+    sim.step_host_end()
+    assert (outs[0]["retina"] == want[2][3]).all() and (outs[0]["joint_positions"] == want[2][0]).all()
+    sim.step_host_begin(cmds[4], mask, outs[0])
+    sim.step_host_end()
+    assert (outs[1]["mask"] == want[3][5]).all() and (outs[1]["depth"] == want[3][4]).all()
+    sim.step_host_end()
+    assert (outs[0]["retina"] == want[4][3]).all() and (outs[0]["object_poses"] == want[4][2]).all()
+    with pytest.raises(RuntimeError):
+        sim.step_host_end()
+
+
+def test_emulated_touch_sensors_scripted_press_and_shelf():
+    from tests.scenarios import check_touch_scenarios
+    check_touch_scenarios(lambda: EmuSim(1, 1))
