@@ -828,31 +828,10 @@ __device__ __forceinline__ double group_sum6(double pr, int s0, int s1, int s2, 
     const double d = __shfl_sync(FULL, pr, s3), e = __shfl_sync(FULL, pr, s4), f = __shfl_sync(FULL, pr, s5);
     return ((a + b) + (c + d)) + (e + f);
 }
-// One warp per env, 32 warps per SM.  The schedule and the blocks are read-only here and stream from L2 (the images of the
-// envs in flight — ~14 KB each — stay L2-resident; a block is one or two 128-byte lines); the applied impulses, the only
-// thing the sweep updates besides dv, live in shared memory by row id.  (Measured alternatives, same results: the whole image
-// in shared memory, one env per warp — 12 warps per SM, and lane-per-(env, group) streams, 7 envs per warp — 2 warps per SM:
-// both residency-bound at 1.9 ms for 4096 envs.)
-#ifndef SOLVE_MIN_BLOCKS
-#define SOLVE_MIN_BLOCKS 8
-#endif
-struct SolveEpi { SolveHead head; KinWs kin; };
-#define SOLVE_SMEM_DOUBLES ((int)(sizeof(SolveEpi) / 8) > RR_MAX_ROWS ? (int)(sizeof(SolveEpi) / 8) : RR_MAX_ROWS)
-#define SOLVE_SMEM_BYTES ((size_t)SOLVE_SMEM_DOUBLES * 8)
-__global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
-    RR_DYN_SMEM(smem_raw);
-    double* const smem = reinterpret_cast<double*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
-    double* const sapp = smem;                                 // applied impulses by row id (during the sweep)
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
-    if (e >= st.N) return;
-    const int N = st.N;
-    const double dt = cf.dt;
-    const double* gimg = st.handoff + (size_t)e * RR_IMG_DOUBLES;
-    const SolveHead* gh = reinterpret_cast<const SolveHead*>(gimg);
-    const int nA0 = gh->n_slotsA[0], nA1 = gh->n_slotsA[1], nB = gh->n_slotsB, nc = gh->nc;
-    const unsigned int* gsched = reinterpret_cast<const unsigned int*>(gimg + HEAD_DOUBLES);
-    const double* gblk = gimg + GBLK_BASE;
+// The Gauss-Seidel sweep of one env (see SolveHead).  SS: the schedule pointers point into shared memory.
+template <bool SS>
+__device__ __forceinline__ void pgs_sweep(const unsigned int* const schedA0, const unsigned int* const schedA1, const unsigned int* const schedB0, const double* const gblk,
+                                          double* const sapp, const int nA0, const int nA1, const int nB, const int lane, const rr_config& cf, double& dv_out, int& iters_out) {
     // dv in owner layout: lane k < 11 owns the arm dof k, lane 11+6o+c the object component.
     const int grp = lane_group(lane);
     const bool ingrp = grp < 4;
@@ -863,19 +842,11 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
     // shuffle sources of the group sum: the six lanes of a free body; for arm lanes the row's dof, then lane 31 (always 0)
     const bool isobj = grp >= 1 && grp < 4;
     const int s1 = isobj ? seg0 + 1 : 31, s2 = isobj ? seg0 + 2 : 31, s3 = isobj ? seg0 + 3 : 31, s4 = isobj ? seg0 + 4 : 31, s5 = isobj ? seg0 + 5 : 31;
-    // ---- applied impulses: zero, except the warm start of the normal rows
-    for (int k = lane; k < RR_MAX_ROWS; k += 32) sapp[k] = 0.0;
-    __syncwarp();
-    for (int c = lane; c < nc; c += 32) {
-        const unsigned int nr = gh->nrm_rel[c];
-        sapp[RID_NORMAL + c] = gblk[2 * (nr & 0x7fffu) + ((nr & 0x8000u) ? 2 * RR_NDOF + 5 : 17)];
-    }
-    __syncwarp();
     double dv = 0.0;
     int iters = 0; double res = 0.0;
     {
         for (int slot = 0; slot < nA0; slot++) {             // warm start: dv of the normal rows' initial impulses
-            const uint2 w = *reinterpret_cast<const uint2*>(gsched + GSCHED_A(0) + 8 * slot + 2 * g4);
+            const uint2 w = *reinterpret_cast<const uint2*>(schedA0 + 8 * slot + 2 * g4);
             if (ingrp && w.x != ENT_IDLE && (w.x >> 16) == ENT_NORMAL) {
                 const double a = sapp[w.y & 0xffffu];
                 if (a != 0.0) dv += gblk[2 * (w.x & 0x7fffu) + myk2 + 1] * a;
@@ -885,17 +856,16 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
             res = 0.0;
             const int par = it & 1;
             // ---- phase A: single rows (joint limits + motors, normals, spinning, rolling), one slot at a time
-            const unsigned int* sched = gsched + GSCHED_A(par) + 2 * g4;
+            const unsigned int* sched = (par ? schedA1 : schedA0) + 2 * g4;
             const int nA = par ? nA1 : nA0;
+            unsigned int nx = nA > 3 ? sched[8 * 3] : ENT_IDLE;                 // word 0 of the entry three slots ahead (loaded one slot early)
             for (int slot = 0; slot < nA; slot++) {
                 const uint2 w = *reinterpret_cast<const uint2*>(sched + 8 * slot);
                 const bool act = ingrp && w.x != ENT_IDLE;
                 const unsigned int kind = w.x >> 16;
                 const double* b = gblk + 2 * (act ? (w.x & 0x7fffu) : 0u);
-                if (slot + 2 < nA) {                          // the blocks two slots ahead are on their way into L1
-                    const unsigned int nx = sched[8 * (slot + 2)];
-                    if (ingrp && nx != ENT_IDLE) RR_PREFETCH_L1(gblk + 2 * (nx & 0x7fffu) + myk2);
-                }
+                if (ingrp && nx != ENT_IDLE) RR_PREFETCH_L1(gblk + 2 * (nx & 0x7fffu) + myk2);      // the blocks three slots ahead are on their way into L1
+                nx = slot + 4 < nA ? sched[8 * (slot + 4)] : ENT_IDLE;
                 double J = 0.0, rr = 0.0, rhs = 0.0, inv = 0.0, rinv = 0.0, lo = 0.0, hi = 0.0, app = 0.0;
                 bool on = act;
                 const int rid = act ? (int)(w.y & 0xffffu) : 0;
@@ -931,7 +901,7 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
                 __syncwarp();
             }
             // ---- phase B: friction pairs with the implicit cone
-            const unsigned int* schedb = gsched + GSCHED_B + 2 * g4;
+            const unsigned int* schedb = schedB0 + 2 * g4;
             for (int slot = 0; slot < nB; slot++) {
                 const uint2 w = *reinterpret_cast<const uint2*>(schedb + 8 * slot);
                 const bool act = ingrp && w.x != ENT_IDLE;
@@ -973,6 +943,58 @@ __global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevSt
             if (res <= cf.residual_threshold) break;
         }
     }
+    dv_out = dv; iters_out = iters;
+}
+
+// One warp per env, 32 warps per SM.  The schedule and the blocks are read-only here and stream from L2 (the images of the
+// envs in flight — ~14 KB each — stay L2-resident; a block is one or two 128-byte lines); the applied impulses, the only
+// thing the sweep updates besides dv, live in shared memory by row id.  (Measured alternatives, same results: the whole image
+// in shared memory, one env per warp — 12 warps per SM, and lane-per-(env, group) streams, 7 envs per warp — 2 warps per SM:
+// both residency-bound at 1.9 ms for 4096 envs.)
+#ifndef SOLVE_MIN_BLOCKS
+#define SOLVE_MIN_BLOCKS 8
+#endif
+struct SolveEpi { SolveHead head; KinWs kin; };
+#define SOLVE_SMEM_DOUBLES ((int)(sizeof(SolveEpi) / 8) > RR_MAX_ROWS ? (int)(sizeof(SolveEpi) / 8) : RR_MAX_ROWS)
+#ifndef SOLVE_SCHED_WORDS
+#define SOLVE_SCHED_WORDS 512       // words of the slot schedule kept in shared memory (64 slots; longer schedules are read from the image)
+#endif
+#define SOLVE_SMEM_BYTES ((size_t)SOLVE_SMEM_DOUBLES * 8 + SOLVE_SCHED_WORDS * 4)
+__global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
+    RR_DYN_SMEM(smem_raw);
+    double* const smem = reinterpret_cast<double*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
+    double* const sapp = smem;                                 // applied impulses by row id (during the sweep)
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (e >= st.N) return;
+    const int N = st.N;
+    const double dt = cf.dt;
+    const double* gimg = st.handoff + (size_t)e * RR_IMG_DOUBLES;
+    const SolveHead* gh = reinterpret_cast<const SolveHead*>(gimg);
+    const int nA0 = gh->n_slotsA[0], nA1 = gh->n_slotsA[1], nB = gh->n_slotsB, nc = gh->nc;
+    const unsigned int* gsched = reinterpret_cast<const unsigned int*>(gimg + HEAD_DOUBLES);
+    const double* gblk = gimg + GBLK_BASE;
+    // ---- applied impulses: zero, except the warm start of the normal rows
+    for (int k = lane; k < RR_MAX_ROWS; k += 32) sapp[k] = 0.0;
+    __syncwarp();
+    for (int c = lane; c < nc; c += 32) {
+        const unsigned int nr = gh->nrm_rel[c];
+        sapp[RID_NORMAL + c] = gblk[2 * (nr & 0x7fffu) + ((nr & 0x8000u) ? 2 * RR_NDOF + 5 : 17)];
+    }
+    __syncwarp();
+    // ---- the slot schedule comes into shared memory when it fits (it is read by every lane in every slot of every iteration)
+    unsigned int* const ssched = reinterpret_cast<unsigned int*>(smem + SOLVE_SMEM_DOUBLES);
+    const bool sched_smem = 8 * (nA0 + nA1 + nB) <= SOLVE_SCHED_WORDS;
+    if (sched_smem) {
+        for (int k = lane; k < 8 * nA0; k += 32) ssched[k] = gsched[GSCHED_A(0) + k];
+        for (int k = lane; k < 8 * nA1; k += 32) ssched[8 * nA0 + k] = gsched[GSCHED_A(1) + k];
+        for (int k = lane; k < 8 * nB; k += 32) ssched[8 * (nA0 + nA1) + k] = gsched[GSCHED_B + k];
+    }
+    __syncwarp();
+    double dv = 0.0;
+    int iters = 0;
+    if (sched_smem) pgs_sweep<true>(ssched, ssched + 8 * nA0, ssched + 8 * (nA0 + nA1), gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
+    else pgs_sweep<false>(gsched + GSCHED_A(0), gsched + GSCHED_A(1), gsched + GSCHED_B, gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
     // ---- impulse write-back (warm start of the next step) and gripper touch sensors (robot.py:131-163)
     int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
     double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;

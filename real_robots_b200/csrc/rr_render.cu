@@ -622,6 +622,172 @@ __device__ __forceinline__ Rec load_rec(const Rec* __restrict__ p) {
     return r;
 }
 
+// --------------------------------------------------------------------------------------------- flattened raster (RASTER_FLAT)
+// The per-pixel work of a record has two halves of very different weight: the coverage scan of its bounding box (cheap, ~85 %
+// of the candidates fail) and the exact barycentrics / depth / z-test of a covered pixel (nine Markstein divisions).  With one
+// lane walking one box both halves run at 10-13 active lanes of 32.  Here a warp keeps the records of its current work item
+// in registers (one per lane, or one per group of lanes) and
+//   scan  : small boxes are FLATTENED — the (record, pixel) pairs of the 32 records of a chunk are numbered consecutively
+//           (prefix sum of the box areas) and dealt to the lanes 32 at a time, each lane fetching the few set-up values of its
+//           pair's record from the owner lane with shuffles; medium / huge boxes are walked in lockstep by the lanes that
+//           share them;
+//   queue : candidates that are covered and not already behind the z-buffer are appended to a per-warp queue in shared
+//           memory (pixel, coverage class, owner lane);
+//   drain : whenever 32 are queued (and at the end of the work item) every lane takes one, fetches the record's depth set-up
+//           from the owner lane with shuffles and does the exact evaluation + atomicMax — all 32 lanes busy.
+// The arithmetic per fragment is unchanged (same functions, same operands), so the images stay bit-identical.
+#ifndef RASTER_FLAT
+#define RASTER_FLAT 0
+#endif
+#define FQ_SIZE 64
+struct LaneRec {           // a record unpacked in registers, plus what the scan needs
+    float A0x, A0y, s00, s01, s10, s11, uz, w0, w1, w2, yw0, yw1, yw2, yuz, cz0, cz1, cz2;
+    unsigned int keylo, flags, zb;
+    int x0, x1, ya, yb, wdt, n;           // in-strip part of the bounding box: rows ya..yb, wdt columns from x0, n candidates
+};
+struct FragQueue { unsigned int* q; int head, count; };
+
+__device__ __forceinline__ void lane_rec_load(const Rec* __restrict__ recs, unsigned int ridx, bool valid, int row0, LaneRec& L) {
+    L.n = 0; L.wdt = 1; L.x0 = 0; L.x1 = 0; L.ya = row0; L.yb = row0 - 1; L.zb = 0u; L.keylo = 0u; L.flags = 0u;
+    L.A0x = L.A0y = L.s00 = L.s01 = L.s10 = L.s11 = 0.f; L.uz = 1.f; L.w0 = L.w1 = L.w2 = 1.f; L.yw0 = L.yw1 = L.yw2 = 1.f; L.yuz = 1.f; L.cz0 = L.cz1 = L.cz2 = 0.f;
+    if (!valid) return;
+    const Rec rec = load_rec(recs + ridx);
+    Screen S; Edge E; Recip R; float cz[3]; rec_unpack(rec, S, E, R, cz);
+    L.A0x = S.p2[0][0]; L.A0y = S.p2[0][1]; L.s00 = E.s00; L.s01 = E.s01; L.s10 = E.s10; L.s11 = E.s11; L.uz = E.uz;
+    L.w0 = S.w[0]; L.w1 = S.w[1]; L.w2 = S.w[2]; L.yw0 = R.yw[0]; L.yw1 = R.yw[1]; L.yw2 = R.yw[2]; L.yuz = R.yuz;
+    L.cz0 = cz[0]; L.cz1 = cz[1]; L.cz2 = cz[2]; L.keylo = rec.keylo; L.flags = rec.flags;
+    L.zb = depth_bound_bits(R, cz);
+    L.x0 = S.x0; L.x1 = S.x1; L.ya = max(S.y0, row0); L.yb = min(S.y1, row0 + STRIP_ROWS - 1);
+    L.wdt = S.x1 - S.x0 + 1;
+    L.n = L.ya > L.yb ? 0 : L.wdt * (L.yb - L.ya + 1);
+}
+// coverage class of pixel (px, py) for the triangle whose set-up is given; ux, uy out
+__device__ __forceinline__ int cover_px(float A0x, float A0y, float s00, float s01, float s10, float s11, float uz, int px, int py) {
+    const float s02 = A0x - (float)px, s12 = A0y - (float)py;
+    const float ux = s01 * s12 - s02 * s11, uy = s02 * s10 - s00 * s12;
+    return coverage_class(ux, uy, uz);
+}
+// queue entry: px [0,9) | row in strip [9,15) | coverage class [15,17) | owner lane [17,22)
+__device__ __forceinline__ void fq_push(FragQueue& Q, bool have, unsigned int ent) {
+    const unsigned int m = __ballot_sync(0xffffffffu, have);
+    if (have) Q.q[(Q.head + Q.count + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))) & (FQ_SIZE - 1)] = ent;
+    Q.count += __popc(m);
+}
+// every lane takes one queued fragment (the first n_take of the queue), evaluates it exactly and updates the z-buffer
+__device__ __forceinline__ void fq_drain(unsigned long long* keys, int row0, FragQueue& Q, int n_take, const LaneRec& L) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    const bool mine = lane < n_take;
+    const unsigned int ent = mine ? Q.q[(Q.head + lane) & (FQ_SIZE - 1)] : 0u;
+    const int owner = (int)(ent >> 17) & 31;
+    const unsigned int F = 0xffffffffu;
+    Screen S; Edge E; Recip R; float cz[3];
+    S.p2[0][0] = __shfl_sync(F, L.A0x, owner); S.p2[0][1] = __shfl_sync(F, L.A0y, owner);
+    E.s00 = __shfl_sync(F, L.s00, owner); E.s01 = __shfl_sync(F, L.s01, owner); E.s10 = __shfl_sync(F, L.s10, owner); E.s11 = __shfl_sync(F, L.s11, owner);
+    E.uz = __shfl_sync(F, L.uz, owner); E.degenerate = false;
+    S.w[0] = __shfl_sync(F, L.w0, owner); S.w[1] = __shfl_sync(F, L.w1, owner); S.w[2] = __shfl_sync(F, L.w2, owner);
+    R.yw[0] = __shfl_sync(F, L.yw0, owner); R.yw[1] = __shfl_sync(F, L.yw1, owner); R.yw[2] = __shfl_sync(F, L.yw2, owner);
+    R.yuz = __shfl_sync(F, L.yuz, owner);
+    cz[0] = __shfl_sync(F, L.cz0, owner); cz[1] = __shfl_sync(F, L.cz1, owner); cz[2] = __shfl_sync(F, L.cz2, owner);
+    const unsigned int keylo = __shfl_sync(F, L.keylo, owner), flags = __shfl_sync(F, L.flags, owner);
+    R.ok = (flags & REC_OK) != 0; R.tight = (flags & REC_TIGHT) != 0;
+    if (mine) {
+        const int px = (int)(ent & 511u), pr = (int)(ent >> 9) & 63, cls = (int)(ent >> 15) & 3, py = row0 + pr;
+        float ux, uy; bary_u(S, E, (float)px, (float)py, ux, uy);
+        float bs[3], bc[3];
+        bool keep = true;
+        if (cls == 1 && R.tight) frag_bar_in(S, E, R, ux, uy, bc);
+        else {
+            frag_bar_r(S, E, R, px, py, bs, bc);
+            if (cls == 2 && (bs[0] < 0 || bs[1] < 0 || bs[2] < 0)) keep = false;
+        }
+        const float fd = -1.f * dot3r(cz[0], cz[1], cz[2], bc);
+        if (!(fd >= -1e30f)) keep = false;                                // z-buffer cleared to -1e30 (also drops NaN)
+        if (!(flags & REC_CLIPPED) && (fd < -c_render.farPlane || fd > -c_render.nearPlane)) keep = false;
+        if (keep) {
+            const unsigned long long key = ((unsigned long long)order_bits(fd) << 32) | keylo;
+            unsigned long long* slot = &keys[pr * RR_W + px];
+            STAT(9, 1);
+            if (*reinterpret_cast<volatile unsigned long long*>(slot) < key) { STAT(10, 1); atomicMax(slot, key); }
+        }
+    }
+    Q.head = (Q.head + n_take) & (FQ_SIZE - 1); Q.count -= n_take;
+    __syncwarp();
+}
+// medium / huge boxes: lane takes candidates start, start + stride, ... of ITS record (L), all lanes in lockstep
+__device__ __forceinline__ void scan_lockstep(unsigned long long* keys, int row0, const LaneRec& L, int start, int stride, FragQueue& Q) {
+    const int lane = threadIdx.x & 31;
+    const int n = L.n, wdt = L.wdt;
+    int sy = 0, dy = 0;
+    if (stride != 1) {
+        // (k + 0.5) / wdt is at least 0.5 / 320 away from an integer, so the float quotient truncates to the exact k / wdt
+        const float rw = __frcp_rn((float)wdt);
+        sy = (int)(((float)start + 0.5f) * rw); dy = (int)(((float)stride + 0.5f) * rw);
+    } else dy = (wdt == 1) ? 1 : 0;
+    int x = L.x0 + (start - sy * wdt), y = L.ya + sy;
+    const int dx = stride - dy * wdt;
+    int i = start;
+    while (__any_sync(0xffffffffu, i < n)) {
+        bool have = false; unsigned int ent = 0u;
+        if (i < n) {
+            const int px = x, py = y;
+            i += stride; x += dx; y += dy; if (x > L.x1) { x -= wdt; y++; }
+            const int cls = cover_px(L.A0x, L.A0y, L.s00, L.s01, L.s10, L.s11, L.uz, px, py);
+            STAT(6, 1);
+            if (cls) {
+                STAT(7, 1);
+                const unsigned int cur = reinterpret_cast<volatile unsigned int*>(&keys[(py - row0) * RR_W + px])[1];
+                if (cur <= L.zb) { have = true; ent = (unsigned int)px | ((unsigned int)(py - row0) << 9) | ((unsigned int)cls << 15) | ((unsigned int)lane << 17); }
+                else STAT(8, 1);
+            }
+        }
+        fq_push(Q, have, ent);
+        if (Q.count >= 32) fq_drain(keys, row0, Q, 32, L);
+    }
+}
+// small boxes, one record per lane (n <= SMALL_AREA each): the (record, pixel) pairs of the chunk, 32 at a time
+__device__ __forceinline__ void scan_flat(unsigned long long* keys, int row0, const LaneRec& L, FragQueue& Q) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int F = 0xffffffffu;
+    int off = L.n;                                    // inclusive prefix sum of the candidate counts
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(F, off, d); if (lane >= d) off += t; }
+    const int total = __shfl_sync(F, off, 31);
+    off -= L.n;                                       // exclusive: first flat index of this lane's record
+    const int geo = L.x0 | ((L.ya - row0) << 9) | (L.wdt << 15);
+    int first = 0;                                    // records that start before `base`
+    for (int base = 0; base < total; base += 32) {
+        // the records with candidates (a prefix of the lanes, each with n >= 1) start at distinct flat indices: mark the starts that
+        // fall into this window; the owner of flat index f is the last record starting at or before f
+        const unsigned int mybit = (L.n > 0 && off >= base && off < base + 32) ? 1u << (off - base) : 0u;
+        const unsigned int starts = __reduce_or_sync(F, mybit);
+        const int f = base + lane;
+        const int owner = first - 1 + __popc(starts & (0xffffffffu >> (31 - lane)));
+        first += __popc(starts);
+        const int o = owner < 0 ? 0 : owner;
+        const float A0x = __shfl_sync(F, L.A0x, o), A0y = __shfl_sync(F, L.A0y, o), s00 = __shfl_sync(F, L.s00, o), s01 = __shfl_sync(F, L.s01, o);
+        const float s10 = __shfl_sync(F, L.s10, o), s11 = __shfl_sync(F, L.s11, o), uz = __shfl_sync(F, L.uz, o);
+        const int g = __shfl_sync(F, geo, o), ooff = __shfl_sync(F, off, o);
+        const unsigned int zb = __shfl_sync(F, L.zb, o);
+        bool have = false; unsigned int ent = 0u;
+        if (f < total) {
+            const int k = f - ooff, wdt = g >> 15;
+            const int ky = (int)(((float)k + 0.5f) * __frcp_rn((float)wdt));        // exact k / wdt (see scan_lockstep)
+            const int px = (g & 511) + (k - ky * wdt), pr = ((g >> 9) & 63) + ky;
+            const int cls = cover_px(A0x, A0y, s00, s01, s10, s11, uz, px, row0 + pr);
+            STAT(6, 1);
+            if (cls) {
+                STAT(7, 1);
+                const unsigned int cur = reinterpret_cast<volatile unsigned int*>(&keys[pr * RR_W + px])[1];
+                if (cur <= zb) { have = true; ent = (unsigned int)px | ((unsigned int)pr << 9) | ((unsigned int)cls << 15) | ((unsigned int)o << 17); }
+                else STAT(8, 1);
+            }
+        }
+        fq_push(Q, have, ent);
+        if (Q.count >= 32) fq_drain(keys, row0, Q, 32, L);
+    }
+}
+
 // shading of a pixel from barycentrics of the ORIGINAL triangle (Shader::fragment)
 __device__ __forceinline__ unsigned int shade_bar(const float* __restrict__ M, const ShapeRenderConst& sh, const float* __restrict__ tv,
                                                   const uint8_t* __restrict__ texdata, const float* bar) {
@@ -736,6 +902,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
     RR_DYN_SMEM(smem_raw);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float* Mbuf = reinterpret_cast<float*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8);       // two matrix tiles with TMA_MATS
+    unsigned int* fq_all = reinterpret_cast<unsigned int*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8 + (TMA_MATS ? 2 : 1) * RR_NSHAPES * MAT_STRIDE * 4);   // per-warp fragment queues
     __shared__ __align__(8) unsigned long long s_mbar[2];
     __shared__ int s_envq[2];
     __shared__ int s_env, s_nrec, s_ncull, s_chunk, s_medc, s_rgrp, s_nlist[3 * NSTRIPS];   // s_nlist[class][strip]
@@ -903,6 +1070,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
             // record per lane, pulled in 32-record chunks.
             {
                 int phase = 0, hb = tid / HUGE_GROUP;
+                FragQueue FQ; FQ.q = fq_all + (tid >> 5) * FQ_SIZE; FQ.head = 0; FQ.count = 0;
                 for (;;) {
                     unsigned int ridx = 0; int start = 0, stride = 1; bool valid = false;
                     if (phase == 0) {
@@ -926,7 +1094,14 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                         valid = rb + lane < nsmall;
                         if (valid) ridx = list[rb + lane];
                     }
-                    if (valid) {
+                    // RASTER_FLAT bits: 1 small boxes flattened, 2 medium boxes through the fragment queue, 4 huge boxes through it
+                    if ((phase == 2 && (RASTER_FLAT & 1)) || (phase == 1 && (RASTER_FLAT & 2)) || (phase == 0 && (RASTER_FLAT & 4))) {
+                        // (every lane of the warp goes through here: the scan and the drain are warp-wide)
+                        LaneRec L; lane_rec_load(recs, ridx, valid, row0, L);
+                        if (phase == 2) scan_flat(keys, row0, L, FQ);
+                        else scan_lockstep(keys, row0, L, start, stride, FQ);
+                        while (FQ.count > 0) fq_drain(keys, row0, FQ, min(FQ.count, 32), L);       // the records change with the next work item
+                    } else if (valid) {
                         const Rec rec = load_rec(recs + ridx);
                         Screen S; Edge E; Recip R; float cz[3]; rec_unpack(rec, S, E, R, cz);
                         raster_pixels(keys, S, E, R, cz, rec.keylo, !(rec.flags & REC_CLIPPED), row0, start, stride);
@@ -1050,7 +1225,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
 // --------------------------------------------------------------------------------------------- host side
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return -1; } } while (0)
 
-static const size_t RASTER_SMEM = (size_t)STRIP_ROWS * RR_W * 8 + (TMA_MATS ? 2 : 1) * RR_NSHAPES * MAT_STRIDE * 4;
+static const size_t RASTER_SMEM = (size_t)STRIP_ROWS * RR_W * 8 + (TMA_MATS ? 2 : 1) * RR_NSHAPES * MAT_STRIDE * 4 + (RASTER_FLAT ? (RTHREADS / 32) * FQ_SIZE * 4 : 0);
 static double* g_static_frames[16] = {0};
 
 // Per-triangle model-space plane for the conservative back-face pre-test: unit normal n (orientation of e1 x e2) and

@@ -152,6 +152,11 @@ template <typename T> static inline T __shfl_xor_sync(unsigned mask, T v, int la
     const int s = simt::warp_arrive(mask, simt::to_bits(v));
     return simt::from_bits<T>(simt::g_blk.warps[simt::warp_id()].buf[s][(simt::lane_id() ^ lanemask) & 31]);
 }
+template <typename T> static inline T __shfl_up_sync(unsigned mask, T v, int delta) {
+    const int s = simt::warp_arrive(mask, simt::to_bits(v));
+    const int src = simt::lane_id() - delta;
+    return simt::from_bits<T>(simt::g_blk.warps[simt::warp_id()].buf[s][src >= 0 ? src : simt::lane_id()]);
+}
 template <typename T> static inline T __shfl_down_sync(unsigned mask, T v, int delta) {
     const int s = simt::warp_arrive(mask, simt::to_bits(v));
     const int src = simt::lane_id() + delta;
