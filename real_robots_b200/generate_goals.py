@@ -21,8 +21,10 @@ SHELF_Z = {"cube": 0.40, "tomato": 0.40, "mustard": 0.395}
 TABLE_Z = {"cube": 0.33, "tomato": 0.34, "mustard": 0.33}
 
 
-def generate_position(rng, obj, fixed, table_plane):
-    """generatePosition (:79-108): x range by table plane, y in [-.45,.45], z = 0.40 on the table / 0.50 above the shelf."""
+def generate_position(rng, obj, fixed, table_plane, base_quat=None):
+    """generatePosition (:79-108): x range by table plane, y in [-.45,.45], z = 0.40 on the table / 0.50 above the shelf.
+    A fixed orientation is the one the object SETTLES in after a reset (basePosition[obj][3:], :100, :418), passed in
+    base_quat; without it (host-only tests) the nominal Euler angles of Kuka.object_poses are used."""
     if table_plane is None:
         min_x, max_x = -.25, .25
     elif table_plane:
@@ -33,18 +35,18 @@ def generate_position(rng, obj, fixed, table_plane):
     y = rng.random() * 0.9 - 0.45
     z = 0.40 if x <= 0.05 else 0.50
     if fixed:
-        quat = euler_to_quat(BASE_ORIENTATION[obj])
+        quat = list(base_quat[obj]) if base_quat is not None else euler_to_quat(BASE_ORIENTATION[obj])
     else:
         quat = euler_to_quat((rng.random(3) * math.pi * 2).tolist())
     return np.array([x, y, z] + list(quat))
 
 
-def draw_start_poses(rng, objects, fixed_orientation, table_plane, min_separation):
+def draw_start_poses(rng, objects, fixed_orientation, table_plane, min_separation, base_quat=None):
     """The sampling half of drawPosition (:133-165): permute objects, redraw an object until it clears the others."""
     poses = {}
     for obj in rng.permutation(objects):
         while True:
-            p = generate_position(rng, obj, fixed_orientation, table_plane)
+            p = generate_position(rng, obj, fixed_orientation, table_plane, base_quat)
             others = [q[:3] for q in poses.values()]
             if not others or min(np.linalg.norm(p[:3] - o) for o in others) >= min_separation:
                 poses[obj] = p
@@ -54,13 +56,16 @@ def draw_start_poses(rng, objects, fixed_orientation, table_plane, min_separatio
 
 def settle(env, max_t=1000):
     """runEnv (:21-68), batched: zero action until every object moved < 1e-4 m and < 1e-3 in quaternion for 21
-    consecutive steps (and t > 10).  Returns (still[N] bool, poses[N, n_obj, 7])."""
+    consecutive steps (and t > 10).  runEnv returns at the step an env meets the test, so every env's poses are LATCHED at
+    that step (the batch keeps stepping for the slower envs) and written back before returning, velocities zeroed, so that a
+    render after settle() shows the latched state.  Returns (still[N] bool, poses[N, n_obj, 7])."""
     import torch
     N = env.n_envs
     zero = torch.zeros(N, 9, dtype=torch.float64, device=env.device)
     pos = env.sim.read_state()[2].clone()
     stable = torch.zeros(N, dtype=torch.int64, device=env.device)
     still = torch.zeros(N, dtype=torch.bool, device=env.device)
+    latched = pos.clone()
     for t in range(max_t):
         env.sim.step(zero)
         new = env.sim.read_state()[2].clone()
@@ -68,11 +73,15 @@ def settle(env, max_t=1000):
         dq = torch.minimum((new[:, :, 3:] - pos[:, :, 3:]).norm(dim=2), (new[:, :, 3:] + pos[:, :, 3:]).norm(dim=2)).max(dim=1).values
         ok = (dpos < 0.0001) & (dq < 0.001) & (t > 10)
         stable = torch.where(ok, stable + 1, torch.zeros_like(stable))
-        still |= stable > 20
+        now = (stable > 20) & ~still
+        latched = torch.where(now[:, None, None], new, latched)
+        still |= now
         pos = new
         if bool(still.all()):
             break
-    return still, pos
+    latched = torch.where(still[:, None, None], latched, pos)
+    env.set_object_poses(latched.contiguous(), mask=still)
+    return still, latched
 
 
 def _min_separation(poses):
@@ -101,6 +110,11 @@ def generate_goals(n_goals, n_objects=1, challenge='2D', seed=2020, device=0, ba
     plane = True if challenge == '2D' else None
     N = batch or max(8, 2 * n_goals)
     env = VecREALRobotEnv(N, device=device, objects=n_objects, action_type='joints', additional_obs=True)
+    # basePosition (:415-418): the poses the objects settle in after a reset; fixed-orientation goals use THOSE orientations
+    env.reset(render=False)
+    _, base = settle(env, 200)
+    base = base[0].cpu().numpy()
+    base_quat = {name: base[o, 3:7].copy() for o, name in enumerate(objects)}
     goals = []
     for _ in range(max_rounds):
         if len(goals) >= n_goals:
@@ -109,7 +123,7 @@ def generate_goals(n_goals, n_objects=1, challenge='2D', seed=2020, device=0, ba
         for phase in range(2):                       # 0 = initial placement, 1 = goal placement
             start = np.zeros((N, n_objects, 7))
             for e in range(N):
-                poses = draw_start_poses(rng, objects, fixed, plane, min_objects_dist)
+                poses = draw_start_poses(rng, objects, fixed, plane, min_objects_dist, base_quat)
                 for o, name in enumerate(objects):
                     start[e, o] = poses[name]
             env.reset(render=False)
@@ -156,7 +170,7 @@ def save_goals(goals, path):
 def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(description="Generate a REALRobot2020 goals dataset on the GPU")
-    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=None, help="seed of the goal draws (default: none, as in the reference)")
     ap.add_argument("--n_2d_goals", type=int, default=25)
     ap.add_argument("--n_25d_goals", type=int, default=15)
     ap.add_argument("--n_3d_goals", type=int, default=10)
@@ -167,7 +181,7 @@ def main(argv=None):
     # generate_goals.py:425-433: 2D and 2.5D goals keep objects 0.25 m apart, 3D goals may touch; start and goal 0.2 m apart
     for k, (ch, n, sep) in enumerate((('2D', a.n_2d_goals, 0.25), ('2.5D', a.n_25d_goals, 0.25), ('3D', a.n_3d_goals, 0.0))):
         if n > 0:
-            goals += generate_goals(n, a.n_obj, ch, seed=a.seed + k, min_start_goal_dist=0.2, min_objects_dist=sep)
+            goals += generate_goals(n, a.n_obj, ch, seed=None if a.seed is None else a.seed + k, min_start_goal_dist=0.2, min_objects_dist=sep)
     name = a.file or "goals-REAL2020-s{}-{}-{}-{}-{}.npy".format(a.seed, a.n_2d_goals, a.n_25d_goals, a.n_3d_goals, a.n_obj)
     save_goals(goals, name)
     print("wrote %d goals to %s.npz" % (len(goals), name))

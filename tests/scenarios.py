@@ -73,3 +73,63 @@ def check_touch_scenarios(make_sim, steps_press=40, steps_shelf=40):
                     skin_on_shelf = True         # would be reported if table_upper were a base link (contact threshold 0.1, robot.py:47)
     assert shelf_impulse > 0.0 and skin_on_shelf           # the gripper did press on the shelf, skins within the contact threshold
     return good / steps_press
+
+
+def integration_stub_client(lib_path, n_objects=1):
+    """Executes the ctypes binding INTEGRATION.md section B shows a maintainer of the reference (the B200Client class, verbatim
+    from the document) against the library at lib_path; returns a client instance."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"## B\..*?```python\n(.*?)```", text, re.S).group(1)
+    assert 'C.CDLL("libreal_b200.so")' in block
+    ns = {}
+    exec(block.replace('C.CDLL("libreal_b200.so")', "C.CDLL(%r)" % lib_path), ns)
+    blob = os.path.join(root, "real_robots_b200", "assets", "scene.rrb")
+    return ns["B200Client"](n_objects, blob=blob)
+
+
+def contact_rich_tracking(step_fn, state_fn, set_state_fn, N=32, T=400, seed=3):
+    """Random-policy episodes with arm / object / table contacts, CUDA path against the oracle.
+
+    step_fn(actions[N,9]), state_fn() -> (q[N,11], qd, obj[N,3,13]) numpy, set_state_fn(q, qd, obj).
+    Returns (tracked, agree, flips): `tracked` = fraction of envs whose FREE-RUNNING joints stay within 1e-6 of the oracle's
+    for T steps; then, restarting both sides from the oracle's state every step, `agree` = fraction of (env, step) pairs that
+    agree to 1e-9 after one step, and `flips` = the largest one-step difference among the others.  A pair that disagrees is a
+    discrete narrowphase decision taken differently (witness point of a face-to-face contact, EPA face of coplanar
+    candidates) on poses that differ in the last bits — not accumulated rounding: there is nothing in between."""
+    lo = np.array([-2.09, -2.09, -2.96, -2.09, -2.96, -2.09, -3.05, 0, 0]); hi = -lo; hi[7:] = np.pi / 2
+    rng = np.random.default_rng(seed)
+
+    def policy(steps):
+        a = rng.uniform(lo, hi, size=(N, 9))
+        for _ in range(steps):
+            redraw = rng.random(N) < 0.05
+            a = np.where(redraw[:, None], rng.uniform(lo, hi, size=(N, 9)), a)
+            yield a.copy()
+    orcs = [Oracle(3) for _ in range(N)]
+    tracked = np.ones(N, bool)
+    for a in policy(T):
+        step_fn(a)
+        for e in range(N):
+            orcs[e].step(a[e])
+        q = state_fn()[0]
+        oq = np.array([o.get_state()[0] for o in orcs])
+        tracked &= np.abs(q - oq).max(axis=1) < 1e-6
+    good, total, flips = 0, 0, 0.0
+    for a in policy(T // 4):
+        st = [o.get_state() for o in orcs]
+        for e in range(N):
+            orcs[e].set_state(*st[e])
+        set_state_fn(np.stack([s[0] for s in st]), np.stack([s[1] for s in st]), np.stack([s[2] for s in st]))
+        step_fn(a)
+        for e in range(N):
+            orcs[e].step(a[e])
+        q, _, obj = state_fn()
+        oq = np.array([o.get_state()[0] for o in orcs]); oobj = np.array([o.get_state()[2] for o in orcs])
+        err = np.maximum(np.abs(q - oq).max(axis=1), np.abs(obj - oobj).reshape(N, -1).max(axis=1))
+        good += int((err < 1e-9).sum()); total += N
+        if (err >= 1e-9).any():
+            flips = max(flips, float(err[err >= 1e-9].max()))
+    return float(tracked.mean()), good / total, flips

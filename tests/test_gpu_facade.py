@@ -361,3 +361,18 @@ def test_c4_macro_action_evaluate_vectorised_equals_the_serial_facade(tmp_path):
     serial = np.array(s_scores['2D'])
     assert serial.shape == (K,)
     assert np.abs(serial - vec[:K]).max() < 1e-9, (serial, vec[:K])
+
+
+def test_integration_md_binding_stub_on_the_gpu():
+    """INTEGRATION.md section B's ctypes binding, executed verbatim against libreal_b200.so: a step through it equals the oracle."""
+    from real_robots_b200 import _lib
+    from tests.scenarios import integration_stub_client
+    client = integration_stub_client(_lib.LIB_PATH, n_objects=1)
+    o = Oracle(1)
+    a = np.array([0.3, -0.2, 0.1, -0.4, 0.0, 0.5, 0.2, 0.3, 0.2])
+    for _ in range(3):
+        client.step(a, True)
+        o.step(a)
+    assert np.abs(client.joints[0] - o.read()[0]).max() < 1e-9
+    r, d, m = o.render()
+    assert (client.mask[0] == m).all() and (client.rgb[0] == r).all() and (client.depth[0] == d).all()

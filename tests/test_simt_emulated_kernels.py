@@ -197,3 +197,20 @@ def test_emulated_host_buffer_path_and_pipelined_begin_end():
 def test_emulated_touch_sensors_scripted_press_and_shelf():
     from tests.scenarios import check_touch_scenarios
     check_touch_scenarios(lambda: EmuSim(1, 1))
+
+
+def test_integration_md_binding_stub_runs_against_the_c_abi():
+    """INTEGRATION.md section B's B200Client (the binding a maintainer of the reference would add), executed verbatim —
+    here against the emulated build of the library; tests/test_gpu_facade.py does the same against libreal_b200.so."""
+    from tests.scenarios import integration_stub_client
+    from tests.simt import emu
+    client = integration_stub_client(emu.build(), n_objects=1)
+    o = Oracle(1)
+    a = np.array([0.3, -0.2, 0.1, -0.4, 0.0, 0.5, 0.2, 0.3, 0.2])
+    for _ in range(3):
+        client.step(a, True)
+        o.step(a)
+    assert np.abs(client.joints[0] - o.read()[0]).max() < 1e-9
+    r, d, m = o.render()
+    assert (client.mask[0] == m).all() and (client.rgb[0] == r).all() and (client.depth[0] == d).all()
+    assert np.abs(client.objs[0, 0, :3] - o.get_state()[2][0, :3]).max() < 1e-9
