@@ -32,7 +32,7 @@ def _worker(rank, world, port, q):
     a = env.sample_random_actions(g)
     for _ in range(40):
         obs, _, _, _ = env.step({'joint_command': a, 'render': True})
-    # score gather over NCCL: goal g of the global list lives on rank g // n
+    # score gather over NCCL: the goals are partitioned into contiguous shards (evaluate.shard_range)
     G = world * n - 3                                              # ragged last shard
     lo, hi = shard_range(G, rank, world)
     goal = obs['object_positions'].contiguous() + 0.05
@@ -69,7 +69,10 @@ def test_score_gather_and_retina_handoff_over_nccl():
     assert (ret0 == ret1).all()                                    # an env's images do not depend on the GPU that hosts it
     G = 2 * 8 - 3
     assert vec0.shape == (G,) and (vec0 == vec1).all() and np.isfinite(vec0).all()
-    assert (vec0[:8] == loc0).all() and (vec0[8:] == loc1[:G - 8]).all()
+    from real_robots_b200.evaluate import shard_range
+    (lo0, hi0), (lo1, hi1) = shard_range(G, 0, 2), shard_range(G, 1, 2)
+    assert (lo0, hi1) == (0, G) and hi0 == lo1 and len(loc0) == hi0 - lo0 and len(loc1) == hi1 - lo1
+    assert (vec0[lo0:hi0] == loc0).all() and (vec0[lo1:hi1] == loc1).all()
     small = ret0.reshape(8, 60, 4, 80, 4, 3).astype(np.float32).mean(axis=(2, 4)).round().clip(0, 255).astype(np.uint8)
     assert every0.shape == (16, 60, 80, 3) and (every0 == every1).all() and (every0[:8] == small).all() and (every0[8:] == small).all()
     assert learner1 is None and learner0.shape == (16, 30, 40, 3)
