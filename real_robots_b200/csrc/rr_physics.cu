@@ -721,8 +721,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
                         if (myk < 3) rr = m.oIinv[myo][3 * myk] * m.Jtmp[11 + 6 * myo] + m.oIinv[myo][3 * myk + 1] * m.Jtmp[12 + 6 * myo] + m.oIinv[myo][3 * myk + 2] * m.Jtmp[13 + 6 * myo];
                         else rr = J * m.oinvm[myo];
                     }
-                    const double den = warp_sum(J * rr);
-                    const double relv = warp_sum(J * (lane < RR_NDOF ? vel : ovel));
+                    double den, relv; warp_sum2(J * rr, J * (lane < RR_NDOF ? vel : ovel), den, relv);      // two reductions for the price of one
                     const double inv = den > 0 ? 1.0 / den : 0.0;
                     double rhs, app0 = 0.0, lo = 0.0, hi = 1e10;         // normal rows: [0, 1e10]; the others: lo = the coefficient, limits follow the normal impulse
                     if (di == 0) {

@@ -250,10 +250,15 @@ def test_settle_detector_and_placement_thresholds_match_reference():
     for max_t in fake_env.MAX_TS:
         env = type("E", (), {})()
         env.n_envs, env.device, env.sim = len(scripts), torch.device("cpu"), FakeSim()
-        still, _ = gg.settle(env, max_t=max_t)
+        written = {}
+        env.set_object_poses = lambda pq, mask=None: written.update(pq=pq.clone(), mask=mask.clone())
+        still, poses = gg.settle(env, max_t=max_t)
         for i, sc in enumerate(scripts):
-            failed, _t = META["settle"]["%s/%d" % (sc, max_t)]
+            failed, t_ref = META["settle"]["%s/%d" % (sc, max_t)]
             assert bool(still[i]) == (not failed), (sc, max_t)
+            if not failed:      # the poses are latched at the step the env met the test (runEnv returns there), not at the end of the batch
+                assert np.allclose(poses[i, 0].numpy(), fake_env.scripted_pose(sc, int(t_ref) + 1)), (sc, max_t, t_ref)
+        assert (written["mask"] == still).all() and torch.equal(written["pq"], poses)
     zs = (0.30, 0.329, 0.331, 0.339, 0.341, 0.394, 0.396, 0.399, 0.401, 0.45)
     for obj, want in META["shelf_table_thresholds"].items():
         mine = [z for z in zs if z < gg.TABLE_Z[obj]] + [-z for z in zs if z > gg.SHELF_Z[obj]]
