@@ -945,13 +945,16 @@ __device__ __forceinline__ void pgs_sweep(const unsigned int* const schedA0, con
     dv_out = dv; iters_out = iters;
 }
 
-// One warp per env, 32 warps per SM.  The schedule and the blocks are read-only here and stream from L2 (the images of the
+// One warp per env, 24 warps per SM.  The schedule and the blocks are read-only here and stream from L2 (the images of the
 // envs in flight — ~14 KB each — stay L2-resident; a block is one or two 128-byte lines); the applied impulses, the only
 // thing the sweep updates besides dv, live in shared memory by row id.  (Measured alternatives, same results: the whole image
 // in shared memory, one env per warp — 12 warps per SM, and lane-per-(env, group) streams, 7 envs per warp — 2 warps per SM:
 // both residency-bound at 1.9 ms for 4096 envs.)
+#ifndef SOLVE_WPB
+#define SOLVE_WPB 4
+#endif
 #ifndef SOLVE_MIN_BLOCKS
-#define SOLVE_MIN_BLOCKS 8
+#define SOLVE_MIN_BLOCKS 6           // 24 warps per SM, 85 registers (no spills): measured best of 4 / 5 / 6 / 7 / 8 blocks x 4 warps, 10 / 12 x 2, 20 / 24 x 1
 #endif
 struct SolveEpi { SolveHead head; KinWs kin; };
 #define SOLVE_SMEM_DOUBLES ((int)(sizeof(SolveEpi) / 8) > RR_MAX_ROWS ? (int)(sizeof(SolveEpi) / 8) : RR_MAX_ROWS)
@@ -959,12 +962,12 @@ struct SolveEpi { SolveHead head; KinWs kin; };
 #define SOLVE_SCHED_WORDS 512       // words of the slot schedule kept in shared memory (64 slots; longer schedules are read from the image)
 #endif
 #define SOLVE_SMEM_BYTES ((size_t)SOLVE_SMEM_DOUBLES * 8 + SOLVE_SCHED_WORDS * 4)
-__global__ void __launch_bounds__(WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
+__global__ void __launch_bounds__(SOLVE_WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
     RR_DYN_SMEM(smem_raw);
     double* const smem = reinterpret_cast<double*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
     double* const sapp = smem;                                 // applied impulses by row id (during the sweep)
     const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * WPB + (threadIdx.x >> 5);
+    const int e = blockIdx.x * SOLVE_WPB + (threadIdx.x >> 5);
     if (e >= st.N) return;
     const int N = st.N;
     const double dt = cf.dt;
@@ -1261,7 +1264,7 @@ int rrk_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_robot, &ctx->robot, sizeof(RobotConst)));
     g_phys_owner[ctx->device & 63] = ctx;
     CK(cudaFuncSetAttribute(k_step_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
-    CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * WPB)));
+    CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * SOLVE_WPB)));
     CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FkMem) * WPB)));
     return 0;
 }
@@ -1319,7 +1322,7 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
     if (ctx->cfg.enable_contacts && rrk_collide(ctx, s) != 0) return -1;
     ProfScope ps(ctx, 0, s);
     RR_LAUNCH(k_step_dyn, nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s)(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
-    RR_LAUNCH(k_step_solve, nblk(ctx->N, WPB), WPB * 32, SOLVE_SMEM_BYTES * WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
+    RR_LAUNCH(k_step_solve, nblk(ctx->N, SOLVE_WPB), SOLVE_WPB * 32, SOLVE_SMEM_BYTES * SOLVE_WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
     ctx->launches += 2;
     CK(cudaGetLastError());
     return 0;
