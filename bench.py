@@ -265,8 +265,16 @@ def run_ours(args):
     sim.profile(False)
     sampler.stop_flag = True
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    # per rank: timed region and the sum of the kernels' own durations (the ranks roll out different seeds, and the solver's
+    # duration follows the most contact-laden envs of a rank: the spread between ranks is workload, not communication)
+    mine = torch.tensor([ms / K, sum(v[0] / max(v[1], 1) for v in prof.values())], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
+    per_rank = [[round(float(x), 3) for x in t.tolist()] for t in per_rank]
     ms_max = float(tms.item())
     value = world * args.envs * K / (ms_max * 1e-3)
 
@@ -364,6 +372,7 @@ def run_ours(args):
                     "ceiling_how": "plain pinned D2H copy of one step's images (%.2f GB per rank), all ranks at once, slowest rank" % (args.envs * IMG_BYTES / 1e9)},
             "collective_check": collective,
             "gpu_launches": launches,
+            "per_rank_ms": {"ms_per_step": [p[0] for p in per_rank], "kernel_sum_ms": [p[1] for p in per_rank]},
             "clocks": sampler.summary(),
         }
         if args.cpu_baseline:
