@@ -397,8 +397,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--settle", type=int, default=60, help="untimed physics-only pre-roll steps before the warm-up")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
-    ap.add_argument("--traffic", type=float, default=4.85e9,
-                    help="dram bytes (read + write) per 4096-env k_raster launch from the ncu capture in profiles/r01c_ncu_full_summary.json (0.47 GB read + 4.38 GB written)")
+    ap.add_argument("--traffic", type=float, default=4.86e9,
+                    help="dram bytes (read + write) per 4096-env k_raster launch from the ncu capture in profiles/r02_ncu_full_summary.json (0.48 GB read + 4.38 GB written)")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":
