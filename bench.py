@@ -237,8 +237,8 @@ def run_ours(args):
 
     def step(t):
         sim.step(acts[t])
-        sim.read_state()
-        sim.render()
+        sim.render()              # before read_state: the rasteriser starts while the solver's heavy-env kernel still runs (it waits
+        sim.read_state()          # per env inside the kernel); read_state joins that kernel first
 
     # untimed pre-roll: after reset the objects are in the air (robot.py:19-24) and land ~27 steps later; the timed
     # region should see the steady state of a random-policy rollout (resting and arm contacts), not the free fall

@@ -161,7 +161,8 @@ int  rr_set_contacts(rr_ctx* ctx, const int32_t* hdr, const double* pts, void* s
  * bit 1: every contact was object-vs-static, so the solver took its object-parallel path; bit 2: a NaN / infinite joint
  * command arrived — where the reference asserts np.isfinite(a).all() (robot.py:189) a batched step cannot raise per env, the
  * command acts as a full +-max step and never reaches the state; bit 3: the state had become non-finite and the env was put
- * back into its initial state, as rr_reset would). */
+ * back into its initial state, as rr_reset would; bits 16-31: the length of the env's Gauss-Seidel schedule in slots per iteration,
+ * a friction-pair slot counted twice — what orders the envs inside the solver kernel). */
 int  rr_diag(rr_ctx* ctx, int32_t* out, void* stream);
 
 #ifdef __cplusplus

@@ -269,7 +269,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
     alloc((void**)&st.q, 11 * N * 8); alloc((void**)&st.qd, 11 * N * 8); alloc((void**)&st.target, 11 * N * 8);
     alloc((void**)&st.obj, 39 * N * 8); alloc((void**)&st.touch, 4 * N * 8); alloc((void**)&st.link_frames, 16 * 12 * N * 8);
-    alloc((void**)&st.render_mats, N * RR_NSHAPES * RR_MAT_STRIDE * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.col_flags, N * 4); alloc((void**)&st.timestep, N * 8);
+    alloc((void**)&st.render_mats, N * RR_NSHAPES * RR_MAT_STRIDE * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.col_flags, N * 4); alloc((void**)&st.ready, N * 4); alloc((void**)&st.solve_order, (size_t)RR_SOLVE_CLASSES * (N + 1) * 4); alloc((void**)&st.timestep, N * 8);
     for (int k = 0; k < 2; k++) {
         alloc((void**)&ctx->d_cmd[k], N * 9 * 8); alloc((void**)&ctx->d_mask[k], N); alloc((void**)&ctx->d_joint[k], N * 9 * 8);
         alloc((void**)&ctx->d_touch[k], N * 4 * 8); alloc((void**)&ctx->d_objpose[k], N * 3 * 7 * 8);
@@ -281,6 +281,8 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     alloc((void**)&st.handoff, N * RR_IMG_DOUBLES * 8);
     if (e != cudaSuccess) { ctx->err = std::string("rr_create: device allocation failed: ") + cudaGetErrorString(e); return fail(-1); }
     ctx->man_parity = 0;
+    { const char* ea = getenv("RR_EAGER_COLLIDE"); ctx->eager_collide = !(ea && ea[0] == '0'); }
+    { const char* ea = getenv("RR_HEAVY_SOLVER"); ctx->heavy_solver = !(ea && ea[0] == '0'); }
     if (rrk_reset(ctx, nullptr, 0) != 0) return fail(-1);
     if (rrk_render_build_static(ctx) != 0) return fail(-1);
     if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "rr_create: initial reset failed"; return fail(-1); }
@@ -293,8 +295,9 @@ int rr_destroy(rr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     rrk_physics_unbind(ctx); rrk_collide_unbind(ctx); rrk_render_unbind(ctx);
+    if (ctx->side_stream) { cudaStreamDestroy(ctx->side_stream); cudaEventDestroy(ctx->ev_solved); cudaEventDestroy(ctx->ev_collided); cudaEventDestroy(ctx->ev_dyn); cudaEventDestroy(ctx->ev_heavy); }
     DevState& st = ctx->st;
-    void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.col_flags, st.timestep,
+    void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.col_flags, st.ready, st.solve_order, st.timestep,
                     st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.handoff,
                     ctx->d_cmd[0], ctx->d_mask[0], ctx->d_joint[0], ctx->d_touch[0], ctx->d_objpose[0], ctx->d_rgb[0], ctx->d_depth[0], ctx->d_seg[0],
                     ctx->d_cmd[1], ctx->d_mask[1], ctx->d_joint[1], ctx->d_touch[1], ctx->d_objpose[1], ctx->d_rgb[1], ctx->d_depth[1], ctx->d_seg[1],
@@ -302,6 +305,7 @@ int rr_destroy(rr_ctx* ctx) {
                     ctx->d_static_keys, ctx->d_static_img};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_late_timeout) { cudaFreeHost(ctx->h_late_timeout); cudaFree(ctx->d_late_timeout); }
     if (ctx->host_compute) {
         for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->host_ev[i]);
         for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->host_done[i]);
@@ -358,6 +362,7 @@ int rr_score(rr_ctx* ctx, const double* goal_xyz, double* score, void* stream) {
 }
 int rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, int* n_pairs_host, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    if (rrk_join_heavy(ctx, s) != 0) return -1;
     const int p = ctx->man_parity;
     const size_t N = (size_t)ctx->N;
     cudaError_t e = cudaSuccess;
@@ -371,6 +376,7 @@ int rr_contacts(rr_ctx* ctx, int32_t* hdr, double* pts, int32_t* pairs_host, int
 int rr_set_contacts(rr_ctx* ctx, const int32_t* hdr, const double* pts, void* stream) {
     ARG(hdr != nullptr && pts != nullptr, "rr_set_contacts: hdr / pts is NULL");
     cudaStream_t s = (cudaStream_t)stream;
+    if (rrk_drop_collide_ahead(ctx, s) != 0) return -1;
     const int p = ctx->man_parity;
     const size_t N = (size_t)ctx->N;
     cudaError_t e = cudaMemcpyAsync(ctx->st.man_hdr[p], hdr, N * RR_MAX_MANIFOLDS * 2 * 4, cudaMemcpyDeviceToDevice, s);
@@ -400,6 +406,7 @@ int rr_profile_read(rr_ctx* ctx, double* ms_total, long long* launches) {
     return 0;
 }
 int rr_diag(rr_ctx* ctx, int32_t* out, void* stream) {
+    if (rrk_join_heavy(ctx, (cudaStream_t)stream) != 0) return -1;
     cudaError_t e = cudaMemcpyAsync(out, ctx->st.diag, (size_t)ctx->N * 16, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return -1; }
     return 0;

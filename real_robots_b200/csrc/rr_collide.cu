@@ -385,16 +385,9 @@ k_collide(DevState st, const double* __restrict__ hull_verts, const int* __restr
     const int N = st.N;
     const double thr = cf.contact_breaking;
 
-    // ---- control_objects_limits (env.py:257-264): lanes 0..n_objects-1 teleport their object if out of bounds
-    if (lane < n_objects) {
-        double* base = st.obj + (size_t)lane * 13 * N + e;
-        double px = base[0], pz = base[(size_t)2 * N];
-        if (pz < c_col.table_pos[2] || (px > 0.11 && pz < 0.29)) {
-            for (int k = 0; k < 7; k++) base[(size_t)k * N] = c_col.obj_init[lane][k];
-            for (int k = 7; k < 13; k++) base[(size_t)k * N] = 0.0;
-        }
-    }
-    __syncwarp();
+    // control_objects_limits (env.py:257-264) runs before the step's collision detection: an object out of bounds collides at its
+    // initial pose.  This kernel only READS the state (it may run ahead of the step, beside the rasteriser of the previous one);
+    // k_step_dyn applies the same test and writes the teleported state.
     // ---- world frames and AABBs of the 22 shapes (lane = shape)
     if (lane < RR_NSHAPES) {
         const int s = lane, body = c_col.shape_body[s], link = c_col.shape_link[s];
@@ -409,6 +402,11 @@ k_collide(DevState st, const double* __restrict__ hull_verts, const int* __restr
             const int o = body - 2;
             double q[4];
             for (int k = 0; k < 4; k++) q[k] = st.obj[((size_t)o * 13 + 3 + k) * N + e];
+            for (int k = 0; k < 3; k++) p[k] = st.obj[((size_t)o * 13 + k) * N + e];
+            if (p[2] < c_col.table_pos[2] || (p[0] > 0.11 && p[2] < 0.29)) {
+                for (int k = 0; k < 3; k++) p[k] = c_col.obj_init[o][k];
+                for (int k = 0; k < 4; k++) q[k] = c_col.obj_init[o][3 + k];
+            }
             double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
             double sc = 2.0 / d;
             double xs = q[0] * sc, ys = q[1] * sc, zs = q[2] * sc;
@@ -418,7 +416,6 @@ k_collide(DevState st, const double* __restrict__ hull_verts, const int* __restr
             R[0] = 1.0 - (yy + zz); R[1] = xy - wz; R[2] = xz + wy;
             R[3] = xy + wz; R[4] = 1.0 - (xx + zz); R[5] = yz - wx;
             R[6] = xz - wy; R[7] = yz + wx; R[8] = 1.0 - (xx + yy);
-            for (int k = 0; k < 3; k++) p[k] = st.obj[((size_t)o * 13 + k) * N + e];
         }
         for (int k = 0; k < 9; k++) m.R[s][k] = R[k];
         for (int k = 0; k < 3; k++) m.p[s][k] = p[k];
@@ -581,7 +578,8 @@ int rrk_collide_upload_constants(rr_ctx* ctx) {
     return 0;
 }
 
-int rrk_collide(rr_ctx* ctx, cudaStream_t s) {
+// flip = false: the look-ahead launch of rrk_step; the new manifolds become current when the next step adopts them
+int rrk_collide(rr_ctx* ctx, cudaStream_t s, bool flip) {
     if (bind_collide(ctx, s)) return -1;
     const int in = ctx->man_parity, out = 1 - in;
     {
@@ -591,7 +589,7 @@ int rrk_collide(rr_ctx* ctx, cudaStream_t s) {
     }
     ctx->launches++;
     CK(cudaGetLastError());
-    ctx->man_parity = out;
+    if (flip) ctx->man_parity = out;
     return 0;
 }
 

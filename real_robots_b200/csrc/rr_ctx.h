@@ -37,6 +37,7 @@
 #define RR_ROWS_A (RID_ROLL + 2 * RR_MAX_CONTACTS)           // 216 single rows
 #define RID_FRIC RR_ROWS_A                                   // + 2 c + {0, 1}
 #define RR_MAX_ROWS (RID_FRIC + 2 * RR_MAX_CONTACTS)         // 312
+#define RR_SOLVE_CLASSES 4
 #define RR_IDLE 0xff
 
 // ---- constant robot / scene description (uploaded to __constant__ memory once per process+device)
@@ -84,6 +85,10 @@ struct DevState {
     double* link_frames;  // [16][12][N]  world_from_link R(9) + p(3), COM frames
     float*  render_mats;  // [N][22][40] per-shape matrices for the rasteriser (see rr_render.cu)
     int*    diag;     // [N][4]
+    int*    solve_order; // [RR_SOLVE_CLASSES + RR_SOLVE_CLASSES * N]: per cost class a counter and the envs of that class (k_step_dyn appends,
+                        // k_step_solve's warp w takes the w-th env of the concatenation: the longest sweeps start first)
+    int*    ready;      // [N] serial number of the last step whose state k_step_solve_heavy finished for this env (what a rasteriser
+                        // launched before that kernel ended waits for, see rrk_render)
     int*    col_flags;  // [N] written by k_collide (1: a non-empty manifold found no slot), merged into diag by k_step_solve
     long long* timestep;  // [N]
     int*    man_hdr[2];   // [N][RR_MAX_MANIFOLDS][2]  (pair index or -1, point count), double buffered
@@ -106,6 +111,16 @@ struct rr_ctx {
     double aabb_c[RR_NSHAPES][3], aabb_h[RR_NSHAPES][3];
     int pair_a[RR_MAX_PAIRS], pair_b[RR_MAX_PAIRS], n_pairs;
     int man_parity;            // which manifold buffer holds the current contacts
+    // look-ahead narrowphase: the contacts of step t+1 depend on the poses after step t only, so rrk_step launches k_collide for
+    // the NEXT step on a side stream right after the solver (it then overlaps whatever the caller does next, normally the
+    // rasteriser); the next rrk_step waits for it and flips man_parity.  Anything that edits poses or manifolds drops it.
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_solved = nullptr, ev_collided = nullptr, ev_dyn = nullptr, ev_heavy = nullptr;
+    bool collide_ahead = false, eager_collide = true;
+    int heavy_cap = 0;         // envs k_step_solve_heavy took at most in the last step
+    int* d_late_timeout = nullptr; int* h_late_timeout = nullptr;   // k_raster's bounded wait for that kernel ran out (pinned mirror)
+    int step_serial = 0;       // rrk_step calls so far (the ticket k_step_solve_heavy leaves in DevState::ready)
+    bool heavy_pending = false; // k_step_solve_heavy of the last step has not been joined into the caller's stream yet
+    bool heavy_solver = true;  // the envs with the longest Gauss-Seidel schedules go to k_step_solve_heavy on the side stream (rr_physics.cu)
     int n_tris;
     void* d_rec_scratch; void* d_list_scratch; int* d_work_counter; uint8_t* d_tri_shape; int raster_grid;   // persistent rasteriser
     void* h_collide_const; float cull_hmax;   // host copies of per-context __constant__ data that are built on the fly
@@ -167,6 +182,8 @@ int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uin
 int rrk_render_camera(rr_ctx* ctx, const RenderConst* cam, const uint8_t* mask, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);
 void rr_set_camera_consts(RenderConst& C, const float* view16, const float* proj16);
 int rrk_collide_upload_constants(rr_ctx* ctx);
-int rrk_collide(rr_ctx* ctx, cudaStream_t s);
+int rrk_collide(rr_ctx* ctx, cudaStream_t s, bool flip = true);
+int rrk_drop_collide_ahead(rr_ctx* ctx, cudaStream_t s);
+int rrk_join_heavy(rr_ctx* ctx, cudaStream_t s);     // every reader / writer of the state but the eye-camera rasteriser calls this first
 int rrk_clear_manifolds(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s);
 int rrk_ik(rr_ctx* ctx, const uint8_t* mask, const double* pos_quat, double* out, int max_iter, double residual, cudaStream_t s);

@@ -57,6 +57,11 @@ struct SolveHead {
 #define GBLK_BASE (HEAD_DOUBLES + (16 * RR_SLOTS_A + 8 * RR_SLOTS_B) / 2)   // first block, in doubles
 static_assert(sizeof(SolveHead) % 16 == 0, "the schedule words and blocks must stay 16-byte aligned");
 static_assert(GBLK_BASE % 2 == 0 && GBLK_BASE + RR_NC_ROWS * RR_ARM_BLK + RR_MAX_CONTACTS * 6 * (RR_ARM_BLK + RR_OBJ_BLK) <= RR_IMG_DOUBLES, "solver image too small");
+#ifndef SOLVE_COST_0
+#define SOLVE_COST_0 48     // cost classes of k_step_dyn's ordering (an env whose contacts are all object-vs-static: 16 + 2 * 4 = 24);
+#define SOLVE_COST_1 32     // the classes above the last one are "heavy" (k_step_solve_heavy)
+#define SOLVE_COST_2 24
+#endif
 // k_step_dyn's own workspace
 struct WarpMem {
     double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
@@ -804,6 +809,10 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
         hand->n_slotsB = max(max(cur[0], cur[1]), max(cur[2], cur[3]));
         hand->n_nc = n_nc; hand->nc = nc; hand->overflow = overflow; hand->fault = m.fault; hand->simple = simple;
         hand->n_rows_total = n_rows_total; hand->n_blk_doubles = blk_top;
+        // cost class of the sweep (slots per iteration; a pair slot counts twice): k_step_solve starts the longest chains first
+        const int cost = (hand->n_slotsA[0] + hand->n_slotsA[1]) / 2 + 2 * hand->n_slotsB;
+        const int cls = cost > SOLVE_COST_0 ? 0 : cost > SOLVE_COST_1 ? 1 : cost > SOLVE_COST_2 ? 2 : 3;
+        st.solve_order[RR_SOLVE_CLASSES + cls * N + atomicAdd(&st.solve_order[cls], 1)] = e;
     }
     // ---- hand the state over
     if (lane < RR_NDOF) { hand->q[lane] = m.q[lane]; hand->qd[lane] = m.qd[lane]; hand->target[lane] = m.target[lane]; }
@@ -827,8 +836,9 @@ __device__ __forceinline__ double group_sum6(double pr, int s0, int s1, int s2, 
     const double d = __shfl_sync(FULL, pr, s3), e = __shfl_sync(FULL, pr, s4), f = __shfl_sync(FULL, pr, s5);
     return ((a + b) + (c + d)) + (e + f);
 }
-// The Gauss-Seidel sweep of one env (see SolveHead).  SS: the schedule pointers point into shared memory.
-template <bool SS>
+// The Gauss-Seidel sweep of one env (see SolveHead).  SS: the schedule pointers point into shared memory; BG: the blocks are in
+// global memory (streamed from L2, prefetched three slots ahead) — otherwise they were copied into shared memory too.
+template <bool SS, bool BG>
 __device__ __forceinline__ void pgs_sweep(const unsigned int* const schedA0, const unsigned int* const schedA1, const unsigned int* const schedB0, const double* const gblk,
                                           double* const sapp, const int nA0, const int nA1, const int nB, const int lane, const rr_config& cf, double& dv_out, int& iters_out) {
     // dv in owner layout: lane k < 11 owns the arm dof k, lane 11+6o+c the object component.
@@ -863,7 +873,7 @@ __device__ __forceinline__ void pgs_sweep(const unsigned int* const schedA0, con
                 const bool act = ingrp && w.x != ENT_IDLE;
                 const unsigned int kind = w.x >> 16;
                 const double* b = gblk + 2 * (act ? (w.x & 0x7fffu) : 0u);
-                if (ingrp && nx != ENT_IDLE) RR_PREFETCH_L1(gblk + 2 * (nx & 0x7fffu) + myk2);      // the blocks three slots ahead are on their way into L1
+                if (BG && ingrp && nx != ENT_IDLE) RR_PREFETCH_L1(gblk + 2 * (nx & 0x7fffu) + myk2);      // the blocks three slots ahead are on their way into L1
                 nx = slot + 4 < nA ? sched[8 * (slot + 4)] : ENT_IDLE;
                 double J = 0.0, rr = 0.0, rhs = 0.0, inv = 0.0, rinv = 0.0, lo = 0.0, hi = 0.0, app = 0.0;
                 bool on = act;
@@ -962,13 +972,38 @@ struct SolveEpi { SolveHead head; KinWs kin; };
 #define SOLVE_SCHED_WORDS 512       // words of the slot schedule kept in shared memory (64 slots; longer schedules are read from the image)
 #endif
 #define SOLVE_SMEM_BYTES ((size_t)SOLVE_SMEM_DOUBLES * 8 + SOLVE_SCHED_WORDS * 4)
-__global__ void __launch_bounds__(SOLVE_WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects) {
-    RR_DYN_SMEM(smem_raw);
-    double* const smem = reinterpret_cast<double*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
+// Heavy envs: the few envs (2-5 % under a random policy) whose arm touches something have schedules 1.5-3.5x as long as the rest,
+// and a Gauss-Seidel chain cannot be split: started together with the others, the longest of them alone set the kernel's duration
+// (2.2 ms against 1.0 ms for a batch without them).  They get a kernel of their own, launched beside the main one on a
+// high-priority stream: one warp per block, schedule AND blocks in shared memory (latency per slot ~5x lower than from L2), each
+// block taking the heaviest envs first.  Same code, same arithmetic.
+#define HEAVY_SCHED_WORDS (16 * RR_SLOTS_A + 8 * RR_SLOTS_B)
+#ifndef HEAVY_BLK_DOUBLES
+#define HEAVY_BLK_DOUBLES 8192     // 64 KB of row blocks; an env with more streams them from L2 like the main kernel
+#endif
+#define HEAVY_SMEM_BYTES ((size_t)SOLVE_SMEM_DOUBLES * 8 + HEAVY_SCHED_WORDS * 4 + (size_t)HEAVY_BLK_DOUBLES * 8)
+#ifndef HEAVY_GRID
+#define HEAVY_GRID 148
+#define HEAVY_PER_BLOCK 2
+#endif
+// the idx-th env in order of decreasing cost class (every env is in exactly one class list)
+__device__ __forceinline__ int solve_pick(const DevState& st, int idx) {
+    int cls = 0;
+#pragma unroll
+    for (int k = 0; k < RR_SOLVE_CLASSES - 1; k++) { const int n = st.solve_order[k]; if (cls == k && idx >= n) { idx -= n; cls = k + 1; } }
+    return st.solve_order[RR_SOLVE_CLASSES + cls * st.N + idx];
+}
+// how many envs the heavy kernel takes: the classes above the last one, as far as its grid goes
+__device__ __forceinline__ int solve_n_heavy(const DevState& st, int heavy_cap) {
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < RR_SOLVE_CLASSES - 1; k++) n += st.solve_order[k];
+    return min(n, heavy_cap);
+}
+template <bool HEAVY>
+__device__ __forceinline__ void solve_env(const DevState& st, const int e, double* const smem, unsigned int* const ssched, const int sched_cap, double* const sblk,
+                                          int* __restrict__ man_hdr, double* __restrict__ man_pts, const rr_config& cf, const int n_objects, const int lane) {
     double* const sapp = smem;                                 // applied impulses by row id (during the sweep)
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * SOLVE_WPB + (threadIdx.x >> 5);
-    if (e >= st.N) return;
     const int N = st.N;
     const double dt = cf.dt;
     const double* gimg = st.handoff + (size_t)e * RR_IMG_DOUBLES;
@@ -985,18 +1020,24 @@ __global__ void __launch_bounds__(SOLVE_WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve
     }
     __syncwarp();
     // ---- the slot schedule comes into shared memory when it fits (it is read by every lane in every slot of every iteration)
-    unsigned int* const ssched = reinterpret_cast<unsigned int*>(smem + SOLVE_SMEM_DOUBLES);
-    const bool sched_smem = 8 * (nA0 + nA1 + nB) <= SOLVE_SCHED_WORDS;
+    const bool sched_smem = 8 * (nA0 + nA1 + nB) <= sched_cap;
     if (sched_smem) {
         for (int k = lane; k < 8 * nA0; k += 32) ssched[k] = gsched[GSCHED_A(0) + k];
         for (int k = lane; k < 8 * nA1; k += 32) ssched[8 * nA0 + k] = gsched[GSCHED_A(1) + k];
         for (int k = lane; k < 8 * nB; k += 32) ssched[8 * (nA0 + nA1) + k] = gsched[GSCHED_B + k];
     }
+    bool blk_smem = false;
+    if (HEAVY) {
+        const int nd = gh->n_blk_doubles;
+        blk_smem = sched_smem && nd <= HEAVY_BLK_DOUBLES;
+        if (blk_smem) for (int k = 2 * lane; k < nd; k += 64) *reinterpret_cast<double2*>(sblk + k) = *reinterpret_cast<const double2*>(gblk + k);
+    }
     __syncwarp();
     double dv = 0.0;
     int iters = 0;
-    if (sched_smem) pgs_sweep<true>(ssched, ssched + 8 * nA0, ssched + 8 * (nA0 + nA1), gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
-    else pgs_sweep<false>(gsched + GSCHED_A(0), gsched + GSCHED_A(1), gsched + GSCHED_B, gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
+    if (HEAVY && blk_smem) pgs_sweep<true, false>(ssched, ssched + 8 * nA0, ssched + 8 * (nA0 + nA1), sblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
+    else if (sched_smem) pgs_sweep<true, true>(ssched, ssched + 8 * nA0, ssched + 8 * (nA0 + nA1), gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
+    else pgs_sweep<false, true>(gsched + GSCHED_A(0), gsched + GSCHED_A(1), gsched + GSCHED_B, gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
     // ---- impulse write-back (warm start of the next step) and gripper touch sensors (robot.py:131-163)
     int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
     double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
@@ -1096,8 +1137,29 @@ __global__ void __launch_bounds__(SOLVE_WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve
     }
     if (lane < RR_NUM_TOUCH) st.touch[(size_t)lane * N + e] = lane == 0 ? touch[0] : (lane == 1 ? touch[1] : (lane == 2 ? touch[2] : touch[3]));
     if (lane == 0) {
-        st.diag[4 * e] = rows_live; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (simple ? 2 : 0) | (fault << 2) | (cf.enable_contacts ? (st.col_flags[e] << 4) : 0);   // bit 0: contact cap hit, bit 1: every contact is object-vs-static, bits 2-3: faults, bit 4: manifold slots exhausted
+        st.diag[4 * e] = rows_live; st.diag[4 * e + 1] = iters; st.diag[4 * e + 2] = nc; st.diag[4 * e + 3] = overflow | (simple ? 2 : 0) | (fault << 2) | (cf.enable_contacts ? (st.col_flags[e] << 4) : 0) | ((((nA0 + nA1) >> 1) + 2 * nB) << 16);   // bit 0: contact cap hit, bit 1: every contact is object-vs-static, bits 2-3: faults, bit 4: manifold slots exhausted, bits 16-31: sweep cost (slots per iteration, pair slots twice)
         st.timestep[e] += 1;
+    }
+}
+__global__ void __launch_bounds__(SOLVE_WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects, int heavy_cap) {
+    RR_DYN_SMEM(smem_raw);
+    double* const smem = reinterpret_cast<double*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
+    const int idx = blockIdx.x * SOLVE_WPB + (threadIdx.x >> 5) + solve_n_heavy(st, heavy_cap);      // the heavy kernel has the first ones
+    if (idx >= st.N) return;
+    solve_env<false>(st, solve_pick(st, idx), smem, reinterpret_cast<unsigned int*>(smem + SOLVE_SMEM_DOUBLES), SOLVE_SCHED_WORDS, nullptr, man_hdr, man_pts, cf, n_objects, threadIdx.x & 31);
+}
+__global__ void __launch_bounds__(32) k_step_solve_heavy(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects, int heavy_cap, int ticket) {
+    RR_DYN_SMEM(smem_raw);
+    double* const smem = reinterpret_cast<double*>(smem_raw);
+    unsigned int* const ssched = reinterpret_cast<unsigned int*>(smem + SOLVE_SMEM_DOUBLES);
+    double* const sblk = reinterpret_cast<double*>(ssched + HEAVY_SCHED_WORDS);
+    const int n = solve_n_heavy(st, heavy_cap);
+    for (int idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        const int e = solve_pick(st, idx);
+        solve_env<true>(st, e, smem, ssched, HEAVY_SCHED_WORDS, sblk, man_hdr, man_pts, cf, n_objects, threadIdx.x);
+        __threadfence();                      // the env's state, frames and observations are out before the ticket is
+        __syncwarp();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(st.ready + e) = ticket;
     }
 }
 
@@ -1265,6 +1327,7 @@ int rrk_upload_constants(rr_ctx* ctx) {
     g_phys_owner[ctx->device & 63] = ctx;
     CK(cudaFuncSetAttribute(k_step_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
     CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * SOLVE_WPB)));
+    CK(cudaFuncSetAttribute(k_step_solve_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAVY_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FkMem) * WPB)));
     return 0;
 }
@@ -1278,6 +1341,7 @@ static int launch_fk(rr_ctx* ctx, cudaStream_t s) {
     return 0;
 }
 int rrk_reset(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
+    if (rrk_drop_collide_ahead(ctx, s)) return -1;
     if (bind_physics(ctx, s)) return -1;
     RR_LAUNCH(k_reset, nblk(ctx->N, 128), 128, 0, s)(ctx->st, mask, ctx->n_objects, ctx->st.man_hdr[ctx->man_parity]);
     ctx->launches++;
@@ -1285,6 +1349,7 @@ int rrk_reset(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
     return launch_fk(ctx, s);
 }
 int rrk_set_object_pose(rr_ctx* ctx, const uint8_t* mask, int obj, const double* pq, cudaStream_t s) {
+    if (rrk_drop_collide_ahead(ctx, s)) return -1;
     if (bind_physics(ctx, s)) return -1;
     RR_LAUNCH(k_set_object_pose, nblk(ctx->N, 128), 128, 0, s)(ctx->st, mask, obj, pq);
     ctx->launches++;
@@ -1298,12 +1363,14 @@ __global__ void k_clear_manifolds(int N, const uint8_t* __restrict__ mask, int* 
     for (int k = 0; k < RR_MAX_MANIFOLDS; k++) { man_hdr[((size_t)e * RR_MAX_MANIFOLDS + k) * 2] = -1; man_hdr[((size_t)e * RR_MAX_MANIFOLDS + k) * 2 + 1] = 0; }
 }
 int rrk_clear_manifolds(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s) {
+    if (rrk_drop_collide_ahead(ctx, s)) return -1;
     RR_LAUNCH(k_clear_manifolds, nblk(ctx->N, 128), 128, 0, s)(ctx->N, mask, ctx->st.man_hdr[ctx->man_parity]);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 int rrk_set_state(rr_ctx* ctx, const double* q, const double* qd, const double* obj, cudaStream_t s) {
+    if (rrk_drop_collide_ahead(ctx, s)) return -1;
     if (bind_physics(ctx, s)) return -1;
     if (rrk_clear_manifolds(ctx, nullptr, s) != 0) return -1;
     RR_LAUNCH(k_set_state, nblk(ctx->N, 128), 128, 0, s)(ctx->st, q, qd, obj);
@@ -1312,22 +1379,81 @@ int rrk_set_state(rr_ctx* ctx, const double* q, const double* qd, const double* 
     return launch_fk(ctx, s);
 }
 int rrk_get_state(rr_ctx* ctx, double* q, double* qd, double* obj, cudaStream_t s) {
+    if (rrk_join_heavy(ctx, s)) return -1;
     RR_LAUNCH(k_get_state, nblk(ctx->N, 128), 128, 0, s)(ctx->st, q, qd, obj);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
+// An editor of poses or manifolds on stream s invalidates the look-ahead narrowphase: wait for it (it reads what is about to be
+// written), then forget it — the next step collides in line.
+int rrk_drop_collide_ahead(rr_ctx* ctx, cudaStream_t s) {
+    if (rrk_join_heavy(ctx, s)) return -1;
+    if (!ctx->collide_ahead) return 0;
+    CK(cudaStreamWaitEvent(s, ctx->ev_collided, 0));
+    ctx->collide_ahead = false;
+    return 0;
+}
+// the context's side stream (highest priority: what runs there is short and on somebody's critical path) and its events
+static int side_streams(rr_ctx* ctx) {
+    if (ctx->side_stream) return 0;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&ctx->ev_solved, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_collided, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_dyn, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_heavy, cudaEventDisableTiming));
+    return 0;
+}
+int rrk_join_heavy(rr_ctx* ctx, cudaStream_t s) {
+    if (!ctx->heavy_pending) return 0;
+    CK(cudaStreamWaitEvent(s, ctx->ev_heavy, 0));
+    ctx->heavy_pending = false;
+    return 0;
+}
 int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
     if (bind_physics(ctx, s)) return -1;
-    if (ctx->cfg.enable_contacts && rrk_collide(ctx, s) != 0) return -1;
-    ProfScope ps(ctx, 0, s);
-    RR_LAUNCH(k_step_dyn, nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s)(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
-    RR_LAUNCH(k_step_solve, nblk(ctx->N, SOLVE_WPB), SOLVE_WPB * 32, SOLVE_SMEM_BYTES * SOLVE_WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
-    ctx->launches += 2;
-    CK(cudaGetLastError());
+    if (rrk_join_heavy(ctx, s)) return -1;
+    ctx->step_serial++;
+    if (ctx->cfg.enable_contacts) {
+        if (ctx->collide_ahead) {            // the previous step already collided at the poses it produced
+            CK(cudaStreamWaitEvent(s, ctx->ev_collided, 0));
+            ctx->man_parity ^= 1;
+            ctx->collide_ahead = false;
+        } else if (rrk_collide(ctx, s) != 0) return -1;
+    }
+    const bool heavy = ctx->heavy_solver && ctx->cfg.enable_contacts;
+    if ((heavy || ctx->eager_collide) && side_streams(ctx)) return -1;
+    const int heavy_cap = heavy ? HEAVY_GRID * HEAVY_PER_BLOCK : 0;
+    ctx->heavy_cap = heavy_cap;
+    {
+        ProfScope ps(ctx, 0, s);
+        CK(cudaMemsetAsync(ctx->st.solve_order, 0, RR_SOLVE_CLASSES * sizeof(int), s));
+        RR_LAUNCH(k_step_dyn, nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s)(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
+        if (heavy) {         // enqueued before the main kernel, on the high-priority stream: its blocks are placed first
+            CK(cudaEventRecord(ctx->ev_dyn, s));
+            CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_dyn, 0));
+            RR_LAUNCH(k_step_solve_heavy, HEAVY_GRID, 32, HEAVY_SMEM_BYTES, ctx->side_stream)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects, heavy_cap, ctx->step_serial);
+            CK(cudaEventRecord(ctx->ev_heavy, ctx->side_stream));
+            ctx->heavy_pending = true;     // joined by whoever touches the state next (rrk_join_heavy); the eye-camera rasteriser waits per env instead
+            ctx->launches++;
+        }
+        RR_LAUNCH(k_step_solve, nblk(ctx->N, SOLVE_WPB), SOLVE_WPB * 32, SOLVE_SMEM_BYTES * SOLVE_WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects, heavy_cap);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+    }
+    if (ctx->cfg.enable_contacts && ctx->eager_collide) {
+        CK(cudaEventRecord(ctx->ev_solved, s));
+        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_solved, 0));
+        if (rrk_collide(ctx, ctx->side_stream, false) != 0) return -1;
+        CK(cudaEventRecord(ctx->ev_collided, ctx->side_stream));
+        ctx->collide_ahead = true;
+    }
     return 0;
 }
 int rrk_read_state(rr_ctx* ctx, double* joint, double* touch, double* objpose, cudaStream_t s) {
+    if (rrk_join_heavy(ctx, s)) return -1;
     if (bind_physics(ctx, s)) return -1;
     RR_LAUNCH(k_read_state, nblk(ctx->N, 128), 128, 0, s)(ctx->st, joint, touch, objpose, ctx->n_objects);
     ctx->launches++;
@@ -1335,6 +1461,7 @@ int rrk_read_state(rr_ctx* ctx, double* joint, double* touch, double* objpose, c
     return 0;
 }
 int rrk_link_pose(rr_ctx* ctx, int link, double* out, cudaStream_t s) {
+    if (rrk_join_heavy(ctx, s)) return -1;
     if (bind_physics(ctx, s)) return -1;
     RR_LAUNCH(k_link_pose, nblk(ctx->N, 128), 128, 0, s)(ctx->st, link, out);
     ctx->launches++;
@@ -1342,6 +1469,7 @@ int rrk_link_pose(rr_ctx* ctx, int link, double* out, cudaStream_t s) {
     return 0;
 }
 int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s) {
+    if (rrk_join_heavy(ctx, s)) return -1;
     if (bind_physics(ctx, s)) return -1;
     RR_LAUNCH(k_score, nblk(ctx->N, 128), 128, 0, s)(ctx->st, goal, score, ctx->n_objects);
     ctx->launches++;
@@ -1349,6 +1477,7 @@ int rrk_score(rr_ctx* ctx, const double* goal, double* score, cudaStream_t s) {
     return 0;
 }
 int rrk_shape_frames(rr_ctx* ctx, double* frames, cudaStream_t s) {
+    if (rrk_join_heavy(ctx, s)) return -1;
     if (bind_physics(ctx, s)) return -1;
     RR_LAUNCH(k_shape_frames, nblk(ctx->N, 128), 128, 0, s)(ctx->st, frames, ctx->n_objects);
     ctx->launches++;
@@ -1451,6 +1580,7 @@ __global__ void k_ik(DevState st, const uint8_t* __restrict__ mask, const double
 }
 
 int rrk_ik(rr_ctx* ctx, const uint8_t* mask, const double* pos_quat, double* out, int max_iter, double residual, cudaStream_t s) {
+    if (rrk_join_heavy(ctx, s)) return -1;
     if (bind_physics(ctx, s)) return -1;
     RR_LAUNCH(k_ik, nblk(ctx->N, 64), 64, 0, s)(ctx->st, mask, pos_quat, out, max_iter, residual);
     ctx->launches++;

@@ -135,12 +135,9 @@ __device__ float cofactor4(const float M[4][4], int row, int col) {
 
 // --------------------------------------------------------------------------------------------- setup kernel
 // frames: f64 [N][22][12] or NULL (then read the simulated state)
-__global__ void k_render_setup(DevState st, const double* __restrict__ frames, float* __restrict__ mats, int n_objects,
-                               const double* __restrict__ static_frames /* [22][12] for non-robot, non-object shapes */,
-                               int env_begin, int env_count) {
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= env_count * RR_NSHAPES) return;
-    int e = env_begin + gid / RR_NSHAPES, s = gid % RR_NSHAPES;
+// matrices of shape s of env e (see the file header); called by k_render_setup and, for an env whose state arrives late, by k_raster
+__device__ void render_setup_shape(const DevState& st, const double* __restrict__ frames, float* __restrict__ mats, const int n_objects,
+                                   const double* __restrict__ static_frames /* [22][12] for non-robot, non-object shapes */, const int e, const int s) {
     float* out = mats + ((size_t)e * RR_NSHAPES + s) * MAT_STRIDE;
     const ShapeRenderConst& sh = c_render.shape[s];
     int body = sh.objectAndLink & 0xffffff, link = (sh.objectAndLink >> 24) - 1;
@@ -149,11 +146,12 @@ __global__ void k_render_setup(DevState st, const double* __restrict__ frames, f
     if (frames) {
         for (int k = 0; k < 12; k++) F[k] = frames[((size_t)e * RR_NSHAPES + s) * 12 + k];
     } else if (body == 0 && link >= 0) {
-        for (int k = 0; k < 12; k++) F[k] = st.link_frames[((size_t)link * 12 + k) * st.N + e];
+        for (int k = 0; k < 12; k++) F[k] = __ldcg(&st.link_frames[((size_t)link * 12 + k) * st.N + e]);   // L2 reads: k_raster calls this for envs whose
+                                                                                                            // neighbours in these arrays may still be written
     } else if (body >= 2) {
         int o = body - 2;
         double q[4];
-        for (int k = 0; k < 4; k++) q[k] = st.obj[((size_t)o * 13 + 3 + k) * st.N + e];
+        for (int k = 0; k < 4; k++) q[k] = __ldcg(&st.obj[((size_t)o * 13 + 3 + k) * st.N + e]);
         double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
         double sc = 2.0 / d;
         double xs = q[0] * sc, ys = q[1] * sc, zs = q[2] * sc;
@@ -163,7 +161,7 @@ __global__ void k_render_setup(DevState st, const double* __restrict__ frames, f
         F[0] = 1.0 - (yy + zz); F[1] = xy - wz; F[2] = xz + wy;
         F[3] = xy + wz; F[4] = 1.0 - (xx + zz); F[5] = yz - wx;
         F[6] = xz - wy; F[7] = yz + wx; F[8] = 1.0 - (xx + yy);
-        for (int k = 0; k < 3; k++) F[9 + k] = st.obj[((size_t)o * 13 + k) * st.N + e];
+        for (int k = 0; k < 3; k++) F[9 + k] = __ldcg(&st.obj[((size_t)o * 13 + k) * st.N + e]);
     } else {
         for (int k = 0; k < 12; k++) F[k] = static_frames[s * 12 + k];
     }
@@ -219,6 +217,23 @@ __global__ void k_render_setup(DevState st, const double* __restrict__ frames, f
     const double bound = (sqrt(cn) + sqrt(rad) + (double)c_cull_hmax) * 1.001;
     out[43] = (orth < 1e-5 && bound == bound) ? (float)bound : FLT_MAX;
 }
+__global__ void k_render_setup(DevState st, const double* __restrict__ frames, float* __restrict__ mats, int n_objects, const double* __restrict__ static_frames,
+                               int env_begin, int env_count) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= env_count * RR_NSHAPES) return;
+    render_setup_shape(st, frames, mats, n_objects, static_frames, env_begin + gid / RR_NSHAPES, gid % RR_NSHAPES);
+}
+// rrk_render right after rrk_step: the solver's heavy kernel (rr_physics.cu) may still be running.  The rasteriser then takes the
+// envs in the solver's order, lightest first, and for the heavy ones at the end waits for the ticket that kernel leaves per env,
+// then computes the env's matrices itself (k_render_setup saw a half-written state for them).  The heavy kernel's blocks were
+// launched before the solver's main kernel, which this launch follows in stream order: they are resident, the wait cannot deadlock
+// (a bounded spin all the same: a time-out sets *timeout and renders what is there; the host reports it at the next call).
+struct LateEnvs {
+    const int* order;          // DevState::solve_order, or nullptr: identity order, nobody is late
+    const int* ready; int ticket, heavy_cap;
+    DevState st; int n_objects; const double* static_frames; float* mats;
+    int* timeout;
+};
 
 // --------------------------------------------------------------------------------------------- triangle setup
 struct Tri {
@@ -896,7 +911,7 @@ __global__ void __launch_bounds__(RTHREADS, RBLOCKS)
 k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const float4* __restrict__ planes, int n_tris,
          const uint8_t* __restrict__ texdata, const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch,
          unsigned short* __restrict__ cull_scratch, int* __restrict__ work_counter,
-         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N, const StaticLayer SL) {
+         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N, const StaticLayer SL, const LateEnvs LE) {
     unsigned long long* __restrict__ static_keys = SL.keys;
     const unsigned int static_bits = SL.bits; const int skip_front = SL.skip_front;
     RR_DYN_SMEM(smem_raw);
@@ -905,6 +920,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
     unsigned int* fq_all = reinterpret_cast<unsigned int*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8 + (TMA_MATS ? 2 : 1) * RR_NSHAPES * MAT_STRIDE * 4);   // per-warp fragment queues
     __shared__ __align__(8) unsigned long long s_mbar[2];
     __shared__ int s_envq[2];
+    __shared__ int s_eid, s_late;
     __shared__ int s_env, s_nrec, s_ncull, s_chunk, s_medc, s_rgrp, s_nlist[3 * NSTRIPS];   // s_nlist[class][strip]
     const int tid = threadIdx.x, lane = tid & 31;
     Rec* recs = rec_scratch + (size_t)blockIdx.x * REC_MAX;
@@ -949,11 +965,36 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         const int e = env_begin + cur_env;
 #else
         float* M = Mbuf;
-        if (tid == 0) { s_env = atomicAdd(work_counter, 1); s_nrec = 0; s_ncull = 0; s_chunk = 0; s_medc = 0; s_rgrp = 0; }
+        if (tid == 0) {
+            s_env = atomicAdd(work_counter, 1); s_nrec = 0; s_ncull = 0; s_chunk = 0; s_medc = 0; s_rgrp = 0;
+            s_eid = s_env; s_late = 0;
+            if (LE.order && s_env < N) {          // the solver's order backwards: lightest envs first, the heavy kernel's envs last
+                int idx = N - 1 - s_env, n_heavy = 0, cls = 0;
+                for (int k = 0; k < RR_SOLVE_CLASSES - 1; k++) { const int n = LE.order[k]; n_heavy += n; if (cls == k && idx >= n) { idx -= n; cls = k + 1; } }
+                const int e_ = LE.order[RR_SOLVE_CLASSES + cls * N + idx];
+                s_eid = e_;
+                if (N - 1 - s_env < min(n_heavy, LE.heavy_cap)) {
+                    s_late = 1;
+#ifndef RR_SIMT_EMU_BUILD
+                    const long long t0 = clock64();
+                    while (*reinterpret_cast<const volatile int*>(LE.ready + e_) != LE.ticket) {
+                        __nanosleep(500);
+                        if (clock64() - t0 > 4000000000ll) { atomicExch(LE.timeout, 1); break; }      // ~2 s
+                    }
+                    __threadfence();
+#endif
+                }
+            }
+        }
         if (tid < 3 * NSTRIPS) s_nlist[tid] = 0;
         __syncthreads();
         if (s_env >= N) break;
-        const int e = env_begin + s_env;
+        const int e = env_begin + s_eid;
+        if (s_late) {
+            if (tid < RR_NSHAPES) render_setup_shape(LE.st, nullptr, LE.mats, LE.n_objects, LE.static_frames, e, tid);
+            __threadfence_block();
+            __syncthreads();
+        }
 #endif
         const size_t img = (size_t)e * RR_W * RR_H;
         const bool on = env_mask ? (env_mask[e] != 0) : true;
@@ -1347,6 +1388,18 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
                         int env_begin, int env_count, bool eye_camera, cudaStream_t s) {
     if (env_count <= 0) return 0;
     if (bind_render(ctx, s)) return -1;
+    if (ctx->h_late_timeout && *ctx->h_late_timeout) { ctx->err = "k_raster timed out waiting for k_step_solve_heavy (an earlier rr_render returned stale images)"; return -1; }
+    // right after rr_step the solver's heavy kernel may still run on the context's side stream: the eye-camera render of all envs
+    // does not wait for it here but per env inside k_raster (LateEnvs); everything else joins it first
+    const bool late = ctx->heavy_pending && eye_camera && frames == nullptr && env_begin == 0 && env_count == ctx->N && !TMA_MATS;
+    if (!late && rrk_join_heavy(ctx, s) != 0) return -1;
+    LateEnvs LE; memset(&LE, 0, sizeof LE);
+    if (late) {
+        if (!ctx->h_late_timeout) { CK(cudaMallocHost(&ctx->h_late_timeout, sizeof(int))); *ctx->h_late_timeout = 0; CK(cudaMalloc((void**)&ctx->d_late_timeout, sizeof(int))); CK(cudaMemsetAsync(ctx->d_late_timeout, 0, sizeof(int), s)); }
+        LE.order = ctx->st.solve_order; LE.ready = ctx->st.ready; LE.ticket = ctx->step_serial; LE.heavy_cap = ctx->heavy_cap;
+        LE.st = ctx->st; LE.n_objects = ctx->n_objects; LE.static_frames = g_static_frames[ctx->device]; LE.mats = ctx->st.render_mats;
+        LE.timeout = ctx->d_late_timeout;
+    }
     int total = env_count * RR_NSHAPES;
     {
         ProfScope ps(ctx, 1, s);
@@ -1360,7 +1413,7 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
     const StaticLayer SL = static_layer(ctx);
 #define RASTER_ARGS(RGB, DEP, SEG, MASK, NENV) ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris, \
         ctx->d_tex, MASK, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, (unsigned short*)ctx->d_cull_scratch, \
-        ctx->d_work_counter, RGB, DEP, SEG, env_begin, NENV, SL
+        ctx->d_work_counter, RGB, DEP, SEG, env_begin, NENV, SL, LE
     CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), s));
     {
         ProfScope ps(ctx, 2, s);
@@ -1371,6 +1424,10 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
 #undef RASTER_ARGS
     ctx->launches++;
     CK(cudaGetLastError());
+    if (late) {
+        if (rrk_join_heavy(ctx, s) != 0) return -1;          // formally; k_raster has waited for every one of its envs
+        CK(cudaMemcpyAsync(ctx->h_late_timeout, ctx->d_late_timeout, sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
     return 0;
 }
 // Once per context (rr_create, after the first reset): matrices of env 0, then the static shapes of that env — their
@@ -1385,7 +1442,7 @@ int rrk_render_build_static(rr_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), 0));
     RR_LAUNCH(k_raster<1>, 1, RTHREADS, RASTER_SMEM, 0)(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris,
         ctx->d_tex, nullptr, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, (unsigned short*)ctx->d_cull_scratch,
-        ctx->d_work_counter, const_cast<uint8_t*>(SL.rgb), const_cast<float*>(SL.depth), const_cast<int32_t*>(SL.seg), 0, 1, SL);
+        ctx->d_work_counter, const_cast<uint8_t*>(SL.rgb), const_cast<float*>(SL.depth), const_cast<int32_t*>(SL.seg), 0, 1, SL, LateEnvs{});
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     ctx->launches += 2;

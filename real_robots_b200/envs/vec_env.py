@@ -58,15 +58,17 @@ class VecREALRobotEnv:
 
     # ------------------------------------------------------------------ observations
     def _observe(self, render_mask):
-        joints, touch, objs = self.sim.read_state()
         K = Kuka.ObsSpaces
-        obs = {K.JOINT_POSITIONS: joints, K.TOUCH_SENSORS: touch}
+        obs = {}
         if render_mask is None:
             # render off for every env: the reference returns its cached zero arrays (env.py:114-122, 273-275) and so do we —
             # one zero image per kind, broadcast over the env axis (read-only views), no kernel launch, no 3.46 GB of zero stores
             rgb, depth, seg = self._zero_images()
         else:
+            # rendered before the state read-out: right after a step the rasteriser overlaps the tail of the solver (rr_render)
             rgb, depth, seg = self.sim.render(mask=render_mask, want_mask=self.additional_obs)
+        joints, touch, objs = self.sim.read_state()
+        obs[K.JOINT_POSITIONS], obs[K.TOUCH_SENSORS] = joints, touch
         obs[K.RETINA], obs[K.DEPTH] = rgb, depth
         if self.additional_obs:
             obs[K.MASK] = seg

@@ -18,4 +18,9 @@ for name in ("time_step", "bench"):
     rows, nc, fl = d[:, 0], d[:, 2], d[:, 3]
     print(name, "rows pct 50/90/99/max", np.percentile(rows, [50, 90, 99]).tolist(), rows.max(), "contacts 50/90/99/max", np.percentile(nc, [50, 90, 99]).tolist(), nc.max(),
           "non-simple frac %.3f" % ((fl & 2) == 0).mean(), "cap hit", int((fl & 1).sum()))
+    cost = (fl >> 16) & 0xffff
+    print("   sweep cost (slots/iteration, pair slots twice): pct 50/90/96/98/99/99.9", np.percentile(cost, [50, 90, 96, 98, 99, 99.9]).tolist(), "max", cost.max(),
+          "classes >72 / >48 / >32 / rest:", int((cost > 72).sum()), int(((cost > 48) & (cost <= 72)).sum()), int(((cost > 32) & (cost <= 48)).sum()), int((cost <= 32).sum()),
+          " sum of cost %d, of which cost>32: %d" % (cost.sum(), cost[cost > 32].sum()))
+    print("   histogram (cost: envs):", {int(c): int((cost == c).sum()) for c in np.unique(cost)})
     sim.close()

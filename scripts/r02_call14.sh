@@ -1,0 +1,21 @@
+#!/bin/bash
+# heavy-env solver kernel + look-ahead narrowphase: A/B on one B200
+mkdir -p gpurun_out
+{
+for hv in 0 1; do
+  echo "== heavy $hv"
+  RR_HEAVY_SOLVER=$hv python scripts/time_step.py
+  RR_HEAVY_SOLVER=$hv ACT_SCALE=0 python scripts/time_step.py
+  RR_HEAVY_SOLVER=$hv python scripts/time_bench_step.py
+done
+for cfg in "0 0" "1 0" "1 1"; do
+  set -- $cfg
+  echo "== bench heavy $1 eager $2"
+  RR_HEAVY_SOLVER=$1 RR_EAGER_COLLIDE=$2 python bench.py --steps 60 --warmup 5 --no-cpu-baseline | tail -1
+done
+} > gpurun_out/r02_call14.log 2>&1
+python -m pytest tests -m gpu -q > gpurun_out/r02_call14_pytest.log 2>&1; tail -5 gpurun_out/r02_call14_pytest.log
+grep -v "^{" gpurun_out/r02_call14.log; grep "^{" gpurun_out/r02_call14.log | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['value'], d['ms_per_step'], d['roofline']['kernels_ms_per_step'], d['e2e']['value'])"

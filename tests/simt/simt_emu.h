@@ -217,6 +217,7 @@ template <typename T> static inline T atomicExch(T* p, T v) { T o = *p; *p = v; 
 
 // ---- scalar intrinsics
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
 template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
 template <typename T> static inline void __stcg(T* p, T v) { *p = v; }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
@@ -263,6 +264,8 @@ template <typename S> static inline cudaError_t cudaMemcpyFromSymbol(void* d, co
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)(uintptr_t)1; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (cudaStream_t)(uintptr_t)1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return cudaSuccess; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)(uintptr_t)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }

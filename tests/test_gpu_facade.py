@@ -275,11 +275,15 @@ def test_cartesian_8192_envs_full_observation():
     n0 = env.sim.launch_count()
     obs_off, reward, done, _ = env.step({'cartesian_command': cart, 'gripper_command': grip, 'render': False})
     n1 = env.sim.launch_count()
-    obs, reward, done, _ = env.step({'cartesian_command': cart, 'gripper_command': grip, 'render': True})
+    env.step({'cartesian_command': cart, 'gripper_command': grip, 'render': False})
     n2 = env.sim.launch_count()
-    # first step: IK + step kernels, no raster launch at all (render off for every env: cached zero images, env.py:273-275);
-    # second step: no IK (request cache), but render set-up + rasteriser
-    assert (n2 - n1) - (n1 - n0) == 1
+    obs, reward, done, _ = env.step({'cartesian_command': cart, 'gripper_command': grip, 'render': True})
+    n3 = env.sim.launch_count()
+    # first step: IK + the narrowphase in line (the reset dropped the look-ahead one) + step kernels, no raster launch at all (render
+    # off for every env: cached zero images, env.py:273-275); second: no IK (request cache), the narrowphase was launched by the
+    # first step; third: render set-up + rasteriser on top
+    assert (n1 - n0) - (n2 - n1) == 2
+    assert (n3 - n2) - (n2 - n1) == 2
     assert not obs_off['retina'].any() and obs_off['retina'].shape == (N, 240, 320, 3)
     for e in (0, 1, 77, 4095):
         ref = Oracle(3).ik(cart[e, :3].cpu().numpy(), cart[e, 3:].cpu().numpy())[0]

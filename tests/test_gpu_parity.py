@@ -608,3 +608,28 @@ def test_touch_sensors_scripted_press_and_shelf():
             return h.cpu().numpy(), p.cpu().numpy(), pairs
     frac = check_touch_scenarios(Sim)
     print("touch readings equal to the oracle's on %.0f %% of the pressed steps" % (100 * frac))
+
+
+def test_render_right_after_step_equals_render_after_join():
+    """rr_render straight after rr_step overlaps the solver's heavy-env kernel and the look-ahead narrowphase (side stream): k_raster
+    takes the envs lightest first, waits per env for the heavy kernel's ticket and builds those envs' matrices itself.  Same images,
+    bit for bit, as rendering after rr_read_state (which joins that kernel first), over a random-policy rollout with arm contacts;
+    and the states of the two contexts stay identical (the narrowphase that runs ahead only reads the state)."""
+    import bench
+    N = 1024
+    a, b = BatchedSim(N, 3), BatchedSim(N, 3)
+    acts = bench.random_policy_actions(torch, 90, N, torch.device("cuda"), 7)
+    heavy = 0
+    for t in range(90):
+        a.step(acts[t]); b.step(acts[t])
+        if t >= 60:
+            ra = [x.clone() for x in a.render()]
+            b.read_state()
+            rb = b.render()
+            for x, y in zip(ra, rb):
+                assert torch.equal(x, y), t
+            heavy = max(heavy, int((((b.diag()[:, 3] >> 16) & 0xffff) > 24).sum()))
+    assert heavy >= 5                                   # some envs did go through the heavy kernel
+    for x, y in zip(a.get_state(), b.get_state()):
+        assert torch.equal(x, y)
+    a.close(); b.close()
