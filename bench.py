@@ -359,7 +359,10 @@ def run_ours(args):
                          "frac": achieved / peak if peak else None, "traffic": (args.traffic * args.envs / 4096 if args.traffic else None),
                          "algorithmic_bytes": args.envs * IMG_BYTES, "peak_source": peak_src,
                          "ms_per_launch": raster_ms, "launches": r_n,
-                         "kernels_ms_per_step": {k: (v[0] / max(v[1], 1)) for k, v in prof.items()},
+                         "kernels_ms_per_step": {k: (v[0] / max(s_n, 1)) for k, v in prof.items()},
+                         "kernels_note": "CUDA-event time per step on the stream each kernel runs on.  step = k_step_dyn + k_step_solve; the solver's "
+                                         "heavy-env kernel and the look-ahead narrowphase of the next step (collide) run on side streams beside "
+                                         "k_raster, so the entries overlap and do not add up to ms_per_step",
                          # SURVEY §8(d) secondary rates of the rasteriser: 17 578 scene triangles and 76 800 pixels per env
                          "secondary": {"triangles_per_s": args.envs * 17578 / (raster_ms * 1e-3) if raster_ms > 0 else None,
                                        "pixels_per_s": args.envs * 76800 / (raster_ms * 1e-3) if raster_ms > 0 else None,

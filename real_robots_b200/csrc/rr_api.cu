@@ -269,7 +269,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
     alloc((void**)&st.q, 11 * N * 8); alloc((void**)&st.qd, 11 * N * 8); alloc((void**)&st.target, 11 * N * 8);
     alloc((void**)&st.obj, 39 * N * 8); alloc((void**)&st.touch, 4 * N * 8); alloc((void**)&st.link_frames, 16 * 12 * N * 8);
-    alloc((void**)&st.render_mats, N * RR_NSHAPES * RR_MAT_STRIDE * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.col_flags, N * 4); alloc((void**)&st.ready, N * 4); alloc((void**)&st.solve_order, (size_t)RR_SOLVE_CLASSES * (N + 1) * 4); alloc((void**)&st.timestep, N * 8);
+    alloc((void**)&st.render_mats, N * RR_NSHAPES * RR_MAT_STRIDE * 4); alloc((void**)&st.diag, N * 4 * 4); alloc((void**)&st.col_flags, N * 4); alloc((void**)&st.ready, N * 4); alloc((void**)&st.solve_pos, N * 4); alloc((void**)&st.solve_order, (size_t)RR_SOLVE_CLASSES * (N + 1) * 4); alloc((void**)&st.timestep, N * 8);
     for (int k = 0; k < 2; k++) {
         alloc((void**)&ctx->d_cmd[k], N * 9 * 8); alloc((void**)&ctx->d_mask[k], N); alloc((void**)&ctx->d_joint[k], N * 9 * 8);
         alloc((void**)&ctx->d_touch[k], N * 4 * 8); alloc((void**)&ctx->d_objpose[k], N * 3 * 7 * 8);
@@ -295,9 +295,9 @@ int rr_destroy(rr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     rrk_physics_unbind(ctx); rrk_collide_unbind(ctx); rrk_render_unbind(ctx);
-    if (ctx->side_stream) { cudaStreamDestroy(ctx->side_stream); cudaEventDestroy(ctx->ev_solved); cudaEventDestroy(ctx->ev_collided); cudaEventDestroy(ctx->ev_dyn); cudaEventDestroy(ctx->ev_heavy); }
+    if (ctx->side_stream) { cudaStreamDestroy(ctx->side_stream); cudaEventDestroy(ctx->ev_solved); cudaEventDestroy(ctx->ev_collided); cudaEventDestroy(ctx->ev_dyn); cudaEventDestroy(ctx->ev_heavy); cudaEventDestroy(ctx->ev_collided_heavy); cudaStreamDestroy(ctx->side_stream2); }
     DevState& st = ctx->st;
-    void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.col_flags, st.ready, st.solve_order, st.timestep,
+    void* ptrs[] = {st.q, st.qd, st.target, st.obj, st.touch, st.link_frames, st.render_mats, st.diag, st.col_flags, st.ready, st.solve_pos, st.solve_order, st.timestep,
                     st.man_hdr[0], st.man_hdr[1], st.man_pts[0], st.man_pts[1], st.handoff,
                     ctx->d_cmd[0], ctx->d_mask[0], ctx->d_joint[0], ctx->d_touch[0], ctx->d_objpose[0], ctx->d_rgb[0], ctx->d_depth[0], ctx->d_seg[0],
                     ctx->d_cmd[1], ctx->d_mask[1], ctx->d_joint[1], ctx->d_touch[1], ctx->d_objpose[1], ctx->d_rgb[1], ctx->d_depth[1], ctx->d_seg[1],

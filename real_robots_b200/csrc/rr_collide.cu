@@ -376,12 +376,16 @@ __device__ int sort_cached_points(const ColMem& m, V3 pn, double pdist) {
 #endif
 __global__ void __launch_bounds__(CWPB * 32, COLLIDE_MIN_BLOCKS)
 k_collide(DevState st, const double* __restrict__ hull_verts, const int* __restrict__ man_hdr_in, const double* __restrict__ man_pts_in,
-          int* __restrict__ man_hdr_out, double* __restrict__ man_pts_out, rr_config cf, int n_objects) {
+          int* __restrict__ man_hdr_out, double* __restrict__ man_pts_out, rr_config cf, int n_objects, int mode, int heavy_cap) {
     __shared__ ColMem smem[CWPB];
     ColMem& m = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * CWPB + (threadIdx.x >> 5);
+    int e = blockIdx.x * CWPB + (threadIdx.x >> 5);
     if (e >= st.N) return;
+    // mode 0: every env.  The look-ahead launches of rrk_step come in two parts: mode 1 skips the envs of the solver's heavy kernel
+    // (still running), mode 2 follows that kernel and takes exactly those (warp w: the w-th of them)
+    if (mode == 1 && solve_is_heavy(st, e, heavy_cap)) return;
+    if (mode == 2) { if (e >= solve_n_heavy(st, heavy_cap)) return; e = solve_pick(st, e); }
     const int N = st.N;
     const double thr = cf.contact_breaking;
 
@@ -579,13 +583,14 @@ int rrk_collide_upload_constants(rr_ctx* ctx) {
 }
 
 // flip = false: the look-ahead launch of rrk_step; the new manifolds become current when the next step adopts them
-int rrk_collide(rr_ctx* ctx, cudaStream_t s, bool flip) {
+int rrk_collide(rr_ctx* ctx, cudaStream_t s, bool flip, int mode) {
     if (bind_collide(ctx, s)) return -1;
     const int in = ctx->man_parity, out = 1 - in;
     {
         ProfScope ps(ctx, 3, s);
-        RR_LAUNCH(k_collide, (ctx->N + CWPB - 1) / CWPB, CWPB * 32, 0, s)(ctx->st, ctx->d_hull_verts, ctx->st.man_hdr[in], ctx->st.man_pts[in],
-                                                                 ctx->st.man_hdr[out], ctx->st.man_pts[out], ctx->cfg, ctx->n_objects);
+        const int n = mode == 2 ? (ctx->heavy_cap < ctx->N ? ctx->heavy_cap : ctx->N) : ctx->N;
+        RR_LAUNCH(k_collide, (n + CWPB - 1) / CWPB, CWPB * 32, 0, s)(ctx->st, ctx->d_hull_verts, ctx->st.man_hdr[in], ctx->st.man_pts[in],
+                                                            ctx->st.man_hdr[out], ctx->st.man_pts[out], ctx->cfg, ctx->n_objects, mode, ctx->heavy_cap);
     }
     ctx->launches++;
     CK(cudaGetLastError());

@@ -87,6 +87,7 @@ struct DevState {
     int*    diag;     // [N][4]
     int*    solve_order; // [RR_SOLVE_CLASSES + RR_SOLVE_CLASSES * N]: per cost class a counter and the envs of that class (k_step_dyn appends,
                         // k_step_solve's warp w takes the w-th env of the concatenation: the longest sweeps start first)
+    int*    solve_pos;  // [N] (class << 24) | position in the class list: where solve_order has the env
     int*    ready;      // [N] serial number of the last step whose state k_step_solve_heavy finished for this env (what a rasteriser
                         // launched before that kernel ended waits for, see rrk_render)
     int*    col_flags;  // [N] written by k_collide (1: a non-empty manifold found no slot), merged into diag by k_step_solve
@@ -95,6 +96,31 @@ struct DevState {
     double* man_pts[2];   // [N][RR_MAX_MANIFOLDS][4][RR_PT_STRIDE]
     double* handoff;      // [N][RR_IMG_DOUBLES] per-env solver image passed from k_step_dyn to k_step_solve (only its used head is touched)
 };
+
+// ---- the solver's env order (DevState::solve_order), shared by the kernels of rr_physics.cu, rr_collide.cu and rr_render.cu
+// the idx-th env in order of decreasing cost class (every env is in exactly one class list)
+__device__ __forceinline__ int solve_pick(const DevState& st, int idx) {
+    int cls = 0;
+#pragma unroll
+    for (int k = 0; k < RR_SOLVE_CLASSES - 1; k++) { const int n = st.solve_order[k]; if (cls == k && idx >= n) { idx -= n; cls = k + 1; } }
+    return st.solve_order[RR_SOLVE_CLASSES + cls * st.N + idx];
+}
+// how many envs the heavy kernel takes: the classes above the last one, as far as its grid goes
+__device__ __forceinline__ int solve_n_heavy(const DevState& st, int heavy_cap) {
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < RR_SOLVE_CLASSES - 1; k++) n += st.solve_order[k];
+    return min(n, heavy_cap);
+}
+// is env e one of them?
+__device__ __forceinline__ bool solve_is_heavy(const DevState& st, int e, int heavy_cap) {
+    const int cp = st.solve_pos[e], cls = cp >> 24;
+    if (cls >= RR_SOLVE_CLASSES - 1) return false;
+    int idx = cp & 0xffffff;
+    for (int k = 0; k < cls; k++) idx += st.solve_order[k];
+    return idx < heavy_cap;
+}
+
 
 struct rr_ctx {
     int device;
@@ -114,7 +140,9 @@ struct rr_ctx {
     // look-ahead narrowphase: the contacts of step t+1 depend on the poses after step t only, so rrk_step launches k_collide for
     // the NEXT step on a side stream right after the solver (it then overlaps whatever the caller does next, normally the
     // rasteriser); the next rrk_step waits for it and flips man_parity.  Anything that edits poses or manifolds drops it.
-    cudaStream_t side_stream = nullptr; cudaEvent_t ev_solved = nullptr, ev_collided = nullptr, ev_dyn = nullptr, ev_heavy = nullptr;
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_solved = nullptr, ev_collided = nullptr, ev_dyn = nullptr, ev_heavy = nullptr, ev_collided_heavy = nullptr;
+    cudaStream_t side_stream2 = nullptr;   // the look-ahead narrowphase of the main solver kernel's envs (the heavy kernel's envs follow that kernel on side_stream)
+    bool collide_ahead_split = false;
     bool collide_ahead = false, eager_collide = true;
     int heavy_cap = 0;         // envs k_step_solve_heavy took at most in the last step
     int* d_late_timeout = nullptr; int* h_late_timeout = nullptr;   // k_raster's bounded wait for that kernel ran out (pinned mirror)
@@ -182,7 +210,7 @@ int rrk_render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, uin
 int rrk_render_camera(rr_ctx* ctx, const RenderConst* cam, const uint8_t* mask, uint8_t* rgb, float* depth, int32_t* seg, cudaStream_t s);
 void rr_set_camera_consts(RenderConst& C, const float* view16, const float* proj16);
 int rrk_collide_upload_constants(rr_ctx* ctx);
-int rrk_collide(rr_ctx* ctx, cudaStream_t s, bool flip = true);
+int rrk_collide(rr_ctx* ctx, cudaStream_t s, bool flip = true, int mode = 0);   // mode 1 / 2: all but / only the heavy kernel's envs
 int rrk_drop_collide_ahead(rr_ctx* ctx, cudaStream_t s);
 int rrk_join_heavy(rr_ctx* ctx, cudaStream_t s);     // every reader / writer of the state but the eye-camera rasteriser calls this first
 int rrk_clear_manifolds(rr_ctx* ctx, const uint8_t* mask, cudaStream_t s);

@@ -812,7 +812,9 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
         // cost class of the sweep (slots per iteration; a pair slot counts twice): k_step_solve starts the longest chains first
         const int cost = (hand->n_slotsA[0] + hand->n_slotsA[1]) / 2 + 2 * hand->n_slotsB;
         const int cls = cost > SOLVE_COST_0 ? 0 : cost > SOLVE_COST_1 ? 1 : cost > SOLVE_COST_2 ? 2 : 3;
-        st.solve_order[RR_SOLVE_CLASSES + cls * N + atomicAdd(&st.solve_order[cls], 1)] = e;
+        const int pos = atomicAdd(&st.solve_order[cls], 1);
+        st.solve_order[RR_SOLVE_CLASSES + cls * N + pos] = e;
+        st.solve_pos[e] = (cls << 24) | pos;
     }
     // ---- hand the state over
     if (lane < RR_NDOF) { hand->q[lane] = m.q[lane]; hand->qd[lane] = m.qd[lane]; hand->target[lane] = m.target[lane]; }
@@ -986,20 +988,6 @@ struct SolveEpi { SolveHead head; KinWs kin; };
 #define HEAVY_GRID 148
 #define HEAVY_PER_BLOCK 2
 #endif
-// the idx-th env in order of decreasing cost class (every env is in exactly one class list)
-__device__ __forceinline__ int solve_pick(const DevState& st, int idx) {
-    int cls = 0;
-#pragma unroll
-    for (int k = 0; k < RR_SOLVE_CLASSES - 1; k++) { const int n = st.solve_order[k]; if (cls == k && idx >= n) { idx -= n; cls = k + 1; } }
-    return st.solve_order[RR_SOLVE_CLASSES + cls * st.N + idx];
-}
-// how many envs the heavy kernel takes: the classes above the last one, as far as its grid goes
-__device__ __forceinline__ int solve_n_heavy(const DevState& st, int heavy_cap) {
-    int n = 0;
-#pragma unroll
-    for (int k = 0; k < RR_SOLVE_CLASSES - 1; k++) n += st.solve_order[k];
-    return min(n, heavy_cap);
-}
 template <bool HEAVY>
 __device__ __forceinline__ void solve_env(const DevState& st, const int e, double* const smem, unsigned int* const ssched, const int sched_cap, double* const sblk,
                                           int* __restrict__ man_hdr, double* __restrict__ man_pts, const rr_config& cf, const int n_objects, const int lane) {
@@ -1391,6 +1379,7 @@ int rrk_drop_collide_ahead(rr_ctx* ctx, cudaStream_t s) {
     if (rrk_join_heavy(ctx, s)) return -1;
     if (!ctx->collide_ahead) return 0;
     CK(cudaStreamWaitEvent(s, ctx->ev_collided, 0));
+    if (ctx->collide_ahead_split) CK(cudaStreamWaitEvent(s, ctx->ev_collided_heavy, 0));
     ctx->collide_ahead = false;
     return 0;
 }
@@ -1404,6 +1393,8 @@ static int side_streams(rr_ctx* ctx) {
     CK(cudaEventCreateWithFlags(&ctx->ev_collided, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_dyn, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_heavy, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_collided_heavy, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithPriority(&ctx->side_stream2, cudaStreamNonBlocking, hi));
     return 0;
 }
 int rrk_join_heavy(rr_ctx* ctx, cudaStream_t s) {
@@ -1419,6 +1410,7 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
     if (ctx->cfg.enable_contacts) {
         if (ctx->collide_ahead) {            // the previous step already collided at the poses it produced
             CK(cudaStreamWaitEvent(s, ctx->ev_collided, 0));
+            if (ctx->collide_ahead_split) CK(cudaStreamWaitEvent(s, ctx->ev_collided_heavy, 0));
             ctx->man_parity ^= 1;
             ctx->collide_ahead = false;
         } else if (rrk_collide(ctx, s) != 0) return -1;
@@ -1444,11 +1436,21 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
         CK(cudaGetLastError());
     }
     if (ctx->cfg.enable_contacts && ctx->eager_collide) {
+        // the narrowphase of the NEXT step (it only reads the state): for the heavy kernel's envs behind that kernel on its stream,
+        // for the others (or for all, without a heavy kernel) behind the main solver kernel on a stream of its own
         CK(cudaEventRecord(ctx->ev_solved, s));
-        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_solved, 0));
-        if (rrk_collide(ctx, ctx->side_stream, false) != 0) return -1;
-        CK(cudaEventRecord(ctx->ev_collided, ctx->side_stream));
-        ctx->collide_ahead = true;
+        if (heavy) {
+            CK(cudaStreamWaitEvent(ctx->side_stream2, ctx->ev_solved, 0));
+            if (rrk_collide(ctx, ctx->side_stream2, false, 1) != 0) return -1;
+            CK(cudaEventRecord(ctx->ev_collided, ctx->side_stream2));
+            if (rrk_collide(ctx, ctx->side_stream, false, 2) != 0) return -1;
+            CK(cudaEventRecord(ctx->ev_collided_heavy, ctx->side_stream));
+        } else {
+            CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_solved, 0));
+            if (rrk_collide(ctx, ctx->side_stream, false, 0) != 0) return -1;
+            CK(cudaEventRecord(ctx->ev_collided, ctx->side_stream));
+        }
+        ctx->collide_ahead = true; ctx->collide_ahead_split = heavy;
     }
     return 0;
 }

@@ -59,6 +59,9 @@ __constant__ float c_cull_hmax;      // largest 'smallest altitude' over all tri
                                    // the tile base becomes a run-time value in every matrix access and the load it hides is one
                                    // L2 round trip per env.  0: plain coalesced loads + a barrier.
 #endif
+#ifndef RASTER_LATE_SPARE
+#define RASTER_LATE_SPARE 4        // CTAs k_raster leaves out of its grid when other kernels of the step still have to start (see render_range)
+#endif
 #ifndef GEO_PREFETCH
 #define GEO_PREFETCH 1             // geometry passes load the next round's indices / planes one round ahead
 #endif
@@ -1418,6 +1421,8 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
     {
         ProfScope ps(ctx, 2, s);
         int grid = ctx->raster_grid < env_count ? ctx->raster_grid : env_count;
+        // late mode: the heavy kernel's narrowphase follows it while this kernel runs — leave it two SMs (persistent CTAs never give way)
+        if (late && grid > 4 * RASTER_LATE_SPARE) grid -= RASTER_LATE_SPARE;
         if (use_static) RR_LAUNCH(k_raster<2>, grid, RTHREADS, RASTER_SMEM, s)(RASTER_ARGS(rgb, depth, seg, mask, env_count));
         else RR_LAUNCH(k_raster<0>, grid, RTHREADS, RASTER_SMEM, s)(RASTER_ARGS(rgb, depth, seg, mask, env_count));
     }
