@@ -976,9 +976,12 @@ struct SolveEpi { SolveHead head; KinWs kin; };
 #define SOLVE_SMEM_BYTES ((size_t)SOLVE_SMEM_DOUBLES * 8 + SOLVE_SCHED_WORDS * 4)
 // Heavy envs: the few envs (2-5 % under a random policy) whose arm touches something have schedules 1.5-3.5x as long as the rest,
 // and a Gauss-Seidel chain cannot be split: started together with the others, the longest of them alone set the kernel's duration
-// (2.2 ms against 1.0 ms for a batch without them).  They get a kernel of their own, launched beside the main one on a
-// high-priority stream: one warp per block, schedule AND blocks in shared memory (latency per slot ~5x lower than from L2), each
-// block taking the heaviest envs first.  Same code, same arithmetic.
+// (2.2 ms against 1.0 ms for a batch without them).  They get a kernel of their own on a side stream, launched beside the main one:
+// one warp per block, schedule AND blocks in shared memory, each block taking the heaviest envs first; same code, same arithmetic.
+// The chain is hardly faster there (a slot is ~100 dependent fp64 / shuffle instructions; the L2 round trip the main kernel
+// prefetches around was not what bounded it) — the point is that nothing on the step's critical path waits for it: rr_render's
+// rasteriser starts when the MAIN kernel is done, takes the heavy envs last and waits for each one's ticket (DevState::ready);
+// whoever else touches the state joins the side stream first (rrk_join_heavy).
 #define HEAVY_SCHED_WORDS (16 * RR_SLOTS_A + 8 * RR_SLOTS_B)
 #ifndef HEAVY_BLK_DOUBLES
 #define HEAVY_BLK_DOUBLES 8192     // 64 KB of row blocks; an env with more streams them from L2 like the main kernel
@@ -1383,18 +1386,23 @@ int rrk_drop_collide_ahead(rr_ctx* ctx, cudaStream_t s) {
     ctx->collide_ahead = false;
     return 0;
 }
-// the context's side stream (highest priority: what runs there is short and on somebody's critical path) and its events
+// the context's side streams and their events
+#ifndef SIDE_PRIORITY_MASK
+#define SIDE_PRIORITY_MASK 0     // measured on B200: a high-priority heavy kernel slows the main solver kernel by what it gains itself (6.80 vs 6.72 ms per bench step)
+#endif
 static int side_streams(rr_ctx* ctx) {
     if (ctx->side_stream) return 0;
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CK(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+    int mask = SIDE_PRIORITY_MASK;          // bit 0: the heavy kernel's stream, bit 1: the look-ahead narrowphase's
+    { const char* ea = getenv("RR_SIDE_PRIORITY"); if (ea && ea[0] >= '0' && ea[0] <= '3') mask = ea[0] - '0'; }
+    CK(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, (mask & 1) ? hi : 0));
     CK(cudaEventCreateWithFlags(&ctx->ev_solved, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_collided, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_dyn, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_heavy, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_collided_heavy, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithPriority(&ctx->side_stream2, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&ctx->side_stream2, cudaStreamNonBlocking, (mask & 2) ? hi : 0));
     return 0;
 }
 int rrk_join_heavy(rr_ctx* ctx, cudaStream_t s) {
@@ -1423,7 +1431,7 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
         ProfScope ps(ctx, 0, s);
         CK(cudaMemsetAsync(ctx->st.solve_order, 0, RR_SOLVE_CLASSES * sizeof(int), s));
         RR_LAUNCH(k_step_dyn, nblk(ctx->N, WPB), WPB * 32, sizeof(WarpMem) * WPB, s)(ctx->st, cmd, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects);
-        if (heavy) {         // enqueued before the main kernel, on the high-priority stream: its blocks are placed first
+        if (heavy) {         // enqueued before the main kernel: its blocks are placed first
             CK(cudaEventRecord(ctx->ev_dyn, s));
             CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_dyn, 0));
             RR_LAUNCH(k_step_solve_heavy, HEAVY_GRID, 32, HEAVY_SMEM_BYTES, ctx->side_stream)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects, heavy_cap, ctx->step_serial);
@@ -1443,6 +1451,8 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
             CK(cudaStreamWaitEvent(ctx->side_stream2, ctx->ev_solved, 0));
             if (rrk_collide(ctx, ctx->side_stream2, false, 1) != 0) return -1;
             CK(cudaEventRecord(ctx->ev_collided, ctx->side_stream2));
+            // (behind the main solver kernel as well, so that it does not compete with it for SMs)
+            CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_solved, 0));
             if (rrk_collide(ctx, ctx->side_stream, false, 2) != 0) return -1;
             CK(cudaEventRecord(ctx->ev_collided_heavy, ctx->side_stream));
         } else {

@@ -228,9 +228,10 @@ __global__ void k_render_setup(DevState st, const double* __restrict__ frames, f
 }
 // rrk_render right after rrk_step: the solver's heavy kernel (rr_physics.cu) may still be running.  The rasteriser then takes the
 // envs in the solver's order, lightest first, and for the heavy ones at the end waits for the ticket that kernel leaves per env,
-// then computes the env's matrices itself (k_render_setup saw a half-written state for them).  The heavy kernel's blocks were
-// launched before the solver's main kernel, which this launch follows in stream order: they are resident, the wait cannot deadlock
-// (a bounded spin all the same: a time-out sets *timeout and renders what is there; the host reports it at the next call).
+// then computes the env's matrices itself (k_render_setup saw a half-written state for them).  The heavy kernel was
+// enqueued before the solver's main kernel, which this launch follows in stream order: its blocks have had idle SMs to start on
+// long before a CTA of this kernel can spin on them.  The spin is bounded all the same: a time-out (~2 s) sets *timeout and renders
+// what is there, and the host reports it at the next call.
 struct LateEnvs {
     const int* order;          // DevState::solve_order, or nullptr: identity order, nobody is late
     const int* ready; int ticket, heavy_cap;
