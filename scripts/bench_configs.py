@@ -27,14 +27,15 @@ import real_robots
 env = real_robots.make('REALRobot2020-R2J3-v0')
 obs = env.reset()
 rng = np.random.default_rng(1234)
-a = env.action_space['joint_command'].sample() if hasattr(env.action_space, '__getitem__') else rng.uniform(-1, 1, 9)
+lo_a, hi_a = env.action_space['joint_command'].low, env.action_space['joint_command'].high
+a = rng.uniform(lo_a, hi_a)          # (not action_space.sample(): gym's own generator is not seeded, and one env's step time depends on what its arm touches)
 for render in (True, False):
     for t in range(50):
         env.step({'joint_command': a, 'render': render})
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for t in range(1000):
         if rng.random() < 0.05:
-            a = env.action_space['joint_command'].sample()
+            a = rng.uniform(lo_a, hi_a)
         obs, _, done, _ = env.step({'joint_command': a, 'render': render})
     dt = time.perf_counter() - t0
     print("C1  REALRobot2020-R2J3-v0, 1 env, render %-5s: %7.3f ms/step  %10.0f env-steps/s  (gym facade, numpy obs, wall clock)" % (render, dt, 1000 / dt))
