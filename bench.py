@@ -264,6 +264,17 @@ def run_ours(args):
     prof = sim.profile_read()
     sim.profile(False)
     sampler.stop_flag = True
+    # the rasteriser by itself (after the timed region, not part of it): inside a step the look-ahead narrowphase and the solver's
+    # heavy-env kernel run beside it, so its in-step duration is longer than its own
+    raster_alone_ms = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        sim.profile(True)
+        for _ in range(5):
+            sim.render()
+        alone = sim.profile_read()
+        sim.profile(False)
+        raster_alone_ms = alone["raster"][0] / max(alone["raster"][1], 1)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     # per rank: timed region and the sum of the kernels' own durations (the ranks roll out different seeds, and the solver's
     # duration follows the most contact-laden envs of a rank: the spread between ranks is workload, not communication)
@@ -359,6 +370,10 @@ def run_ours(args):
                          "frac": achieved / peak if peak else None, "traffic": (args.traffic * args.envs / 4096 if args.traffic else None),
                          "algorithmic_bytes": args.envs * IMG_BYTES, "peak_source": peak_src,
                          "ms_per_launch": raster_ms, "launches": r_n,
+                         "alone": {"ms_per_launch": raster_alone_ms, "achieved": (args.envs * IMG_BYTES / (raster_alone_ms * 1e-3) / 1e9) if raster_alone_ms else None,
+                                   "frac": (args.envs * IMG_BYTES / (raster_alone_ms * 1e-3) / 1e9 / peak) if raster_alone_ms and peak else None,
+                                   "how": "5 rr_render launches after the timed region with nothing beside them; achieved / frac above are the in-step "
+                                          "launches, which share the GPU with the look-ahead narrowphase and the solver's heavy-env kernel"},
                          "kernels_ms_per_step": {k: (v[0] / max(s_n, 1)) for k, v in prof.items()},
                          "kernels_note": "CUDA-event time per step on the stream each kernel runs on.  step = k_step_dyn + k_step_solve; the solver's "
                                          "heavy-env kernel and the look-ahead narrowphase of the next step (collide) run on side streams beside "

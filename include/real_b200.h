@@ -77,7 +77,13 @@ int  rr_get_state(rr_ctx* ctx, double* q, double* qd, double* obj, void* stream)
 
 /* replaces: step_joints up to and including scene.global_step() (env.py:326-340):
  * limitActionByJoint (env.py:314-321), control_objects_limits (env.py:257-264), Kuka.apply_action
- * (robot.py:188-201), one pybullet stepSimulation at dt (env.py:340).  joint_cmd: f64[N,9]. */
+ * (robot.py:188-201), one pybullet stepSimulation at dt (env.py:340).  joint_cmd: f64[N,9].
+ * Stream semantics: everything the caller can observe is ordered on `stream`.  Internally the context owns two side streams: when
+ * rr_step returns, the solver kernel of the few envs with very long constraint schedules and the collision detection of the NEXT
+ * step (which only reads the new poses) are still in flight there.  Every other entry point first makes its stream wait for them;
+ * rr_render (eye camera, all envs) does not — its kernel takes those envs last and waits for each one on the device — so calling
+ * rr_render right after rr_step overlaps the three.  RR_HEAVY_SOLVER=0 / RR_EAGER_COLLIDE=0 (read at rr_create) switch the two
+ * mechanisms off: same results, strictly sequential kernels (needed to capture a step into a CUDA graph). */
 int  rr_step(rr_ctx* ctx, const double* joint_cmd, void* stream);
 
 /* replaces: Kuka.calc_state (robot.py:203-211), get_touch_sensors (robot.py:152-163) and, for R1,
