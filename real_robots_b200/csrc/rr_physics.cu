@@ -838,6 +838,9 @@ __device__ __forceinline__ double group_sum6(double pr, int s0, int s1, int s2, 
     const double d = __shfl_sync(FULL, pr, s3), e = __shfl_sync(FULL, pr, s4), f = __shfl_sync(FULL, pr, s5);
     return ((a + b) + (c + d)) + (e + f);
 }
+#ifndef SWEEP_WAR_FENCE
+#define SWEEP_WAR_FENCE() __syncwarp()
+#endif
 // The Gauss-Seidel sweep of one env (see SolveHead).  SS: the schedule pointers point into shared memory; BG: the blocks are in
 // global memory (streamed from L2, prefetched three slots ahead) — otherwise they were copied into shared memory too.
 template <bool SS, bool BG>
@@ -907,8 +910,9 @@ __device__ __forceinline__ void pgs_sweep(const unsigned int* const schedA0, con
                     dv += rr * delta;
                     const double r = delta * rinv;
                     res = fmax(res, r * r);
-                    if (leader) sapp[rid] = app;
                 }
+                SWEEP_WAR_FENCE();                            // every lane has read this slot's impulses (the shuffles above converge the
+                if (on && leader) sapp[rid] = app;           // warp; this orders the shared-memory accesses as well)
                 __syncwarp();
             }
             // ---- phase B: friction pairs with the implicit cone
@@ -945,8 +949,9 @@ __device__ __forceinline__ void pgs_sweep(const unsigned int* const schedA0, con
                     dv += rra * da; dv += rrb * db;
                     const double qa = da * rinva, qb = db * rinvb;
                     res = fmax(res, fmax(qa * qa, qb * qb));
-                    if (leader) { sapp[r0] = wa; sapp[r0 + 1] = wb; }
                 }
+                SWEEP_WAR_FENCE();
+                if (act && leader) { sapp[r0] = wa; sapp[r0 + 1] = wb; }
                 __syncwarp();
             }
             res = warp_max(res);

@@ -11,6 +11,10 @@ a = torch.from_numpy(rng.uniform(lo, hi, (N, 9))).cuda()
 for t in range(45):
     if t == 30: a = torch.from_numpy(rng.uniform(lo, hi, (N, 9))).cuda()
     sim.step(a)
+for t in range(6):                 # render straight after the step: k_raster's late-env path beside the heavy-env solver kernel and the look-ahead narrowphase
+    sim.step(a); sim.render(); sim.read_state()
+sim.set_object_pose(0, torch.tensor([[-0.1, 0.0, 0.6, 0, 0, 0, 1.0]] * N, dtype=torch.float64, device="cuda"))   # drops the look-ahead narrowphase
+sim.step(a)
 sim.read_state(); sim.render()
 sim.render(mask=torch.tensor([1, 0, 1, 0, 1, 1], dtype=torch.uint8, device="cuda"))
 pq = torch.tensor([[-0.1, 0.0, 0.5, 0.7, 0.7, 0, 0]] * N, dtype=torch.float64, device="cuda")
