@@ -37,7 +37,7 @@
 #define RR_ROWS_A (RID_ROLL + 2 * RR_MAX_CONTACTS)           // 216 single rows
 #define RID_FRIC RR_ROWS_A                                   // + 2 c + {0, 1}
 #define RR_MAX_ROWS (RID_FRIC + 2 * RR_MAX_CONTACTS)         // 312
-#define RR_SOLVE_CLASSES 4
+#define RR_SOLVE_CLASSES 8     // cost classes of the solver's env order: schedule length above 64, 56, 48, 40, 32, 28, 24 slots per iteration, the rest
 #define RR_IDLE 0xff
 
 // ---- constant robot / scene description (uploaded to __constant__ memory once per process+device)

@@ -57,11 +57,14 @@ struct SolveHead {
 #define GBLK_BASE (HEAD_DOUBLES + (16 * RR_SLOTS_A + 8 * RR_SLOTS_B) / 2)   // first block, in doubles
 static_assert(sizeof(SolveHead) % 16 == 0, "the schedule words and blocks must stay 16-byte aligned");
 static_assert(GBLK_BASE % 2 == 0 && GBLK_BASE + RR_NC_ROWS * RR_ARM_BLK + RR_MAX_CONTACTS * 6 * (RR_ARM_BLK + RR_OBJ_BLK) <= RR_IMG_DOUBLES, "solver image too small");
-#ifndef SOLVE_COST_0
-#define SOLVE_COST_0 48     // cost classes of k_step_dyn's ordering (an env whose contacts are all object-vs-static: 16 + 2 * 4 = 24);
-#define SOLVE_COST_1 32     // the classes above the last one are "heavy" (k_step_solve_heavy)
-#define SOLVE_COST_2 24
+#ifndef SOLVE_HEAVY_ABOVE
+#define SOLVE_HEAVY_ABOVE 24
 #endif
+// cost class of a schedule (slots per iteration, a pair slot counted twice; an env whose contacts are all object-vs-static: 16 + 2 * 4 =
+// 24): the classes above the last one are "heavy" (k_step_solve_heavy takes the first HEAVY_GRID of them, longest first)
+__device__ __forceinline__ int solve_cost_class(int cost) {
+    return cost > 64 ? 0 : cost > 56 ? 1 : cost > 48 ? 2 : cost > 40 ? 3 : cost > 32 ? 4 : cost > 28 ? 5 : cost > SOLVE_HEAVY_ABOVE ? 6 : 7;
+}
 // k_step_dyn's own workspace
 struct WarpMem {
     double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
@@ -811,7 +814,7 @@ __global__ void __launch_bounds__(WPB * 32) k_step_dyn(DevState st, const double
         hand->n_rows_total = n_rows_total; hand->n_blk_doubles = blk_top;
         // cost class of the sweep (slots per iteration; a pair slot counts twice): k_step_solve starts the longest chains first
         const int cost = (hand->n_slotsA[0] + hand->n_slotsA[1]) / 2 + 2 * hand->n_slotsB;
-        const int cls = cost > SOLVE_COST_0 ? 0 : cost > SOLVE_COST_1 ? 1 : cost > SOLVE_COST_2 ? 2 : 3;
+        const int cls = solve_cost_class(cost);
         const int pos = atomicAdd(&st.solve_order[cls], 1);
         st.solve_order[RR_SOLVE_CLASSES + cls * N + pos] = e;
         st.solve_pos[e] = (cls << 24) | pos;
@@ -841,9 +844,9 @@ __device__ __forceinline__ double group_sum6(double pr, int s0, int s1, int s2, 
 #ifndef SWEEP_WAR_FENCE
 #define SWEEP_WAR_FENCE() __syncwarp()
 #endif
-// The Gauss-Seidel sweep of one env (see SolveHead).  SS: the schedule pointers point into shared memory; BG: the blocks are in
-// global memory (streamed from L2, prefetched three slots ahead) — otherwise they were copied into shared memory too.
-template <bool SS, bool BG>
+// The Gauss-Seidel sweep of one env (see SolveHead).  SS: the schedule pointers point into shared memory.  The blocks are streamed
+// from L2, prefetched three slots ahead.
+template <bool SS>
 __device__ __forceinline__ void pgs_sweep(const unsigned int* const schedA0, const unsigned int* const schedA1, const unsigned int* const schedB0, const double* const gblk,
                                           double* const sapp, const int nA0, const int nA1, const int nB, const int lane, const rr_config& cf, double& dv_out, int& iters_out) {
     // dv in owner layout: lane k < 11 owns the arm dof k, lane 11+6o+c the object component.
@@ -878,7 +881,7 @@ __device__ __forceinline__ void pgs_sweep(const unsigned int* const schedA0, con
                 const bool act = ingrp && w.x != ENT_IDLE;
                 const unsigned int kind = w.x >> 16;
                 const double* b = gblk + 2 * (act ? (w.x & 0x7fffu) : 0u);
-                if (BG && ingrp && nx != ENT_IDLE) RR_PREFETCH_L1(gblk + 2 * (nx & 0x7fffu) + myk2);      // the blocks three slots ahead are on their way into L1
+                if (ingrp && nx != ENT_IDLE) RR_PREFETCH_L1(gblk + 2 * (nx & 0x7fffu) + myk2);      // the blocks three slots ahead are on their way into L1
                 nx = slot + 4 < nA ? sched[8 * (slot + 4)] : ENT_IDLE;
                 double J = 0.0, rr = 0.0, rhs = 0.0, inv = 0.0, rinv = 0.0, lo = 0.0, hi = 0.0, app = 0.0;
                 bool on = act;
@@ -982,22 +985,19 @@ struct SolveEpi { SolveHead head; KinWs kin; };
 // Heavy envs: the few envs (2-5 % under a random policy) whose arm touches something have schedules 1.5-3.5x as long as the rest,
 // and a Gauss-Seidel chain cannot be split: started together with the others, the longest of them alone set the kernel's duration
 // (2.2 ms against 1.0 ms for a batch without them).  They get a kernel of their own on a side stream, launched beside the main one:
-// one warp per block, schedule AND blocks in shared memory, each block taking the heaviest envs first; same code, same arithmetic.
-// The chain is hardly faster there (a slot is ~100 dependent fp64 / shuffle instructions; the L2 round trip the main kernel
-// prefetches around was not what bounded it) — the point is that nothing on the step's critical path waits for it: rr_render's
+// one warp per block, the whole schedule in shared memory, one env each; same code, same arithmetic.  The chain is not faster there
+// (a slot is ~100 dependent fp64 / shuffle instructions: keeping the row blocks in shared memory too was measured and changed
+// nothing) — the point is that nothing on the step's critical path waits for it: rr_render's
 // rasteriser starts when the MAIN kernel is done, takes the heavy envs last and waits for each one's ticket (DevState::ready);
 // whoever else touches the state joins the side stream first (rrk_join_heavy).
 #define HEAVY_SCHED_WORDS (16 * RR_SLOTS_A + 8 * RR_SLOTS_B)
-#ifndef HEAVY_BLK_DOUBLES
-#define HEAVY_BLK_DOUBLES 8192     // 64 KB of row blocks; an env with more streams them from L2 like the main kernel
-#endif
-#define HEAVY_SMEM_BYTES ((size_t)SOLVE_SMEM_DOUBLES * 8 + HEAVY_SCHED_WORDS * 4 + (size_t)HEAVY_BLK_DOUBLES * 8)
+#define HEAVY_SMEM_BYTES ((size_t)SOLVE_SMEM_DOUBLES * 8 + HEAVY_SCHED_WORDS * 4)
 #ifndef HEAVY_GRID
-#define HEAVY_GRID 148
-#define HEAVY_PER_BLOCK 2
+#define HEAVY_GRID 192        // one env per block, all resident at once.  Not more: their narrowphase (4 envs per block, ~0.6 ms each) has
+#define HEAVY_PER_BLOCK 1     // to fit under the rasteriser on the SMs that kernel leaves free; the envs beyond go to the main kernel, first
 #endif
 template <bool HEAVY>
-__device__ __forceinline__ void solve_env(const DevState& st, const int e, double* const smem, unsigned int* const ssched, const int sched_cap, double* const sblk,
+__device__ __forceinline__ void solve_env(const DevState& st, const int e, double* const smem, unsigned int* const ssched, const int sched_cap,
                                           int* __restrict__ man_hdr, double* __restrict__ man_pts, const rr_config& cf, const int n_objects, const int lane) {
     double* const sapp = smem;                                 // applied impulses by row id (during the sweep)
     const int N = st.N;
@@ -1022,18 +1022,11 @@ __device__ __forceinline__ void solve_env(const DevState& st, const int e, doubl
         for (int k = lane; k < 8 * nA1; k += 32) ssched[8 * nA0 + k] = gsched[GSCHED_A(1) + k];
         for (int k = lane; k < 8 * nB; k += 32) ssched[8 * (nA0 + nA1) + k] = gsched[GSCHED_B + k];
     }
-    bool blk_smem = false;
-    if (HEAVY) {
-        const int nd = gh->n_blk_doubles;
-        blk_smem = sched_smem && nd <= HEAVY_BLK_DOUBLES;
-        if (blk_smem) for (int k = 2 * lane; k < nd; k += 64) *reinterpret_cast<double2*>(sblk + k) = *reinterpret_cast<const double2*>(gblk + k);
-    }
     __syncwarp();
     double dv = 0.0;
     int iters = 0;
-    if (HEAVY && blk_smem) pgs_sweep<true, false>(ssched, ssched + 8 * nA0, ssched + 8 * (nA0 + nA1), sblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
-    else if (sched_smem) pgs_sweep<true, true>(ssched, ssched + 8 * nA0, ssched + 8 * (nA0 + nA1), gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
-    else pgs_sweep<false, true>(gsched + GSCHED_A(0), gsched + GSCHED_A(1), gsched + GSCHED_B, gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
+    if (sched_smem) pgs_sweep<true>(ssched, ssched + 8 * nA0, ssched + 8 * (nA0 + nA1), gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
+    else pgs_sweep<false>(gsched + GSCHED_A(0), gsched + GSCHED_A(1), gsched + GSCHED_B, gblk, sapp, nA0, nA1, nB, lane, cf, dv, iters);
     // ---- impulse write-back (warm start of the next step) and gripper touch sensors (robot.py:131-163)
     int* hdr = man_hdr + (size_t)e * RR_MAX_MANIFOLDS * 2;
     double* pts = man_pts + (size_t)e * RR_MAX_MANIFOLDS * 4 * RR_PT_STRIDE;
@@ -1142,17 +1135,16 @@ __global__ void __launch_bounds__(SOLVE_WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve
     double* const smem = reinterpret_cast<double*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
     const int idx = blockIdx.x * SOLVE_WPB + (threadIdx.x >> 5) + solve_n_heavy(st, heavy_cap);      // the heavy kernel has the first ones
     if (idx >= st.N) return;
-    solve_env<false>(st, solve_pick(st, idx), smem, reinterpret_cast<unsigned int*>(smem + SOLVE_SMEM_DOUBLES), SOLVE_SCHED_WORDS, nullptr, man_hdr, man_pts, cf, n_objects, threadIdx.x & 31);
+    solve_env<false>(st, solve_pick(st, idx), smem, reinterpret_cast<unsigned int*>(smem + SOLVE_SMEM_DOUBLES), SOLVE_SCHED_WORDS, man_hdr, man_pts, cf, n_objects, threadIdx.x & 31);
 }
 __global__ void __launch_bounds__(32) k_step_solve_heavy(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects, int heavy_cap, int ticket) {
     RR_DYN_SMEM(smem_raw);
     double* const smem = reinterpret_cast<double*>(smem_raw);
     unsigned int* const ssched = reinterpret_cast<unsigned int*>(smem + SOLVE_SMEM_DOUBLES);
-    double* const sblk = reinterpret_cast<double*>(ssched + HEAVY_SCHED_WORDS);
     const int n = solve_n_heavy(st, heavy_cap);
     for (int idx = blockIdx.x; idx < n; idx += gridDim.x) {
         const int e = solve_pick(st, idx);
-        solve_env<true>(st, e, smem, ssched, HEAVY_SCHED_WORDS, sblk, man_hdr, man_pts, cf, n_objects, threadIdx.x);
+        solve_env<true>(st, e, smem, ssched, HEAVY_SCHED_WORDS, man_hdr, man_pts, cf, n_objects, threadIdx.x);
         __threadfence();                      // the env's state, frames and observations are out before the ticket is
         __syncwarp();
         if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(st.ready + e) = ticket;

@@ -1,0 +1,9 @@
+#!/bin/bash
+for lib in default hv148 hv256 hv296; do
+  if [ $lib = default ]; then unset RR_LIB; else export RR_LIB=real_robots_b200/variants/lib_$lib.so; fi
+  python bench.py --steps 60 --warmup 5 --no-cpu-baseline --e2e-steps 2 | tail -1 | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print('$lib', round(d['value']), round(d['ms_per_step'], 3), {k: round(v, 3) for k, v in d['roofline']['kernels_ms_per_step'].items()})"
+  python scripts/c5_breakdown.py 2>&1 | grep "C5"
+done

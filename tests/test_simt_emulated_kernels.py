@@ -218,11 +218,10 @@ def test_integration_md_binding_stub_runs_against_the_c_abi():
 
 
 def test_emulated_heavy_solver_kernel_is_the_same_arithmetic():
-    """Envs with long Gauss-Seidel schedules (the arm touches something) are solved by k_step_solve_heavy (schedule and row
-    blocks in shared memory, launched beside k_step_solve), the others by k_step_solve in order of decreasing schedule length.
+    """Envs with long Gauss-Seidel schedules (the arm touches something) are solved by k_step_solve_heavy (schedule in shared memory, launched beside
+    k_step_solve), the others by k_step_solve in order of decreasing schedule length.
     Same code path for the arithmetic: the state after 25 steps is identical bit for bit with the heavy kernel switched off
-    (RR_HEAVY_SOLVER=0) and with a heavy kernel whose shared memory holds no env's blocks (-DHEAVY_BLK_DOUBLES=64: streams them
-    from the image), and with a heavy kernel that has room for ONE env (-DHEAVY_GRID=1 -DHEAVY_PER_BLOCK=1: the second heavy env
+    (RR_HEAVY_SOLVER=0) and with a heavy kernel that has room for ONE env (-DHEAVY_GRID=1 -DHEAVY_PER_BLOCK=1: the second heavy env
     of the batch falls to the main kernel, which takes it first); the pressed envs did go through it (schedule length above the heavy
     threshold of 24)."""
     from tests.scenarios import scripted_press
@@ -231,7 +230,7 @@ def test_emulated_heavy_solver_kernel_is_the_same_arithmetic():
     q = np.stack([st[0], rest[0], st[0]]); qd = np.stack([st[1], rest[1], st[1]]); ob = np.stack([st[2], rest[2], st[2]])
     cmds = np.stack([cmd, np.zeros(9), cmd])
     finals, costs = [], []
-    for env_off, flags in ((False, ()), (True, ()), (False, ("-DHEAVY_BLK_DOUBLES=64",)), (False, ("-DHEAVY_GRID=1", "-DHEAVY_PER_BLOCK=1"))):
+    for env_off, flags in ((False, ()), (True, ()), (False, ("-DHEAVY_GRID=1", "-DHEAVY_PER_BLOCK=1"))):
         if env_off:
             os.environ["RR_HEAVY_SOLVER"] = "0"
         try:
@@ -245,7 +244,7 @@ def test_emulated_heavy_solver_kernel_is_the_same_arithmetic():
             cost = max(cost, int((sim.diag()[0, 3] >> 16) & 0xffff))
         finals.append(sim.get_state()); costs.append(cost)
         sim.close()
-    assert costs[0] > 24 and costs[0] == costs[1] == costs[2] == costs[3]
+    assert costs[0] > 24 and costs[0] == costs[1] == costs[2]
     for other in finals[1:]:
         for a, b in zip(finals[0], other):
             assert np.array_equal(a, b)
