@@ -82,8 +82,11 @@ int  rr_get_state(rr_ctx* ctx, double* q, double* qd, double* obj, void* stream)
  * rr_step returns, the solver kernel of the few envs with very long constraint schedules and the collision detection of the NEXT
  * step (which only reads the new poses) are still in flight there.  Every other entry point first makes its stream wait for them;
  * rr_render (eye camera, all envs) does not — its kernel takes those envs last and waits for each one on the device — so calling
- * rr_render right after rr_step overlaps the three.  RR_HEAVY_SOLVER=0 / RR_EAGER_COLLIDE=0 (read at rr_create) switch the two
- * mechanisms off: same results, strictly sequential kernels (needed to capture a step into a CUDA graph). */
+ * rr_render right after rr_step overlaps the three.  The split of the solver only pays when a render follows (back-to-back physics
+ * steps are faster unsplit), so a step is split iff the previous step was followed by an rr_render of all envs; RR_HEAVY_SOLVER=1 / 0
+ * (read at rr_create) forces it on / off, RR_EAGER_COLLIDE=0 moves the collision detection back to the beginning of its own step.
+ * Same results in every combination; with both at 0 the kernels of a step are strictly sequential on `stream` (needed to capture
+ * a step into a CUDA graph). */
 int  rr_step(rr_ctx* ctx, const double* joint_cmd, void* stream);
 
 /* replaces: Kuka.calc_state (robot.py:203-211), get_touch_sensors (robot.py:152-163) and, for R1,

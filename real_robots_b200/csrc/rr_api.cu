@@ -282,7 +282,7 @@ int rr_create(rr_ctx** out, int device, int n_envs, int n_objects, const char* b
     if (e != cudaSuccess) { ctx->err = std::string("rr_create: device allocation failed: ") + cudaGetErrorString(e); return fail(-1); }
     ctx->man_parity = 0;
     { const char* ea = getenv("RR_EAGER_COLLIDE"); ctx->eager_collide = !(ea && ea[0] == '0'); }
-    { const char* ea = getenv("RR_HEAVY_SOLVER"); ctx->heavy_solver = !(ea && ea[0] == '0'); }
+    { const char* ea = getenv("RR_HEAVY_SOLVER"); ctx->heavy_mode = (ea && ea[0] == '0') ? 0 : (ea && ea[0] == '1') ? 1 : -1; }
     if (rrk_reset(ctx, nullptr, 0) != 0) return fail(-1);
     if (rrk_render_build_static(ctx) != 0) return fail(-1);
     if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "rr_create: initial reset failed"; return fail(-1); }

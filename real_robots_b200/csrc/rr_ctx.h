@@ -148,7 +148,10 @@ struct rr_ctx {
     int* d_late_timeout = nullptr; int* h_late_timeout = nullptr;   // k_raster's bounded wait for that kernel ran out (pinned mirror)
     int step_serial = 0;       // rrk_step calls so far (the ticket k_step_solve_heavy leaves in DevState::ready)
     bool heavy_pending = false; // k_step_solve_heavy of the last step has not been joined into the caller's stream yet
-    bool heavy_solver = true;  // the envs with the longest Gauss-Seidel schedules go to k_step_solve_heavy on the side stream (rr_physics.cu)
+    // The heavy kernel pays when a rasteriser follows the step and hides it; back-to-back physics steps are ~0.6 ms faster with every env
+    // in the main kernel (the heavy envs' solve -> narrowphase chain is then overlapped by the bulk instead of serialised behind it).
+    // heavy_mode -1 (default): split the step iff the previous step was followed by an eye-camera render of all envs; 0 / 1: never / always
+    int heavy_mode = -1; bool render_followed = true, rendered_since_step = false;
     int n_tris;
     void* d_rec_scratch; void* d_list_scratch; int* d_work_counter; uint8_t* d_tri_shape; int raster_grid;   // persistent rasteriser
     void* h_collide_const; float cull_hmax;   // host copies of per-context __constant__ data that are built on the fly

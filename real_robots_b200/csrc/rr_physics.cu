@@ -66,31 +66,40 @@ __device__ __forceinline__ int solve_cost_class(int cost) {
     return cost > 64 ? 0 : cost > 56 ? 1 : cost > 48 ? 2 : cost > 40 ? 3 : cost > 32 ? 4 : cost > 28 ? 5 : cost > SOLVE_HEAVY_ABOVE ? 6 : 7;
 }
 // k_step_dyn's own workspace
+// 14 144 B per env: four blocks of four envs per SM.  The forward-dynamics workspace (ABA: dead once aba_minv has the M^-1 columns) and
+// the workspace of the constraint rows (first written after that) share their bytes.
 struct WarpMem {
     double q[RR_NDOF], qd[RR_NDOF], target[RR_NDOF];
     double Minv[RR_NDOF][RR_NDOF];
-    // non-contact rows (limits then motors) while they are being set up
-    double r_rhs[RR_NC_ROWS], r_inv[RR_NC_ROWS], r_rinv[RR_NC_ROWS], r_lo[RR_NC_ROWS], r_hi[RR_NC_ROWS], r_sign[RR_NC_ROWS];
-    int r_dof[RR_NC_ROWS];
-    int n_rows;
     int fault;
-    unsigned char c_grp[RR_MAX_CONTACTS], c_flags[RR_MAX_CONTACTS];   // per contact: group mask (bit 0 arm, bit 1+o object o); bit 0 spinning row, bit 1 rolling rows, bit 2 wide
-    unsigned short c_base[RR_MAX_CONTACTS];                           // first block of the contact (16-byte units)
     KinWs k;
-    double v[RR_NL][6];       // spatial velocity (ang, lin) in link frame
-    double c[RR_NL][6];       // Coriolis acceleration
-    double p[RR_NL][6];       // zero-acceleration force
-    double IA[RR_NL][36];     // articulated inertia
-    double h[RR_NL][6];
-    double invD[RR_NL];
-    double Y[RR_NL];
-    double acc[RR_NL][6];
-    double X[36], T[36], Ia[36], pa[6], Ic[6];
-    double tau[RR_NDOF], qdd[RR_NDOF];
-    double dof_axis[RR_NDOF][3], dof_piv[RR_NDOF][3];   // world joint axis / pivot per dof
-    double opos[RR_MAX_OBJECTS][3], ovel[RR_MAX_OBJECTS][6], oIinv[RR_MAX_OBJECTS][9], oinvm[RR_MAX_OBJECTS];
-    double Jtmp[32];
+    union {
+        struct {      // forward dynamics
+            double v[RR_NL][6];       // spatial velocity (ang, lin) in link frame
+            double c[RR_NL][6];       // Coriolis acceleration
+            double p[RR_NL][6];       // zero-acceleration force
+            double IA[RR_NL][36];     // articulated inertia
+            double h[RR_NL][6];
+            double invD[RR_NL];
+            double Y[RR_NL];
+            double acc[RR_NL][6];
+            double X[36], T[36], Ia[36], pa[6], Ic[6];
+            double tau[RR_NDOF], qdd[RR_NDOF];
+        };
+        struct {      // constraint rows
+            // non-contact rows (limits then motors) while they are being set up
+            double r_rhs[RR_NC_ROWS], r_inv[RR_NC_ROWS], r_rinv[RR_NC_ROWS], r_lo[RR_NC_ROWS], r_hi[RR_NC_ROWS], r_sign[RR_NC_ROWS];
+            int r_dof[RR_NC_ROWS];
+            int n_rows;
+            unsigned char c_grp[RR_MAX_CONTACTS], c_flags[RR_MAX_CONTACTS];   // per contact: group mask (bit 0 arm, bit 1+o object o); bit 0 spinning row, bit 1 rolling rows, bit 2 wide
+            unsigned short c_base[RR_MAX_CONTACTS];                           // first block of the contact (16-byte units)
+            double dof_axis[RR_NDOF][3], dof_piv[RR_NDOF][3];   // world joint axis / pivot per dof
+            double opos[RR_MAX_OBJECTS][3], ovel[RR_MAX_OBJECTS][6], oIinv[RR_MAX_OBJECTS][9], oinvm[RR_MAX_OBJECTS];
+            double Jtmp[32];
+        };
+    };
 };
+static_assert(sizeof(WarpMem) <= 14336, "k_step_dyn: four blocks of WPB = 4 envs per SM need <= 56 KB of shared memory per block");
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
@@ -1420,7 +1429,9 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
             ctx->collide_ahead = false;
         } else if (rrk_collide(ctx, s) != 0) return -1;
     }
-    const bool heavy = ctx->heavy_solver && ctx->cfg.enable_contacts;
+    if (ctx->step_serial > 1) ctx->render_followed = ctx->rendered_since_step;      // (step_serial was just incremented)
+    ctx->rendered_since_step = false;
+    const bool heavy = ctx->cfg.enable_contacts && (ctx->heavy_mode == 1 || (ctx->heavy_mode < 0 && ctx->render_followed));
     if ((heavy || ctx->eager_collide) && side_streams(ctx)) return -1;
     const int heavy_cap = heavy ? HEAVY_GRID * HEAVY_PER_BLOCK : 0;
     ctx->heavy_cap = heavy_cap;

@@ -231,8 +231,7 @@ def test_emulated_heavy_solver_kernel_is_the_same_arithmetic():
     cmds = np.stack([cmd, np.zeros(9), cmd])
     finals, costs = [], []
     for env_off, flags in ((False, ()), (True, ()), (False, ("-DHEAVY_GRID=1", "-DHEAVY_PER_BLOCK=1"))):
-        if env_off:
-            os.environ["RR_HEAVY_SOLVER"] = "0"
+        os.environ["RR_HEAVY_SOLVER"] = "0" if env_off else "1"      # 1: always (the default splits a step only when a render followed the last one)
         try:
             sim = EmuSim(3, 3, build_flags=flags)
         finally:
