@@ -150,8 +150,9 @@ struct rr_ctx {
     bool heavy_pending = false; // k_step_solve_heavy of the last step has not been joined into the caller's stream yet
     // The heavy kernel pays when a rasteriser follows the step and hides it; back-to-back physics steps are ~0.6 ms faster with every env
     // in the main kernel (the heavy envs' solve -> narrowphase chain is then overlapped by the bulk instead of serialised behind it).
-    // heavy_mode -1 (default): split the step iff the previous step was followed by an eye-camera render of all envs; 0 / 1: never / always
-    int heavy_mode = -1; bool render_followed = true, rendered_since_step = false;
+    // heavy_mode -1 (default): split the step iff the previous step was followed FIRST by an eye-camera render of all envs (a caller that
+    // reads the state before it renders joins the heavy kernel before the rasteriser can hide it); 0 / 1: never / always
+    int heavy_mode = -1; bool render_followed = true, rendered_since_step = false, touched_since_step = false;
     int n_tris;
     void* d_rec_scratch; void* d_list_scratch; int* d_work_counter; uint8_t* d_tri_shape; int raster_grid;   // persistent rasteriser
     void* h_collide_const; float cull_hmax;   // host copies of per-context __constant__ data that are built on the fly

@@ -1412,6 +1412,7 @@ static int side_streams(rr_ctx* ctx) {
     return 0;
 }
 int rrk_join_heavy(rr_ctx* ctx, cudaStream_t s) {
+    ctx->touched_since_step = true;
     if (!ctx->heavy_pending) return 0;
     CK(cudaStreamWaitEvent(s, ctx->ev_heavy, 0));
     ctx->heavy_pending = false;
@@ -1430,7 +1431,7 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
         } else if (rrk_collide(ctx, s) != 0) return -1;
     }
     if (ctx->step_serial > 1) ctx->render_followed = ctx->rendered_since_step;      // (step_serial was just incremented)
-    ctx->rendered_since_step = false;
+    ctx->rendered_since_step = false; ctx->touched_since_step = false;
     const bool heavy = ctx->cfg.enable_contacts && (ctx->heavy_mode == 1 || (ctx->heavy_mode < 0 && ctx->render_followed));
     if ((heavy || ctx->eager_collide) && side_streams(ctx)) return -1;
     const int heavy_cap = heavy ? HEAVY_GRID * HEAVY_PER_BLOCK : 0;

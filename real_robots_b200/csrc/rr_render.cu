@@ -1395,7 +1395,8 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
     if (ctx->h_late_timeout && *ctx->h_late_timeout) { ctx->err = "k_raster timed out waiting for k_step_solve_heavy (an earlier rr_render returned stale images)"; return -1; }
     // right after rr_step the solver's heavy kernel may still run on the context's side stream: the eye-camera render of all envs
     // does not wait for it here but per env inside k_raster (LateEnvs); everything else joins it first
-    if (eye_camera && frames == nullptr && env_begin == 0 && env_count == ctx->N) ctx->rendered_since_step = true;     // see rr_ctx::heavy_mode
+    // (see rr_ctx::heavy_mode: the split pays when this render is the first thing after the step — a caller that reads the state first has joined the heavy kernel already)
+    if (eye_camera && frames == nullptr && env_begin == 0 && env_count == ctx->N && !ctx->touched_since_step) ctx->rendered_since_step = true;
     const bool late = ctx->heavy_pending && eye_camera && frames == nullptr && env_begin == 0 && env_count == ctx->N && !TMA_MATS;
     if (!late && rrk_join_heavy(ctx, s) != 0) return -1;
     LateEnvs LE; memset(&LE, 0, sizeof LE);
