@@ -19,7 +19,7 @@ for r in rows[1:]:
     a[0] += 1; a[1] += float(r[iv].replace(",", ""))
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(prof, tag + "_launches_summary.txt"), "w") as f:
-    f.write("# ncu launch list (%s): ncu --metrics gpu__time_duration.sum --clock-control none -s 190 (r02) | 300 (r02b) -c 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 3\n" % tag)
+    f.write("# ncu launch list (%s): ncu --metrics gpu__time_duration.sum --clock-control none -s 190 -c 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 3\n" % tag)
     f.write("# cold-cache, serialised per-launch times: compare SHARES, not absolutes. unit: ns.  (bench + e2e legs: the e2e leg renders in 16 chunks of 256 envs)\n")
     f.write("%-40s %8s %14s %8s %12s\n" % ("kernel", "launches", "total", "share", "avg"))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -36,7 +36,7 @@ keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
-out = {"command": "ncu --set full --clock-control none --import-source on -k regex:\"k_raster|k_step_dyn|k_step_solve|k_collide\" -s 192 -c 4 (r02) | -s 320 -c 7 (r02b) python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 3",
+out = {"command": "ncu --set full --clock-control none --import-source on -k regex:\"k_raster|k_step_dyn|k_step_solve|k_collide\" -s 192 -c 4 (r02) | -s 194 -c 10 (r02c) python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 3",
        "units": {k: units[h.index(k)] for k in keys if k in h}, "kernels": []}
 for v in r[2:]:
     d = {k: v[h.index(k)] for k in keys if k in h}
