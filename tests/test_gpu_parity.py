@@ -665,3 +665,58 @@ def test_late_env_render_small_batch_with_mask_and_state_edits():
     for x, y in zip(a.get_state(), b.get_state()):
         assert torch.equal(x, y)
     a.close(); b.close()
+
+
+def test_mixed_call_patterns_equal_the_sequential_schedule(monkeypatch):
+    """The overlapped schedule (look-ahead narrowphase, heavy-env solver kernel on a side stream — used or not depending on what
+    followed the previous step — rasteriser waiting per env) under every call pattern a caller can produce: step only, render first,
+    state read first, masked renders, masked resets, pose edits and checkpoint reads between steps.  A context created with
+    RR_HEAVY_SOLVER=0 RR_EAGER_COLLIDE=0 (strictly sequential kernels) that receives the same calls must agree bit for bit: every image,
+    every read-out, the final state."""
+    import bench
+    N = 512
+    fast = BatchedSim(N, 3)
+    monkeypatch.setenv("RR_HEAVY_SOLVER", "0"); monkeypatch.setenv("RR_EAGER_COLLIDE", "0")
+    seq = BatchedSim(N, 3)
+    monkeypatch.delenv("RR_HEAVY_SOLVER"); monkeypatch.delenv("RR_EAGER_COLLIDE")
+    acts = bench.random_policy_actions(torch, 150, N, torch.device("cuda"), 21)
+    rng = np.random.default_rng(5)
+    for t in range(70):
+        fast.step(acts[t]); seq.step(acts[t])
+    rendered = 0
+    for t in range(70, 150):
+        pat = int(rng.integers(0, 7))
+        outs = []
+        for sim in (fast, seq):
+            sim.step(acts[t])
+            o = []
+            if pat == 1:
+                o += [x.clone() for x in sim.render()]
+            elif pat == 2:
+                o += [x.clone() for x in sim.read_state()] + [x.clone() for x in sim.render()]
+            elif pat == 3:
+                o += [x.clone() for x in sim.render()] + [x.clone() for x in sim.read_state()]
+            elif pat == 4:
+                m = torch.from_numpy((np.arange(N) % 3 != t % 3).astype(np.uint8)).cuda()
+                o += [x.clone() for x in sim.render(mask=m)]
+            elif pat == 5:
+                m = torch.from_numpy((np.arange(N) % 7 == t % 7).astype(np.uint8)).cuda()
+                sim.reset(m)
+                o += [x.clone() for x in sim.render()]
+            elif pat == 6:
+                pq = torch.tensor([[-0.12, 0.1, 0.5, 0, 0, 0, 1.0]] * N, dtype=torch.float64, device='cuda')
+                sim.set_object_pose(t % 3, pq, torch.from_numpy((np.arange(N) % 11 == 0).astype(np.uint8)).cuda())
+                o += [x.clone() for x in sim.get_state()]
+            outs.append(o)
+        rendered += pat in (1, 2, 3, 4, 5)
+        for x, y in zip(*outs):
+            assert torch.equal(x, y), (t, pat)
+    assert rendered > 20
+    for x, y in zip(fast.get_state(), seq.get_state()):
+        assert torch.equal(x, y)
+    hf, pf, _ = fast.contacts(); hs, ps, _ = seq.contacts()
+    assert torch.equal(hf, hs)
+    live = (torch.arange(4, device='cuda')[None, None, :] < hf[:, :, 1:2]) & (hf[:, :, 0:1] >= 0)      # points of the manifolds in use
+    assert torch.equal(pf[live], ps[live]) and int(live.sum()) > N
+    assert int((fast.faults() != 0).sum()) == 0
+    fast.close(); seq.close()
