@@ -363,11 +363,10 @@ __device__ __forceinline__ float div_fast(float a, float b, float y, bool ok) {
 }
 // same, without the range guards: only valid when the caller has established the operand ranges (see raster_one)
 __device__ __forceinline__ float div_fast_ng(float a, float b, float y) {
-    float q = a * y;
-    if (a == 0.f) return q;
-    float r = __fmaf_rn(-b, q, a); q = __fmaf_rn(r, y, q);
+    const float q0 = a * y;                 // a == +-0: the quotient is q0 (the corrections below would turn -0 into +0); a select, not a branch
+    float r = __fmaf_rn(-b, q0, a), q = __fmaf_rn(r, y, q0);
     r = __fmaf_rn(-b, q, a); q = __fmaf_rn(r, y, q);
-    return q;
+    return a == 0.f ? q0 : q;
 }
 __device__ __forceinline__ bool recip_ok(float b) { const float ab = fabsf(b); return ab > 1e-12f && ab < 1e12f; }
 struct Recip { float yuz, yw[3]; bool ok, tight; };
