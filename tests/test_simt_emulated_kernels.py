@@ -271,3 +271,27 @@ def test_emulated_render_right_after_step_takes_the_late_env_path():
         for x, y in zip(ra, rb):
             assert np.array_equal(x, y)
     assert ra[0][1].any() and not np.array_equal(ra[0][0], ra[0][1])
+
+
+def test_emulated_solver_split_follows_the_call_pattern():
+    """rr_step splits the solver over two kernels (and the look-ahead narrowphase over two launches) only when the previous step was
+    followed FIRST by a render of all envs — otherwise nothing could hide the heavy kernel.  Counted in kernel launches per rr_step:
+    dynamics + solver + look-ahead narrowphase = 3 unsplit, + heavy solver + second narrowphase launch = 5 split."""
+    sim = EmuSim(2, 3)
+    cmd = np.zeros((2, 9))
+
+    def step_launches():
+        n = sim.lib.rr_launch_count(sim.ctx)
+        sim.step(cmd)
+        return sim.lib.rr_launch_count(sim.ctx) - n
+    assert step_launches() == 6          # first step of a context: split by default, and the narrowphase runs in line (nothing looked ahead yet)
+    assert step_launches() == 3          # nothing rendered after the first step
+    sim.render()
+    assert step_launches() == 5          # a render came first
+    sim.read_state(); sim.render()
+    assert step_launches() == 3          # the state was read before the render: the heavy kernel would have been joined anyway
+    sim.render(); sim.read_state()
+    assert step_launches() == 5
+    sim.render(mask=np.array([1, 0], np.uint8))
+    assert step_launches() == 5          # a masked render of all envs counts
+    sim.close()
