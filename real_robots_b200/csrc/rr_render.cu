@@ -914,7 +914,9 @@ __global__ void __launch_bounds__(RTHREADS, RBLOCKS)
 k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const uint8_t* __restrict__ tri_shape, const float4* __restrict__ planes, int n_tris,
          const uint8_t* __restrict__ texdata, const uint8_t* __restrict__ env_mask, Rec* __restrict__ rec_scratch, unsigned short* __restrict__ list_scratch,
          unsigned short* __restrict__ cull_scratch, int* __restrict__ work_counter,
-         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N, const StaticLayer SL, const LateEnvs LE) {
+         uint8_t* __restrict__ rgb, float* __restrict__ depth, int32_t* __restrict__ seg, int env_begin, int N, const StaticLayer SL, const LateEnvs LE, const int split) {
+    // split > 1 (small batches): an env is `split` work items, item k taking the strips k, k + split, ... — every item does the env's whole
+    // geometry (its own scratch), the strips are independent, so a few envs spread over split x as many CTAs.
     unsigned long long* __restrict__ static_keys = SL.keys;
     const unsigned int static_bits = SL.bits; const int skip_front = SL.skip_front;
     RR_DYN_SMEM(smem_raw);
@@ -923,7 +925,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
     unsigned int* fq_all = reinterpret_cast<unsigned int*>(smem_raw + (size_t)STRIP_ROWS * RR_W * 8 + (TMA_MATS ? 2 : 1) * RR_NSHAPES * MAT_STRIDE * 4);   // per-warp fragment queues
     __shared__ __align__(8) unsigned long long s_mbar[2];
     __shared__ int s_envq[2];
-    __shared__ int s_eid, s_late;
+    __shared__ int s_eid, s_late, s_part;
     __shared__ int s_env, s_nrec, s_ncull, s_chunk, s_medc, s_rgrp, s_nlist[3 * NSTRIPS];   // s_nlist[class][strip]
     const int tid = threadIdx.x, lane = tid & 31;
     Rec* recs = rec_scratch + (size_t)blockIdx.x * REC_MAX;
@@ -969,7 +971,9 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
 #else
         float* M = Mbuf;
         if (tid == 0) {
-            s_env = atomicAdd(work_counter, 1); s_nrec = 0; s_ncull = 0; s_chunk = 0; s_medc = 0; s_rgrp = 0;
+            const int item = atomicAdd(work_counter, 1);
+            s_nrec = 0; s_ncull = 0; s_chunk = 0; s_medc = 0; s_rgrp = 0;
+            s_env = split > 1 ? item / split : item; s_part = split > 1 ? item - s_env * split : 0;
             s_eid = s_env; s_late = 0;
             if (LE.order && s_env < N) {          // the solver's order backwards: lightest envs first, the heavy kernel's envs last
                 int idx = N - 1 - s_env, n_heavy = 0, cls = 0;
@@ -1002,7 +1006,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         const size_t img = (size_t)e * RR_W * RR_H;
         const bool on = env_mask ? (env_mask[e] != 0) : true;
         if (!on) {   // reference returns cached zero arrays when render is off (env.py:114-122, 273-275)
-            for (int i = tid; i < RR_H * RR_W / 4; i += RTHREADS) {
+            for (int i = tid; i < RR_H * RR_W / 4 && s_part == 0; i += RTHREADS) {
                 size_t o = img + 4 * (size_t)i;
                 if (rgb) { unsigned int* p = reinterpret_cast<unsigned int*>(rgb + o * 3); p[0] = 0; p[1] = 0; p[2] = 0; }
                 if (depth) *reinterpret_cast<float4*>(depth + o) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1103,8 +1107,15 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
         __threadfence_block();
         __syncthreads();
         // ---- strips (two barriers each: raster | shade + store + clear), both phases self-scheduled
-        for (int strip = 0; strip < NSTRIPS; strip++) {
+        const int part = s_part;
+        if (MODE == 2 && split > 1) {          // the previous item's resolve pass left the static keys of some other strip behind
+            __syncthreads();
+            for (int i = tid; i < STRIP_ROWS * RR_W; i += RTHREADS) keys[i] = static_keys[(size_t)part * STRIP_ROWS * RR_W + i];
+            __syncthreads();
+        }
+        for (int strip = part; strip < NSTRIPS; strip += split) {
             const int row0 = strip * STRIP_ROWS;
+            const int next_row0 = strip + split >= NSTRIPS ? 0 : row0 + split * STRIP_ROWS;      // whose static keys the resolve pass leaves in the key buffer
             const int nsmall = min(s_nlist[strip], REC_MAX), nmed = min(s_nlist[NSTRIPS + strip], REC_MAX), nbig = min(s_nlist[2 * NSTRIPS + strip], REC_MAX);
             const unsigned short* list = lists + (size_t)strip * 2 * REC_MAX;
             if (tid == 0) s_rgrp = 0;
@@ -1182,7 +1193,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                         }
                         if (depth) __stcs(reinterpret_cast<float4*>(depth + o), __ldg(reinterpret_cast<const float4*>(SL.depth + po)));
                         if (seg) __stcs(reinterpret_cast<int4*>(seg + o), __ldg(reinterpret_cast<const int4*>(SL.seg + po)));
-                        const ulonglong2* nk = reinterpret_cast<const ulonglong2*>(static_keys + (size_t)((strip + 1 == NSTRIPS ? 0 : row0 + STRIP_ROWS) + r) * RR_W + 4 * x4);
+                        const ulonglong2* nk = reinterpret_cast<const ulonglong2*>(static_keys + (size_t)(next_row0 + r) * RR_W + 4 * x4);
                         ulonglong2* kq = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
                         __syncwarp();                             // the keys replaced here were read by other lanes above
                         kq[0] = __ldg(nk); kq[1] = __ldg(nk + 1);
@@ -1207,7 +1218,7 @@ k_raster(const float* __restrict__ mats, const float* __restrict__ tris, const u
                 const int i = g * 32 + lane;
                 const int r = i / (RR_W / 4), x4 = i % (RR_W / 4);
                 // MODE 2: the keys this lane consumes are replaced by the static keys of the same pixels of the next strip
-                const ulonglong2* nk = reinterpret_cast<const ulonglong2*>(static_keys + (size_t)((strip + 1 == NSTRIPS ? 0 : row0 + STRIP_ROWS) + r) * RR_W + 4 * x4);
+                const ulonglong2* nk = reinterpret_cast<const ulonglong2*>(static_keys + (size_t)(next_row0 + r) * RR_W + 4 * x4);
                 if (!__any_sync(0xffffffffu, covered)) {          // nothing but background in these 128 pixels (keys already zero)
                     if (MODE == 2) {
                         ulonglong2* kq = reinterpret_cast<ulonglong2*>(keys + r * RR_W + 4 * x4);
@@ -1337,7 +1348,7 @@ int rrk_render_upload_constants(rr_ctx* ctx) {
         if (per_sm0 < per_sm) per_sm = per_sm0;
         if (per_sm < 1) { ctx->err = "k_raster does not fit on this device"; return -1; }
         ctx->raster_grid = prop.multiProcessorCount * per_sm;           // persistent: one wave of CTAs, envs pulled from a counter
-        if (ctx->raster_grid > ctx->N) ctx->raster_grid = ctx->N;
+        if (ctx->raster_grid > ctx->N * NSTRIPS) ctx->raster_grid = ctx->N * NSTRIPS;      // (small batches: up to one CTA per strip)
         CK(cudaMalloc(&ctx->d_rec_scratch, (size_t)ctx->raster_grid * REC_MAX * sizeof(Rec)));
         CK(cudaMalloc(&ctx->d_work_counter, sizeof(int)));
         CK(cudaMalloc(&ctx->d_list_scratch, (size_t)ctx->raster_grid * NSTRIPS * 2 * REC_MAX * sizeof(unsigned short)));
@@ -1418,11 +1429,14 @@ static int render_range(rr_ctx* ctx, const uint8_t* mask, const double* frames, 
     const StaticLayer SL = static_layer(ctx);
 #define RASTER_ARGS(RGB, DEP, SEG, MASK, NENV) ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris, \
         ctx->d_tex, MASK, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, (unsigned short*)ctx->d_cull_scratch, \
-        ctx->d_work_counter, RGB, DEP, SEG, env_begin, NENV, SL, LE
+        ctx->d_work_counter, RGB, DEP, SEG, env_begin, NENV, SL, LE, split
     CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), s));
     {
         ProfScope ps(ctx, 2, s);
-        int grid = ctx->raster_grid < env_count ? ctx->raster_grid : env_count;
+        // small batches: the six strips of an env go to up to six CTAs (see k_raster); not beside the late-env path, whose CTAs write the env's matrices
+        int split = 1;
+        if (!late && !TMA_MATS) for (int sp : {6, 3, 2}) if (NSTRIPS % sp == 0 && env_count * sp <= ctx->raster_grid) { split = sp; break; }
+        int grid = ctx->raster_grid < env_count * split ? ctx->raster_grid : env_count * split;
         // late mode: the heavy kernel's narrowphase follows it while this kernel runs — leave it two SMs (persistent CTAs never give way)
         if (late && grid > 4 * RASTER_LATE_SPARE) grid -= RASTER_LATE_SPARE;
         if (use_static) RR_LAUNCH(k_raster<2>, grid, RTHREADS, RASTER_SMEM, s)(RASTER_ARGS(rgb, depth, seg, mask, env_count));
@@ -1449,7 +1463,7 @@ int rrk_render_build_static(rr_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(int), 0));
     RR_LAUNCH(k_raster<1>, 1, RTHREADS, RASTER_SMEM, 0)(ctx->st.render_mats, ctx->d_tris, ctx->d_tri_shape, (const float4*)ctx->d_planes, ctx->n_tris,
         ctx->d_tex, nullptr, (Rec*)ctx->d_rec_scratch, (unsigned short*)ctx->d_list_scratch, (unsigned short*)ctx->d_cull_scratch,
-        ctx->d_work_counter, const_cast<uint8_t*>(SL.rgb), const_cast<float*>(SL.depth), const_cast<int32_t*>(SL.seg), 0, 1, SL, LateEnvs{});
+        ctx->d_work_counter, const_cast<uint8_t*>(SL.rgb), const_cast<float*>(SL.depth), const_cast<int32_t*>(SL.seg), 0, 1, SL, LateEnvs{}, 1);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     ctx->launches += 2;
