@@ -53,8 +53,9 @@ def run(script, obj, kern, src, dst, extra=()):
     open(os.path.join(prof, dst), "w").write(res)
 run("ncu_phases.py", "rr_render.o", "k_raster", "rr_render.cu", tag + "_k_raster_phases.txt")
 run("ncu_lines.py", "rr_render.o", "k_raster", None, tag + "_k_raster_hot_lines.txt", ["30"])
-run("ncu_phases.py", "rr_physics.o", "k_step_solve", "rr_physics.cu", tag + "_k_step_solve_phases.txt")
-run("ncu_lines.py", "rr_physics.o", "k_step_solve", None, tag + "_k_step_solve_hot_lines.txt", ["30"])
+run("ncu_phases.py", "rr_physics.o", "k_step_solve$", "rr_physics.cu", tag + "_k_step_solve_phases.txt")
+run("ncu_lines.py", "rr_physics.o", "k_step_solve$", None, tag + "_k_step_solve_hot_lines.txt", ["30"])
+run("ncu_phases.py", "rr_physics.o", "k_step_solve_heavy", "rr_physics.cu", tag + "_k_step_solve_heavy_phases.txt")
 run("ncu_phases.py", "rr_physics.o", "k_step_dyn", "rr_physics.cu", tag + "_k_step_dyn_phases.txt")
 run("ncu_phases.py", "rr_collide.o", "k_collide", "rr_collide.cu", tag + "_k_collide_phases.txt")
 print("profiles written for", tag)

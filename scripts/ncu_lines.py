@@ -14,7 +14,7 @@ infn = False
 for l in sass.splitlines():
     m = re.match(r"\s*\.text\.(\S+):", l)
     if m:
-        infn = kern in m.group(1)
+        infn = re.search(kern.replace("$", r"(?![A-Za-z_])"), m.group(1)) is not None     # 'k_step_solve$' does not match k_step_solve_heavy
         continue
     if not infn:
         continue
