@@ -983,8 +983,9 @@ __device__ __forceinline__ void pgs_sweep(const unsigned int* const schedA0, con
 #define SOLVE_WPB 4
 #endif
 #ifndef SOLVE_MIN_BLOCKS
-#define SOLVE_MIN_BLOCKS 6           // 24 warps per SM, 85 registers (no spills): measured best of 4 / 5 / 6 / 7 / 8 blocks x 4 warps, 10 / 12 x 2, 20 / 24 x 1
-#endif
+#define SOLVE_MIN_BLOCKS 6           // blocks per SM of the main kernel when it has every env (24 warps, 80 registers): the long chains of the
+#define SOLVE_MIN_BLOCKS_SPLIT 7     // heavy envs want latency; when they have their own kernel, 7 (28 warps, 72 registers) — measured best of
+#endif                               // 5 / 6 / 7 / 8 blocks x 4 warps, 14 x 2, 28 x 1, 3 x 8 in either mode (back-to-back steps 3.52 vs 4.05 ms, bench step 6.55 vs 6.45)
 struct SolveEpi { SolveHead head; KinWs kin; };
 #define SOLVE_SMEM_DOUBLES ((int)(sizeof(SolveEpi) / 8) > RR_MAX_ROWS ? (int)(sizeof(SolveEpi) / 8) : RR_MAX_ROWS)
 #ifndef SOLVE_SCHED_WORDS
@@ -1139,7 +1140,8 @@ __device__ __forceinline__ void solve_env(const DevState& st, const int e, doubl
         st.timestep[e] += 1;
     }
 }
-__global__ void __launch_bounds__(SOLVE_WPB * 32, SOLVE_MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects, int heavy_cap) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(SOLVE_WPB * 32, MIN_BLOCKS) k_step_solve(DevState st, int* __restrict__ man_hdr, double* __restrict__ man_pts, rr_config cf, int n_objects, int heavy_cap) {
     RR_DYN_SMEM(smem_raw);
     double* const smem = reinterpret_cast<double*>(smem_raw + (size_t)(threadIdx.x >> 5) * SOLVE_SMEM_BYTES);
     const int idx = blockIdx.x * SOLVE_WPB + (threadIdx.x >> 5) + solve_n_heavy(st, heavy_cap);      // the heavy kernel has the first ones
@@ -1323,7 +1325,8 @@ int rrk_upload_constants(rr_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_robot, &ctx->robot, sizeof(RobotConst)));
     g_phys_owner[ctx->device & 63] = ctx;
     CK(cudaFuncSetAttribute(k_step_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpMem) * WPB)));
-    CK(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * SOLVE_WPB)));
+    CK(cudaFuncSetAttribute(k_step_solve<SOLVE_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * SOLVE_WPB)));
+    CK(cudaFuncSetAttribute(k_step_solve<SOLVE_MIN_BLOCKS_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SOLVE_SMEM_BYTES * SOLVE_WPB)));
     CK(cudaFuncSetAttribute(k_step_solve_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAVY_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FkMem) * WPB)));
     return 0;
@@ -1448,7 +1451,8 @@ int rrk_step(rr_ctx* ctx, const double* cmd, cudaStream_t s) {
             ctx->heavy_pending = true;     // joined by whoever touches the state next (rrk_join_heavy); the eye-camera rasteriser waits per env instead
             ctx->launches++;
         }
-        RR_LAUNCH(k_step_solve, nblk(ctx->N, SOLVE_WPB), SOLVE_WPB * 32, SOLVE_SMEM_BYTES * SOLVE_WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects, heavy_cap);
+        if (heavy) RR_LAUNCH(k_step_solve<SOLVE_MIN_BLOCKS_SPLIT>, nblk(ctx->N, SOLVE_WPB), SOLVE_WPB * 32, SOLVE_SMEM_BYTES * SOLVE_WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects, heavy_cap);
+        else RR_LAUNCH(k_step_solve<SOLVE_MIN_BLOCKS>, nblk(ctx->N, SOLVE_WPB), SOLVE_WPB * 32, SOLVE_SMEM_BYTES * SOLVE_WPB, s)(ctx->st, ctx->st.man_hdr[ctx->man_parity], ctx->st.man_pts[ctx->man_parity], ctx->cfg, ctx->n_objects, heavy_cap);
         ctx->launches += 2;
         CK(cudaGetLastError());
     }
